@@ -1,0 +1,169 @@
+/*
+ * mfb200 -- C ABI of the B200-native implicit matrix-factorisation hot path.
+ *
+ * Drop-in boundary for the reference's (Stamatios-Korres/recommendation_Gans) implicit-MF
+ * fit / predict / evaluate path.  The reference has no FFI of its own (pure Python on torch);
+ * each entry point below replaces the torch/numpy/CPython work done at the cited reference
+ * lines, and is bound from Python with ctypes (recommendation_gans_b200/_native.py; the
+ * reference-side stub is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - Every function returns MFB_OK (0) or a negative mfb_status; mfb_last_error() gives text.
+ *   - Pointers named d_* are DEVICE pointers (borrowed for the call; torch owns parameter and
+ *     optimiser-state storage), h_* are HOST pointers.  No torch types cross this boundary.
+ *   - Ids are int64 (the reference keeps all ids as torch.int64, implicit.py:264-268).
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it.  Calls that return
+ *     host data synchronise that stream before returning.
+ *   - Not re-entrant per model handle; no internal threads.
+ */
+#ifndef MFB200_H
+#define MFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFB200_VERSION 100
+
+typedef struct mfb_model mfb_model; /* opaque */
+typedef void *mfb_stream;           /* cudaStream_t */
+
+typedef enum {
+  MFB_OK = 0,
+  MFB_ERR_INVALID = -1,     /* bad argument */
+  MFB_ERR_CUDA = -2,        /* CUDA runtime error (text in mfb_last_error) */
+  MFB_ERR_RANGE = -3,       /* id >= table size  (reference: ValueError, implicit.py:222-236) */
+  MFB_ERR_SHAPE = -4,       /* hinge/bpr with len(neg) != len(pos) (reference: torch broadcast RuntimeError) */
+  MFB_ERR_UNSUPPORTED = -5, /* feature outside the hot path */
+  MFB_ERR_NOMEM = -6
+} mfb_status;
+
+/* spotlight/losses.py:20,59,99,133 */
+typedef enum {
+  MFB_LOSS_POINTWISE = 0,
+  MFB_LOSS_BPR = 1,
+  MFB_LOSS_HINGE = 2,
+  MFB_LOSS_ADAPTIVE_HINGE = 3
+} mfb_loss;
+
+/* spotlight/optimizers.py:4-15 -> torch.optim.SGD (momentum 0) / torch.optim.Adam (dense) */
+typedef enum { MFB_OPT_SGD = 0, MFB_OPT_ADAM = 1 } mfb_optimizer;
+
+/* BilinearNet parameters (spotlight/factorization/representations.py:47-60) and the
+ * optimiser configuration (implicit.py:182-192).  All tables row-major fp32 on the device. */
+typedef struct {
+  int32_t num_users;
+  int32_t num_items;
+  int32_t dim;
+  int32_t optimizer; /* mfb_optimizer */
+  double lr;
+  double beta1;
+  double beta2;
+  double eps;
+  double weight_decay;
+  float *d_user_emb;  /* [num_users, dim] */
+  float *d_item_emb;  /* [num_items, dim] */
+  float *d_user_bias; /* [num_users, 1]   */
+  float *d_item_bias; /* [num_items, 1]   */
+  /* Adam moments, same shapes as the parameters (NULL for SGD) */
+  float *d_user_emb_m, *d_user_emb_v;
+  float *d_item_emb_m, *d_item_emb_v;
+  float *d_user_bias_m, *d_user_bias_v;
+  float *d_item_bias_m, *d_item_bias_v;
+  int32_t fast_math; /* 0: IEEE sqrt/div in the optimiser replay (parity mode); 1: MUFU approximations */
+  int32_t reserved;
+} mfb_model_desc;
+
+int mfb_version(void);
+const char *mfb_last_error(void);
+
+/* ---- model handle ------------------------------------------------------------------ */
+/* Replaces ImplicitFactorizationModel._initialize (implicit.py:163-199): binds the four
+ * tables and the optimiser.  `opt_step` starts at 0 (torch Adam state['step']). */
+int mfb_model_create(const mfb_model_desc *desc, mfb_model **out);
+int mfb_model_destroy(mfb_model *m);
+int64_t mfb_model_step(const mfb_model *m);      /* optimiser steps taken so far */
+int mfb_model_set_step(mfb_model *m, int64_t t); /* e.g. when resuming from torch optimiser state */
+
+/* ---- MT19937 index streams (integer work, bit-exact) -------------------------------- */
+/* State layout = CPython random.getstate()[1] / numpy RandomState.get_state()[1:3]:
+ * 624 words followed by the position (h_state[624] in 0..624).  Updated in place. */
+
+/* implicit.py:352,370  random.choices(neg_examples, k): writes the k sampled (user,item)
+ * pairs, gathered from the population arrays, consuming exactly 2k words of the stream. */
+int mfb_mt_choices_pairs(uint32_t *h_state, const int64_t *d_pop_users, const int64_t *d_pop_items,
+                         int64_t pop_len, int64_t k, int64_t *d_out_users, int64_t *d_out_items,
+                         mfb_stream stream);
+/* same stream, indices only (random.choices(range(pop_len), k)) */
+int mfb_mt_choices_indices(uint32_t *h_state, int64_t pop_len, int64_t k, int64_t *d_out, mfb_stream stream);
+/* spotlight/sampling.py:33  random_state.randint(0, num_items, count, dtype=int64):
+ * masked rejection on 32-bit draws; consumes a data-dependent number of words. */
+int mfb_mt_sample_items(uint32_t *h_state, int64_t num_items, int64_t count, int64_t *d_out, mfb_stream stream);
+/* raw tempered 32-bit outputs (test hook) */
+int mfb_mt_words(uint32_t *h_state, int64_t nwords, uint32_t *d_out, mfb_stream stream);
+
+/* ---- forward / predict ---------------------------------------------------------------- */
+/* BilinearNet.forward (representations.py:62-91) on m (user,item) pairs:
+ * out[j] = sigmoid(<U[u_j],V[i_j]> + bu[u_j] + bi[i_j]).  Also ImplicitFactorizationModel.predict
+ * in its pairwise form (implicit.py:381-415).  Brings lazily-updated rows up to date first. */
+int mfb_predict_pairs(mfb_model *m, const int64_t *d_users, const int64_t *d_items, int64_t count,
+                      float *d_out, mfb_stream stream);
+/* predict(user_id) for all items (implicit.py:410-415, _components.py:8-25) */
+int mfb_predict_user(mfb_model *m, int64_t user, float *d_out, mfb_stream stream);
+
+/* ---- losses on probability vectors (spotlight/losses.py:20-172, 1-D tensors) ---------- */
+/* d_loss: 1 float.  d_dpos/d_dneg may be NULL (forward only); otherwise dLoss/dpred. */
+int mfb_loss_forward_backward(int loss, const float *d_pos, int64_t n_pos, const float *d_neg, int64_t n_neg,
+                              float *d_loss, float *d_dpos, float *d_dneg, mfb_stream stream);
+
+/* ---- training ------------------------------------------------------------------------- */
+/* Fused replacement of the inner loop of ImplicitFactorizationModel.fit
+ * (implicit.py:290-298 -> run_train_iteration, implicit.py:347-364) over
+ * nsteps = ceil(n_pos / batch) consecutive minibatches:
+ *   step s uses positives [s*batch, min((s+1)*batch, n_pos)) and the n_neg*batch negative
+ *   pairs d_neg_*[s*n_neg*batch ...] (k uses the full batch even on the last partial batch).
+ * Forward, loss, backward and the optimiser update have DENSE-optimiser semantics (every row
+ * of every table steps every iteration) implemented with row-sparse traffic: rows not in a
+ * batch are brought up to date lazily (mfb_flush, or when next gathered).
+ * d_step_losses[s] receives the batch loss of step s (what loss.item() returns). */
+int mfb_train_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const int64_t *d_pos_items,
+                    int64_t n_pos, int32_t batch, int32_t n_neg, const int64_t *d_neg_users,
+                    const int64_t *d_neg_items, float *d_step_losses, mfb_stream stream);
+/* run_val_iteration (implicit.py:366-379) over consecutive minibatches: same batching, no update. */
+int mfb_loss_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const int64_t *d_pos_items,
+                   int64_t n_pos, int32_t batch, int32_t n_neg, const int64_t *d_neg_users,
+                   const int64_t *d_neg_items, float *d_step_losses, mfb_stream stream);
+/* Apply all pending dense-optimiser updates to every row (before any external read of the
+ * tables: predict, evaluation, best-model copy, checkpoint; implicit.py:321-324,338-343). */
+int mfb_flush(mfb_model *m, mfb_stream stream);
+
+/* Host-buffer entry (end-to-end path): positives in pageable/pinned HOST memory, negatives drawn
+ * on the device from the MT19937 stream in h_state (random.choices semantics over the device
+ * population arrays); per-step losses are returned in h_step_losses.  H2D of the ids and D2H of
+ * the losses happen inside the call.  Equivalent to one training epoch of implicit.py:289-298. */
+int mfb_train_epoch_host(mfb_model *m, int loss, const int64_t *h_pos_users, const int64_t *h_pos_items,
+                         int64_t n_pos, int32_t batch, int32_t n_neg, uint32_t *h_state,
+                         const int64_t *d_pop_users, const int64_t *d_pop_items, int64_t pop_len,
+                         float *h_step_losses, mfb_stream stream);
+
+/* ---- full-catalog evaluation ------------------------------------------------------------ */
+/* Scores every listed user against all items and keeps the top-k (k <= MFB_MAX_TOPK) item ids,
+ * best first, ties -> lower item id, ranking on the pre-sigmoid score; items in the user's
+ * train row (CSR, sorted indices; may be NULL) rank last (evaluation.py:160-169).
+ * Replaces the per-user predict + argsort loop of precision_recall_score. */
+#define MFB_MAX_TOPK 32
+int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
+             const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
+             mfb_stream stream);
+/* _get_precision_recall (evaluation.py:108-113): hits[u*nk + j] = |topk[u,:ks[j]] ∩ test_row(u)|,
+ * ntargets[u] = len(test_row(u)).  ks ascending, ks[nk-1] <= k. */
+int mfb_topk_hits(const int32_t *d_topk_ids, const int64_t *d_user_ids, int64_t n_users, int32_t k,
+                  const int64_t *d_test_indptr, const int32_t *d_test_indices, const int32_t *h_ks, int32_t nk,
+                  int32_t *d_hits, int32_t *d_ntargets, mfb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFB200_H */

@@ -1,0 +1,165 @@
+// Model handle, error reporting and optimiser scalar tables of the mfb200 C ABI.
+// mfb_model_create replaces ImplicitFactorizationModel._initialize (implicit.py:163-199): it binds
+// the BilinearNet tables (torch-owned storage) and the optimiser hyper-parameters.
+#include <math.h>
+#include <stdarg.h>
+
+#include "mfb_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void mfb_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *mfb_last_error(void) { return g_err; }
+extern "C" int mfb_version(void) { return MFB200_VERSION; }
+
+// step_size[t] = lr / (1 - beta1^t), bc2_sqrt[t] = sqrt(1 - beta2^t): computed in double exactly as
+// torch/optim/adam.py does in Python floats, then rounded to fp32 when they meet fp32 tensors.
+int mfb_ensure_scalars(mfb_model *m, int64_t upto) {
+  if (m->desc.optimizer != MFB_OPT_ADAM) return MFB_OK;
+  if (upto < m->scalars_cap) return MFB_OK;
+  int64_t cap = m->scalars_cap > 0 ? m->scalars_cap : 4096;
+  while (cap <= upto) cap *= 2;
+  if (cap >= (1ll << 31)) {
+    mfb_set_error("optimiser step count too large");
+    return MFB_ERR_UNSUPPORTED;
+  }
+  m->h_step_size.resize(cap);
+  m->h_bc2_sqrt.resize(cap);
+  for (int64_t t = (m->scalars_cap > 0 ? m->scalars_cap : 0); t < cap; ++t) {
+    if (t == 0) {
+      m->h_step_size[0] = 0.f;
+      m->h_bc2_sqrt[0] = 1.f;
+      continue;
+    }
+    double bc1 = 1.0 - pow(m->desc.beta1, (double)t);
+    double bc2 = 1.0 - pow(m->desc.beta2, (double)t);
+    m->h_step_size[t] = (float)(m->desc.lr / bc1);
+    m->h_bc2_sqrt[t] = (float)sqrt(bc2);
+  }
+  // the old arrays may still be read by queued kernels: drain before replacing them
+  MFB_CUDA(cudaDeviceSynchronize());
+  MFB_CHECK(m->d_step_size.reserve((size_t)cap * sizeof(float)));
+  MFB_CHECK(m->d_bc2_sqrt.reserve((size_t)cap * sizeof(float)));
+  MFB_CUDA(cudaMemcpy(m->d_step_size.ptr, m->h_step_size.data(), (size_t)cap * sizeof(float), cudaMemcpyHostToDevice));
+  MFB_CUDA(cudaMemcpy(m->d_bc2_sqrt.ptr, m->h_bc2_sqrt.data(), (size_t)cap * sizeof(float), cudaMemcpyHostToDevice));
+  m->opt.step_size = m->d_step_size.as<float>();
+  m->opt.bc2_sqrt = m->d_bc2_sqrt.as<float>();
+  m->scalars_cap = cap;
+  return MFB_OK;
+}
+
+extern "C" int mfb_model_create(const mfb_model_desc *d, mfb_model **out) {
+  if (!d || !out) return MFB_ERR_INVALID;
+  *out = nullptr;
+  if (d->num_users <= 0 || d->num_items <= 0 || d->dim <= 0 || d->dim > 512) {
+    mfb_set_error("model_create: bad shape users=%d items=%d dim=%d (dim must be 1..512)", d->num_users,
+                  d->num_items, d->dim);
+    return MFB_ERR_INVALID;
+  }
+  if (!d->d_user_emb || !d->d_item_emb || !d->d_user_bias || !d->d_item_bias) {
+    mfb_set_error("model_create: null parameter table");
+    return MFB_ERR_INVALID;
+  }
+  if (d->optimizer != MFB_OPT_SGD && d->optimizer != MFB_OPT_ADAM) {
+    mfb_set_error("model_create: optimizer %d unsupported (SGD without momentum, Adam)", d->optimizer);
+    return MFB_ERR_UNSUPPORTED;
+  }
+  if (d->optimizer == MFB_OPT_ADAM &&
+      (!d->d_user_emb_m || !d->d_user_emb_v || !d->d_item_emb_m || !d->d_item_emb_v || !d->d_user_bias_m ||
+       !d->d_user_bias_v || !d->d_item_bias_m || !d->d_item_bias_v)) {
+    mfb_set_error("model_create: Adam needs exp_avg / exp_avg_sq buffers for all four tables");
+    return MFB_ERR_INVALID;
+  }
+  if (d->dim % 4 == 0) {
+    const uintptr_t align = (uintptr_t)d->d_user_emb | (uintptr_t)d->d_item_emb | (uintptr_t)d->d_user_emb_m |
+                            (uintptr_t)d->d_user_emb_v | (uintptr_t)d->d_item_emb_m | (uintptr_t)d->d_item_emb_v;
+    if (align & 15) {
+      mfb_set_error("model_create: tables must be 16-byte aligned");
+      return MFB_ERR_INVALID;
+    }
+  }
+  mfb_model *m = new mfb_model();
+  m->desc = *d;
+  auto bind = [&](TableView &T, int rows, float *p, float *pm, float *pv, float *b, float *bm, float *bv) {
+    T.p = p; T.m = pm; T.v = pv; T.bp = b; T.bm = bm; T.bv = bv; T.rows = rows; T.last = nullptr;
+  };
+  bind(m->users, d->num_users, d->d_user_emb, d->d_user_emb_m, d->d_user_emb_v, d->d_user_bias, d->d_user_bias_m,
+       d->d_user_bias_v);
+  bind(m->items, d->num_items, d->d_item_emb, d->d_item_emb_m, d->d_item_emb_v, d->d_item_bias, d->d_item_bias_m,
+       d->d_item_bias_v);
+  int rc = m->last_users.reserve((size_t)d->num_users * sizeof(int32_t));
+  if (rc == MFB_OK) rc = m->last_items.reserve((size_t)d->num_items * sizeof(int32_t));
+  if (rc != MFB_OK) {
+    delete m;
+    return rc;
+  }
+  cudaMemset(m->last_users.ptr, 0, (size_t)d->num_users * sizeof(int32_t));
+  cudaMemset(m->last_items.ptr, 0, (size_t)d->num_items * sizeof(int32_t));
+  m->users.last = m->last_users.as<int32_t>();
+  m->items.last = m->last_items.as<int32_t>();
+  OptView &o = m->opt;
+  o.kind = d->optimizer;
+  o.fast = d->fast_math;
+  o.lr = (float)d->lr;
+  o.beta1 = (float)d->beta1;
+  o.beta2 = (float)d->beta2;
+  o.eps = (float)d->eps;
+  o.wd = (float)d->weight_decay;
+  const float w = (float)(1.0 - d->beta1);  // exp_avg.lerp_(grad, 1 - beta1): weight is a Python double -> fp32
+  o.lerp_small = fabsf(w) < 0.5f;
+  o.lerp_coeff = o.lerp_small ? w : (w - 1.0f);
+  o.one_minus_beta2 = (float)(1.0 - d->beta2);
+  o.step_size = nullptr;
+  o.bc2_sqrt = nullptr;
+  rc = mfb_ensure_scalars(m, 4095);
+  if (rc != MFB_OK) {
+    delete m;
+    return rc;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    mfb_set_error("model_create: %s", cudaGetErrorString(e));
+    delete m;
+    return MFB_ERR_CUDA;
+  }
+  *out = m;
+  return MFB_OK;
+}
+
+extern "C" int mfb_model_destroy(mfb_model *m) {
+  if (!m) return MFB_OK;
+  cudaDeviceSynchronize();
+  DevBuf *bufs[] = {&m->d_step_size, &m->d_bc2_sqrt, &m->last_users, &m->last_items, &m->ws_slots, &m->ws_keys_a,
+                    &m->ws_keys_b, &m->ws_vals_a, &m->ws_vals_b, &m->ws_hist, &m->ws_rows, &m->ws_pred, &m->ws_dz,
+                    &m->ws_scalars, &m->ws_ids, &m->ws_neg_u, &m->ws_neg_i, &m->ws_words, &m->ws_losses};
+  for (DevBuf *b : bufs) b->release();
+  delete m;
+  return MFB_OK;
+}
+
+extern "C" int64_t mfb_model_step(const mfb_model *m) { return m ? m->step : -1; }
+
+extern "C" int mfb_model_set_step(mfb_model *m, int64_t t) {
+  if (!m || t < 0) return MFB_ERR_INVALID;
+  if (m->flushed_step != m->step) {
+    mfb_set_error("set_step: flush pending updates first");
+    return MFB_ERR_INVALID;
+  }
+  // all rows are current: re-base the per-row counters
+  cudaDeviceSynchronize();
+  if (t != m->step) {
+    // rows are all at m->step == flushed_step; make them current for t
+    std::vector<int32_t> fill_u((size_t)m->users.rows, (int32_t)t), fill_i((size_t)m->items.rows, (int32_t)t);
+    MFB_CUDA(cudaMemcpy(m->users.last, fill_u.data(), fill_u.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    MFB_CUDA(cudaMemcpy(m->items.last, fill_i.data(), fill_i.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  m->step = t;
+  m->flushed_step = t;
+  return mfb_ensure_scalars(m, t + 1);
+}

@@ -1,0 +1,253 @@
+// Full-catalog evaluation: user x item scoring with the train-interaction mask and top-k fused,
+// so the score matrix never reaches HBM.  Replaces the per-user loop of
+// spotlight/evaluation.py:155-180 (model.predict(user) -> mask -> argsort -> set intersections).
+//
+// This file holds the exact-fp32 CUDA-core path: scores are sequential-FMA dot products
+// (d = 0..D-1) + user bias + item bias, ranked on the pre-sigmoid value with ties -> lower item
+// id.  It is the reference ordering the tensor-core path (mfb_eval_tc.cu) is
+// re-scored against, and the path used for shapes the tensor-core kernel does not cover.
+#include <math.h>
+
+#include "mfb_internal.cuh"
+
+namespace {
+
+constexpr int EV_THREADS = 256;
+constexpr int EV_ITEMS = 128;   // items per tile
+constexpr int EV_USERS = 16;    // users per CTA (2 groups of 8, one group per half of the CTA)
+constexpr int EV_UPT = 8;       // users per thread
+constexpr float MASKED_SCORE = -3.402823466e38f;  // ranks after every real score, before empty slots
+
+// Warp-resident sorted top-k list: lane r holds the r-th best (value, id).
+struct TopK {
+  float val;
+  int id;
+};
+
+__device__ __forceinline__ void topk_insert(TopK &mine, float nv, int nid, int lane, int k) {
+  // candidates arrive in ascending item id, so a new entry goes after every entry with val >= nv
+  unsigned ge = __ballot_sync(0xffffffffu, mine.val >= nv);
+  int pos = __popc(ge);
+  float up_v = __shfl_up_sync(0xffffffffu, mine.val, 1);
+  int up_i = __shfl_up_sync(0xffffffffu, mine.id, 1);
+  if (lane > pos) {
+    mine.val = up_v;
+    mine.id = up_i;
+  } else if (lane == pos) {
+    mine.val = nv;
+    mine.id = nid;
+  }
+  (void)k;
+}
+
+// grid: ceil(n_users / EV_USERS).  dynamic smem: Vs[EV_ITEMS][D+1] | Us[EV_USERS][D] | S[EV_USERS][EV_ITEMS]
+__global__ void __launch_bounds__(EV_THREADS) k_topk_exact(const long long *__restrict__ user_ids, int n_users,
+                                                           TableView users, TableView items, int D,
+                                                           const long long *__restrict__ indptr,
+                                                           const int *__restrict__ indices, int k,
+                                                           int *__restrict__ out_ids, float *__restrict__ out_scores) {
+  extern __shared__ float smem[];
+  const int ldv = D + 1;
+  float *Vs = smem;
+  float *Us = Vs + EV_ITEMS * ldv;
+  float *S = Us + EV_USERS * D;
+  __shared__ long long s_uid[EV_USERS];
+  __shared__ float s_ub[EV_USERS];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int u0 = blockIdx.x * EV_USERS;
+  const int I = items.rows;
+
+  if (tid < EV_USERS) {
+    int ui = u0 + tid;
+    long long uid = (ui < n_users) ? user_ids[ui] : -1;
+    s_uid[tid] = uid;
+    s_ub[tid] = (uid >= 0) ? users.bp[uid] : 0.f;
+  }
+  __syncthreads();
+  // user rows transposed ([d][user]) so a thread reads its 8 users at one d with two LDS.128
+  for (int e = tid; e < EV_USERS * D; e += EV_THREADS) {
+    int u = e / D, d = e - u * D;
+    long long uid = s_uid[u];
+    Us[d * EV_USERS + u] = (uid >= 0) ? users.p[uid * D + d] : 0.f;
+  }
+
+  // each warp owns two users of the tile for masking / top-k
+  TopK top[2];
+  long long cur[2], end[2];
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    top[w].val = -INFINITY;
+    top[w].id = 0x7fffffff;
+    long long uid = s_uid[wid * 2 + w];
+    cur[w] = end[w] = 0;
+    if (uid >= 0 && indptr != nullptr) {
+      cur[w] = indptr[uid];
+      end[w] = indptr[uid + 1];
+    }
+  }
+
+  const int item_l = tid & (EV_ITEMS - 1);
+  const int ugrp = tid / EV_ITEMS;  // 0 or 1 -> users ugrp*8 .. ugrp*8+7
+
+  for (int i0 = 0; i0 < I; i0 += EV_ITEMS) {
+    __syncthreads();  // previous tile fully consumed (also covers the Us fill on the first pass)
+    // stage the item tile: coalesced global reads, padded rows in smem
+    for (int e = tid; e < EV_ITEMS * D; e += EV_THREADS) {
+      int r = e / D, d = e - r * D;
+      int it = i0 + r;
+      Vs[r * ldv + d] = (it < I) ? items.p[(long long)it * D + d] : 0.f;
+    }
+    __syncthreads();
+    {
+      float acc[EV_UPT];
+#pragma unroll
+      for (int u = 0; u < EV_UPT; ++u) acc[u] = 0.f;
+      const float *vrow = Vs + item_l * ldv;
+      const float *ubase = Us + ugrp * EV_UPT;
+      for (int d = 0; d < D; ++d) {
+        const float v = vrow[d];
+        const float4 ua = *reinterpret_cast<const float4 *>(ubase + d * EV_USERS);
+        const float4 ub = *reinterpret_cast<const float4 *>(ubase + d * EV_USERS + 4);
+        acc[0] = fmaf(ua.x, v, acc[0]);
+        acc[1] = fmaf(ua.y, v, acc[1]);
+        acc[2] = fmaf(ua.z, v, acc[2]);
+        acc[3] = fmaf(ua.w, v, acc[3]);
+        acc[4] = fmaf(ub.x, v, acc[4]);
+        acc[5] = fmaf(ub.y, v, acc[5]);
+        acc[6] = fmaf(ub.z, v, acc[6]);
+        acc[7] = fmaf(ub.w, v, acc[7]);
+      }
+      const int it = i0 + item_l;
+      const float ib = (it < I) ? items.bp[it] : 0.f;
+#pragma unroll
+      for (int u = 0; u < EV_UPT; ++u) {
+        int ul = ugrp * EV_UPT + u;
+        S[ul * EV_ITEMS + item_l] = (acc[u] + s_ub[ul]) + ib;
+      }
+    }
+    __syncthreads();
+    // mask + top-k: warp wid handles users 2*wid, 2*wid+1
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int ul = wid * 2 + w;
+      if (s_uid[ul] < 0) continue;  // warp-uniform
+      float *srow = S + ul * EV_ITEMS;
+      // train items inside [i0, i0+EV_ITEMS): CSR indices are sorted, cursor only moves forward
+      const int hi = i0 + EV_ITEMS;
+      while (cur[w] < end[w]) {
+        long long p = cur[w] + lane;
+        int idx = (p < end[w]) ? indices[p] : 0x7fffffff;
+        bool in = idx < hi;
+        if (in && idx >= i0) srow[idx - i0] = MASKED_SCORE;
+        unsigned nin = __popc(__ballot_sync(0xffffffffu, in));
+        cur[w] += nin;
+        if (nin < 32) break;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < EV_ITEMS / 32; ++c) {
+        const int il = c * 32 + lane;
+        const int it = i0 + il;
+        float sc = srow[il];
+        float thr = __shfl_sync(0xffffffffu, top[w].val, k - 1);
+        unsigned cand = __ballot_sync(0xffffffffu, (it < I) && (sc > thr));
+        while (cand) {
+          int src = __ffs(cand) - 1;
+          cand &= cand - 1;
+          float nv = __shfl_sync(0xffffffffu, sc, src);
+          int nid = i0 + c * 32 + src;
+          thr = __shfl_sync(0xffffffffu, top[w].val, k - 1);
+          if (nv > thr) topk_insert(top[w], nv, nid, lane, k);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    const int ui = u0 + wid * 2 + w;
+    if (ui < n_users && lane < k) {
+      out_ids[(long long)ui * k + lane] = top[w].id;
+      if (out_scores) {
+        float z = top[w].val;
+        out_scores[(long long)ui * k + lane] = (z == MASKED_SCORE) ? 0.f : 1.0f / (1.0f + expf(-z));
+      }
+    }
+  }
+}
+
+// hits[u, j] = |topk[u, :ks[j]] ∩ test_row(user_ids[u])|  (evaluation.py:108-113); one thread per user
+__global__ void k_topk_hits(const int *__restrict__ topk, const long long *__restrict__ user_ids, int n_users, int k,
+                            const long long *__restrict__ indptr, const int *__restrict__ indices, int k0, int k1,
+                            int k2, int k3, int nk, int *__restrict__ hits, int *__restrict__ ntargets) {
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_users) return;
+  const int ks[4] = {k0, k1, k2, k3};
+  long long uid = user_ids[u];
+  long long lo = indptr[uid], hi = indptr[uid + 1];
+  ntargets[u] = (int)(hi - lo);
+  int h = 0, next = 0;
+  for (int r = 0; r < k; ++r) {
+    int id = topk[(long long)u * k + r];
+    long long a = lo, b = hi;
+    while (a < b) {
+      long long mid = (a + b) >> 1;
+      if (indices[mid] < id) a = mid + 1; else b = mid;
+    }
+    if (a < hi && indices[a] == id) ++h;
+    while (next < nk && ks[next] == r + 1) hits[(long long)u * nk + next++] = h;
+  }
+}
+
+}  // namespace
+
+extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
+                        const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
+                        mfb_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!m || !d_user_ids || !d_out_ids || n_users < 0) return MFB_ERR_INVALID;
+  if (k <= 0 || k > MFB_MAX_TOPK || k > m->items.rows) {
+    mfb_set_error("topk: k=%d outside 1..min(%d, num_items)", k, MFB_MAX_TOPK);
+    return MFB_ERR_UNSUPPORTED;
+  }
+  if ((d_train_indptr == nullptr) != (d_train_indices == nullptr)) return MFB_ERR_INVALID;
+  if (n_users == 0) return MFB_OK;
+  MFB_CHECK(mfb_flush(m, stream));
+  const int D = m->desc.dim;
+  size_t smem = ((size_t)EV_ITEMS * (D + 1) + (size_t)EV_USERS * D + (size_t)EV_USERS * EV_ITEMS) * sizeof(float);
+  if (smem > 220 * 1024) {
+    mfb_set_error("topk: embedding_dim %d needs %zu B of shared memory", D, smem);
+    return MFB_ERR_UNSUPPORTED;
+  }
+  MFB_CUDA(cudaFuncSetAttribute(k_topk_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)((n_users + EV_USERS - 1) / EV_USERS);
+  k_topk_exact<<<grid, EV_THREADS, smem, st>>>((const long long *)d_user_ids, (int)n_users, m->users, m->items, D,
+                                               (const long long *)d_train_indptr, d_train_indices, k, d_out_ids,
+                                               d_out_scores);
+  MFB_KERNEL_CHECK();
+  return MFB_OK;
+}
+
+extern "C" int mfb_topk_hits(const int32_t *d_topk_ids, const int64_t *d_user_ids, int64_t n_users, int32_t k,
+                             const int64_t *d_test_indptr, const int32_t *d_test_indices, const int32_t *h_ks,
+                             int32_t nk, int32_t *d_hits, int32_t *d_ntargets, mfb_stream stream) {
+  if (!d_topk_ids || !d_user_ids || !d_test_indptr || !d_test_indices || !h_ks || !d_hits || !d_ntargets)
+    return MFB_ERR_INVALID;
+  if (nk < 1 || nk > 4) {
+    mfb_set_error("topk_hits: 1..4 cut-offs per call (got %d)", nk);
+    return MFB_ERR_UNSUPPORTED;
+  }
+  int ks[4] = {0, 0, 0, 0};
+  for (int j = 0; j < nk; ++j) {
+    ks[j] = h_ks[j];
+    if (ks[j] < 1 || ks[j] > k || (j > 0 && ks[j] <= ks[j - 1])) {
+      mfb_set_error("topk_hits: cut-offs must be ascending within 1..k");
+      return MFB_ERR_INVALID;
+    }
+  }
+  if (n_users == 0) return MFB_OK;
+  k_topk_hits<<<(unsigned)((n_users + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      d_topk_ids, (const long long *)d_user_ids, (int)n_users, k, (const long long *)d_test_indptr, d_test_indices,
+      ks[0], ks[1], ks[2], ks[3], nk, d_hits, d_ntargets);
+  MFB_KERNEL_CHECK();
+  return MFB_OK;
+}

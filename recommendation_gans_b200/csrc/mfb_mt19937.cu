@@ -1,0 +1,250 @@
+// MT19937 index streams on the device (integer work, bit-exact with CPython `random` and numpy
+// `RandomState`): replaces the host-side negative draws of the reference
+//   implicit.py:352,370      random.choices(neg_examples, k = num_neg * batch)
+//   spotlight/sampling.py:33 random_state.randint(0, num_items, shape, dtype=int64)
+// The generator state travels as (624 words, position) exactly as random.getstate()[1], so the
+// host RNG objects stay in sync with what the reference would have consumed.
+#include "mfb_internal.cuh"
+
+namespace {
+
+constexpr int MT_N = 624;
+constexpr int MT_M = 397;
+constexpr int MT_THREADS = 256;
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9D2C5680u;
+  y ^= (y << 15) & 0xEFC60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+__device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t nxt, uint32_t far) {
+  uint32_t y = (cur & 0x80000000u) | (nxt & 0x7FFFFFFFu);
+  return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+}
+
+// One CTA walks the stream sequentially; the 624-word regeneration is done in three
+// data-parallel phases (new[k] needs old[k], old[k+1] and old/new[(k+397)%624]).
+// state_io: 624 words + position (625 uint32).  out may be nullptr (advance only).
+__global__ void __launch_bounds__(MT_THREADS) k_mt_generate(uint32_t *state_io, unsigned long long nwords,
+                                                            uint32_t *out) {
+  __shared__ uint32_t buf[2][MT_N];
+  const int tid = threadIdx.x;
+  int cur = 0;
+  for (int i = tid; i < MT_N; i += MT_THREADS) buf[0][i] = state_io[i];
+  int pos = (int)state_io[MT_N];
+  __syncthreads();
+  unsigned long long emitted = 0;
+  while (emitted < nwords) {
+    if (pos >= MT_N) {
+      const uint32_t *o = buf[cur];
+      uint32_t *n = buf[cur ^ 1];
+      // phase A: k in [0,227): far = old[k+397]
+      if (tid < MT_N - MT_M) n[tid] = mt_mix(o[tid], o[tid + 1], o[tid + MT_M]);
+      __syncthreads();
+      // phase B: k in [227,454): far = new[k-227]
+      {
+        int k = tid + (MT_N - MT_M);
+        if (k < 2 * (MT_N - MT_M)) n[k] = mt_mix(o[k], o[k + 1], n[k - (MT_N - MT_M)]);
+      }
+      __syncthreads();
+      // phase C: k in [454,624): far = new[k-227]; k=623 wraps to new[0]
+      {
+        int k = tid + 2 * (MT_N - MT_M);
+        if (k < MT_N) {
+          uint32_t nxt = (k == MT_N - 1) ? n[0] : o[k + 1];
+          n[k] = mt_mix(o[k], nxt, n[k - (MT_N - MT_M)]);
+        }
+      }
+      __syncthreads();
+      cur ^= 1;
+      pos = 0;
+    }
+    unsigned long long left = nwords - emitted;
+    int take = (left < (unsigned long long)(MT_N - pos)) ? (int)left : (MT_N - pos);
+    if (out != nullptr) {
+      for (int i = tid; i < take; i += MT_THREADS) out[emitted + i] = mt_temper(buf[cur][pos + i]);
+    }
+    emitted += take;
+    pos += take;
+    __syncthreads();
+  }
+  for (int i = tid; i < MT_N; i += MT_THREADS) state_io[i] = buf[cur][i];
+  if (tid == 0) state_io[MT_N] = (uint32_t)pos;
+}
+
+// random.random(): a = w0 >> 5, b = w1 >> 6, x = (a*2^26 + b) / 2^53; index = floor(x * n).
+__global__ void k_choices(const uint32_t *__restrict__ words, long long k, long long pop_len,
+                          const long long *__restrict__ pop_u, const long long *__restrict__ pop_i,
+                          long long *__restrict__ out_u, long long *__restrict__ out_i,
+                          long long *__restrict__ out_idx) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= k) return;
+  uint32_t a = words[2 * s] >> 5;
+  uint32_t b = words[2 * s + 1] >> 6;
+  double x = __dmul_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 1.0 / 9007199254740992.0);
+  long long idx = (long long)floor(__dmul_rn(x, (double)pop_len));
+  if (out_idx) out_idx[s] = idx;
+  if (out_u) {
+    out_u[s] = pop_u[idx];
+    out_i[s] = pop_i[idx];
+  }
+}
+
+// numpy legacy masked rejection: accept (w & mask) when <= rng, in stream order.
+// Single CTA; writes the first `count` accepted values, the number of stream words consumed to
+// obtain them (result[0]) and the total number accepted among nwords (result[1]).
+__global__ void __launch_bounds__(1024) k_masked_compact(const uint32_t *__restrict__ words, long long nwords,
+                                                         uint32_t mask, uint32_t rng, long long count,
+                                                         long long *__restrict__ out, long long *__restrict__ result) {
+  __shared__ int warp_sums[32];
+  __shared__ long long base_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    base_s = 0;
+    result[0] = -1;
+  }
+  __syncthreads();
+  for (long long start = 0; start < nwords; start += 1024) {
+    long long i = start + tid;
+    uint32_t v = 0;
+    int ok = 0;
+    if (i < nwords) {
+      v = words[i] & mask;
+      ok = (v <= rng);
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, ok);
+    int in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      int c = warp_sums[w];
+      if (w < wid) before += c;
+      total += c;
+    }
+    long long rank = base_s + before + in_warp;
+    if (ok && rank < count) {
+      out[rank] = (long long)v;
+      if (rank == count - 1) result[0] = i + 1;
+    }
+    __syncthreads();
+    if (tid == 0) base_s += total;
+    __syncthreads();
+    if (base_s >= count) break;
+  }
+  if (tid == 0) result[1] = base_s;
+}
+
+DevBuf g_state, g_words, g_result;  // library-global scratch for the model-less RNG entry points
+
+int upload_state(const uint32_t *h_state, cudaStream_t st) {
+  MFB_CHECK(g_state.reserve(625 * sizeof(uint32_t)));
+  if (h_state[624] > 624) {
+    mfb_set_error("MT19937 position %u out of range", h_state[624]);
+    return MFB_ERR_INVALID;
+  }
+  MFB_CUDA(cudaMemcpyAsync(g_state.ptr, h_state, 625 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  return MFB_OK;
+}
+
+}  // namespace
+
+// Generates nwords outputs into d_words (may be nullptr: advance only) and updates h_state.
+int mfb_mt_generate(uint32_t *h_state, int64_t nwords, uint32_t *d_words, cudaStream_t st) {
+  if (nwords < 0) return MFB_ERR_INVALID;
+  MFB_CHECK(upload_state(h_state, st));
+  if (nwords > 0) {
+    k_mt_generate<<<1, MT_THREADS, 0, st>>>(g_state.as<uint32_t>(), (unsigned long long)nwords, d_words);
+    MFB_KERNEL_CHECK();
+  }
+  MFB_CUDA(cudaMemcpyAsync(h_state, g_state.ptr, 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  return MFB_OK;
+}
+
+extern "C" int mfb_mt_words(uint32_t *h_state, int64_t nwords, uint32_t *d_out, mfb_stream stream) {
+  if (!h_state || (nwords > 0 && !d_out)) return MFB_ERR_INVALID;
+  return mfb_mt_generate(h_state, nwords, d_out, (cudaStream_t)stream);
+}
+
+static int choices_impl(uint32_t *h_state, const int64_t *d_pop_users, const int64_t *d_pop_items, int64_t pop_len,
+                        int64_t k, int64_t *d_out_users, int64_t *d_out_items, int64_t *d_out_idx, cudaStream_t st) {
+  if (!h_state || pop_len <= 0 || k < 0) {
+    mfb_set_error("mt_choices: bad arguments (pop_len=%lld, k=%lld)", (long long)pop_len, (long long)k);
+    return MFB_ERR_INVALID;
+  }
+  if (k == 0) return MFB_OK;
+  MFB_CHECK(g_words.reserve((size_t)(2 * k) * sizeof(uint32_t)));
+  MFB_CHECK(mfb_mt_generate(h_state, 2 * k, g_words.as<uint32_t>(), st));
+  int threads = 256;
+  long long blocks = (k + threads - 1) / threads;
+  k_choices<<<(unsigned)blocks, threads, 0, st>>>(g_words.as<uint32_t>(), k, pop_len, (const long long *)d_pop_users,
+                                                  (const long long *)d_pop_items, (long long *)d_out_users,
+                                                  (long long *)d_out_items, (long long *)d_out_idx);
+  MFB_KERNEL_CHECK();
+  return MFB_OK;
+}
+
+extern "C" int mfb_mt_choices_pairs(uint32_t *h_state, const int64_t *d_pop_users, const int64_t *d_pop_items,
+                                    int64_t pop_len, int64_t k, int64_t *d_out_users, int64_t *d_out_items,
+                                    mfb_stream stream) {
+  if (!d_pop_users || !d_pop_items || !d_out_users || !d_out_items) return MFB_ERR_INVALID;
+  return choices_impl(h_state, d_pop_users, d_pop_items, pop_len, k, d_out_users, d_out_items, nullptr,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int mfb_mt_choices_indices(uint32_t *h_state, int64_t pop_len, int64_t k, int64_t *d_out,
+                                      mfb_stream stream) {
+  if (!d_out) return MFB_ERR_INVALID;
+  return choices_impl(h_state, nullptr, nullptr, pop_len, k, nullptr, nullptr, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int mfb_mt_sample_items(uint32_t *h_state, int64_t num_items, int64_t count, int64_t *d_out,
+                                   mfb_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h_state || num_items <= 0 || count < 0 || (count > 0 && !d_out) || num_items > 0xFFFFFFFFll) {
+    mfb_set_error("mt_sample_items: bad arguments (num_items=%lld, count=%lld)", (long long)num_items,
+                  (long long)count);
+    return MFB_ERR_INVALID;
+  }
+  if (count == 0) return MFB_OK;
+  const uint32_t rng = (uint32_t)(num_items - 1);
+  if (rng == 0) {  // numpy returns zeros without touching the stream
+    MFB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)count * sizeof(int64_t), st));
+    return MFB_OK;
+  }
+  uint32_t mask = rng;
+  mask |= mask >> 1;
+  mask |= mask >> 2;
+  mask |= mask >> 4;
+  mask |= mask >> 8;
+  mask |= mask >> 16;
+  uint32_t saved[625];
+  memcpy(saved, h_state, sizeof(saved));
+  double accept = ((double)rng + 1.0) / ((double)mask + 1.0);
+  int64_t est = (int64_t)((double)count / accept * 1.05) + 4096;
+  MFB_CHECK(g_result.reserve(2 * sizeof(long long)));
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    uint32_t tmp[625];
+    memcpy(tmp, saved, sizeof(tmp));
+    MFB_CHECK(g_words.reserve((size_t)est * sizeof(uint32_t)));
+    MFB_CHECK(mfb_mt_generate(tmp, est, g_words.as<uint32_t>(), st));
+    k_masked_compact<<<1, 1024, 0, st>>>(g_words.as<uint32_t>(), est, mask, rng, count, (long long *)d_out,
+                                         g_result.as<long long>());
+    MFB_KERNEL_CHECK();
+    long long res[2];
+    MFB_CUDA(cudaMemcpyAsync(res, g_result.ptr, sizeof(res), cudaMemcpyDeviceToHost, st));
+    MFB_CUDA(cudaStreamSynchronize(st));
+    if (res[0] > 0) {
+      // advance the caller's state by exactly the number of words the reference would consume
+      memcpy(h_state, saved, sizeof(saved));
+      return mfb_mt_generate(h_state, res[0], nullptr, st);
+    }
+    est *= 2;
+  }
+  mfb_set_error("mt_sample_items: rejection sampling did not converge");
+  return MFB_ERR_INVALID;
+}

@@ -1,0 +1,155 @@
+"""Ranking evaluation (reference: spotlight/evaluation.py:108-190).
+
+`precision_recall_score` keeps the reference's signature and return value (two scalars: the mean
+over evaluated users and over all requested k) but replaces the per-user
+predict -> mask -> argsort -> set-intersection loop with two CUDA kernels: fused scoring + train mask
++ top-k (mfb_topk; no score matrix is materialised) and a hit counter (mfb_topk_hits).
+Ranking is on the pre-sigmoid score with ties -> lower item id (the reference's own tie order is
+whatever numpy's unstable argsort produces).
+"""
+import numpy as np
+import torch
+
+FLOAT_MAX = np.finfo(np.float32).max
+
+
+def _native_engine(model):
+    net = getattr(model, '_net', None)
+    if net is None or not hasattr(net, '_engine'):
+        raise NotImplementedError('evaluation: only models backed by the CUDA BilinearNet are supported')
+    eng = getattr(model, '_engine_', None)
+    return eng if eng is not None else net._engine()
+
+
+def _csr_to_device(csr, device):
+    csr = csr.tocsr()
+    csr.sum_duplicates()
+    csr.sort_indices()
+    indptr = torch.from_numpy(csr.indptr.astype(np.int64)).to(device)
+    indices = torch.from_numpy(csr.indices.astype(np.int32)).to(device)
+    return indptr, indices
+
+
+def _get_precision_recall(predictions, targets, k):
+    """Host mirror of evaluation.py:108-113 (kept for API parity; the GPU path uses mfb_topk_hits)."""
+    predictions = predictions[:k]
+    num_hit = len(set(predictions).intersection(set(targets)))
+    return float(num_hit) / k, float(num_hit) / len(targets)
+
+
+def topk_for_users(model, user_ids, k, train=None):
+    """Top-k item ids (best first) for each listed user; train items rank last when `train` is given."""
+    eng = _native_engine(model)
+    indptr = indices = None
+    if train is not None:
+        indptr, indices = _csr_to_device(train.tocsr(), eng.device)
+    return eng.topk(np.asarray(user_ids, dtype=np.int64), int(k), indptr, indices)
+
+
+def precision_recall_score(model, test, train=None, k=10):
+    eng = _native_engine(model)
+    test_csr = test.tocsr()
+    train_csr = train.tocsr() if train is not None else None
+    ks = np.array([k]) if np.isscalar(k) else np.asarray(k)
+    order = np.argsort(ks, kind='stable')
+    ks_sorted = np.unique(ks)
+    kmax = int(ks_sorted[-1])
+    row_len = np.diff(test_csr.indptr)
+    user_ids = np.nonzero(row_len)[0].astype(np.int64)       # users with >= 1 test item (evaluation.py:157)
+    cold_start_users = 0
+    if train_csr is not None:
+        cold_start_users = int((np.diff(train_csr.indptr)[user_ids] == 0).sum())
+    if len(user_ids) == 0:
+        print("Cold start users: ", cold_start_users)
+        return np.mean(np.array([])), np.mean(np.array([]))
+    t_indptr, t_indices = _csr_to_device(test_csr, eng.device)
+    m_indptr = m_indices = None
+    if train_csr is not None:
+        m_indptr, m_indices = _csr_to_device(train_csr, eng.device)
+    d_users = torch.from_numpy(user_ids).to(eng.device)
+    topk = eng.topk(d_users, kmax, m_indptr, m_indices)
+    hits = np.zeros((len(user_ids), len(ks_sorted)), dtype=np.int64)
+    ntargets = None
+    for c0 in range(0, len(ks_sorted), 4):                    # the hit kernel takes <= 4 cut-offs per call
+        chunk = ks_sorted[c0:c0 + 4]
+        h, nt = eng.topk_hits(topk, d_users, t_indptr, t_indices, chunk)
+        hits[:, c0:c0 + len(chunk)] = h.cpu().numpy()
+        ntargets = nt.cpu().numpy()
+    col = {int(kk): j for j, kk in enumerate(ks_sorted)}
+    cols = [col[int(kk)] for kk in ks]
+    precision = hits[:, cols].astype(np.float64) / ks.astype(np.float64)[None, :]
+    recall = hits[:, cols].astype(np.float64) / ntargets.astype(np.float64)[:, None]
+    del order
+    print("Cold start users: ", cold_start_users)
+    return np.mean(precision.squeeze()), np.mean(recall.squeeze())
+
+
+def rmse_score(net, user_ids, item_ids):
+    """Sum of squared (1 - prediction) over the batch (evaluation.py:187-190; logged as "BCE")."""
+    predictions = net(user_ids, item_ids)
+    diff = 1.0 - predictions.detach().cpu().numpy()
+    return np.sum(diff ** 2)
+
+
+def _all_rank_hits(eng, topk, d_users, t_indptr, t_indices, k):
+    """cum[u, r] = number of test items of user u among its first r+1 recommendations."""
+    cum = np.zeros((topk.shape[0], k), dtype=np.int64)
+    ntargets = None
+    for c0 in range(0, k, 4):
+        chunk = np.arange(c0 + 1, min(c0 + 4, k) + 1)
+        h, nt = eng.topk_hits(topk, d_users, t_indptr, t_indices, chunk)
+        cum[:, c0:c0 + len(chunk)] = h.cpu().numpy()
+        ntargets = nt.cpu().numpy()
+    return cum, ntargets
+
+
+def map_at_k(model, test, k=5):
+    """Mean average precision@k over users with test items (evaluation.py:278-353): no train mask,
+    apk normalised by min(len(targets), k); a user whose only target is item 0 scores 0.0, as in the
+    reference's `if not actual.any()` check (evaluation.py:308-309)."""
+    eng = _native_engine(model)
+    test_csr = test.tocsr()
+    user_ids = np.nonzero(np.diff(test_csr.indptr))[0].astype(np.int64)
+    if len(user_ids) == 0:
+        return np.mean(np.array([]))
+    t_indptr, t_indices = _csr_to_device(test_csr, eng.device)
+    d_users = torch.from_numpy(user_ids).to(eng.device)
+    kk = min(int(k), eng.num_items)
+    topk = eng.topk(d_users, kk)
+    cum, ntargets = _all_rank_hits(eng, topk, d_users, t_indptr, t_indices, kk)
+    flags = np.diff(np.concatenate([np.zeros((len(user_ids), 1), dtype=np.int64), cum], axis=1), axis=1)
+    score = (flags * cum / np.arange(1, kk + 1)[None, :]).sum(axis=1)
+    apk_ = score / np.minimum(ntargets, k)
+    csr = test_csr
+    all_zero_targets = np.array([not csr.indices[csr.indptr[u]:csr.indptr[u + 1]].any() for u in user_ids])
+    apk_[all_zero_targets] = 0.0
+    return np.mean(apk_)
+
+
+def evaluate_popItems(item_popularity, test, k=10):
+    """Most-popular-items baseline (evaluation.py:215-243).  Host-side by nature: no model involved."""
+    test_csr = test.tocsr()
+    pop_top = item_popularity.values.argsort()[::-1][:k]
+    ks = np.array([k]) if np.isscalar(k) else np.asarray(k)
+    precision, recall = [], []
+    for u in np.nonzero(np.diff(test_csr.indptr))[0]:
+        targets = test_csr.indices[test_csr.indptr[u]:test_csr.indptr[u + 1]]
+        p, r = zip(*[_get_precision_recall(pop_top, targets, x) for x in ks])
+        precision.append(p)
+        recall.append(r)
+    return np.mean(precision), np.mean(recall),
+
+
+def evaluate_random(item_popularity, test, k=10):
+    """Random-recommendation baseline (evaluation.py:245-276); draws from the global numpy RNG."""
+    all_items = test.num_items
+    test_csr = test.tocsr()
+    ks = np.array([k]) if np.isscalar(k) else np.asarray(k)
+    precision, recall = [], []
+    for u in np.nonzero(np.diff(test_csr.indptr))[0]:
+        targets = test_csr.indices[test_csr.indptr[u]:test_csr.indptr[u + 1]]
+        predictions = np.random.choice(all_items, len(targets))
+        p, r = zip(*[_get_precision_recall(predictions, targets, x) for x in ks])
+        precision.append(p)
+        recall.append(r)
+    return np.mean(np.array(precision).squeeze()), np.mean(np.array(recall).squeeze())

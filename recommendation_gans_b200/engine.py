@@ -1,0 +1,308 @@
+"""Host-side owner of one native model handle (include/mfb200.h).
+
+`MFEngine` borrows the four BilinearNet tables (torch `nn.Parameter` storage) and the torch
+optimiser's hyper-parameters/state tensors, and exposes the fused CUDA path: negative draws,
+training steps, validation losses, predict, top-k evaluation.  No torch ops run on this path;
+torch supplies device memory and the current stream only.
+"""
+import ctypes
+import random as _py_random
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _as_i64_cuda(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.int64)).to(device)
+
+
+# ---------------------------------------------------------------------------------------------
+# MT19937 state plumbing: the device sampler continues the HOST generator objects' streams, so the
+# global `random` module / a numpy RandomState end up exactly where the reference leaves them.
+# ---------------------------------------------------------------------------------------------
+def _get_py_state(rng):
+    version, internal, gauss = rng.getstate()
+    return np.array(internal, dtype=np.uint32), (version, gauss)
+
+
+def _set_py_state(rng, arr, extra):
+    rng.setstate((extra[0], tuple(int(v) for v in arr), extra[1]))
+
+
+def _get_np_state(rs):
+    name, key, pos, has_gauss, cached = rs.get_state()
+    if name != 'MT19937':
+        raise NotImplementedError('only MT19937 RandomState streams are supported')
+    arr = np.empty(625, dtype=np.uint32)
+    arr[:624] = key
+    arr[624] = pos
+    return arr, (has_gauss, cached)
+
+
+def _set_np_state(rs, arr, extra):
+    rs.set_state(('MT19937', arr[:624].copy(), int(arr[624]), extra[0], extra[1]))
+
+
+def sample_items_device(num_items, count, random_state, device=None):
+    """spotlight/sampling.py:33 on the GPU: continues `random_state`'s MT19937 stream."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = device or torch.device('cuda', torch.cuda.current_device())
+    out = torch.empty(int(count), dtype=torch.int64, device=device)
+    state, extra = _get_np_state(random_state)
+    N.check(lib.mfb_mt_sample_items(N.hptr(state), int(num_items), int(count), N.dptr(out), N.stream_ptr()),
+            'sample_items')
+    _set_np_state(random_state, state, extra)
+    return out
+
+
+def choices_indices_device(pop_len, k, rng=None, device=None):
+    """Index stream of random.choices(range(pop_len), k=k), continuing `rng` (default: global random)."""
+    N.require_cuda()
+    lib = N.load_library()
+    rng = rng or _py_random
+    device = device or torch.device('cuda', torch.cuda.current_device())
+    out = torch.empty(int(k), dtype=torch.int64, device=device)
+    state, extra = _get_py_state(rng)
+    N.check(lib.mfb_mt_choices_indices(N.hptr(state), int(pop_len), int(k), N.dptr(out), N.stream_ptr()), 'choices')
+    _set_py_state(rng, state, extra)
+    return out
+
+
+def mt_words_device(state625, nwords, device=None):
+    N.require_cuda()
+    lib = N.load_library()
+    device = device or torch.device('cuda', torch.cuda.current_device())
+    out = torch.empty(int(nwords), dtype=torch.int32, device=device)
+    N.check(lib.mfb_mt_words(N.hptr(state625), int(nwords), N.dptr(out), N.stream_ptr()), 'mt_words')
+    return out
+
+
+def loss_forward_backward(kind, pos, neg, need_grad):
+    """spotlight/losses.py on 1-D probability tensors -> (loss, dpos, dneg)."""
+    N.require_cuda()
+    lib = N.load_library()
+    pos = pos.detach().contiguous().float()
+    neg_c = None if neg is None else neg.detach().contiguous().float()
+    loss = torch.empty((), dtype=torch.float32, device=pos.device)
+    dpos = torch.empty_like(pos) if need_grad else None
+    dneg = (torch.empty_like(neg_c) if need_grad else None) if neg_c is not None else None
+    with torch.cuda.device(pos.device):
+        N.check(lib.mfb_loss_forward_backward(N.LOSS[kind], N.dptr(pos), pos.numel(), N.dptr(neg_c),
+                                              0 if neg_c is None else neg_c.numel(), N.dptr(loss), N.dptr(dpos),
+                                              N.dptr(dneg), N.stream_ptr()), kind + '_loss')
+    return loss, dpos, dneg
+
+
+class MFEngine(object):
+    """Native handle bound to a BilinearNet and (optionally) a torch optimiser.
+
+    optimizer=None gives a forward-only engine (predict / evaluate)."""
+
+    def __init__(self, net, optimizer=None, fast_math=False):
+        N.require_cuda()
+        self._lib = N.load_library()
+        self._handle = ctypes.c_void_p(0)
+        ue, ie = net.user_embeddings.weight, net.item_embeddings.weight
+        ub, ib = net.user_biases.weight, net.item_biases.weight
+        for name, p in (('user_embeddings', ue), ('item_embeddings', ie), ('user_biases', ub), ('item_biases', ib)):
+            if not p.is_cuda:
+                raise RuntimeError('mfb200: %s must live on a CUDA device (no CPU path exists)' % name)
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise TypeError('mfb200: %s must be contiguous float32' % name)
+        if ue.shape[1] != ie.shape[1] or ub.shape != (ue.shape[0], 1) or ib.shape != (ie.shape[0], 1):
+            raise ValueError('mfb200: BilinearNet tables have inconsistent shapes')
+        self.device = ue.device
+        self.num_users, self.num_items, self.dim = ue.shape[0], ie.shape[0], ue.shape[1]
+        self._params = (ue, ie, ub, ib)      # keep storage alive while the handle borrows it
+        self._optimizer = optimizer
+        self._state_tensors = []
+        desc = N.ModelDesc()
+        desc.num_users, desc.num_items, desc.dim = self.num_users, self.num_items, self.dim
+        desc.d_user_emb, desc.d_item_emb = ue.data_ptr(), ie.data_ptr()
+        desc.d_user_bias, desc.d_item_bias = ub.data_ptr(), ib.data_ptr()
+        desc.fast_math = 1 if fast_math else 0
+        kind, hyper = self._parse_optimizer(optimizer)
+        desc.optimizer = kind
+        desc.lr, desc.beta1, desc.beta2 = hyper['lr'], hyper['beta1'], hyper['beta2']
+        desc.eps, desc.weight_decay = hyper['eps'], hyper['weight_decay']
+        self.optimizer_kind = kind
+        if kind == N.OPT_ADAM:
+            moments = []
+            for p in (ue, ie, ub, ib):
+                st = optimizer.state[p]
+                if 'exp_avg' not in st:       # same layout torch.optim.Adam creates lazily
+                    st['step'] = torch.tensor(0.0, dtype=torch.float32)
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                moments.append((st['exp_avg'], st['exp_avg_sq']))
+                self._state_tensors += [st['exp_avg'], st['exp_avg_sq']]
+            (desc.d_user_emb_m, desc.d_user_emb_v) = (moments[0][0].data_ptr(), moments[0][1].data_ptr())
+            (desc.d_item_emb_m, desc.d_item_emb_v) = (moments[1][0].data_ptr(), moments[1][1].data_ptr())
+            (desc.d_user_bias_m, desc.d_user_bias_v) = (moments[2][0].data_ptr(), moments[2][1].data_ptr())
+            (desc.d_item_bias_m, desc.d_item_bias_v) = (moments[3][0].data_ptr(), moments[3][1].data_ptr())
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            N.check(self._lib.mfb_model_create(ctypes.byref(desc), ctypes.byref(self._handle)), 'model_create')
+        if kind == N.OPT_ADAM:
+            start = int(float(optimizer.state[ue]['step']))
+            if start:
+                self._call('mfb_model_set_step', start)
+
+    # -- optimiser introspection (implicit.py:182-192 builds it through optimizer_func) --------
+    @staticmethod
+    def _parse_optimizer(opt):
+        hyper = dict(lr=0.0, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0)
+        if opt is None:
+            return N.OPT_SGD, hyper
+        if len(opt.param_groups) != 1:
+            raise NotImplementedError('mfb200: a single parameter group is supported')
+        g = opt.param_groups[0]
+        if g.get('maximize', False) or g.get('differentiable', False):
+            raise NotImplementedError('mfb200: maximize/differentiable optimisers are not supported')
+        hyper['lr'] = float(g['lr'])
+        hyper['weight_decay'] = float(g.get('weight_decay', 0.0))
+        if isinstance(opt, torch.optim.Adam) and not isinstance(opt, torch.optim.AdamW):
+            if g.get('amsgrad', False) or g.get('decoupled_weight_decay', False):
+                raise NotImplementedError('mfb200: amsgrad / decoupled weight decay are not supported')
+            hyper['beta1'], hyper['beta2'] = float(g['betas'][0]), float(g['betas'][1])
+            hyper['eps'] = float(g['eps'])
+            return N.OPT_ADAM, hyper
+        if isinstance(opt, torch.optim.SGD):
+            if g.get('momentum', 0) != 0 or g.get('dampening', 0) != 0 or g.get('nesterov', False):
+                raise NotImplementedError('mfb200: SGD momentum/dampening/nesterov are not supported')
+            return N.OPT_SGD, hyper
+        raise NotImplementedError('mfb200: optimiser %s is outside the fused path (Adam and plain SGD are '
+                                  'supported)' % type(opt).__name__)
+
+    def _call(self, name, *args):
+        if not self._handle:
+            raise RuntimeError('mfb200: engine already closed')
+        with torch.cuda.device(self.device):
+            N.check(getattr(self._lib, name)(self._handle, *args), name)
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            self._lib.mfb_model_destroy(self._handle)
+            self._handle = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __deepcopy__(self, memo):
+        return None    # a copied net gets its own (forward-only) engine lazily
+
+    @property
+    def step(self):
+        return int(self._lib.mfb_model_step(self._handle))
+
+    def _sync_optimizer_step(self):
+        if self._optimizer is not None and self.optimizer_kind == N.OPT_ADAM:
+            t = float(self.step)
+            for p in self._params:
+                self._optimizer.state[p]['step'] = torch.tensor(t, dtype=torch.float32)
+
+    # -- negatives ----------------------------------------------------------------------------
+    def draw_negative_pairs(self, pop_users, pop_items, k, rng=None):
+        """random.choices(neg_examples, k=k) (implicit.py:352) continuing `rng` (default: global random)."""
+        rng = rng or _py_random
+        out_u = torch.empty(int(k), dtype=torch.int64, device=self.device)
+        out_i = torch.empty(int(k), dtype=torch.int64, device=self.device)
+        if k == 0:
+            return out_u, out_i
+        state, extra = _get_py_state(rng)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.mfb_mt_choices_pairs(N.hptr(state), N.dptr(pop_users), N.dptr(pop_items),
+                                                   pop_users.numel(), int(k), N.dptr(out_u), N.dptr(out_i),
+                                                   N.stream_ptr()), 'draw_negative_pairs')
+        _set_py_state(rng, state, extra)
+        return out_u, out_i
+
+    # -- training / validation ------------------------------------------------------------------
+    def _steps(self, fn, loss, pos_users, pos_items, batch, n_neg, neg_users, neg_items):
+        pos_users = _as_i64_cuda(pos_users, self.device)
+        pos_items = _as_i64_cuda(pos_items, self.device)
+        n_pos = pos_users.numel()
+        nsteps = (n_pos + batch - 1) // batch
+        if n_neg > 0:
+            neg_users = _as_i64_cuda(neg_users, self.device)
+            neg_items = _as_i64_cuda(neg_items, self.device)
+            need = nsteps * n_neg * batch
+            if neg_users.numel() < need or neg_items.numel() < need:
+                raise ValueError('need %d negative pairs, got %d' % (need, neg_users.numel()))
+        else:
+            neg_users = neg_items = None
+        losses = torch.empty(nsteps, dtype=torch.float32, device=self.device)
+        self._call(fn, N.LOSS[loss], N.dptr(pos_users), N.dptr(pos_items), n_pos, int(batch), int(n_neg),
+                   N.dptr(neg_users), N.dptr(neg_items), N.dptr(losses), N.stream_ptr())
+        return losses
+
+    def train_steps(self, loss, pos_users, pos_items, batch, n_neg, neg_users=None, neg_items=None):
+        out = self._steps('mfb_train_steps', loss, pos_users, pos_items, batch, n_neg, neg_users, neg_items)
+        self._sync_optimizer_step()
+        return out
+
+    def loss_steps(self, loss, pos_users, pos_items, batch, n_neg, neg_users=None, neg_items=None):
+        return self._steps('mfb_loss_steps', loss, pos_users, pos_items, batch, n_neg, neg_users, neg_items)
+
+    def train_epoch_host(self, loss, pos_users_host, pos_items_host, batch, n_neg, pop_users=None, pop_items=None,
+                         rng=None):
+        """End-to-end entry: HOST int64 id arrays in, per-step losses (numpy) out; H2D/D2H inside."""
+        rng = rng or _py_random
+        pu = np.ascontiguousarray(pos_users_host, dtype=np.int64)
+        pi = np.ascontiguousarray(pos_items_host, dtype=np.int64)
+        nsteps = (len(pu) + batch - 1) // batch
+        losses = np.empty(nsteps, dtype=np.float32)
+        state, extra = _get_py_state(rng)
+        self._call('mfb_train_epoch_host', N.LOSS[loss], N.hptr(pu), N.hptr(pi), len(pu), int(batch), int(n_neg),
+                   N.hptr(state), N.dptr(pop_users), N.dptr(pop_items),
+                   0 if pop_users is None else pop_users.numel(), N.hptr(losses), N.stream_ptr())
+        _set_py_state(rng, state, extra)
+        self._sync_optimizer_step()
+        return losses
+
+    def flush(self):
+        self._call('mfb_flush', N.stream_ptr())
+
+    # -- predict / evaluate -----------------------------------------------------------------------
+    def predict_pairs(self, users, items):
+        users = _as_i64_cuda(users, self.device)
+        items = _as_i64_cuda(items, self.device)
+        if users.numel() != items.numel():
+            raise ValueError('user and item id arrays differ in length')
+        out = torch.empty(users.numel(), dtype=torch.float32, device=self.device)
+        self._call('mfb_predict_pairs', N.dptr(users), N.dptr(items), users.numel(), N.dptr(out), N.stream_ptr())
+        return out
+
+    def predict_user(self, user):
+        out = torch.empty(self.num_items, dtype=torch.float32, device=self.device)
+        self._call('mfb_predict_user', int(user), N.dptr(out), N.stream_ptr())
+        return out
+
+    def topk(self, user_ids, k, train_indptr=None, train_indices=None, with_scores=False):
+        user_ids = _as_i64_cuda(user_ids, self.device)
+        n = user_ids.numel()
+        ids = torch.empty((n, k), dtype=torch.int32, device=self.device)
+        scores = torch.empty((n, k), dtype=torch.float32, device=self.device) if with_scores else None
+        self._call('mfb_topk', N.dptr(user_ids), n, N.dptr(train_indptr), N.dptr(train_indices), int(k),
+                   N.dptr(ids), N.dptr(scores), N.stream_ptr())
+        return (ids, scores) if with_scores else ids
+
+    def topk_hits(self, topk_ids, user_ids, test_indptr, test_indices, ks):
+        user_ids = _as_i64_cuda(user_ids, self.device)
+        n, k = topk_ids.shape
+        ks_arr = np.ascontiguousarray(ks, dtype=np.int32)
+        hits = torch.empty((n, len(ks_arr)), dtype=torch.int32, device=self.device)
+        ntargets = torch.empty(n, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.mfb_topk_hits(N.dptr(topk_ids), N.dptr(user_ids), n, int(k), N.dptr(test_indptr),
+                                            N.dptr(test_indices), N.hptr(ks_arr), len(ks_arr), N.dptr(hits),
+                                            N.dptr(ntargets), N.stream_ptr()), 'topk_hits')
+        return hits, ntargets

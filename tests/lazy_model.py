@@ -23,8 +23,10 @@ def loss_and_dpred(kind, pos, neg):
     dpos = np.zeros(b, f32)
     dneg = np.zeros(m, f32)
     if kind == 'pointwise':
-        lp = -np.maximum(np.log(pos), f32(-100))
-        ln = -np.maximum(np.log1p(-neg), f32(-100))
+        with np.errstate(divide='ignore'):
+            lp = -np.maximum(np.log(pos), f32(-100))
+        with np.errstate(divide='ignore'):
+            ln = -np.maximum(np.log(f32(1) - neg), f32(-100))     # torch: (1 - x).log(), clamped at -100
         loss = lp.mean(dtype=np.float64) + ln.mean(dtype=np.float64)
         dpos = ((pos - f32(1)) / np.maximum((f32(1) - pos) * pos, f32(1e-12)) / f32(b)).astype(f32)
         dneg = (neg / np.maximum((f32(1) - neg) * neg, f32(1e-12)) / f32(m)).astype(f32)

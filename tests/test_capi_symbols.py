@@ -1,0 +1,51 @@
+"""CPU-only: the C-ABI library builds for sm_100a, loads without a GPU and exports every symbol
+include/mfb200.h declares (no compute calls here)."""
+import os
+import re
+
+import recommendation_gans_b200  # noqa: F401
+from recommendation_gans_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'mfb200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(mfb_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_header_symbols():
+    lib = N.load_library()
+    names = declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), name
+    assert set(names) == set(N.SIGNATURES), set(names) ^ set(N.SIGNATURES)
+    assert lib.mfb_version() == 100
+
+
+def test_dropin_modules_import_without_gpu():
+    import implicit
+    import spotlight.evaluation
+    import spotlight.losses
+    import spotlight.sampling
+    from spotlight.factorization.representations import BilinearNet
+    assert implicit.__file__.startswith(recommendation_gans_b200.DROPIN_PATH)
+    net = BilinearNet(7, 5, 4)
+    assert sorted(net.state_dict()) == ['item_biases.weight', 'item_embeddings.weight',
+                                        'user_biases.weight', 'user_embeddings.weight']
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from implicit import ImplicitFactorizationModel
+    with pytest.raises(RuntimeError):
+        ImplicitFactorizationModel(experiment_name='cpu_refusal')
+    from spotlight.factorization.representations import BilinearNet
+    net = BilinearNet(7, 5, 4)
+    with pytest.raises(RuntimeError):
+        net(torch.tensor([0, 1]), torch.tensor([1, 2]))

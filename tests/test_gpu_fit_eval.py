@@ -1,0 +1,145 @@
+"""Drop-in API level: ImplicitFactorizationModel.fit / predict / precision_recall_score on the GPU vs
+golden results of the reference's own fit (same seeds, same inputs), and top-k id exactness of the
+evaluation kernel vs the tie-defined oracle ranking."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mf_oracle as O
+from tests.gpu_helpers import make_net, tables_of, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _interactions(u, i, U, I):
+    from spotlight.interactions import Interactions
+    return Interactions(u.astype(np.int32), i.astype(np.int32), num_users=U, num_items=I)
+
+
+@pytest.mark.parametrize('name', ['fit_pointwise', 'fit_bpr'])
+def test_fit_predict_evaluate_match_reference(golden_dir, name, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)                               # the model creates experiments_results/ in cwd
+    from implicit import ImplicitFactorizationModel
+    from spotlight.evaluation import precision_recall_score
+    import spotlight.optimizers as optimizers
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    U, I, D, B, n_neg, n_epochs = [int(x) for x in g['meta']]
+    lr, l2 = [float(x) for x in g['hyper']]
+    a, b = [int(x) for x in g['split']]
+    users, items = g['users'], g['items']
+    train, valid = _interactions(users[:a], items[:a], U, I), _interactions(users[a:b], items[a:b], U, I)
+    test = _interactions(users[b:], items[b:], U, I)
+    net = make_net([g['init%d' % i] for i in range(4)])
+    model = ImplicitFactorizationModel(
+        loss=str(g['loss']), embedding_dim=D, n_iter=n_epochs, batch_size=B, l2=l2, learning_rate=lr,
+        optimizer_func=optimizers.adam_optimizer, representation=net, random_state=np.random.RandomState(0),
+        neg_examples=[tuple(p) for p in g['neg_pairs'].tolist()], num_negative_samples=n_neg,
+        experiment_name='gpu_' + name, use_cuda=True)
+    random.seed(int(g['py_seed']))
+    model.fit(train, valid, verbose=False)
+    # per-epoch summary.csv written like the reference's
+    import csv
+    with open(os.path.join(model.experiment_logs, 'summary.csv')) as f:
+        rows = list(csv.reader(f))
+    assert rows[0] == list(g['summary_header'])
+    summary = np.array([[float(x) for x in r] for r in rows[1:]])
+    np.testing.assert_allclose(summary[:, :2], g['summary'][:, :2], rtol=1e-5)
+    assert model.best_epoch == int(g['best_epoch'])
+    # python's global random stream ends where the reference leaves it
+    assert tuple(int(x) for x in g['py_random_after']) == random.getstate()[1]
+    for i, t in enumerate(tables_of(model._net)):
+        assert rel_err(t, g['final%d' % i]) < 1e-5, i
+    ck = torch.load(os.path.join(model.experiment_saved_models, 'best_model'))
+    assert sorted(ck['network']) == ['item_biases.weight', 'item_embeddings.weight', 'user_biases.weight',
+                                     'user_embeddings.weight']
+    np.testing.assert_allclose(model.predict(3), g['predict_user3'], rtol=1e-5)
+    np.testing.assert_allclose(model.predict(g['predict_pairs_users'], g['predict_pairs_items']),
+                               g['predict_pairs'], rtol=1e-5)
+    with pytest.raises(ValueError):
+        model.predict(U)
+    for k in (5, 10, 20):
+        p, r = precision_recall_score(model, test, train=train, k=k)
+        np.testing.assert_allclose([p, r], g['pr_masked_k%d' % k], atol=2e-3)   # tie order is the only freedom
+        p, r = precision_recall_score(model, test, k=k)
+        np.testing.assert_allclose([p, r], g['pr_nomask_k%d' % k], atol=2e-3)
+    p, r = precision_recall_score(model, test, train=train, k=np.array([5, 10, 20]))
+    np.testing.assert_allclose([p, r], g['pr_masked_karray'], atol=2e-3)
+    res = model.test(test, None, k=5, rmse_flag=True, precision_recall=False, map_recall=True)
+    assert set(res) >= {'k', 'bce', 'map'} and os.path.exists(os.path.join(model.experiment_logs, 'test_summary.json'))
+
+
+def _dyadic_tables(rs, U, I, D):
+    """Embeddings on a coarse dyadic grid: every dot product is exact in fp32 (and bf16/tf32) in any
+    summation order, so top-k ids are well defined bit-for-bit."""
+    ue = rs.randint(-8, 9, (U, D)).astype(np.float32) / 16.0
+    ie = rs.randint(-8, 9, (I, D)).astype(np.float32) / 16.0
+    ub = rs.randint(-4, 5, (U, 1)).astype(np.float32) / 8.0
+    ib = rs.randint(-4, 5, (I, 1)).astype(np.float32) / 8.0
+    return ue, ie, ub, ib
+
+
+@pytest.mark.parametrize('U,I,D,k', [(70, 333, 32, 20), (33, 1000, 128, 10), (5, 40, 16, 32), (130, 257, 50, 5)])
+def test_topk_ids_bit_exact_on_dyadic_grid(U, I, D, k):
+    from recommendation_gans_b200.engine import MFEngine
+    rs = np.random.RandomState(U + I)
+    tabs = _dyadic_tables(rs, U, I, D)
+    net = make_net(tabs)
+    eng = MFEngine(net)
+    tu, ti = rs.randint(0, U, 12 * U), rs.randint(0, I, 12 * U)
+    tu[tu == 2] = 3                                             # user 2: cold start (no train row)
+    train = O.csr_from_pairs(tu, ti, U, I)
+    train.sort_indices()
+    indptr = torch.from_numpy(train.indptr.astype(np.int64)).cuda()
+    indices = torch.from_numpy(train.indices.astype(np.int32)).cuda()
+    user_ids = np.arange(U, dtype=np.int64)[::-1].copy()       # arbitrary order
+    model = O.OracleMF(*[torch.from_numpy(t) for t in tabs])
+    for masked in (True, False):
+        got = eng.topk(user_ids, k, indptr if masked else None, indices if masked else None).cpu().numpy()
+        for row, u in enumerate(user_ids):
+            rated = train[u].indices if masked else None
+            exp = O.topk_stable(model.logits(int(u)), rated, k)
+            assert (got[row] == exp).all(), (u, masked, got[row], exp)
+
+
+def test_topk_more_masked_than_free_items():
+    """k larger than the number of unmasked items: masked items follow, by ascending id."""
+    from recommendation_gans_b200.engine import MFEngine
+    rs = np.random.RandomState(3)
+    U, I, D, k = 4, 24, 8, 20
+    tabs = _dyadic_tables(rs, U, I, D)
+    eng = MFEngine(make_net(tabs))
+    tu = np.repeat(np.arange(U), 15)
+    ti = np.concatenate([rs.permutation(I)[:15] for _ in range(U)])
+    train = O.csr_from_pairs(tu, ti, U, I)
+    train.sort_indices()
+    got = eng.topk(np.arange(U), k, torch.from_numpy(train.indptr.astype(np.int64)).cuda(),
+                   torch.from_numpy(train.indices.astype(np.int32)).cuda()).cpu().numpy()
+    model = O.OracleMF(*[torch.from_numpy(t) for t in tabs])
+    for u in range(U):
+        assert (got[u] == O.topk_stable(model.logits(u), train[u].indices, k)).all()
+
+
+def test_topk_random_fp32_respects_gaps():
+    """Random fp32 embeddings: ids must agree with the oracle wherever the oracle's neighbouring scores
+    differ by more than the fp32 summation-order error bound."""
+    from recommendation_gans_b200.engine import MFEngine
+    rs = np.random.RandomState(5)
+    U, I, D, k = 64, 3000, 64, 20
+    tabs = (rs.normal(0, 0.3, (U, D)).astype(np.float32), rs.normal(0, 0.3, (I, D)).astype(np.float32),
+            rs.normal(0, 0.1, (U, 1)).astype(np.float32), rs.normal(0, 0.1, (I, 1)).astype(np.float32))
+    eng = MFEngine(make_net(tabs))
+    got, scores = eng.topk(np.arange(U), k, with_scores=True)
+    got, scores = got.cpu().numpy(), scores.cpu().numpy()
+    model = O.OracleMF(*[torch.from_numpy(t) for t in tabs])
+    for u in range(U):
+        z = model.logits(u).astype(np.float64)
+        order = np.argsort(-z, kind='stable')
+        bound = 1e-5
+        for r in range(k):
+            gap_ok = (z[order[r]] - z[order[r + 1]] > bound) and (r == 0 or z[order[r - 1]] - z[order[r]] > bound)
+            if gap_ok:
+                assert got[u, r] == order[r]
+        np.testing.assert_allclose(scores[u], 1 / (1 + np.exp(-z[got[u]])), rtol=1e-5)

