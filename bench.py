@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the implicit-MF hot path (BASELINE.json metric: train interactions/s on the
+ML-20M-shape BPR MF config + top-k eval users/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one training minibatch (B = 8192 positive
+interactions + their sampled negative pairs): negative draw (device MT19937, random.choices
+semantics), forward, loss, backward, dense-semantics Adam -- everything
+ImplicitFactorizationModel.run_train_iteration does (implicit.py:347-364).
+
+  value     device-timed throughput, ids already resident in HBM (CUDA events around K steps)
+  e2e       same K steps through the host-buffer entry point (pinned HOST ids -> H2D -> steps ->
+            D2H of the per-step losses), wall clock
+  roofline  HBM roofline of the dominant kernel (k_update) and of the whole step
+  cpu_baseline / --impl reference: the oracle port of the reference's torch-CPU step, timed on the
+            host cores (the reference itself is pure Python on torch and is not shipped to the GPU box)
+N > 1: training does not shard without changing the math ("replicas only"), so every rank
+trains an independent replica; evaluation shards users across ranks.
+"""
+import argparse
+import json
+import math
+import os
+import random
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: ML-20M shape, dim 128, batch 8192, loss 'bpr' (which the reference wires to
+    # adaptive_hinge_loss, implicit.py:194-199), 1 negative pair per positive, Adam(0.5, 0.999), lr 1e-3, l2 1e-5
+    'cfg3': dict(name='ML-20M-shape implicit MF (138493x26744, dim 128), loss=bpr->adaptive_hinge, batch 8192, '
+                      'n_neg 1, Adam(0.5,0.999) lr 1e-3 l2 1e-5',
+                 U=138493, I=26744, D=128, B=8192, n_neg=1, loss='bpr', lr=1e-3, l2=1e-5, n_train=16200213),
+    'cfg2': dict(name='ML-1M-shape implicit MF (6040x3706, dim 64), loss=pointwise, batch 1024, n_neg 5, Adam',
+                 U=6040, I=3706, D=64, B=1024, n_neg=5, loss='pointwise', lr=1e-3, l2=1e-5, n_train=810169),
+    'cfg1': dict(name='ML-100K-shape implicit MF (943x1682, dim 32), loss=bpr->adaptive_hinge, batch 256, n_neg 1',
+                 U=943, I=1682, D=32, B=256, n_neg=1, loss='bpr', lr=1e-3, l2=1e-5, n_train=81000),
+}
+
+
+def loss_kind(name):
+    return {'pointwise': 'pointwise', 'hinge': 'hinge'}.get(name, 'adaptive_hinge')   # implicit.py:194-199
+
+
+def algorithmic_bytes_per_interaction(D, n_neg, adam=True):
+    """rows per positive r = 2(1+n) (pairs mode), each row (D+1) fp32 read p,m,v and
+    written p,m,v under Adam, plus the positive's two int64 ids."""
+    r = 2 * (1 + n_neg)
+    return (6 if adam else 2) * r * (D + 1) * 4 + 16
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p['hbm_gbs'], bf16_tflops=p['bf16_tflops'], source='measured')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source='fallback')    # B200_PROFILING.md fallback
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+                 'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                 'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+                 'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4),
+                 'hw_power_brake': getattr(nv, 'nvmlClocksEventReasonHwPowerBrakeSlowdown', 0x80)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=1.0)
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+def synth_ids(rs, n, hi, zipf):
+    if zipf:
+        p = 1.0 / np.arange(1, hi + 1) ** 1.05
+        return rs.choice(hi, n, p=p / p.sum()).astype(np.int64)
+    return rs.randint(0, hi, n).astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference step (torch CPU ops, all host threads)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(w, steps, warmup, seed=0, max_seconds=150.0, pop=1000000):
+    import torch
+    from oracle import mf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    rs = np.random.RandomState(seed)
+    tabs = O.init_tables(w['U'], w['I'], w['D'], torch_seed=0)
+    B, n_neg = w['B'], w['n_neg']
+    model = O.OracleMF(*tabs, loss=w['loss'], optimizer='adam', lr=w['lr'], l2=w['l2'], batch_size=B,
+                       num_negative_samples=n_neg)
+    neg_list = list(zip(rs.randint(0, w['U'], pop).tolist(), rs.randint(0, w['I'], pop).tolist()))
+    rng = random.Random(0)
+    users = torch.from_numpy(synth_ids(rs, (warmup + steps) * B, w['U'], False))
+    items = torch.from_numpy(synth_ids(rs, (warmup + steps) * B, w['I'], w['zipf']))
+
+    def one(s):
+        # implicit.py:352-354: python random.choices over the tuple list, zip, np.array, from_numpy
+        nu, ni = zip(*rng.choices(neg_list, k=n_neg * B))
+        nu, ni = torch.from_numpy(np.array(nu)).long(), torch.from_numpy(np.array(ni)).long()
+        return model.train_step(users[s * B:(s + 1) * B], items[s * B:(s + 1) * B], nu, ni)
+
+    for s in range(warmup):
+        one(s)
+    t0 = time.perf_counter()
+    done = 0
+    for s in range(warmup, warmup + steps):
+        one(s)
+        done += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=done * B / dt, steps=done, seconds=dt, cores=torch.get_num_threads(),
+                sample='%d full minibatch steps (B=%d) of the same workload, negative population %d pairs'
+                       % (done, B, pop))
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def native_bench(args, w, rank, world):
+    import torch
+    import recommendation_gans_b200  # noqa: F401
+    from recommendation_gans_b200 import _native as N
+    from recommendation_gans_b200.engine import MFEngine
+    from spotlight.factorization.representations import BilinearNet
+    import spotlight.optimizers as optimizers
+
+    local_rank = int(os.environ.get('LOCAL_RANK', rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    K, W = args.steps, args.warmup
+    B, n_neg, D = w['B'], w['n_neg'], w['D']
+    kind = loss_kind(w['loss'])
+    rs = np.random.RandomState(rank)
+    torch.manual_seed(rank)
+    net = BilinearNet(w['U'], w['I'], D).cuda()
+    opt = optimizers.adam_optimizer(net.parameters(), lr=w['lr'], weight_decay=w['l2'])
+    eng = MFEngine(net, opt, fast_math=bool(args.fast_math))
+    lib = N.load_library()
+
+    users_h = synth_ids(rs, (W + K) * B, w['U'], False)
+    items_h = synth_ids(rs, (W + K) * B, w['I'], w['zipf'])
+    pop_u = torch.from_numpy(synth_ids(rs, w['n_train'], w['U'], False)).to(dev)
+    pop_i = torch.from_numpy(synth_ids(rs, w['n_train'], w['I'], False)).to(dev)
+    users_d, items_d = torch.from_numpy(users_h).to(dev), torch.from_numpy(items_h).to(dev)
+    rng = random.Random(rank)
+
+    eng.rng_seed(rng)
+
+    def run(lo, hi):
+        # negatives are drawn on the device from the model's MT19937 stream, chunk by chunk (part of the step)
+        return eng.train_epoch(kind, users_d[lo * B:hi * B], items_d[lo * B:hi * B], B, n_neg, pop_u, pop_i)
+
+    # ---- warm-up (>= 3 steps), then EXACTLY K timed steps on the device clock
+    run(0, W)
+    eng.rng_sync(rng)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = eng.launches + lib.mfb_library_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    losses = run(W, W + K)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    eng.rng_sync(rng)
+    launches = eng.launches + lib.mfb_library_launches() - launches0
+    clk = clocks.summary()
+    final_loss = float(losses[-1].item())
+
+    # ---- end to end: pinned host ids -> H2D -> steps -> D2H losses, through the host-buffer entry point
+    pu = torch.from_numpy(users_h[W * B:(W + K) * B]).pin_memory()
+    pi = torch.from_numpy(items_h[W * B:(W + K) * B]).pin_memory()
+    eng.train_epoch_host(kind, pu.numpy()[:4 * B], pi.numpy()[:4 * B], B, n_neg, pop_u, pop_i, rng=rng)   # warm
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    host_losses = eng.train_epoch_host(kind, pu.numpy(), pi.numpy(), B, n_neg, pop_u, pop_i, rng=rng)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert np.isfinite(host_losses).all()
+
+    # ---- per-kernel device time (separate profiled pass; events bracket every launch)
+    P = min(K, 256)
+    eng.profile(True)
+    eng.train_epoch_host(kind, pu.numpy()[:P * B], pi.numpy()[:P * B], B, n_neg, pop_u, pop_i, rng=rng)
+    prof = eng.profile_read()
+    eng.profile(False)
+
+    # ---- evaluation: full-catalog top-k with train mask, users sharded across ranks
+    ev = eval_bench(eng, w, rank, world, dev, rs)
+
+    # ---- reduce over ranks: max time, summed work
+    t_train, t_e2e, t_eval, n_eval = ms / 1e3, e2e_s, ev['seconds'], ev['users']
+    if dist:
+        t = torch.tensor([t_train, t_e2e, t_eval], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_train, t_e2e, t_eval = [float(x) for x in t.tolist()]
+        c = torch.tensor([n_eval, launches], device=dev, dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        n_eval, launches = int(c[0].item()), int(c[1].item())
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return None
+
+    peaks = measured_peaks()
+    alg_b = algorithmic_bytes_per_interaction(D, n_neg)
+    step_bytes = alg_b * B
+    value = world * K * B / t_train
+    upd_ms, upd_n = prof.get('update', (0.0, 1))
+    upd_us = upd_ms * 1e3 / max(upd_n, 1)
+    upd_bytes = (alg_b - 16) * B                      # every row's p,m,v read + p,m,v write happens in k_update
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('k_update_dram_bytes_per_launch')
+    out = {
+        'metric': 'train interactions/s (ML-20M-shape BPR MF)', 'value': value, 'unit': 'interactions/s',
+        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': t_train * 1e3 / K, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': w['name'], 'items': 'zipf(1.05)' if w['zipf'] else 'uniform',
+                   'parallelism': 'replicas x%d (training does not shard; eval shards users)' % world,
+                   'optimizer_math': 'fast (MUFU sqrt/rcp, ftz)' if args.fast_math else 'ieee',
+                   'l2_policy': 'inputs larger than L2 (tables + Adam state 256 MB, rows gathered at random)',
+                   'negative_population': w['n_train'], 'final_loss': final_loss},
+        'clocks': clk,
+        'e2e': {'value': world * K * B / t_e2e, 'unit': 'interactions/s', 'h2d_bytes_per_step': 16 * B,
+                'd2h_bytes_per_step': 4},
+        'gpu_launches': launches,
+        'roofline': {'bound': 'hbm', 'kernel': 'k_update', 'achieved': upd_bytes / (upd_us * 1e-6) / 1e9 if upd_us else None,
+                     'peak': peaks['hbm_gbs'], 'peak_source': peaks['source'], 'unit': 'GB/s',
+                     'frac': (upd_bytes / (upd_us * 1e-6) / 1e9 / peaks['hbm_gbs']) if upd_us else None,
+                     'traffic': traffic, 'us_per_launch': upd_us, 'algorithmic_bytes_per_launch': upd_bytes},
+        'roofline_step': {'bound': 'hbm', 'achieved': step_bytes / (t_train / K) / 1e9, 'peak': peaks['hbm_gbs'],
+                          'unit': 'GB/s', 'frac': step_bytes / (t_train / K) / 1e9 / peaks['hbm_gbs'],
+                          'algorithmic_bytes_per_step': step_bytes},
+        'kernel_us_per_step': {k: v[0] * 1e3 / P for k, v in prof.items()},
+        'eval': {'metric': 'top-k eval users/s (k=20, train mask, full catalog)', 'value': n_eval / t_eval,
+                 'unit': 'users/s', 'users': n_eval, 'seconds': t_eval, 'kernel': ev['kernel'],
+                 'roofline': {'bound': 'tensor', 'achieved': 2.0 * n_eval * w['I'] * D / t_eval / 1e12,
+                              'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                              'frac': 2.0 * n_eval * w['I'] * D / t_eval / 1e12 / peaks['bf16_tflops']}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_steps(w, steps=args.cpu_steps, warmup=1)
+        out['cpu_baseline'] = {'value': cb['value'], 'unit': 'interactions/s', 'cores': cb['cores'], 'kind': 'port',
+                               'sample': cb['sample']}
+    if dist:
+        dist.destroy_process_group()
+    return out
+
+
+def eval_bench(eng, w, rank, world, dev, rs):
+    """cfg4: precision/recall top-k pass over the rank's shard of users (train mask on)."""
+    import torch
+    U, I = w['U'], w['I']
+    lo, hi = rank * U // world, (rank + 1) * U // world
+    n_tr = 117 * (hi - lo)                          # ML-20M: ~117 train interactions per user
+    tu = np.sort(rs.randint(lo, hi, n_tr))
+    ti = rs.randint(0, I, n_tr)
+    import scipy.sparse as sp
+    csr = sp.coo_matrix((np.ones(n_tr), (tu, ti)), shape=(U, I)).tocsr()
+    csr.sum_duplicates()
+    csr.sort_indices()
+    indptr = torch.from_numpy(csr.indptr.astype(np.int64)).to(dev)
+    indices = torch.from_numpy(csr.indices.astype(np.int32)).to(dev)
+    users = torch.arange(lo, hi, device=dev, dtype=torch.int64)
+    eng.topk(users[:256], 20, indptr, indices)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.topk(users, 20, indptr, indices)
+    e1.record()
+    torch.cuda.synchronize()
+    return dict(seconds=e0.elapsed_time(e1) / 1e3, users=hi - lo, kernel='k_topk_exact (fp32 CUDA cores)')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=1978)      # one ML-20M epoch: ceil(16.2M / 8192)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
+    ap.add_argument('--items', default='uniform', choices=['uniform', 'zipf'])
+    ap.add_argument('--fast-math', type=int, default=1)
+    ap.add_argument('--cpu-steps', type=int, default=120)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    w = dict(WORKLOADS[args.workload])
+    w['zipf'] = args.items == 'zipf'
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        cb = cpu_reference_steps(w, steps=args.steps, warmup=min(args.warmup, 3))
+        line = {'impl': 'reference', 'metric': 'train interactions/s (ML-20M-shape BPR MF)', 'value': cb['value'],
+                'unit': 'interactions/s', 'n_gpus': args.gpus, 'steps': cb['steps'], 'warmup': min(args.warmup, 3),
+                'ms_per_step': cb['seconds'] * 1e3 / max(cb['steps'], 1), 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': w['name'], 'items': 'zipf(1.05)' if w['zipf'] else 'uniform'},
+                'cpu_baseline': {'value': cb['value'], 'unit': 'interactions/s', 'cores': cb['cores'], 'kind': 'port',
+                                 'sample': cb['sample']},
+                'e2e': {'value': cb['value'], 'unit': 'interactions/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+    out = native_bench(args, w, rank, world)
+    if out is not None:
+        print(json.dumps(out))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

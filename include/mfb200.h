@@ -139,6 +139,22 @@ int mfb_loss_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const int
  * tables: predict, evaluation, best-model copy, checkpoint; implicit.py:321-324,338-343). */
 int mfb_flush(mfb_model *m, mfb_stream stream);
 
+/* Negative-sampler stream bound to the model: the MT19937 state (random.getstate()[1] layout) lives on
+ * the device between calls, so whole epochs run without a host round trip per draw. */
+int mfb_model_rng_seed(mfb_model *m, const uint32_t *h_state, mfb_stream stream);
+int mfb_model_rng_state(mfb_model *m, uint32_t *h_state, mfb_stream stream); /* synchronises */
+/* One epoch of implicit.py:289-298 with the negatives drawn on the device, chunk by chunk, from the
+ * model's stream: step s uses random.choices(population, k = n_neg*batch) exactly as implicit.py:352
+ * (2 words per sample, consumed in step order).  Sampling and planning of chunk c+1 overlap the
+ * training of chunk c.  mfb_loss_epoch is the validation pass (implicit.py:308-320; it consumes the
+ * same stream, implicit.py:370). */
+int mfb_train_epoch(mfb_model *m, int loss, const int64_t *d_pos_users, const int64_t *d_pos_items, int64_t n_pos,
+                    int32_t batch, int32_t n_neg, const int64_t *d_pop_users, const int64_t *d_pop_items,
+                    int64_t pop_len, float *d_step_losses, mfb_stream stream);
+int mfb_loss_epoch(mfb_model *m, int loss, const int64_t *d_pos_users, const int64_t *d_pos_items, int64_t n_pos,
+                   int32_t batch, int32_t n_neg, const int64_t *d_pop_users, const int64_t *d_pop_items,
+                   int64_t pop_len, float *d_step_losses, mfb_stream stream);
+
 /* Host-buffer entry (end-to-end path): positives in pageable/pinned HOST memory, negatives drawn
  * on the device from the MT19937 stream in h_state (random.choices semantics over the device
  * population arrays); per-step losses are returned in h_step_losses.  H2D of the ids and D2H of
@@ -162,6 +178,19 @@ int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int
 int mfb_topk_hits(const int32_t *d_topk_ids, const int64_t *d_user_ids, int64_t n_users, int32_t k,
                   const int64_t *d_test_indptr, const int32_t *d_test_indices, const int32_t *h_ks, int32_t nk,
                   int32_t *d_hits, int32_t *d_ntargets, mfb_stream stream);
+
+/* ---- in-situ kernel timing (measurement only) ---------------------------------------------- */
+/* When enabled, every kernel launched for this model is bracketed by CUDA events on the launch
+ * stream.  mfb_profile_read synchronises, then reports per kernel class the summed device time
+ * (ms) and the launch count since the last reset, and resets.  Classes: see mfb_profile_name. */
+#define MFB_PROFILE_CLASSES 12
+int mfb_profile_enable(mfb_model *m, int on);
+int mfb_profile_read(mfb_model *m, double *h_ms, int64_t *h_launches);
+const char *mfb_profile_name(int cls);
+/* total kernels launched by the library for this model since creation (always counted) */
+int64_t mfb_model_launches(const mfb_model *m);
+/* kernels launched by the model-less entry points (MT19937 streams, loss functions, hit counting) */
+int64_t mfb_library_launches(void);
 
 #ifdef __cplusplus
 }

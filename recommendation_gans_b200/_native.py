@@ -63,7 +63,19 @@ SIGNATURES = {
                                 c_void]),
     'mfb_topk_hits': (ctypes.c_int, [c_void, c_void, ctypes.c_int64, ctypes.c_int32, c_void, c_void, c_void,
                                      ctypes.c_int32, c_void, c_void, c_void]),
+    'mfb_model_rng_seed': (ctypes.c_int, [c_void, c_void, c_void]),
+    'mfb_model_rng_state': (ctypes.c_int, [c_void, c_void, c_void]),
+    'mfb_train_epoch': (ctypes.c_int, [c_void, ctypes.c_int, c_void, c_void, ctypes.c_int64, ctypes.c_int32,
+                                       ctypes.c_int32, c_void, c_void, ctypes.c_int64, c_void, c_void]),
+    'mfb_loss_epoch': (ctypes.c_int, [c_void, ctypes.c_int, c_void, c_void, ctypes.c_int64, ctypes.c_int32,
+                                      ctypes.c_int32, c_void, c_void, ctypes.c_int64, c_void, c_void]),
+    'mfb_profile_enable': (ctypes.c_int, [c_void, ctypes.c_int]),
+    'mfb_profile_read': (ctypes.c_int, [c_void, c_void, c_void]),
+    'mfb_profile_name': (ctypes.c_char_p, [ctypes.c_int]),
+    'mfb_model_launches': (ctypes.c_int64, [c_void]),
+    'mfb_library_launches': (ctypes.c_int64, []),
 }
+PROFILE_CLASSES = 12
 
 _lib = None
 

@@ -15,6 +15,10 @@ void mfb_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+static int64_t g_library_launches = 0;
+void mfb_count_library_launch(int n) { g_library_launches += n; }
+extern "C" int64_t mfb_library_launches(void) { return g_library_launches; }
+
 extern "C" const char *mfb_last_error(void) { return g_err; }
 extern "C" int mfb_version(void) { return MFB200_VERSION; }
 
@@ -31,25 +35,32 @@ int mfb_ensure_scalars(mfb_model *m, int64_t upto) {
   }
   m->h_step_size.resize(cap);
   m->h_bc2_sqrt.resize(cap);
+  m->h_inv_bc2_sqrt.resize(cap);
   for (int64_t t = (m->scalars_cap > 0 ? m->scalars_cap : 0); t < cap; ++t) {
     if (t == 0) {
       m->h_step_size[0] = 0.f;
       m->h_bc2_sqrt[0] = 1.f;
+      m->h_inv_bc2_sqrt[0] = 1.f;
       continue;
     }
     double bc1 = 1.0 - pow(m->desc.beta1, (double)t);
     double bc2 = 1.0 - pow(m->desc.beta2, (double)t);
     m->h_step_size[t] = (float)(m->desc.lr / bc1);
     m->h_bc2_sqrt[t] = (float)sqrt(bc2);
+    m->h_inv_bc2_sqrt[t] = (float)(1.0 / sqrt(bc2));
   }
   // the old arrays may still be read by queued kernels: drain before replacing them
   MFB_CUDA(cudaDeviceSynchronize());
   MFB_CHECK(m->d_step_size.reserve((size_t)cap * sizeof(float)));
   MFB_CHECK(m->d_bc2_sqrt.reserve((size_t)cap * sizeof(float)));
+  MFB_CHECK(m->d_inv_bc2_sqrt.reserve((size_t)cap * sizeof(float)));
+  MFB_CUDA(cudaMemcpy(m->d_inv_bc2_sqrt.ptr, m->h_inv_bc2_sqrt.data(), (size_t)cap * sizeof(float),
+                      cudaMemcpyHostToDevice));
   MFB_CUDA(cudaMemcpy(m->d_step_size.ptr, m->h_step_size.data(), (size_t)cap * sizeof(float), cudaMemcpyHostToDevice));
   MFB_CUDA(cudaMemcpy(m->d_bc2_sqrt.ptr, m->h_bc2_sqrt.data(), (size_t)cap * sizeof(float), cudaMemcpyHostToDevice));
   m->opt.step_size = m->d_step_size.as<float>();
   m->opt.bc2_sqrt = m->d_bc2_sqrt.as<float>();
+  m->opt.inv_bc2_sqrt = m->d_inv_bc2_sqrt.as<float>();
   m->scalars_cap = cap;
   return MFB_OK;
 }
@@ -117,6 +128,7 @@ extern "C" int mfb_model_create(const mfb_model_desc *d, mfb_model **out) {
   o.one_minus_beta2 = (float)(1.0 - d->beta2);
   o.step_size = nullptr;
   o.bc2_sqrt = nullptr;
+  o.inv_bc2_sqrt = nullptr;
   rc = mfb_ensure_scalars(m, 4095);
   if (rc != MFB_OK) {
     delete m;
@@ -135,10 +147,29 @@ extern "C" int mfb_model_create(const mfb_model_desc *d, mfb_model **out) {
 extern "C" int mfb_model_destroy(mfb_model *m) {
   if (!m) return MFB_OK;
   cudaDeviceSynchronize();
-  DevBuf *bufs[] = {&m->d_step_size, &m->d_bc2_sqrt, &m->last_users, &m->last_items, &m->ws_slots, &m->ws_keys_a,
+  DevBuf *bufs[] = {&m->d_step_size, &m->d_bc2_sqrt, &m->d_inv_bc2_sqrt, &m->last_users, &m->last_items, &m->ws_slots, &m->ws_keys_a,
                     &m->ws_keys_b, &m->ws_vals_a, &m->ws_vals_b, &m->ws_hist, &m->ws_rows, &m->ws_pred, &m->ws_dz,
-                    &m->ws_scalars, &m->ws_ids, &m->ws_neg_u, &m->ws_neg_i, &m->ws_words, &m->ws_losses};
+                    &m->ws_scalars, &m->ws_ids, &m->ws_neg_u, &m->ws_neg_i, &m->ws_words, &m->ws_losses,
+                    &m->ws_seg, &m->ws_partial, &m->ws_tickets};
   for (DevBuf *b : bufs) b->release();
+  for (PlanBuf &pb : m->plan) {
+    DevBuf *pbufs[] = {&pb.slots, &pb.keys_a, &pb.keys_b, &pb.vals_a, &pb.vals_b, &pb.seg, &pb.pred, &pb.gmax,
+                       &pb.words, &pb.neg_u, &pb.neg_i};
+    for (DevBuf *b : pbufs) b->release();
+  }
+  m->rng_state.release();
+  if (m->st_side) cudaStreamDestroy(m->st_side);
+  if (m->st_plan) cudaStreamDestroy(m->st_plan);
+  for (cudaEvent_t e : m->ev_plan) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev_done) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev_upd) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev_pc) if (e) cudaEventDestroy(e);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
+  for (auto &r : m->prof.recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto e : m->prof.pool) cudaEventDestroy(e);
   delete m;
   return MFB_OK;
 }
@@ -162,4 +193,69 @@ extern "C" int mfb_model_set_step(mfb_model *m, int64_t t) {
   m->step = t;
   m->flushed_step = t;
   return mfb_ensure_scalars(m, t + 1);
+}
+
+static const char *kProfNames[MFB_PROFILE_CLASSES] = {"sample", "pack", "sort", "catchup", "forward", "loss",
+                                                      "update", "flush", "predict", "topk", "step", "other"};
+
+extern "C" const char *mfb_profile_name(int cls) {
+  return (cls >= 0 && cls < MFB_PROFILE_CLASSES) ? kProfNames[cls] : "";
+}
+
+extern "C" int mfb_profile_enable(mfb_model *m, int on) {
+  if (!m) return MFB_ERR_INVALID;
+  m->prof.on = on != 0;
+  return MFB_OK;
+}
+
+extern "C" int64_t mfb_model_launches(const mfb_model *m) { return m ? m->prof.launches : -1; }
+
+extern "C" int mfb_profile_read(mfb_model *m, double *h_ms, int64_t *h_launches) {
+  if (!m || !h_ms || !h_launches) return MFB_ERR_INVALID;
+  MFB_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < MFB_PROFILE_CLASSES; ++c) {
+    h_ms[c] = 0.0;
+    h_launches[c] = 0;
+  }
+  for (auto &r : m->prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      h_ms[r.cls] += ms;
+      h_launches[r.cls] += 1;
+    }
+    m->prof.pool.push_back(r.a);
+    m->prof.pool.push_back(r.b);
+  }
+  m->prof.recs.clear();
+  return MFB_OK;
+}
+
+// ---- negative-sampler stream bound to the model -------------------------------------------------
+extern "C" int mfb_model_rng_seed(mfb_model *m, const uint32_t *h_state, mfb_stream stream) {
+  if (!m || !h_state) return MFB_ERR_INVALID;
+  if (h_state[624] > 624) {
+    mfb_set_error("MT19937 position %u out of range", h_state[624]);
+    return MFB_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  MFB_CHECK(m->rng_state.reserve(625 * sizeof(uint32_t)));
+  // earlier draws may still be queued on the planner stream
+  if (m->st_plan) MFB_CUDA(cudaStreamSynchronize(m->st_plan));
+  MFB_CUDA(cudaMemcpyAsync(m->rng_state.ptr, h_state, 625 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  m->rng_seeded = true;
+  return MFB_OK;
+}
+
+extern "C" int mfb_model_rng_state(mfb_model *m, uint32_t *h_state, mfb_stream stream) {
+  if (!m || !h_state) return MFB_ERR_INVALID;
+  if (!m->rng_seeded) {
+    mfb_set_error("model rng was never seeded");
+    return MFB_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->st_plan) MFB_CUDA(cudaStreamSynchronize(m->st_plan));
+  MFB_CUDA(cudaMemcpyAsync(h_state, m->rng_state.ptr, 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  return MFB_OK;
 }

@@ -220,9 +220,11 @@ extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users
   }
   MFB_CUDA(cudaFuncSetAttribute(k_topk_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((n_users + EV_USERS - 1) / EV_USERS);
+  int tk = m->prof.begin(PK_TOPK, st);
   k_topk_exact<<<grid, EV_THREADS, smem, st>>>((const long long *)d_user_ids, (int)n_users, m->users, m->items, D,
                                                (const long long *)d_train_indptr, d_train_indices, k, d_out_ids,
                                                d_out_scores);
+  m->prof.end(tk, st);
   MFB_KERNEL_CHECK();
   return MFB_OK;
 }
@@ -245,6 +247,7 @@ extern "C" int mfb_topk_hits(const int32_t *d_topk_ids, const int64_t *d_user_id
     }
   }
   if (n_users == 0) return MFB_OK;
+  mfb_count_library_launch(1);
   k_topk_hits<<<(unsigned)((n_users + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       d_topk_ids, (const long long *)d_user_ids, (int)n_users, k, (const long long *)d_test_indptr, d_test_indices,
       ks[0], ks[1], ks[2], ks[3], nk, d_hits, d_ntargets);

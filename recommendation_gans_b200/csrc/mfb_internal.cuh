@@ -10,6 +10,7 @@
 #include "../../include/mfb200.h"
 
 void mfb_set_error(const char *fmt, ...);
+void mfb_count_library_launch(int n);  // kernels launched by model-less entry points
 
 #define MFB_CUDA(call)                                                                      \
   do {                                                                                      \
@@ -78,28 +79,76 @@ struct OptView {
   float one_minus_beta2;
   const float *step_size;     // [t] -> lr/(1-beta1^t)   (Python double -> fp32), index 1..cap
   const float *bc2_sqrt;      // [t] -> sqrt(1-beta2^t)
+  const float *inv_bc2_sqrt;  // [t] -> 1/sqrt(1-beta2^t)  (fast-math replay)
+};
+
+enum ProfClass {
+  PK_SAMPLE = 0, PK_PACK, PK_SORT, PK_CATCHUP, PK_FORWARD, PK_LOSS, PK_UPDATE, PK_FLUSH, PK_PREDICT, PK_TOPK,
+  PK_STEP, PK_OTHER
+};
+
+struct Profiler {
+  bool on = false;
+  int64_t launches = 0;  // always counted
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  // usage: auto t = prof.begin(cls, st, nkernels); launch...; prof.end(t, st);
+  int begin(int cls, cudaStream_t st, int nkernels = 1) {
+    launches += nkernels;
+    if (!on) return -1;
+    Rec r; r.cls = cls; r.a = get(); r.b = get();
+    cudaEventRecord(r.a, st);
+    recs.push_back(r);
+    return (int)recs.size() - 1;
+  }
+  void end(int tok, cudaStream_t st) {
+    if (tok >= 0) cudaEventRecord(recs[tok].b, st);
+  }
+};
+
+// Planner output for one chunk of steps (double-buffered: chunk c+1 is planned on its own stream
+// while chunk c trains).
+struct PlanBuf {
+  DevBuf slots, keys_a, keys_b, vals_a, vals_b, seg, pred, gmax, words, neg_u, neg_i;
+  uint32_t *skeys = nullptr, *svals = nullptr;
 };
 
 struct mfb_model {
   mfb_model_desc desc;
+  Profiler prof;
+  PlanBuf plan[2];
+  cudaStream_t st_side = nullptr, st_plan = nullptr;   // look-ahead catch-up / planner streams
+  cudaEvent_t ev_plan[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_upd[4] = {nullptr, nullptr, nullptr, nullptr}, ev_pc[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_join = nullptr;
+  DevBuf rng_state;            // device-resident MT19937 state (624 words + position) of the negative sampler
+  bool rng_seeded = false;
   TableView users, items;
   OptView opt;
   int64_t step = 0;            // optimiser steps applied so far
   int64_t flushed_step = 0;    // all rows are current for this step
   // per-step scalar tables
-  std::vector<float> h_step_size, h_bc2_sqrt;
-  DevBuf d_step_size, d_bc2_sqrt;
+  std::vector<float> h_step_size, h_bc2_sqrt, h_inv_bc2_sqrt;
+  DevBuf d_step_size, d_bc2_sqrt, d_inv_bc2_sqrt;
   int64_t scalars_cap = 0;
   DevBuf last_users, last_items;
   // training workspaces
   DevBuf ws_slots, ws_keys_a, ws_keys_b, ws_vals_a, ws_vals_b, ws_hist, ws_rows, ws_pred, ws_dz, ws_scalars;
-  DevBuf ws_ids, ws_neg_u, ws_neg_i, ws_words, ws_losses;
+  DevBuf ws_ids, ws_neg_u, ws_neg_i, ws_words, ws_losses, ws_seg, ws_partial, ws_tickets;
 };
 
 int mfb_ensure_scalars(mfb_model *m, int64_t upto);
 
 // ---- MT19937 (mfb_mt19937.cu)
 int mfb_mt_generate(uint32_t *h_state, int64_t nwords, uint32_t *d_words, cudaStream_t st);
+int mfb_mt_generate_async(uint32_t *d_state, int64_t nwords, uint32_t *d_words, cudaStream_t st);
+int mfb_choices_async(const uint32_t *d_words, int64_t k, int64_t pop_len, const int64_t *d_pop_users,
+                      const int64_t *d_pop_items, int64_t *d_out_users, int64_t *d_out_items, cudaStream_t st);
 
 // ---- radix sort (mfb_sort.cu): stable LSD sort of (key,val) pairs on bits [0,nbits)
 // keys_a/vals_a hold the input; result pointer returned in *out_keys/*out_vals (a or b).

@@ -152,11 +152,33 @@ int upload_state(const uint32_t *h_state, cudaStream_t st) {
 
 }  // namespace
 
+// Device-resident stream: advances d_state (625 words) by nwords outputs, no host round trip.
+int mfb_mt_generate_async(uint32_t *d_state, int64_t nwords, uint32_t *d_words, cudaStream_t st) {
+  if (nwords <= 0) return MFB_OK;
+  mfb_count_library_launch(1);
+  k_mt_generate<<<1, MT_THREADS, 0, st>>>(d_state, (unsigned long long)nwords, d_words);
+  MFB_KERNEL_CHECK();
+  return MFB_OK;
+}
+
+// random.choices index mapping of 2k words -> k (user,item) pairs gathered from the population
+int mfb_choices_async(const uint32_t *d_words, int64_t k, int64_t pop_len, const int64_t *d_pop_users,
+                      const int64_t *d_pop_items, int64_t *d_out_users, int64_t *d_out_items, cudaStream_t st) {
+  if (k <= 0) return MFB_OK;
+  mfb_count_library_launch(1);
+  k_choices<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(d_words, k, pop_len, (const long long *)d_pop_users,
+                                                         (const long long *)d_pop_items, (long long *)d_out_users,
+                                                         (long long *)d_out_items, nullptr);
+  MFB_KERNEL_CHECK();
+  return MFB_OK;
+}
+
 // Generates nwords outputs into d_words (may be nullptr: advance only) and updates h_state.
 int mfb_mt_generate(uint32_t *h_state, int64_t nwords, uint32_t *d_words, cudaStream_t st) {
   if (nwords < 0) return MFB_ERR_INVALID;
   MFB_CHECK(upload_state(h_state, st));
   if (nwords > 0) {
+    mfb_count_library_launch(1);
     k_mt_generate<<<1, MT_THREADS, 0, st>>>(g_state.as<uint32_t>(), (unsigned long long)nwords, d_words);
     MFB_KERNEL_CHECK();
   }
@@ -181,6 +203,7 @@ static int choices_impl(uint32_t *h_state, const int64_t *d_pop_users, const int
   MFB_CHECK(mfb_mt_generate(h_state, 2 * k, g_words.as<uint32_t>(), st));
   int threads = 256;
   long long blocks = (k + threads - 1) / threads;
+  mfb_count_library_launch(1);
   k_choices<<<(unsigned)blocks, threads, 0, st>>>(g_words.as<uint32_t>(), k, pop_len, (const long long *)d_pop_users,
                                                   (const long long *)d_pop_items, (long long *)d_out_users,
                                                   (long long *)d_out_items, (long long *)d_out_idx);
@@ -232,6 +255,7 @@ extern "C" int mfb_mt_sample_items(uint32_t *h_state, int64_t num_items, int64_t
     memcpy(tmp, saved, sizeof(tmp));
     MFB_CHECK(g_words.reserve((size_t)est * sizeof(uint32_t)));
     MFB_CHECK(mfb_mt_generate(tmp, est, g_words.as<uint32_t>(), st));
+    mfb_count_library_launch(1);
     k_masked_compact<<<1, 1024, 0, st>>>(g_words.as<uint32_t>(), est, mask, rng, count, (long long *)d_out,
                                          g_result.as<long long>());
     MFB_KERNEL_CHECK();

@@ -30,16 +30,19 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint32_t *__r
   for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) hist[(long long)d * nblk + blockIdx.x] = h[d];
 }
 
-// Exclusive scan of hist[RADIX*nblk] (digit-major) by one CTA.
-__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ hist, long long total) {
-  __shared__ uint32_t warp_tot[32];
-  __shared__ uint32_t carry_s;
+// Per-digit exclusive scan across blocks: CTA d scans hist[d*nblk .. (d+1)*nblk) in place and writes
+// the digit's total; the scatter kernel turns the 256 totals into digit bases itself.
+__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ hist, int nblk,
+                                                     uint32_t *__restrict__ totals) {
+  __shared__ uint32_t warp_tot[32], warp_excl[32];
+  __shared__ uint32_t carry_s, chunk_total;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint32_t *h = hist + (long long)blockIdx.x * nblk;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (long long start = 0; start < total; start += 1024) {
-    long long i = start + tid;
-    uint32_t v = (i < total) ? hist[i] : 0u;
+  for (int start = 0; start < nblk; start += 1024) {
+    const int i = start + tid;
+    const uint32_t v = (i < nblk) ? h[i] : 0u;
     uint32_t x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -48,18 +51,24 @@ __global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ hist
     }
     if (lane == 31) warp_tot[wid] = x;
     __syncthreads();
-    uint32_t before = 0, all = 0;
-    for (int w = 0; w < 32; ++w) {
-      uint32_t c = warp_tot[w];
-      if (w < wid) before += c;
-      all += c;
+    if (wid == 0) {  // scan the 32 warp totals
+      const uint32_t w = warp_tot[lane];
+      uint32_t ws = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += y;
+      }
+      warp_excl[lane] = ws - w;
+      if (lane == 31) chunk_total = ws;
     }
-    uint32_t carry = carry_s;
-    if (i < total) hist[i] = carry + before + x - v;
     __syncthreads();
-    if (tid == 0) carry_s = carry + all;
+    if (i < nblk) h[i] = carry_s + warp_excl[wid] + x - v;
+    __syncthreads();
+    if (tid == 0) carry_s += chunk_total;
     __syncthreads();
   }
+  if (tid == 0) totals[blockIdx.x] = carry_s;
 }
 
 // Each warp owns a contiguous span of the block's tile and walks it in order, so ranks are
@@ -69,10 +78,27 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t *
                                                                 const uint32_t *__restrict__ vals_in,
                                                                 uint32_t *__restrict__ keys_out,
                                                                 uint32_t *__restrict__ vals_out, long long n, int shift,
-                                                                const uint32_t *__restrict__ hist, int nblk) {
+                                                                const uint32_t *__restrict__ hist, int nblk,
+                                                                const uint32_t *__restrict__ totals) {
   __shared__ uint32_t cnt[SORT_WARPS][RADIX];
+  __shared__ uint32_t dbase[RADIX];
+  __shared__ uint32_t wtot[SORT_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&cnt[0][0])[i] = 0;
+  {  // exclusive scan of the 256 digit totals (SORT_THREADS == RADIX)
+    const uint32_t v = totals[tid];
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wtot[wid] = x;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < wid; ++w) before += wtot[w];
+    dbase[tid] = before + x - v;
+  }
   __syncthreads();
   const long long wbase = (long long)blockIdx.x * TILE + (long long)wid * WARP_SPAN;
   // pass 1: per-warp digit counts
@@ -86,7 +112,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t *
   __syncthreads();
   // exclusive prefix over warps, seeded with the block's global base for each digit
   for (int d = tid; d < RADIX; d += SORT_THREADS) {
-    uint32_t run = hist[(long long)d * nblk + blockIdx.x];
+    uint32_t run = dbase[d] + hist[(long long)d * nblk + blockIdx.x];
     for (int w = 0; w < SORT_WARPS; ++w) {
       uint32_t c = cnt[w][d];
       cnt[w][d] = run;
@@ -129,15 +155,17 @@ int mfb_radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, u
     return MFB_ERR_INVALID;
   }
   int nblk = (int)((n + TILE - 1) / TILE);
-  long long total = (long long)RADIX * nblk;
+  long long total = (long long)RADIX * nblk + RADIX;
   MFB_CHECK(hist.reserve((size_t)total * sizeof(uint32_t)));
+  uint32_t *totals = hist.as<uint32_t>() + (long long)RADIX * nblk;
+  static_assert(SORT_THREADS == RADIX, "scatter scans the digit totals with one thread per digit");
   uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
   for (int shift = 0; shift < nbits; shift += RADIX_BITS) {
     k_radix_hist<<<nblk, SORT_THREADS, 0, st>>>(kin, n, shift, hist.as<uint32_t>(), nblk);
     MFB_KERNEL_CHECK();
-    k_radix_scan<<<1, 1024, 0, st>>>(hist.as<uint32_t>(), total);
+    k_radix_scan<<<RADIX, 1024, 0, st>>>(hist.as<uint32_t>(), nblk, totals);
     MFB_KERNEL_CHECK();
-    k_radix_scatter<<<nblk, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist.as<uint32_t>(), nblk);
+    k_radix_scatter<<<nblk, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist.as<uint32_t>(), nblk, totals);
     MFB_KERNEL_CHECK();
     uint32_t *t = kin;
     kin = kout;

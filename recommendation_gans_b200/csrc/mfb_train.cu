@@ -21,6 +21,7 @@
 
 namespace {
 
+constexpr uint32_t IN_PREV = 0x80000000u;  // planner flag in seg_len[head], see k_segments
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
 
@@ -50,6 +51,25 @@ __device__ __forceinline__ void frag_load(Frag<VEC, NIT> &f, const float *__rest
   }
 }
 
+// L2-only loads (ld.global.cg): for scratch written by other SMs earlier in the same launch
+template <int VEC, int NIT>
+__device__ __forceinline__ void frag_load_cg(Frag<VEC, NIT> &f, const float *__restrict__ row, int D, int lane) {
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int e = (it * 32 + lane) * VEC;
+    if constexpr (VEC == 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < D) v = __ldcg(reinterpret_cast<const float4 *>(row + e));
+      f.x[it * 4 + 0] = v.x;
+      f.x[it * 4 + 1] = v.y;
+      f.x[it * 4 + 2] = v.z;
+      f.x[it * 4 + 3] = v.w;
+    } else {
+      f.x[it] = (e < D) ? __ldcg(row + e) : 0.f;
+    }
+  }
+}
+
 template <int VEC, int NIT>
 __device__ __forceinline__ void frag_store(const Frag<VEC, NIT> &f, float *__restrict__ row, int D, int lane) {
 #pragma unroll
@@ -74,9 +94,16 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ float sigmoidf_acc(float z) { return 1.0f / (1.0f + expf(-z)); }
 
+// MUFU approximations with flush-to-zero: no denormal fix-up code around them (a second-moment
+// below 1.2e-38 means |grad| < 1e-19, i.e. denom == eps either way).
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 
@@ -92,8 +119,9 @@ __device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g,
   m = fmaf(o.lerp_coeff, __fsub_rn(g, m), base);
   v = __fadd_rn(__fmul_rn(v, o.beta2), __fmul_rn(__fmul_rn(o.one_minus_beta2, g), g));
   if (FAST) {
-    float denom = __fadd_rn(__fdividef(sqrt_approx(v), bc2), o.eps);
-    p = __fadd_rn(p, __fdividef(__fmul_rn(neg_ss, m), denom));
+    // bc2 carries 1/bc2_sqrt in fast mode (see row_replay/apply_step): one multiply, no division
+    float denom = fmaf(sqrt_approx(v), bc2, o.eps);
+    p = fmaf(__fmul_rn(neg_ss, m), rcp_approx(denom), p);
   } else {
     float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2), o.eps);
     p = __fadd_rn(p, __fdiv_rn(__fmul_rn(neg_ss, m), denom));
@@ -149,7 +177,7 @@ __device__ __forceinline__ void row_replay(RowState<VEC, NIT> &r, int from, int 
   if (o.kind == MFB_OPT_ADAM) {
     for (int s = from + 1; s <= to; ++s) {
       float neg_ss = -__ldg(o.step_size + s);
-      float bc2 = __ldg(o.bc2_sqrt + s);
+      float bc2 = FAST ? __ldg(o.inv_bc2_sqrt + s) : __ldg(o.bc2_sqrt + s);
 #pragma unroll
       for (int k = 0; k < NIT * VEC; ++k) adam_elem<FAST>(r.p.x[k], r.m.x[k], r.v.x[k], 0.f, neg_ss, bc2, o);
       adam_elem<FAST>(r.bp, r.bm, r.bv, 0.f, neg_ss, bc2, o);
@@ -173,7 +201,8 @@ __device__ __forceinline__ void row_replay(RowState<VEC, NIT> &r, int from, int 
 // [items of all slots] so a stable sort leaves each (step,table,row) group in slot order.
 __global__ void k_pack(const long long *__restrict__ pos_u, const long long *__restrict__ pos_i, long long n_pos,
                        const long long *__restrict__ neg_u, const long long *__restrict__ neg_i, int batch, int m_neg,
-                       long long step0, int nsteps, int rb, int num_users, int num_items, int *__restrict__ slot_u,
+                       long long step0, long long neg_step0, int nsteps, int rb, int num_users, int num_items,
+                       int *__restrict__ slot_u,
                        int *__restrict__ slot_i, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
                        int *__restrict__ err_flag) {
   const int Lfull = batch + m_neg;
@@ -191,7 +220,7 @@ __global__ void k_pack(const long long *__restrict__ pos_u, const long long *__r
     u = pos_u[first + j];
     i = pos_i[first + j];
   } else {
-    long long q = gstep * m_neg + (j - b);
+    long long q = (gstep - neg_step0) * m_neg + (j - b);
     u = neg_u[q];
     i = neg_i[q];
   }
@@ -213,15 +242,21 @@ __global__ void k_pack(const long long *__restrict__ pos_u, const long long *__r
 // ---------------------------------------------------------------------------------------
 // k_catchup: one warp per sorted position; segment heads bring their row to step t-1
 // ---------------------------------------------------------------------------------------
+// Replay length per row is geometrically distributed, so blocks are kept small (CU_WARPS warps):
+// a finished warp then frees its slot instead of waiting for the slowest warp of a big block.
+constexpr int CU_WARPS = 2;
 template <int VEC, int NIT, bool FAST>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_catchup(const uint32_t *__restrict__ skeys, int n, int rb,
+__global__ void __launch_bounds__(CU_WARPS * 32) k_catchup(const uint32_t *__restrict__ skeys,
+                                                           const uint32_t *__restrict__ seg_len, int n, int rb,
                                                            TableView users, TableView items, OptView opt, int D,
-                                                           int t) {
+                                                           int t, int skip_in_prev) {
   const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int q = blockIdx.x * CU_WARPS + (threadIdx.x >> 5);
   if (q >= n) return;
   const uint32_t key = skeys[q];
   if (q > 0 && skeys[q - 1] == key) return;
+  // look-ahead mode: rows that are also in the previous step's batch belong to that step's update
+  if (skip_in_prev && (seg_len[q] & IN_PREV)) return;
   const long long row = key & ((1u << rb) - 1u);
   const TableView &T = ((key >> rb) & 1u) ? items : users;
   const int last = T.last[row];
@@ -238,29 +273,55 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_catchup(const uint32_t *__res
 // k_forward: one warp per slot.  pred[j] = sigmoid(<U[u],V[i]> + bu + bi); optionally snapshots
 // both rows (the values every gradient of this step must be computed from).
 // ---------------------------------------------------------------------------------------
+// (probability, index) packed so that an unsigned 64-bit max picks the largest probability and,
+// among equals, the smallest index -- torch.max(neg, 0) returns the first maximal element.
+__device__ __forceinline__ unsigned long long pack_max(float prob, int idx) {
+  return ((unsigned long long)__float_as_uint(prob) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
+}
+__device__ __forceinline__ float unpack_max_val(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ int unpack_max_idx(unsigned long long v) {
+  return (int)(0xFFFFFFFFu - (uint32_t)(v & 0xFFFFFFFFull));
+}
+
+// When neg_begin >= 0 (adaptive hinge), the maximum over slots j >= neg_begin is reduced per block
+// and folded into *gmax with one (usually skipped) 64-bit atomicMax per block.
 template <int VEC, int NIT>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_forward(const int *__restrict__ slot_u,
                                                            const int *__restrict__ slot_i, int L, TableView users,
                                                            TableView items, int D, float *__restrict__ snap_u,
-                                                           float *__restrict__ snap_i, float *__restrict__ pred) {
-  const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (j >= L) return;
-  const long long u = slot_u[j], i = slot_i[j];
-  Frag<VEC, NIT> fu, fi;
-  frag_load<VEC, NIT>(fu, users.p + u * D, D, lane);
-  frag_load<VEC, NIT>(fi, items.p + i * D, D, lane);
-  float acc = 0.f;
+                                                           float *__restrict__ snap_i, float *__restrict__ pred,
+                                                           int neg_begin, unsigned long long *__restrict__ gmax) {
+  __shared__ unsigned long long wmax[WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.x * WARPS_PER_BLOCK + wid;
+  unsigned long long mine = 0ull;
+  if (j < L) {
+    const long long u = slot_u[j], i = slot_i[j];
+    Frag<VEC, NIT> fu, fi;
+    frag_load<VEC, NIT>(fu, users.p + u * D, D, lane);
+    frag_load<VEC, NIT>(fi, items.p + i * D, D, lane);
+    float acc = 0.f;
 #pragma unroll
-  for (int k = 0; k < NIT * VEC; ++k) acc = fmaf(fu.x[k], fi.x[k], acc);
-  acc = warp_sum(acc);
-  if (snap_u != nullptr) {
-    frag_store<VEC, NIT>(fu, snap_u + (long long)j * D, D, lane);
-    frag_store<VEC, NIT>(fi, snap_i + (long long)j * D, D, lane);
+    for (int k = 0; k < NIT * VEC; ++k) acc = fmaf(fu.x[k], fi.x[k], acc);
+    acc = warp_sum(acc);
+    if (snap_u != nullptr) {
+      frag_store<VEC, NIT>(fu, snap_u + (long long)j * D, D, lane);
+      frag_store<VEC, NIT>(fi, snap_i + (long long)j * D, D, lane);
+    }
+    const float z = (acc + users.bp[u]) + items.bp[i];
+    const float y = sigmoidf_acc(z);
+    if (lane == 0) pred[j] = y;
+    if (neg_begin >= 0 && j >= neg_begin) mine = pack_max(y, j - neg_begin);
   }
-  if (lane == 0) {
-    float z = (acc + users.bp[u]) + items.bp[i];
-    pred[j] = sigmoidf_acc(z);
+  if (neg_begin >= 0) {  // uniform across the grid
+    if (lane == 0) wmax[wid] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long best = wmax[0];
+#pragma unroll
+      for (int w = 1; w < WARPS_PER_BLOCK; ++w) best = wmax[w] > best ? wmax[w] : best;
+      if (best > *reinterpret_cast<volatile unsigned long long *>(gmax)) atomicMax(gmax, best);
+    }
   }
 }
 
@@ -314,10 +375,9 @@ __device__ double block_sum(double v, double *sh) {
   return tot;
 }
 
-__global__ void __launch_bounds__(LOSS_THREADS) k_loss(int kind, const float *__restrict__ pos, int b,
-                                                       const float *__restrict__ neg, int m,
-                                                       float *__restrict__ loss_out, float *__restrict__ dpos,
-                                                       float *__restrict__ dneg, int to_logit) {
+__device__ void loss_block(int kind, const float *__restrict__ pos, int b, const float *__restrict__ neg, int m,
+                           float *__restrict__ loss_out, float *__restrict__ dpos, float *__restrict__ dneg,
+                           int to_logit) {
   __shared__ double sh[LOSS_THREADS / 32];
   __shared__ float sh_max[LOSS_THREADS / 32];
   __shared__ int sh_arg[LOSS_THREADS / 32];
@@ -433,49 +493,122 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_loss(int kind, const float *__
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// k_update: one warp per sorted position; segment heads reduce the slot gradients of their row
-// in slot order and apply optimiser step t.
-//   d/dU[u] += dz_j * V_old[i_j]   d/dbu[u] += dz_j   (and symmetrically for items)
-// ---------------------------------------------------------------------------------------
-template <int VEC, int NIT, bool FAST>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_update(const uint32_t *__restrict__ skeys,
-                                                          const uint32_t *__restrict__ svals, int n, int rb,
-                                                          TableView users, TableView items, OptView opt, int D,
-                                                          const float *__restrict__ snap_u,
-                                                          const float *__restrict__ snap_i,
-                                                          const float *__restrict__ dz, int t) {
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (q >= n) return;
-  const uint32_t key = skeys[q];
-  if (q > 0 && skeys[q - 1] == key) return;
-  const long long row = key & ((1u << rb) - 1u);
-  const bool is_item = (key >> rb) & 1u;
-  const TableView &T = is_item ? items : users;
-  const float *__restrict__ other = is_item ? snap_u : snap_i;
-  const bool adam = opt.kind == MFB_OPT_ADAM;
 
-  Frag<VEC, NIT> g;
-#pragma unroll
-  for (int k = 0; k < NIT * VEC; ++k) g.x[k] = 0.f;
-  float gb = 0.f;
-  for (int q2 = q; q2 < n && skeys[q2] == key; ++q2) {
-    const int j = (int)svals[q2];
-    const float d = dz[j];
-    if (d != 0.f) {
-      Frag<VEC, NIT> o;
-      frag_load<VEC, NIT>(o, other + (long long)j * D, D, lane);
-#pragma unroll
-      for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fadd_rn(g.x[k], __fmul_rn(d, o.x[k]));
-      gb = __fadd_rn(gb, d);
+__global__ void __launch_bounds__(LOSS_THREADS) k_loss(int kind, const float *__restrict__ pos, int b,
+                                                       const float *__restrict__ neg, int m,
+                                                       float *__restrict__ loss_out, float *__restrict__ dpos,
+                                                       float *__restrict__ dneg, int to_logit) {
+  loss_block(kind, pos, b, neg, m, loss_out, dpos, dneg, to_logit);
+}
+
+// Loss values of a whole chunk of steps in one launch (block s <-> step step0+s): the per-step
+// predictions are kept until the chunk ends, so loss.item() costs nothing on the step's critical path.
+__global__ void __launch_bounds__(LOSS_THREADS) k_loss_steps(int kind, const float *__restrict__ pred_chunk,
+                                                             int Lfull, int batch, int m_neg, long long n_pos,
+                                                             long long step0, float *__restrict__ losses) {
+  const long long gstep = step0 + blockIdx.x;
+  const long long first = gstep * batch;
+  const int b = (int)((n_pos - first < batch) ? (n_pos - first) : batch);
+  const float *pred = pred_chunk + (long long)blockIdx.x * Lfull;
+  loss_block(kind, pred, b, pred + b, m_neg, losses + gstep, nullptr, nullptr, 0);
+}
+
+// dLoss/dz of slot j, recomputed where it is consumed (k_update) from the step's predictions and
+// the adaptive-hinge maximum; same formulas as loss_block (torch backward of spotlight/losses.py).
+// Hinge-type terms on probabilities are always active: neg - pos + 1 >= 0 for values in [0, 1].
+__device__ __forceinline__ float slot_dz(int kind, int j, int b, int m, const float *__restrict__ pred,
+                                         float gmax, int jstar) {
+  const float x = pred[j];
+  float d;
+  if (kind == MFB_LOSS_POINTWISE) {
+    const float den = fmaxf((1.0f - x) * x, 1e-12f);
+    d = (j < b) ? __fdiv_rn(__fdiv_rn(x - 1.0f, den), (float)b) : __fdiv_rn(__fdiv_rn(x, den), (float)m);
+  } else if (kind == MFB_LOSS_HINGE) {
+    const float inv_b = 1.0f / (float)b;
+    const float xp = (j < b) ? x : pred[j - b], xn = (j < b) ? pred[j + b] : x;
+    const float a = (((xn - xp) + 1.0f) >= 0.0f) ? inv_b : 0.0f;
+    d = (j < b) ? -a : a;
+  } else if (kind == MFB_LOSS_BPR) {
+    const float inv_b = 1.0f / (float)b;
+    const float xp = (j < b) ? x : pred[j - b], xn = (j < b) ? pred[j + b] : x;
+    const float sg = sigmoidf_acc(xp - xn);
+    const float g = ((-inv_b) * (1.0f - sg)) * sg;
+    d = (j < b) ? g : -g;
+  } else {
+    const float inv_b = 1.0f / (float)b;
+    if (j < b) {
+      d = (((gmax - x) + 1.0f) >= 0.0f) ? -inv_b : 0.0f;
+    } else {
+      d = (j - b == jstar) ? (float)b * inv_b : 0.0f;  // sum over b active positives of 1/b
     }
   }
-  RowState<VEC, NIT> r;
-  row_load<VEC, NIT>(r, T, row, D, lane, adam);
-  if (adam) {
+  return (d * (1.0f - x)) * x;  // sigmoid backward: grad * (1 - y) * y
+}
+
+// ---------------------------------------------------------------------------------------
+// planner: segment table.  After the sort, equal keys (same step, table, row) are adjacent;
+// seg_first[q] = index of the first position of q's segment, seg_len[first] = its length.
+// ---------------------------------------------------------------------------------------
+// seg_len[head] additionally carries IN_PREV (top bit) when the same (table,row) also occurs in the
+// previous step of the chunk: such a row is brought up to date by that step's update, every other
+// row of the step can be caught up ahead of time, concurrently with the previous step.
+__global__ void k_segments(const uint32_t *__restrict__ skeys, long long n, int rb, int Lfull,
+                           uint32_t *__restrict__ seg_first, uint32_t *__restrict__ seg_len) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const uint32_t key = skeys[q];
+  if (q == 0 || skeys[q - 1] != key) {  // head: upper bound of key in (q, n)
+    long long lo = q + 1, hi = n;
+    if (lo < n && skeys[lo] == key) {    // (most segments have length 1 and skip the search)
+      while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (skeys[mid] <= key) lo = mid + 1; else hi = mid;
+      }
+    }
+    uint32_t len = (uint32_t)(lo - q);
+    const uint32_t step = key >> (rb + 1);
+    if (step > 0) {                      // binary search for (step-1, table, row) in the previous step's range
+      const uint32_t want = key - (1u << (rb + 1));
+      long long a = 2ll * (step - 1) * Lfull, e = 2ll * step * Lfull;
+      while (a < e) {
+        long long mid = (a + e) >> 1;
+        if (skeys[mid] < want) a = mid + 1; else e = mid;
+      }
+      if (a < 2ll * step * Lfull && skeys[a] == want) len |= IN_PREV;
+    }
+    seg_first[q] = (uint32_t)q;
+    seg_len[q] = len;
+  } else {                               // inside a segment: lower bound of key in [0, q)
+    long long lo = 0, hi = q - 1;        // skeys[q-1] == key, so the answer is <= q-1
+    if (q >= 2 && skeys[q - 2] != key) {
+      lo = q - 1;
+    } else {
+      while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (skeys[mid] < key) lo = mid + 1; else hi = mid;
+      }
+    }
+    seg_first[q] = (uint32_t)lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_update: one warp per sorted position of the step.  A row's slot gradients form one segment
+//   d/dU[u] += dz_j * V_old[i_j]   d/dbu[u] += dz_j   (and symmetrically for items)
+// which is reduced in slot order.  Segments longer than a window (popular items) are cut at
+// absolute window boundaries (positions that are multiples of UPD_WIN): each piece is summed by
+// its own warp into a partial, and the last piece to finish (atomic ticket) adds the partials in
+// position order and applies optimiser step t.  Piece boundaries depend only on the sorted ids,
+// so the summation order -- and the result -- is identical from run to run.
+// ---------------------------------------------------------------------------------------
+constexpr int UPD_WIN = 32;
+
+template <int VEC, int NIT, bool FAST>
+__device__ __forceinline__ void apply_step(RowState<VEC, NIT> &r, const Frag<VEC, NIT> &g, float gb,
+                                           const OptView &opt, int t) {
+  if (opt.kind == MFB_OPT_ADAM) {
     const float neg_ss = -__ldg(opt.step_size + t);
-    const float bc2 = __ldg(opt.bc2_sqrt + t);
+    const float bc2 = FAST ? __ldg(opt.inv_bc2_sqrt + t) : __ldg(opt.bc2_sqrt + t);
 #pragma unroll
     for (int k = 0; k < NIT * VEC; ++k) adam_elem<FAST>(r.p.x[k], r.m.x[k], r.v.x[k], g.x[k], neg_ss, bc2, opt);
     adam_elem<FAST>(r.bp, r.bm, r.bv, gb, neg_ss, bc2, opt);
@@ -484,10 +617,120 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_update(const uint32_t *__rest
     for (int k = 0; k < NIT * VEC; ++k) sgd_elem(r.p.x[k], g.x[k], opt);
     sgd_elem(r.bp, gb, opt);
   }
+}
+
+template <int VEC, int NIT, bool FAST>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_update(
+    const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals, const uint32_t *__restrict__ seg_first,
+    const uint32_t *__restrict__ seg_len, long long base, int n, int rb, TableView users, TableView items,
+    OptView opt, int D, const float *__restrict__ snap_u, const float *__restrict__ snap_i,
+    const float *__restrict__ pred, int kind, int b, int m_neg, const unsigned long long *__restrict__ gmax_cell,
+    float *__restrict__ partial, int pstride, int *__restrict__ tickets, int t) {
+  const int lane = threadIdx.x & 31;
+  const int ql = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);  // position within the step
+  if (ql >= n) return;
+  const long long q = base + ql;
+  // independent loads first: the kernel is bound by dependent-load latency, not bandwidth
+  const long long first = seg_first[q];
+  const uint32_t key = skeys[q];
+  const uint32_t len_here = seg_len[q];   // meaningful when q is a head
+  int j_next = (int)svals[q];
+  unsigned long long gcell = 0ull;
+  if (kind == MFB_LOSS_ADAPTIVE_HINGE) gcell = *gmax_cell;
+  const bool head = first == q;
+  if (!head && (ql % UPD_WIN) != 0) return;
+  const int fl = (int)(first - base);
+  const int len = (int)((head ? len_here : seg_len[first]) & ~IN_PREV);
+  const int seg_end = fl + len;                                        // local, exclusive
+  const int win_end = (ql / UPD_WIN + 1) * UPD_WIN;
+  const int run_end = seg_end < win_end ? seg_end : win_end;
+  const bool whole = head && run_end == seg_end;
+  const long long row = key & ((1u << rb) - 1u);
+  const bool is_item = (key >> rb) & 1u;
+  const TableView &T = is_item ? items : users;
+  const float *__restrict__ other = is_item ? snap_u : snap_i;
+  const bool adam = opt.kind == MFB_OPT_ADAM;
+  const float gmax = unpack_max_val(gcell);
+  const int jstar = (kind == MFB_LOSS_ADAPTIVE_HINGE) ? unpack_max_idx(gcell) : -1;
+
+  // the row's optimiser state does not depend on the gradient: get it in flight now
+  RowState<VEC, NIT> r;
+  if (whole) row_load<VEC, NIT>(r, T, row, D, lane, adam);
+
+  Frag<VEC, NIT> g;
+#pragma unroll
+  for (int k = 0; k < NIT * VEC; ++k) g.x[k] = 0.f;
+  float gb = 0.f;
+  for (int p0 = ql; p0 < run_end; p0 += 4) {   // 4 slots in flight: ids -> (pred, snapshot row) -> ordered adds
+    int jj[4];
+    bool use[4];
+    float dd[4];
+    Frag<VEC, NIT> o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      jj[u] = (u == 0) ? j_next : ((p0 + u < run_end) ? (int)svals[base + p0 + u] : 0);
+      // adaptive hinge: only the first maximal negative carries gradient (known without its prediction)
+      use[u] = (p0 + u < run_end) && !(kind == MFB_LOSS_ADAPTIVE_HINGE && jj[u] >= b && jj[u] - b != jstar);
+    }
+    if (p0 + 4 < run_end) j_next = (int)svals[base + p0 + 4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dd[u] = 0.f;
+      if (use[u]) {
+        frag_load<VEC, NIT>(o[u], other + (long long)jj[u] * D, D, lane);
+        dd[u] = slot_dz(kind, jj[u], b, m_neg, pred, gmax, jstar);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (use[u] && dd[u] != 0.f) {
+#pragma unroll
+        for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fadd_rn(g.x[k], __fmul_rn(dd[u], o[u].x[k]));
+        gb = __fadd_rn(gb, dd[u]);
+      }
+    }
+  }
+
+  if (!whole) {
+    // piece of a long segment: publish the partial, take a ticket
+    const int first_win = fl / UPD_WIN, last_win = (seg_end - 1) / UPD_WIN;
+    const int npieces = last_win - first_win + 1;
+    const int nwin = (n + UPD_WIN - 1) / UPD_WIN;
+    // partial slots: [0, nwin) pieces that start at a window boundary, [nwin, 2*nwin) pieces that start at a head
+    const int pslot = head ? (nwin + ql / UPD_WIN) : (ql / UPD_WIN);
+    float *pp = partial + (long long)pslot * pstride;
+    frag_store<VEC, NIT>(g, pp, D, lane);
+    if (lane == 0) pp[D] = gb;
+    __threadfence();
+    __syncwarp();
+    int old = 0;
+    if (lane == 0) old = atomicAdd(tickets + fl, 1);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old != npieces - 1) return;
+    if (lane == 0) tickets[fl] = 0;  // self-cleaning for the next step
+    __threadfence();
+    // ordered sum: the head piece, then the window-aligned pieces in position order
+    const bool head_aligned = (fl % UPD_WIN) == 0;
+    const float *hp = partial + (long long)(nwin + first_win) * pstride;
+    frag_load_cg<VEC, NIT>(g, hp, D, lane);
+    gb = __ldcg(hp + D);
+    (void)head_aligned;
+    for (int w = first_win + 1; w <= last_win; ++w) {
+      const float *wp = partial + (long long)w * pstride;
+      Frag<VEC, NIT> o;
+      frag_load_cg<VEC, NIT>(o, wp, D, lane);
+#pragma unroll
+      for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fadd_rn(g.x[k], o.x[k]);
+      gb = __fadd_rn(gb, __ldcg(wp + D));
+    }
+    row_load<VEC, NIT>(r, T, row, D, lane, adam);
+  }
+  apply_step<VEC, NIT, FAST>(r, g, gb, opt, t);
   row_store<VEC, NIT>(r, T, row, D, lane, adam);
   if (lane == 0) T.last[row] = t;
 }
 
+// ---------------------------------------------------------------------------------------
 // k_flush: one warp per row of one table; replay (last, t]
 template <int VEC, int NIT, bool FAST>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_flush(TableView T, OptView opt, int D, int t) {
@@ -568,6 +811,7 @@ int launch_flush(mfb_model *m, cudaStream_t st) {
   MFB_CHECK(mfb_ensure_scalars(m, m->step));
   const int D = m->desc.dim, t = (int)m->step;
   const bool fast = m->desc.fast_math != 0;
+  int tk = m->prof.begin(PK_FLUSH, st, 2);
 #define CALL(V, N)                                                                                      \
   if (fast) {                                                                                           \
     k_flush<V, N, true><<<grid_for_warps(m->users.rows), BLOCK_THREADS, 0, st>>>(m->users, m->opt, D, t); \
@@ -578,6 +822,7 @@ int launch_flush(mfb_model *m, cudaStream_t st) {
   }
   MFB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
+  m->prof.end(tk, st);
   MFB_KERNEL_CHECK();
   m->flushed_step = m->step;
   return MFB_OK;
@@ -629,6 +874,7 @@ extern "C" int mfb_loss_forward_backward(int loss, const float *d_pos, int64_t n
     return MFB_ERR_SHAPE;
   }
   if ((d_dpos == nullptr) != (d_dneg == nullptr) && n_neg > 0) return MFB_ERR_INVALID;
+  mfb_count_library_launch(1);
   k_loss<<<1, LOSS_THREADS, 0, (cudaStream_t)stream>>>(loss, d_pos, (int)n_pos, d_neg, (int)n_neg, d_loss, d_dpos,
                                                        d_dneg, 0);
   MFB_KERNEL_CHECK();
@@ -649,6 +895,7 @@ extern "C" int mfb_predict_pairs(mfb_model *m, const int64_t *d_users, const int
   int *slot_i = slot_u + count;
   int *flag = m->ws_scalars.as<int>();
   MFB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  int tk = m->prof.begin(PK_PREDICT, st, 2);
   k_pack_pairs<<<(unsigned)((count + 255) / 256), 256, 0, st>>>((const long long *)d_users, (const long long *)d_items,
                                                                count, m->users.rows, m->items.rows, slot_u, slot_i,
                                                                flag);
@@ -660,11 +907,12 @@ extern "C" int mfb_predict_pairs(mfb_model *m, const int64_t *d_users, const int
     int L = (int)((count - off < (1 << 24)) ? (count - off) : (1 << 24));
 #define CALL(V, N)                                                                                               \
   k_forward<V, N><<<grid_for_warps(L), BLOCK_THREADS, 0, st>>>(slot_u + off, slot_i + off, L, m->users, m->items, D, \
-                                                                nullptr, nullptr, d_out + off)
+                                                                nullptr, nullptr, d_out + off, -1, nullptr)
     MFB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
     MFB_KERNEL_CHECK();
   }
+  m->prof.end(tk, st);
   return MFB_OK;
 }
 
@@ -679,132 +927,306 @@ extern "C" int mfb_predict_user(mfb_model *m, int64_t user, float *d_out, mfb_st
   Shape sh;
   MFB_CHECK(pick_shape(m->desc.dim, &sh));
   const int D = m->desc.dim, I = m->items.rows;
+  int tk = m->prof.begin(PK_PREDICT, st);
 #define CALL(V, N) \
   k_forward_user<V, N><<<grid_for_warps(I), BLOCK_THREADS, 0, st>>>((long long)user, I, m->users, m->items, D, d_out)
   MFB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
+  m->prof.end(tk, st);
+  MFB_KERNEL_CHECK();
+  return MFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// host pipeline
+//   stream P (planner): pack ids -> radix sort -> segment table, for chunk c+1 while chunk c trains
+//   stream A (caller's): per step  forward -> update ; per chunk  loss values
+//   stream S (side):     catch-up of the rows of step s+1 that are not in step s, during step s
+// ---------------------------------------------------------------------------------------
+struct StepGeom {
+  int D, batch, m_neg, Lfull, rb, chunk, loss;
+  int64_t n_pos, nsteps;
+  bool train, fast, adaptive;
+  // negatives: explicit per-epoch arrays, or drawn per chunk from the model's MT19937 stream
+  const int64_t *pop_users = nullptr, *pop_items = nullptr;
+  int64_t pop_len = 0;
+};
+
+static int ensure_streams(mfb_model *m) {
+  if (m->st_side) return MFB_OK;
+  MFB_CUDA(cudaStreamCreateWithFlags(&m->st_side, cudaStreamNonBlocking));
+  MFB_CUDA(cudaStreamCreateWithFlags(&m->st_plan, cudaStreamNonBlocking));
+  auto mk = [](cudaEvent_t *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
+  for (auto &e : m->ev_plan) MFB_CUDA(mk(&e));
+  for (auto &e : m->ev_done) MFB_CUDA(mk(&e));
+  for (auto &e : m->ev_upd) MFB_CUDA(mk(&e));
+  for (auto &e : m->ev_pc) MFB_CUDA(mk(&e));
+  MFB_CUDA(mk(&m->ev_join));
+  return MFB_OK;
+}
+
+static void chunk_extent(const StepGeom &g, int64_t s0, int *ns, int *b_last, int64_t *nkeys) {
+  *ns = (int)((g.nsteps - s0 < g.chunk) ? (g.nsteps - s0) : g.chunk);
+  const int64_t last_first = (s0 + *ns - 1) * (int64_t)g.batch;
+  *b_last = (int)((g.n_pos - last_first < g.batch) ? (g.n_pos - last_first) : g.batch);
+  // all steps are full except possibly the last of the epoch (which is last in its chunk)
+  *nkeys = 2 * ((int64_t)(*ns - 1) * g.Lfull + (*b_last + g.m_neg));
+}
+
+static int plan_chunk(mfb_model *m, PlanBuf &pb, const StepGeom &g, const int64_t *d_pos_users,
+                      const int64_t *d_pos_items, const int64_t *d_neg_users, const int64_t *d_neg_items, int64_t s0,
+                      int *flag, cudaStream_t sp) {
+  int ns, b_last;
+  int64_t nkeys;
+  chunk_extent(g, s0, &ns, &b_last, &nkeys);
+  const size_t slots = (size_t)g.chunk * g.Lfull;
+  MFB_CHECK(pb.slots.reserve(slots * 2 * sizeof(int)));
+  MFB_CHECK(pb.pred.reserve(slots * sizeof(float)));
+  MFB_CHECK(pb.gmax.reserve((size_t)g.chunk * sizeof(unsigned long long)));
+  MFB_CHECK(pb.keys_a.reserve(slots * 2 * sizeof(uint32_t)));
+  MFB_CHECK(pb.vals_a.reserve(slots * 2 * sizeof(uint32_t)));
+  if (g.train) {
+    MFB_CHECK(pb.keys_b.reserve(slots * 2 * sizeof(uint32_t)));
+    MFB_CHECK(pb.vals_b.reserve(slots * 2 * sizeof(uint32_t)));
+    MFB_CHECK(pb.seg.reserve(slots * 2 * 2 * sizeof(uint32_t)));
+  }
+  int *slot_u = pb.slots.as<int>();
+  int *slot_i = slot_u + slots;
+  const long long total = (long long)ns * g.Lfull;
+  int tk;
+  long long neg_step0 = 0;
+  if (g.pop_len > 0 && g.m_neg > 0) {
+    // random.choices(neg_examples, k = n_neg*batch) for each step of the chunk, in step order
+    const int64_t k = (int64_t)ns * g.m_neg;
+    MFB_CHECK(pb.words.reserve((size_t)(2 * k) * sizeof(uint32_t)));
+    MFB_CHECK(pb.neg_u.reserve((size_t)k * sizeof(int64_t)));
+    MFB_CHECK(pb.neg_i.reserve((size_t)k * sizeof(int64_t)));
+    tk = m->prof.begin(PK_SAMPLE, sp, 0);
+    MFB_CHECK(mfb_mt_generate_async(m->rng_state.as<uint32_t>(), 2 * k, pb.words.as<uint32_t>(), sp));
+    MFB_CHECK(mfb_choices_async(pb.words.as<uint32_t>(), k, g.pop_len, g.pop_users, g.pop_items,
+                                pb.neg_u.as<int64_t>(), pb.neg_i.as<int64_t>(), sp));
+    m->prof.end(tk, sp);
+    d_neg_users = pb.neg_u.as<int64_t>();
+    d_neg_items = pb.neg_i.as<int64_t>();
+    neg_step0 = s0;
+  }
+  tk = m->prof.begin(PK_PACK, sp);
+  k_pack<<<(unsigned)((total + 255) / 256), 256, 0, sp>>>(
+      (const long long *)d_pos_users, (const long long *)d_pos_items, g.n_pos, (const long long *)d_neg_users,
+      (const long long *)d_neg_items, g.batch, g.m_neg, s0, neg_step0, ns, g.rb, m->users.rows, m->items.rows,
+      slot_u, slot_i, pb.keys_a.as<uint32_t>(), pb.vals_a.as<uint32_t>(), flag);
+  m->prof.end(tk, sp);
+  MFB_KERNEL_CHECK();
+  if (g.adaptive) MFB_CUDA(cudaMemsetAsync(pb.gmax.ptr, 0, (size_t)ns * sizeof(unsigned long long), sp));
+  if (g.train) {
+    int nbits = g.rb + 1 + (ns > 1 ? bits_for((uint32_t)(ns - 1)) : 0);
+    tk = m->prof.begin(PK_SORT, sp, 3 * ((nbits + 7) / 8) + 1);
+    MFB_CHECK(mfb_radix_sort_pairs(pb.keys_a.as<uint32_t>(), pb.vals_a.as<uint32_t>(), pb.keys_b.as<uint32_t>(),
+                                   pb.vals_b.as<uint32_t>(), nkeys, nbits, m->ws_hist, &pb.skeys, &pb.svals, sp));
+    uint32_t *seg_first = pb.seg.as<uint32_t>();
+    k_segments<<<(unsigned)((nkeys + 255) / 256), 256, 0, sp>>>(pb.skeys, nkeys, g.rb, g.Lfull, seg_first,
+                                                                seg_first + slots * 2);
+    m->prof.end(tk, sp);
+    MFB_KERNEL_CHECK();
+  }
+  return MFB_OK;
+}
+
+static int launch_catchup(mfb_model *m, const Shape &sh, const StepGeom &g, const uint32_t *k, const uint32_t *slen,
+                          int nk, int t, int skip_in_prev, cudaStream_t st) {
+  const int D = g.D;
+  int tk = m->prof.begin(PK_CATCHUP, st);
+#define CALL(V, N)                                                                                            \
+  if (g.fast)                                                                                                 \
+    k_catchup<V, N, true><<<(nk + CU_WARPS - 1) / CU_WARPS, CU_WARPS * 32, 0, st>>>(k, slen, nk, g.rb, m->users, \
+                                                                                    m->items, m->opt, D, t,   \
+                                                                                    skip_in_prev);            \
+  else                                                                                                        \
+    k_catchup<V, N, false><<<(nk + CU_WARPS - 1) / CU_WARPS, CU_WARPS * 32, 0, st>>>(k, slen, nk, g.rb, m->users, \
+                                                                                     m->items, m->opt, D, t,  \
+                                                                                     skip_in_prev)
+  MFB_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+  m->prof.end(tk, st);
+  MFB_KERNEL_CHECK();
+  return MFB_OK;
+}
+
+static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom &g, int64_t s0,
+                      float *d_step_losses, cudaStream_t st) {
+  int ns, b_last;
+  int64_t nkeys;
+  chunk_extent(g, s0, &ns, &b_last, &nkeys);
+  const int D = g.D, Lfull = g.Lfull, m_neg = g.m_neg;
+  const size_t slots = (size_t)g.chunk * Lfull;
+  const int *slot_u = pb.slots.as<int>();
+  const int *slot_i = slot_u + slots;
+  float *pred_chunk = pb.pred.as<float>();
+  unsigned long long *gmax = pb.gmax.as<unsigned long long>();
+  const uint32_t *seg_first = g.train ? pb.seg.as<uint32_t>() : nullptr;
+  const uint32_t *seg_len = g.train ? seg_first + slots * 2 : nullptr;
+  float *snap_u = g.train ? m->ws_rows.as<float>() : nullptr;
+  float *snap_i = g.train ? snap_u + (size_t)Lfull * D : nullptr;
+  const int pstride = ((D + 1 + 31) / 32) * 32;  // partial rows own whole 128-byte lines
+  cudaStream_t side = m->st_side;
+  int tk;
+
+  if (g.train) {
+    // the side stream may touch tables only after everything queued so far on the main stream
+    MFB_CUDA(cudaEventRecord(m->ev_join, st));
+    MFB_CUDA(cudaStreamWaitEvent(side, m->ev_join, 0));
+  }
+  for (int s = 0; s < ns; ++s) {
+    const int b = (s == ns - 1) ? b_last : g.batch;
+    const int L = b + m_neg;
+    const int *su = slot_u + (size_t)s * Lfull;
+    const int *si = slot_i + (size_t)s * Lfull;
+    float *pred = pred_chunk + (size_t)s * Lfull;
+    const int neg_begin = g.adaptive ? b : -1;
+    if (g.train) {
+      const int t = (int)(m->step + 1);
+      const long long base = 2 * (long long)s * Lfull;
+      const int nk = 2 * L;
+      if (s == 0) {
+        // first step of a chunk: no look-ahead information, catch its rows up in line
+        MFB_CHECK(launch_catchup(m, sh, g, pb.skeys + base, seg_len + base, nk, t, 0, st));
+      } else {
+        MFB_CUDA(cudaStreamWaitEvent(st, m->ev_pc[s & 3], 0));
+      }
+      tk = m->prof.begin(PK_FORWARD, st);
+#define CALL(V, N)                                                                                                 \
+  k_forward<V, N><<<grid_for_warps(L), BLOCK_THREADS, 0, st>>>(su, si, L, m->users, m->items, D, snap_u, snap_i, pred, \
+                                                                neg_begin, gmax + s)
+      MFB_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+      m->prof.end(tk, st);
+      // look-ahead: rows of step s+1 that are not in step s are replayed up to optimiser step t while this
+      // step runs (they are disjoint from everything forward/update of step s touch)
+      if (s + 1 < ns) {
+        const int b1 = (s + 1 == ns - 1) ? b_last : g.batch;
+        const long long base1 = 2 * (long long)(s + 1) * Lfull;
+        if (s >= 1) MFB_CUDA(cudaStreamWaitEvent(side, m->ev_upd[(s - 1) & 3], 0));
+        MFB_CHECK(launch_catchup(m, sh, g, pb.skeys + base1, seg_len + base1, 2 * (b1 + m_neg), t + 1, 1, side));
+        MFB_CUDA(cudaEventRecord(m->ev_pc[(s + 1) & 3], side));
+      }
+      tk = m->prof.begin(PK_UPDATE, st);
+#define CALL(V, N)                                                                                                    \
+  if (g.fast)                                                                                                         \
+    k_update<V, N, true><<<grid_for_warps(nk), BLOCK_THREADS, 0, st>>>(                                               \
+        pb.skeys, pb.svals, seg_first, seg_len, base, nk, g.rb, m->users, m->items, m->opt, D, snap_u, snap_i, pred,  \
+        g.loss, b, m_neg, gmax + s, m->ws_partial.as<float>(), pstride, m->ws_tickets.as<int>(), t);                  \
+  else                                                                                                                \
+    k_update<V, N, false><<<grid_for_warps(nk), BLOCK_THREADS, 0, st>>>(                                              \
+        pb.skeys, pb.svals, seg_first, seg_len, base, nk, g.rb, m->users, m->items, m->opt, D, snap_u, snap_i, pred,  \
+        g.loss, b, m_neg, gmax + s, m->ws_partial.as<float>(), pstride, m->ws_tickets.as<int>(), t)
+      MFB_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+      m->prof.end(tk, st);
+      MFB_KERNEL_CHECK();
+      MFB_CUDA(cudaEventRecord(m->ev_upd[s & 3], st));
+      m->step += 1;
+    } else {
+      tk = m->prof.begin(PK_FORWARD, st);
+#define CALL(V, N)                                                                                                   \
+  k_forward<V, N><<<grid_for_warps(L), BLOCK_THREADS, 0, st>>>(su, si, L, m->users, m->items, D, nullptr, nullptr, pred, \
+                                                                -1, nullptr)
+      MFB_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+      m->prof.end(tk, st);
+      MFB_KERNEL_CHECK();
+    }
+  }
+  // loss values of the whole chunk in one launch (the predictions of every step were kept)
+  tk = m->prof.begin(PK_LOSS, st);
+  k_loss_steps<<<ns, LOSS_THREADS, 0, st>>>(g.loss, pred_chunk, Lfull, g.batch, m_neg, g.n_pos, s0, d_step_losses);
+  m->prof.end(tk, st);
   MFB_KERNEL_CHECK();
   return MFB_OK;
 }
 
 static int run_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const int64_t *d_pos_items, int64_t n_pos,
                      int32_t batch, int32_t n_neg, const int64_t *d_neg_users, const int64_t *d_neg_items,
-                     float *d_step_losses, cudaStream_t st, bool train) {
+                     float *d_step_losses, cudaStream_t st, bool train, const int64_t *d_pop_users = nullptr,
+                     const int64_t *d_pop_items = nullptr, int64_t pop_len = 0) {
   if (!m || !d_pos_users || !d_pos_items || !d_step_losses) return MFB_ERR_INVALID;
   MFB_CHECK(validate_loss_shape(loss, n_pos, batch, n_neg));
-  if (n_neg > 0 && (!d_neg_users || !d_neg_items)) return MFB_ERR_INVALID;
+  const bool from_stream = pop_len > 0;
+  if (n_neg > 0 && !from_stream && (!d_neg_users || !d_neg_items)) return MFB_ERR_INVALID;
+  if (n_neg > 0 && from_stream) {
+    if (!d_pop_users || !d_pop_items) return MFB_ERR_INVALID;
+    if (!m->rng_seeded) {
+      mfb_set_error("negative sampler not seeded (mfb_model_rng_seed)");
+      return MFB_ERR_INVALID;
+    }
+  }
   Shape sh;
   MFB_CHECK(pick_shape(m->desc.dim, &sh));
-  const int D = m->desc.dim;
+  StepGeom g;
+  g.D = m->desc.dim;
   const int64_t m_neg64 = (int64_t)n_neg * batch;
   if (m_neg64 + batch > (1 << 24)) {
     mfb_set_error("batch*(1+n_neg) too large");
     return MFB_ERR_UNSUPPORTED;
   }
-  const int m_neg = (int)m_neg64;
-  const int Lfull = batch + m_neg;
-  const int64_t nsteps = (n_pos + batch - 1) / batch;
+  g.batch = batch;
+  g.m_neg = (int)m_neg64;
+  g.Lfull = batch + g.m_neg;
+  g.n_pos = n_pos;
+  g.nsteps = (n_pos + batch - 1) / batch;
+  g.loss = loss;
+  g.train = train;
+  g.fast = m->desc.fast_math != 0;
+  g.adaptive = loss == MFB_LOSS_ADAPTIVE_HINGE;
+  if (n_neg > 0 && from_stream) {
+    g.pop_users = d_pop_users;
+    g.pop_items = d_pop_items;
+    g.pop_len = pop_len;
+  }
   const uint32_t maxrow = (uint32_t)((m->users.rows > m->items.rows ? m->users.rows : m->items.rows) - 1);
-  const int rb = bits_for(maxrow);
-  int sb_max = 31 - rb;  // bits left for the chunk-local step
+  g.rb = bits_for(maxrow);
+  const int sb_max = 31 - g.rb;  // bits left for the chunk-local step
   if (sb_max < 0) {
     mfb_set_error("tables too large for 32-bit planner keys");
     return MFB_ERR_UNSUPPORTED;
   }
-  int chunk = 1 << (sb_max > 6 ? 6 : sb_max);
-  while (chunk > 1 && (int64_t)chunk * Lfull > (1ll << 25)) chunk >>= 1;  // bound workspace
+  g.chunk = 1 << (sb_max > 6 ? 6 : sb_max);
+  while (g.chunk > 1 && (int64_t)g.chunk * g.Lfull > (1ll << 25)) g.chunk >>= 1;  // bound workspace
+  MFB_CHECK(ensure_streams(m));
   if (!train) MFB_CHECK(launch_flush(m, st));
-  if (train) MFB_CHECK(mfb_ensure_scalars(m, m->step + nsteps));
+  if (train) MFB_CHECK(mfb_ensure_scalars(m, m->step + g.nsteps + 1));
 
-  const size_t slots = (size_t)chunk * Lfull;
-  MFB_CHECK(m->ws_slots.reserve(slots * 2 * sizeof(int)));
-  MFB_CHECK(m->ws_pred.reserve((size_t)Lfull * sizeof(float)));
   MFB_CHECK(m->ws_scalars.reserve(64));
-  int *slot_u = m->ws_slots.as<int>();
-  int *slot_i = slot_u + slots;
   int *flag = m->ws_scalars.as<int>();
   MFB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   if (train) {
-    MFB_CHECK(m->ws_keys_a.reserve(slots * 2 * sizeof(uint32_t)));
-    MFB_CHECK(m->ws_keys_b.reserve(slots * 2 * sizeof(uint32_t)));
-    MFB_CHECK(m->ws_vals_a.reserve(slots * 2 * sizeof(uint32_t)));
-    MFB_CHECK(m->ws_vals_b.reserve(slots * 2 * sizeof(uint32_t)));
-    MFB_CHECK(m->ws_rows.reserve((size_t)Lfull * D * 2 * sizeof(float)));
-    MFB_CHECK(m->ws_dz.reserve((size_t)Lfull * sizeof(float)));
-  } else {
-    // keys are still written by k_pack; give it somewhere to put them
-    MFB_CHECK(m->ws_keys_a.reserve(slots * 2 * sizeof(uint32_t)));
-    MFB_CHECK(m->ws_vals_a.reserve(slots * 2 * sizeof(uint32_t)));
+    const int nwin_full = (2 * g.Lfull + UPD_WIN - 1) / UPD_WIN;
+    const int pstride = ((g.D + 1 + 31) / 32) * 32;
+    MFB_CHECK(m->ws_rows.reserve((size_t)g.Lfull * g.D * 2 * sizeof(float)));
+    MFB_CHECK(m->ws_partial.reserve((size_t)2 * nwin_full * pstride * sizeof(float)));
+    const size_t before = m->ws_tickets.cap;
+    MFB_CHECK(m->ws_tickets.reserve((size_t)2 * g.Lfull * sizeof(int)));
+    if (m->ws_tickets.cap != before) MFB_CUDA(cudaMemsetAsync(m->ws_tickets.ptr, 0, m->ws_tickets.cap, st));
   }
-  float *snap_u = train ? m->ws_rows.as<float>() : nullptr;
-  float *snap_i = train ? snap_u + (size_t)Lfull * D : nullptr;
-  float *pred = m->ws_pred.as<float>();
-  float *dz = train ? m->ws_dz.as<float>() : nullptr;
-  const bool fast = m->desc.fast_math != 0;
-
-  for (int64_t s0 = 0; s0 < nsteps; s0 += chunk) {
-    const int ns = (int)((nsteps - s0 < chunk) ? (nsteps - s0) : chunk);
-    const long long total = (long long)ns * Lfull;
-    k_pack<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        (const long long *)d_pos_users, (const long long *)d_pos_items, n_pos, (const long long *)d_neg_users,
-        (const long long *)d_neg_items, batch, m_neg, s0, ns, rb, m->users.rows, m->items.rows, slot_u, slot_i,
-        m->ws_keys_a.as<uint32_t>(), m->ws_vals_a.as<uint32_t>(), flag);
-    MFB_KERNEL_CHECK();
-    // number of keys actually present: all steps full except possibly the last of the epoch
-    const int64_t last_first = (s0 + ns - 1) * (int64_t)batch;
-    const int b_last = (int)((n_pos - last_first < batch) ? (n_pos - last_first) : batch);
-    const int64_t nkeys = 2 * ((int64_t)(ns - 1) * Lfull + (b_last + m_neg));
-    uint32_t *skeys = nullptr, *svals = nullptr;
-    if (train) {
-      int nbits = rb + 1 + bits_for((uint32_t)(ns > 1 ? ns - 1 : 1));
-      if (ns == 1) nbits = rb + 1;
-      MFB_CHECK(mfb_radix_sort_pairs(m->ws_keys_a.as<uint32_t>(), m->ws_vals_a.as<uint32_t>(),
-                                     m->ws_keys_b.as<uint32_t>(), m->ws_vals_b.as<uint32_t>(), nkeys, nbits,
-                                     m->ws_hist, &skeys, &svals, st));
+  // the planner stream starts after everything already queued on the caller's stream (the ids may have
+  // been produced there) ...
+  cudaStream_t sp = m->st_plan;
+  MFB_CUDA(cudaEventRecord(m->ev_join, st));
+  MFB_CUDA(cudaStreamWaitEvent(sp, m->ev_join, 0));
+  const int64_t nchunks = (g.nsteps + g.chunk - 1) / g.chunk;
+  MFB_CHECK(plan_chunk(m, m->plan[0], g, d_pos_users, d_pos_items, d_neg_users, d_neg_items, 0, flag, sp));
+  MFB_CUDA(cudaEventRecord(m->ev_plan[0], sp));
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int cur = (int)(c & 1), nxt = cur ^ 1;
+    if (c + 1 < nchunks) {
+      // ... and re-uses a plan buffer only after the chunk that trained from it has finished
+      if (c >= 1) MFB_CUDA(cudaStreamWaitEvent(sp, m->ev_done[nxt], 0));
+      MFB_CHECK(plan_chunk(m, m->plan[nxt], g, d_pos_users, d_pos_items, d_neg_users, d_neg_items,
+                           (c + 1) * g.chunk, flag, sp));
+      MFB_CUDA(cudaEventRecord(m->ev_plan[nxt], sp));
     }
-    for (int s = 0; s < ns; ++s) {
-      const int64_t gstep = s0 + s;
-      const int b = (s == ns - 1) ? b_last : batch;
-      const int L = b + m_neg;
-      const int *su = slot_u + (size_t)s * Lfull;
-      const int *si = slot_i + (size_t)s * Lfull;
-      if (train) {
-        const int t = (int)(m->step + 1);
-        const uint32_t *k = skeys + 2 * (size_t)s * Lfull;
-        const uint32_t *v = svals + 2 * (size_t)s * Lfull;
-        const int nk = 2 * L;
-#define CALL(V, N)                                                                                                 \
-  if (fast)                                                                                                        \
-    k_catchup<V, N, true><<<grid_for_warps(nk), BLOCK_THREADS, 0, st>>>(k, nk, rb, m->users, m->items, m->opt, D, t); \
-  else                                                                                                             \
-    k_catchup<V, N, false><<<grid_for_warps(nk), BLOCK_THREADS, 0, st>>>(k, nk, rb, m->users, m->items, m->opt, D, t)
-        MFB_DISPATCH_SHAPE(sh, CALL);
-#undef CALL
-#define CALL(V, N) \
-  k_forward<V, N><<<grid_for_warps(L), BLOCK_THREADS, 0, st>>>(su, si, L, m->users, m->items, D, snap_u, snap_i, pred)
-        MFB_DISPATCH_SHAPE(sh, CALL);
-#undef CALL
-        k_loss<<<1, LOSS_THREADS, 0, st>>>(loss, pred, b, pred + b, m_neg, d_step_losses + gstep, dz, dz + b, 1);
-#define CALL(V, N)                                                                                                   \
-  if (fast)                                                                                                          \
-    k_update<V, N, true><<<grid_for_warps(nk), BLOCK_THREADS, 0, st>>>(k, v, nk, rb, m->users, m->items, m->opt, D,  \
-                                                                        snap_u, snap_i, dz, t);                      \
-  else                                                                                                               \
-    k_update<V, N, false><<<grid_for_warps(nk), BLOCK_THREADS, 0, st>>>(k, v, nk, rb, m->users, m->items, m->opt, D, \
-                                                                         snap_u, snap_i, dz, t)
-        MFB_DISPATCH_SHAPE(sh, CALL);
-#undef CALL
-        MFB_KERNEL_CHECK();
-        m->step += 1;
-      } else {
-#define CALL(V, N) \
-  k_forward<V, N><<<grid_for_warps(L), BLOCK_THREADS, 0, st>>>(su, si, L, m->users, m->items, D, nullptr, nullptr, pred)
-        MFB_DISPATCH_SHAPE(sh, CALL);
-#undef CALL
-        k_loss<<<1, LOSS_THREADS, 0, st>>>(loss, pred, b, pred + b, m_neg, d_step_losses + gstep, nullptr, nullptr, 0);
-        MFB_KERNEL_CHECK();
-      }
-    }
+    MFB_CUDA(cudaStreamWaitEvent(st, m->ev_plan[cur], 0));
+    MFB_CHECK(exec_chunk(m, m->plan[cur], sh, g, c * g.chunk, d_step_losses, st));
+    MFB_CUDA(cudaEventRecord(m->ev_done[cur], st));
   }
   // ids were clamped on the device; report a bad id once, after the queue drains
   MFB_CHECK(check_err_flag(flag, st, train ? "train" : "loss"));
@@ -825,6 +1247,22 @@ extern "C" int mfb_loss_steps(mfb_model *m, int loss, const int64_t *d_pos_users
                    (cudaStream_t)stream, false);
 }
 
+extern "C" int mfb_train_epoch(mfb_model *m, int loss, const int64_t *d_pos_users, const int64_t *d_pos_items,
+                               int64_t n_pos, int32_t batch, int32_t n_neg, const int64_t *d_pop_users,
+                               const int64_t *d_pop_items, int64_t pop_len, float *d_step_losses, mfb_stream stream) {
+  if (n_neg > 0 && pop_len <= 0) return MFB_ERR_INVALID;
+  return run_steps(m, loss, d_pos_users, d_pos_items, n_pos, batch, n_neg, nullptr, nullptr, d_step_losses,
+                   (cudaStream_t)stream, true, d_pop_users, d_pop_items, n_neg > 0 ? pop_len : 0);
+}
+
+extern "C" int mfb_loss_epoch(mfb_model *m, int loss, const int64_t *d_pos_users, const int64_t *d_pos_items,
+                              int64_t n_pos, int32_t batch, int32_t n_neg, const int64_t *d_pop_users,
+                              const int64_t *d_pop_items, int64_t pop_len, float *d_step_losses, mfb_stream stream) {
+  if (n_neg > 0 && pop_len <= 0) return MFB_ERR_INVALID;
+  return run_steps(m, loss, d_pos_users, d_pos_items, n_pos, batch, n_neg, nullptr, nullptr, d_step_losses,
+                   (cudaStream_t)stream, false, d_pop_users, d_pop_items, n_neg > 0 ? pop_len : 0);
+}
+
 extern "C" int mfb_train_epoch_host(mfb_model *m, int loss, const int64_t *h_pos_users, const int64_t *h_pos_items,
                                     int64_t n_pos, int32_t batch, int32_t n_neg, uint32_t *h_state,
                                     const int64_t *d_pop_users, const int64_t *d_pop_items, int64_t pop_len,
@@ -833,24 +1271,20 @@ extern "C" int mfb_train_epoch_host(mfb_model *m, int loss, const int64_t *h_pos
   if (!m || !h_pos_users || !h_pos_items || !h_step_losses) return MFB_ERR_INVALID;
   MFB_CHECK(validate_loss_shape(loss, n_pos, batch, n_neg));
   const int64_t nsteps = (n_pos + batch - 1) / batch;
-  const int64_t k = nsteps * (int64_t)n_neg * batch;
   MFB_CHECK(m->ws_ids.reserve((size_t)n_pos * 2 * sizeof(int64_t)));
   MFB_CHECK(m->ws_losses.reserve((size_t)nsteps * sizeof(float)));
   int64_t *d_u = m->ws_ids.as<int64_t>();
   int64_t *d_i = d_u + n_pos;
+  if (n_neg > 0) {
+    if (!h_state || !d_pop_users || !d_pop_items || pop_len <= 0) return MFB_ERR_INVALID;
+    MFB_CHECK(mfb_model_rng_seed(m, h_state, stream));
+  }
   MFB_CUDA(cudaMemcpyAsync(d_u, h_pos_users, (size_t)n_pos * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   MFB_CUDA(cudaMemcpyAsync(d_i, h_pos_items, (size_t)n_pos * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  int64_t *d_nu = nullptr, *d_ni = nullptr;
-  if (k > 0) {
-    if (!h_state || !d_pop_users || !d_pop_items || pop_len <= 0) return MFB_ERR_INVALID;
-    MFB_CHECK(m->ws_neg_u.reserve((size_t)k * sizeof(int64_t)));
-    MFB_CHECK(m->ws_neg_i.reserve((size_t)k * sizeof(int64_t)));
-    d_nu = m->ws_neg_u.as<int64_t>();
-    d_ni = m->ws_neg_i.as<int64_t>();
-    MFB_CHECK(mfb_mt_choices_pairs(h_state, d_pop_users, d_pop_items, pop_len, k, d_nu, d_ni, stream));
-  }
-  MFB_CHECK(run_steps(m, loss, d_u, d_i, n_pos, batch, n_neg, d_nu, d_ni, m->ws_losses.as<float>(), st, true));
+  MFB_CHECK(run_steps(m, loss, d_u, d_i, n_pos, batch, n_neg, nullptr, nullptr, m->ws_losses.as<float>(), st, true,
+                      d_pop_users, d_pop_items, n_neg > 0 ? pop_len : 0));
   MFB_CUDA(cudaMemcpyAsync(h_step_losses, m->ws_losses.ptr, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
+  if (n_neg > 0) MFB_CHECK(mfb_model_rng_state(m, h_state, stream));
   return MFB_OK;
 }

@@ -166,14 +166,6 @@ class ImplicitFactorizationModel(object):
                              torch.from_numpy(np.ascontiguousarray(pairs[:, 1])).to(dev), self.neg_examples)
         return self._neg_pop
 
-    def _draw(self, nsteps):
-        pop = self._negative_population()
-        if pop is None:
-            return 0, None, None
-        k = nsteps * self._num_negative_samples * self._batch_size      # k uses B even on a partial batch
-        neg_u, neg_i = self._engine_.draw_negative_pairs(pop[0], pop[1], k, rng=random)
-        return self._num_negative_samples, neg_u, neg_i
-
     def fit(self, train_set, valid_set, verbose=False):
         self.train_set = train_set
         user_ids = train_set.user_ids
@@ -189,20 +181,26 @@ class ImplicitFactorizationModel(object):
         val_users_d = torch.from_numpy(np.ascontiguousarray(valid_set.user_ids)).to(dev).long()
         val_items_d = torch.from_numpy(np.ascontiguousarray(valid_set.item_ids)).to(dev).long()
         B = self._batch_size
-        n_train_steps = (len(users_d) + B - 1) // B
-        n_val_steps = (len(val_users_d) + B - 1) // B
+        pop = self._negative_population()
+        n_neg = self._num_negative_samples if pop is not None else 0
+        pop_u, pop_i = (pop[0], pop[1]) if pop is not None else (None, None)
 
         total_losses = {"train_loss": [], "validation_loss": [], "curr_epoch": []}
         for epoch_num in range(self._n_iter):
+            # Negatives: random.choices(neg_examples, k = n_neg * batch) per step (implicit.py:352,370),
+            # drawn on the device from Python's global MT19937 stream -- training steps first, then the
+            # validation steps, exactly the order in which the reference consumes it.
             self._net.train()
-            n_neg, neg_u, neg_i = self._draw(n_train_steps)
-            train_losses = self._engine_.train_steps(self._loss_kind, users_d, items_d, B, n_neg, neg_u, neg_i)
+            if pop is not None:
+                self._engine_.rng_seed(random)
+            train_losses = self._engine_.train_epoch(self._loss_kind, users_d, items_d, B, n_neg, pop_u, pop_i)
             self._net.eval()
-            n_neg, neg_u, neg_i = self._draw(n_val_steps)
-            val_losses = self._engine_.loss_steps(self._loss_kind, val_users_d, val_items_d, B, n_neg, neg_u, neg_i)
+            val_losses = self._engine_.loss_epoch(self._loss_kind, val_users_d, val_items_d, B, n_neg, pop_u, pop_i)
             # one device->host read per epoch replaces three loss.item() syncs per step (implicit.py:294-298)
             train_steps = [float(x) for x in train_losses.cpu().numpy()]
             val_steps = [float(x) for x in val_losses.cpu().numpy()]
+            if pop is not None:
+                self._engine_.rng_sync(random)       # `random` now sits where the reference would leave it
 
             train_epoch_loss = sum(train_steps) / len(train_steps)
             if np.isnan(train_epoch_loss) or train_epoch_loss == 0.0:

@@ -252,6 +252,39 @@ class MFEngine(object):
     def loss_steps(self, loss, pos_users, pos_items, batch, n_neg, neg_users=None, neg_items=None):
         return self._steps('mfb_loss_steps', loss, pos_users, pos_items, batch, n_neg, neg_users, neg_items)
 
+    # -- whole epochs with on-device negative sampling (no host round trip per draw) ---------------
+    def rng_seed(self, rng=None):
+        """Continue `rng`'s (default: the global `random` module's) MT19937 stream on the device."""
+        rng = rng or _py_random
+        state, self._rng_extra = _get_py_state(rng)
+        self._call('mfb_model_rng_seed', N.hptr(state), N.stream_ptr())
+
+    def rng_sync(self, rng=None):
+        """Leave `rng` where the reference's draws would have left it (synchronises)."""
+        rng = rng or _py_random
+        state = np.empty(625, dtype=np.uint32)
+        self._call('mfb_model_rng_state', N.hptr(state), N.stream_ptr())
+        _set_py_state(rng, state, self._rng_extra)
+
+    def _epoch(self, fn, loss, pos_users, pos_items, batch, n_neg, pop_users, pop_items):
+        pos_users = _as_i64_cuda(pos_users, self.device)
+        pos_items = _as_i64_cuda(pos_items, self.device)
+        n_pos = pos_users.numel()
+        nsteps = (n_pos + batch - 1) // batch
+        losses = torch.empty(nsteps, dtype=torch.float32, device=self.device)
+        pop_len = 0 if (pop_users is None or n_neg == 0) else pop_users.numel()
+        self._call(fn, N.LOSS[loss], N.dptr(pos_users), N.dptr(pos_items), n_pos, int(batch), int(n_neg),
+                   N.dptr(pop_users), N.dptr(pop_items), pop_len, N.dptr(losses), N.stream_ptr())
+        return losses
+
+    def train_epoch(self, loss, pos_users, pos_items, batch, n_neg, pop_users=None, pop_items=None):
+        out = self._epoch('mfb_train_epoch', loss, pos_users, pos_items, batch, n_neg, pop_users, pop_items)
+        self._sync_optimizer_step()
+        return out
+
+    def loss_epoch(self, loss, pos_users, pos_items, batch, n_neg, pop_users=None, pop_items=None):
+        return self._epoch('mfb_loss_epoch', loss, pos_users, pos_items, batch, n_neg, pop_users, pop_items)
+
     def train_epoch_host(self, loss, pos_users_host, pos_items_host, batch, n_neg, pop_users=None, pop_items=None,
                          rng=None):
         """End-to-end entry: HOST int64 id arrays in, per-step losses (numpy) out; H2D/D2H inside."""
@@ -267,6 +300,22 @@ class MFEngine(object):
         _set_py_state(rng, state, extra)
         self._sync_optimizer_step()
         return losses
+
+    # -- measurement hooks ------------------------------------------------------------------------
+    def profile(self, on=True):
+        self._call('mfb_profile_enable', 1 if on else 0)
+
+    def profile_read(self):
+        """{kernel class: (summed device ms, launches)} since the last read."""
+        ms = np.zeros(N.PROFILE_CLASSES, dtype=np.float64)
+        cnt = np.zeros(N.PROFILE_CLASSES, dtype=np.int64)
+        self._call('mfb_profile_read', N.hptr(ms), N.hptr(cnt))
+        return {self._lib.mfb_profile_name(c).decode(): (float(ms[c]), int(cnt[c]))
+                for c in range(N.PROFILE_CLASSES) if cnt[c]}
+
+    @property
+    def launches(self):
+        return int(self._lib.mfb_model_launches(self._handle))
 
     def flush(self):
         self._call('mfb_flush', N.stream_ptr())

@@ -108,3 +108,39 @@ def test_forward_matches_reference(golden_dir):
     np.testing.assert_allclose(pred, g['pred'], rtol=1e-5, atol=1e-7)
     with pytest.raises(IndexError):                            # the reference breaks on a single pair
         net(torch.tensor([1]).cuda(), torch.tensor([2]).cuda())
+
+
+@pytest.mark.parametrize('loss,opt,n_neg', [('pointwise', 'adam', 2), ('adaptive_hinge', 'adam', 1),
+                                            ('bpr', 'adam', 1), ('hinge', 'sgd', 1)])
+@pytest.mark.parametrize('fast_math', [False, True], ids=['ieee', 'fast'])
+def test_many_chunks_match_oracle(loss, opt, n_neg, fast_math):
+    """Several planner chunks (look-ahead catch-up, double-buffered planning) and Zipf-skewed items
+    (multi-window segment reduction) against the oracle run on the same inputs."""
+    from oracle import mf_oracle as O
+    torch.set_num_threads(1)
+    rs = np.random.RandomState(17)
+    U, I, D, B = 500, 300, 16, 32
+    n_steps = 150
+    n_pos = n_steps * B - (0 if loss in ('bpr', 'hinge') else 5)     # partial last batch where the loss allows it
+    p = 1.0 / np.arange(1, I + 1) ** 1.05
+    users = rs.randint(0, U, n_pos)
+    items = rs.choice(I, n_pos, p=p / p.sum())
+    neg = np.stack([rs.randint(0, U, n_steps * n_neg * B), rs.randint(0, I, n_steps * n_neg * B)], 1)
+    tabs = [t.numpy() for t in O.init_tables(U, I, D, torch_seed=3)]
+    lr, l2 = (1e-3, 1e-5) if opt == 'adam' else (5e-2, 1e-4)
+    oracle = O.OracleMF(*[torch.from_numpy(t) for t in tabs], optimizer=opt, lr=lr, l2=l2, batch_size=B,
+                        num_negative_samples=n_neg, loss_fn=O.LOSS_FUNCTIONS[loss])
+    ref_losses = []
+    for s in range(n_steps):
+        k = n_neg * B
+        ref_losses.append(oracle.train_step(torch.from_numpy(users[s * B:(s + 1) * B]),
+                                            torch.from_numpy(items[s * B:(s + 1) * B]),
+                                            torch.from_numpy(neg[s * k:(s + 1) * k, 0].copy()),
+                                            torch.from_numpy(neg[s * k:(s + 1) * k, 1].copy())).item())
+    net, _, eng = make_engine(tabs, opt, lr, l2, fast_math)
+    losses = eng.train_steps(loss, users, items, B, n_neg, neg[:, 0].copy(), neg[:, 1].copy()).cpu().numpy()
+    eng.flush()
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-5)
+    for i, (got, exp) in enumerate(zip(tables_of(net), oracle.numpy_tables())):
+        err = rel_err(got, exp)
+        assert err < 1e-5 or (i >= 2 and np.abs(got - exp).max() < 2e-2 * lr), (i, err)
