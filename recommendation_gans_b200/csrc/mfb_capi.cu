@@ -3,6 +3,7 @@
 // the BilinearNet tables (torch-owned storage) and the optimiser hyper-parameters.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "mfb_internal.cuh"
 
@@ -97,6 +98,9 @@ extern "C" int mfb_model_create(const mfb_model_desc *d, mfb_model **out) {
   }
   mfb_model *m = new mfb_model();
   m->desc = *d;
+  if (const char *e = getenv("MFB_EAGER_MAX")) m->tune_eager_max = atoi(e);
+  if (const char *e = getenv("MFB_CHUNK_BITS")) m->tune_chunk_bits = atoi(e) < 0 ? 0 : (atoi(e) > 12 ? 12 : atoi(e));
+  if (const char *e = getenv("MFB_CU_BLOCKS")) m->tune_cu_blocks_per_sm = atoi(e) < 1 ? 1 : atoi(e);
   auto bind = [&](TableView &T, int rows, float *p, float *pm, float *pv, float *b, float *bm, float *bv) {
     T.p = p; T.m = pm; T.v = pv; T.bp = b; T.bm = bm; T.bv = bv; T.rows = rows; T.last = nullptr;
   };
@@ -154,16 +158,13 @@ extern "C" int mfb_model_destroy(mfb_model *m) {
   for (DevBuf *b : bufs) b->release();
   for (PlanBuf &pb : m->plan) {
     DevBuf *pbufs[] = {&pb.slots, &pb.keys_a, &pb.keys_b, &pb.vals_a, &pb.vals_b, &pb.seg, &pb.pred, &pb.gmax,
-                       &pb.words, &pb.neg_u, &pb.neg_i};
+                       &pb.words, &pb.neg_u, &pb.neg_i, &pb.keys_c, &pb.vals_c, &pb.info, &pb.lazy_rows, &pb.lazy_cnt};
     for (DevBuf *b : pbufs) b->release();
   }
   m->rng_state.release();
-  if (m->st_side) cudaStreamDestroy(m->st_side);
   if (m->st_plan) cudaStreamDestroy(m->st_plan);
   for (cudaEvent_t e : m->ev_plan) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_done) if (e) cudaEventDestroy(e);
-  for (cudaEvent_t e : m->ev_upd) if (e) cudaEventDestroy(e);
-  for (cudaEvent_t e : m->ev_pc) if (e) cudaEventDestroy(e);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
   for (auto &r : m->prof.recs) {
     cudaEventDestroy(r.a);

@@ -114,7 +114,8 @@ struct Profiler {
 // Planner output for one chunk of steps (double-buffered: chunk c+1 is planned on its own stream
 // while chunk c trains).
 struct PlanBuf {
-  DevBuf slots, keys_a, keys_b, vals_a, vals_b, seg, pred, gmax, words, neg_u, neg_i;
+  DevBuf slots, keys_a, keys_b, vals_a, vals_b, keys_c, vals_c, seg, info, lazy_rows, lazy_cnt, pred, gmax, words, neg_u,
+      neg_i;
   uint32_t *skeys = nullptr, *svals = nullptr;
 };
 
@@ -122,12 +123,14 @@ struct mfb_model {
   mfb_model_desc desc;
   Profiler prof;
   PlanBuf plan[2];
-  cudaStream_t st_side = nullptr, st_plan = nullptr;   // look-ahead catch-up / planner streams
+  cudaStream_t st_plan = nullptr;   // planner stream
   cudaEvent_t ev_plan[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-  cudaEvent_t ev_upd[4] = {nullptr, nullptr, nullptr, nullptr}, ev_pc[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_join = nullptr;
+  int num_sms = 148;
   DevBuf rng_state;            // device-resident MT19937 state (624 words + position) of the negative sampler
   bool rng_seeded = false;
+  // tuning knobs (environment overrides read at model creation: MFB_EAGER_MAX, MFB_CHUNK_BITS, MFB_CU_BLOCKS)
+  int tune_eager_max = 64, tune_chunk_bits = 6, tune_cu_blocks_per_sm = 2;
   TableView users, items;
   OptView opt;
   int64_t step = 0;            // optimiser steps applied so far

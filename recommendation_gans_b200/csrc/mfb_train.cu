@@ -6,22 +6,33 @@
 // dense torch optimiser step (spotlight/optimizers.py -> torch.optim.Adam / SGD).
 //
 // Semantics are the reference's DENSE optimiser (every row of every table steps every
-// iteration); traffic is row-sparse: each row carries `last` = the optimiser step it
-// is current for, and missed steps (gradient = weight_decay * p) are replayed elementwise in
-// registers when the row is next gathered (k_catchup) or at mfb_flush.
+// iteration); traffic is row-sparse.  Each row carries `last` = the optimiser step it
+// is current for; the zero-gradient steps it misses (gradient = weight_decay * p) are replayed
+// elementwise in registers:
+//   * eagerly, right after the row is updated at step t: the planner knows the row's next use
+//     (t + gap) inside the chunk, so k_update replays it to t + gap - 1 while it still holds
+//     the state -- no extra pass over the row;
+//   * lazily, for a row's first use in a chunk (or a gap longer than the eager bound): the
+//     planner lists those rows per step, and dedicated blocks of k_update(s) bring the rows of
+//     step s+1's list up to date while step s updates its own (disjoint) rows;
+//   * at mfb_flush, for everything else.
 //
-// Per step:  k_catchup (unique rows -> state at t-1)  ->  k_forward (gather, dot, sigmoid; row
-// snapshots)  ->  k_loss (loss value, dLoss/dz per slot)  ->  k_update (per unique row: batch-
-// ordered segment reduction of the slot gradients, optimiser step t).  Unique rows / segments
-// come from the planner's stable radix sort (mfb_sort.cu), so the reduction order is the batch
-// order used by torch's index_add and no atomics are involved.
+// Pipeline
+//   planner stream  sample negatives (MT19937) -> pack ids -> stable radix sort by (step,table,row)
+//                   -> segment table -> re-sort by (table,row) -> next-use gaps + lazy lists -> one
+//                   16-byte record per sorted position.  Chunk c+1 is planned while chunk c trains.
+//   main stream     per step: k_forward (gather, dot, sigmoid, row snapshots, adaptive-hinge max)
+//                   -> k_update (per unique row: batch-ordered segment reduction of slot gradients,
+//                   optimiser step t, eager replay; + lazy catch-up blocks for step s+1).
+//                   per chunk: k_loss_steps (all loss values in one launch).
+// Unique rows / segments come from a stable sort, so the reduction order is the batch order used by
+// torch's index_add; no floating-point atomics anywhere.
 #include <math.h>
 
 #include "mfb_internal.cuh"
 
 namespace {
 
-constexpr uint32_t IN_PREV = 0x80000000u;  // planner flag in seg_len[head], see k_segments
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
 
@@ -239,40 +250,6 @@ __global__ void k_pack(const long long *__restrict__ pos_u, const long long *__r
   vals[ko + L + j] = (uint32_t)j;
 }
 
-// ---------------------------------------------------------------------------------------
-// k_catchup: one warp per sorted position; segment heads bring their row to step t-1
-// ---------------------------------------------------------------------------------------
-// Replay length per row is geometrically distributed, so blocks are kept small (CU_WARPS warps):
-// a finished warp then frees its slot instead of waiting for the slowest warp of a big block.
-constexpr int CU_WARPS = 2;
-template <int VEC, int NIT, bool FAST>
-__global__ void __launch_bounds__(CU_WARPS * 32) k_catchup(const uint32_t *__restrict__ skeys,
-                                                           const uint32_t *__restrict__ seg_len, int n, int rb,
-                                                           TableView users, TableView items, OptView opt, int D,
-                                                           int t, int skip_in_prev) {
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * CU_WARPS + (threadIdx.x >> 5);
-  if (q >= n) return;
-  const uint32_t key = skeys[q];
-  if (q > 0 && skeys[q - 1] == key) return;
-  // look-ahead mode: rows that are also in the previous step's batch belong to that step's update
-  if (skip_in_prev && (seg_len[q] & IN_PREV)) return;
-  const long long row = key & ((1u << rb) - 1u);
-  const TableView &T = ((key >> rb) & 1u) ? items : users;
-  const int last = T.last[row];
-  if (last >= t - 1) return;
-  const bool adam = opt.kind == MFB_OPT_ADAM;
-  RowState<VEC, NIT> r;
-  row_load<VEC, NIT>(r, T, row, D, lane, adam);
-  row_replay<VEC, NIT, FAST>(r, last, t - 1, opt);
-  row_store<VEC, NIT>(r, T, row, D, lane, adam);
-  if (lane == 0) T.last[row] = t - 1;
-}
-
-// ---------------------------------------------------------------------------------------
-// k_forward: one warp per slot.  pred[j] = sigmoid(<U[u],V[i]> + bu + bi); optionally snapshots
-// both rows (the values every gradient of this step must be computed from).
-// ---------------------------------------------------------------------------------------
 // (probability, index) packed so that an unsigned 64-bit max picks the largest probability and,
 // among equals, the smallest index -- torch.max(neg, 0) returns the first maximal element.
 __device__ __forceinline__ unsigned long long pack_max(float prob, int idx) {
@@ -513,22 +490,23 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_loss_steps(int kind, const flo
   loss_block(kind, pred, b, pred + b, m_neg, losses + gstep, nullptr, nullptr, 0);
 }
 
-// dLoss/dz of slot j, recomputed where it is consumed (k_update) from the step's predictions and
-// the adaptive-hinge maximum; same formulas as loss_block (torch backward of spotlight/losses.py).
+// dLoss/dz of slot j, recomputed where it is consumed (k_update) from the step's predictions and the
+// adaptive-hinge maximum; same formulas as loss_block (torch backward of spotlight/losses.py).
 // Hinge-type terms on probabilities are always active: neg - pos + 1 >= 0 for values in [0, 1].
-__device__ __forceinline__ float slot_dz(int kind, int j, int b, int m, const float *__restrict__ pred,
-                                         float gmax, int jstar) {
+template <int KIND>
+__device__ __forceinline__ float slot_dz(int j, int b, int m, const float *__restrict__ pred, float gmax,
+                                         int jstar) {
   const float x = pred[j];
   float d;
-  if (kind == MFB_LOSS_POINTWISE) {
+  if (KIND == MFB_LOSS_POINTWISE) {
     const float den = fmaxf((1.0f - x) * x, 1e-12f);
     d = (j < b) ? __fdiv_rn(__fdiv_rn(x - 1.0f, den), (float)b) : __fdiv_rn(__fdiv_rn(x, den), (float)m);
-  } else if (kind == MFB_LOSS_HINGE) {
+  } else if (KIND == MFB_LOSS_HINGE) {
     const float inv_b = 1.0f / (float)b;
     const float xp = (j < b) ? x : pred[j - b], xn = (j < b) ? pred[j + b] : x;
     const float a = (((xn - xp) + 1.0f) >= 0.0f) ? inv_b : 0.0f;
     d = (j < b) ? -a : a;
-  } else if (kind == MFB_LOSS_BPR) {
+  } else if (KIND == MFB_LOSS_BPR) {
     const float inv_b = 1.0f / (float)b;
     const float xp = (j < b) ? x : pred[j - b], xn = (j < b) ? pred[j + b] : x;
     const float sg = sigmoidf_acc(xp - xn);
@@ -539,21 +517,19 @@ __device__ __forceinline__ float slot_dz(int kind, int j, int b, int m, const fl
     if (j < b) {
       d = (((gmax - x) + 1.0f) >= 0.0f) ? -inv_b : 0.0f;
     } else {
-      d = (j - b == jstar) ? (float)b * inv_b : 0.0f;  // sum over b active positives of 1/b
+      d = (j - b == jstar) ? (float)b * inv_b : 0.0f;  // sum over the b active positives of 1/b
     }
   }
   return (d * (1.0f - x)) * x;  // sigmoid backward: grad * (1 - y) * y
 }
 
 // ---------------------------------------------------------------------------------------
-// planner: segment table.  After the sort, equal keys (same step, table, row) are adjacent;
-// seg_first[q] = index of the first position of q's segment, seg_len[first] = its length.
+// planner kernels (model-independent integer work, bulk per chunk)
 // ---------------------------------------------------------------------------------------
-// seg_len[head] additionally carries IN_PREV (top bit) when the same (table,row) also occurs in the
-// previous step of the chunk: such a row is brought up to date by that step's update, every other
-// row of the step can be caught up ahead of time, concurrently with the previous step.
-__global__ void k_segments(const uint32_t *__restrict__ skeys, long long n, int rb, int Lfull,
-                           uint32_t *__restrict__ seg_first, uint32_t *__restrict__ seg_len) {
+// After the sort, equal keys (same step, table, row) are adjacent: seg_first[q] = first position of
+// q's segment, seg_len[head] = its length.
+__global__ void k_segments(const uint32_t *__restrict__ skeys, long long n, uint32_t *__restrict__ seg_first,
+                           uint32_t *__restrict__ seg_len) {
   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
   const uint32_t key = skeys[q];
@@ -565,19 +541,8 @@ __global__ void k_segments(const uint32_t *__restrict__ skeys, long long n, int 
         if (skeys[mid] <= key) lo = mid + 1; else hi = mid;
       }
     }
-    uint32_t len = (uint32_t)(lo - q);
-    const uint32_t step = key >> (rb + 1);
-    if (step > 0) {                      // binary search for (step-1, table, row) in the previous step's range
-      const uint32_t want = key - (1u << (rb + 1));
-      long long a = 2ll * (step - 1) * Lfull, e = 2ll * step * Lfull;
-      while (a < e) {
-        long long mid = (a + e) >> 1;
-        if (skeys[mid] < want) a = mid + 1; else e = mid;
-      }
-      if (a < 2ll * step * Lfull && skeys[a] == want) len |= IN_PREV;
-    }
     seg_first[q] = (uint32_t)q;
-    seg_len[q] = len;
+    seg_len[q] = (uint32_t)(lo - q);
   } else {                               // inside a segment: lower bound of key in [0, q)
     long long lo = 0, hi = q - 1;        // skeys[q-1] == key, so the answer is <= q-1
     if (q >= 2 && skeys[q - 2] != key) {
@@ -592,16 +557,106 @@ __global__ void k_segments(const uint32_t *__restrict__ skeys, long long n, int 
   }
 }
 
+// Keys for the second, row-major sort: (table,row) only, payload = step-major position.
+__global__ void k_rowkeys(const uint32_t *__restrict__ skeys, long long n, int rb, uint32_t *__restrict__ rkeys,
+                          uint32_t *__restrict__ rvals) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  rkeys[q] = skeys[q] & ((2u << rb) - 1u);  // table bit + row bits
+  rvals[q] = (uint32_t)q;
+}
+
+// The stable (table,row) sort lists every row's uses in step order.  For the head of each use:
+//   seg_gap[head] = steps until the row's next use inside the chunk (0: none)  -> eager replay
+//   and the use is appended to its step's lazy list when nothing will have replayed the row up to it:
+//   first use in the chunk, or the previous use is more than eager_max steps back.
+// List order is arbitrary (atomic append) but every entry is an independent row, so results do not depend on it.
+__global__ void k_next_use(const uint32_t *__restrict__ rkeys, const uint32_t *__restrict__ rvals, long long n, int rb,
+                           const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ seg_first,
+                           const uint32_t *__restrict__ seg_len, uint32_t *__restrict__ seg_gap, int eager_max,
+                           uint32_t *__restrict__ lazy_rows, int *__restrict__ lazy_cnt, int lazy_cap) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t q = rvals[i];
+  if (seg_first[q] != q) return;                        // only heads
+  const uint32_t rk = rkeys[i];
+  const int step = (int)(skeys[q] >> (rb + 1));
+  const long long i2 = i + seg_len[q];                  // the segment's positions are adjacent here too
+  uint32_t gap = 0;
+  if (i2 < n && rkeys[i2] == rk) gap = (skeys[rvals[i2]] >> (rb + 1)) - (uint32_t)step;
+  seg_gap[q] = gap;
+  bool lazy = true;
+  if (i > 0 && rkeys[i - 1] == rk) {                    // previous use: its head decides whether it replays to us
+    const uint32_t pq = seg_first[rvals[i - 1]];
+    const int pgap = step - (int)(skeys[pq] >> (rb + 1));
+    lazy = pgap > 1 && pgap > eager_max;                // pgap == 1: the previous step's own update covers it
+  }
+  if (lazy) {
+    const int at = atomicAdd(lazy_cnt + step, 1);
+    lazy_rows[(long long)step * lazy_cap + at] = rk;
+  }
+}
+
+// One 16-byte record per sorted position, so k_update needs a single load for its bookkeeping.
+struct __align__(16) PosInfo {
+  uint32_t key;    // step | table | row
+  uint32_t first;  // chunk-global position of the segment head
+  uint32_t len;    // segment length
+  uint32_t gap;    // steps to the row's next use in the chunk (0: none)
+};
+
+__global__ void k_posinfo(const uint32_t *__restrict__ skeys, long long n, const uint32_t *__restrict__ seg_first,
+                          const uint32_t *__restrict__ seg_len, const uint32_t *__restrict__ seg_gap,
+                          PosInfo *__restrict__ info) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const uint32_t first = seg_first[q];
+  PosInfo p;
+  p.key = skeys[q];
+  p.first = first;
+  p.len = seg_len[first];
+  p.gap = seg_gap ? seg_gap[first] : 0u;
+  info[q] = p;
+}
+
 // ---------------------------------------------------------------------------------------
-// k_update: one warp per sorted position of the step.  A row's slot gradients form one segment
+// k_update: one warp per sorted position of the step (+ catch-up blocks, see below).
+// A row's slot gradients form one segment
 //   d/dU[u] += dz_j * V_old[i_j]   d/dbu[u] += dz_j   (and symmetrically for items)
 // which is reduced in slot order.  Segments longer than a window (popular items) are cut at
 // absolute window boundaries (positions that are multiples of UPD_WIN): each piece is summed by
 // its own warp into a partial, and the last piece to finish (atomic ticket) adds the partials in
 // position order and applies optimiser step t.  Piece boundaries depend only on the sorted ids,
 // so the summation order -- and the result -- is identical from run to run.
+//
+// Blocks [0, cu_blocks) do not update: they walk the lazy list of the NEXT step and replay those
+// rows (disjoint from this step's rows) up to optimiser step t, so the next forward finds every
+// row current.  With n == 0 the kernel is a pure catch-up pass (first step of a chunk).
 // ---------------------------------------------------------------------------------------
 constexpr int UPD_WIN = 32;
+
+struct UpdArgs {
+  const PosInfo *info;        // chunk-global
+  const uint32_t *svals;      // chunk-global: slot id per sorted position
+  long long base;             // first sorted position of this step
+  int n;                      // sorted positions of this step (2 * slots)
+  int rb, D;
+  TableView users, items;
+  OptView opt;
+  const float *snap_u, *snap_i, *pred;
+  int b, m_neg;
+  const unsigned long long *gmax_cell;
+  float *partial;
+  int pstride;
+  int *tickets;
+  int t;                      // optimiser step applied by this launch
+  int eager_max;
+  // lazy catch-up role
+  int cu_blocks;
+  const uint32_t *lazy_rows;
+  const int *lazy_cnt;
+  int cu_target;              // optimiser step the listed rows are brought to
+};
 
 template <int VEC, int NIT, bool FAST>
 __device__ __forceinline__ void apply_step(RowState<VEC, NIT> &r, const Frag<VEC, NIT> &g, float gb,
@@ -619,39 +674,57 @@ __device__ __forceinline__ void apply_step(RowState<VEC, NIT> &r, const Frag<VEC
   }
 }
 
-template <int VEC, int NIT, bool FAST>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_update(
-    const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals, const uint32_t *__restrict__ seg_first,
-    const uint32_t *__restrict__ seg_len, long long base, int n, int rb, TableView users, TableView items,
-    OptView opt, int D, const float *__restrict__ snap_u, const float *__restrict__ snap_i,
-    const float *__restrict__ pred, int kind, int b, int m_neg, const unsigned long long *__restrict__ gmax_cell,
-    float *__restrict__ partial, int pstride, int *__restrict__ tickets, int t) {
-  const int lane = threadIdx.x & 31;
-  const int ql = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);  // position within the step
-  if (ql >= n) return;
-  const long long q = base + ql;
-  // independent loads first: the kernel is bound by dependent-load latency, not bandwidth
-  const long long first = seg_first[q];
-  const uint32_t key = skeys[q];
-  const uint32_t len_here = seg_len[q];   // meaningful when q is a head
-  int j_next = (int)svals[q];
+template <int VEC, int NIT, bool FAST, int KIND>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_update(const UpdArgs a) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int D = a.D;
+  const bool adam = a.opt.kind == MFB_OPT_ADAM;
+
+  if ((int)blockIdx.x < a.cu_blocks) {
+    // ---- lazy catch-up role ------------------------------------------------------------
+    const int cnt = *a.lazy_cnt;
+    const int stride = a.cu_blocks * WARPS_PER_BLOCK;
+    for (int i = blockIdx.x * WARPS_PER_BLOCK + wid; i < cnt; i += stride) {
+      const uint32_t rk = a.lazy_rows[i];
+      const long long row = rk & ((1u << a.rb) - 1u);
+      const TableView &T = ((rk >> a.rb) & 1u) ? a.items : a.users;
+      const int last = T.last[row];
+      if (last >= a.cu_target) continue;
+      RowState<VEC, NIT> r;
+      row_load<VEC, NIT>(r, T, row, D, lane, adam);
+      row_replay<VEC, NIT, FAST>(r, last, a.cu_target, a.opt);
+      row_store<VEC, NIT>(r, T, row, D, lane, adam);
+      if (lane == 0) T.last[row] = a.cu_target;
+    }
+    return;
+  }
+
+  // ---- update role -----------------------------------------------------------------------
+  const int ql = ((int)blockIdx.x - a.cu_blocks) * WARPS_PER_BLOCK + wid;  // position within the step
+  if (ql >= a.n) return;
+  const long long q = a.base + ql;
+  // independent loads first: this kernel is bound by dependent-load latency, not bandwidth
+  const uint4 raw = *reinterpret_cast<const uint4 *>(a.info + q);
+  const int j0 = (int)a.svals[q];
   unsigned long long gcell = 0ull;
-  if (kind == MFB_LOSS_ADAPTIVE_HINGE) gcell = *gmax_cell;
+  if (KIND == MFB_LOSS_ADAPTIVE_HINGE) gcell = *a.gmax_cell;
+  const uint32_t key = raw.x;
+  const long long first = raw.y;
   const bool head = first == q;
   if (!head && (ql % UPD_WIN) != 0) return;
-  const int fl = (int)(first - base);
-  const int len = (int)((head ? len_here : seg_len[first]) & ~IN_PREV);
-  const int seg_end = fl + len;                                        // local, exclusive
+  const int fl = (int)(first - a.base);
+  const int seg_end = fl + (int)raw.z;                                 // local, exclusive
   const int win_end = (ql / UPD_WIN + 1) * UPD_WIN;
   const int run_end = seg_end < win_end ? seg_end : win_end;
   const bool whole = head && run_end == seg_end;
-  const long long row = key & ((1u << rb) - 1u);
-  const bool is_item = (key >> rb) & 1u;
-  const TableView &T = is_item ? items : users;
-  const float *__restrict__ other = is_item ? snap_u : snap_i;
-  const bool adam = opt.kind == MFB_OPT_ADAM;
+  const long long row = key & ((1u << a.rb) - 1u);
+  const bool is_item = (key >> a.rb) & 1u;
+  const TableView &T = is_item ? a.items : a.users;
+  const float *__restrict__ other = is_item ? a.snap_u : a.snap_i;
+  const float *__restrict__ pred = a.pred;
+  const int b = a.b, m_neg = a.m_neg;
   const float gmax = unpack_max_val(gcell);
-  const int jstar = (kind == MFB_LOSS_ADAPTIVE_HINGE) ? unpack_max_idx(gcell) : -1;
+  const int jstar = (KIND == MFB_LOSS_ADAPTIVE_HINGE) ? unpack_max_idx(gcell) : -1;
 
   // the row's optimiser state does not depend on the gradient: get it in flight now
   RowState<VEC, NIT> r;
@@ -661,29 +734,39 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_update(
 #pragma unroll
   for (int k = 0; k < NIT * VEC; ++k) g.x[k] = 0.f;
   float gb = 0.f;
-  for (int p0 = ql; p0 < run_end; p0 += 4) {   // 4 slots in flight: ids -> (pred, snapshot row) -> ordered adds
+  {  // first slot of the run (most rows have exactly one)
+    // adaptive hinge: only the first maximal negative carries gradient (known without its prediction)
+    const bool use = !(KIND == MFB_LOSS_ADAPTIVE_HINGE && j0 >= b && j0 - b != jstar);
+    if (use) {
+      Frag<VEC, NIT> o;
+      frag_load<VEC, NIT>(o, other + (long long)j0 * D, D, lane);
+      const float d = slot_dz<KIND>(j0, b, m_neg, pred, gmax, jstar);
+#pragma unroll
+      for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fmul_rn(d, o.x[k]);   // 0 + d*o
+      gb = d;
+    }
+  }
+  for (int p0 = ql + 1; p0 < run_end; p0 += 4) {  // remaining slots, 4 in flight, added in slot order
     int jj[4];
     bool use[4];
     float dd[4];
     Frag<VEC, NIT> o[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      jj[u] = (u == 0) ? j_next : ((p0 + u < run_end) ? (int)svals[base + p0 + u] : 0);
-      // adaptive hinge: only the first maximal negative carries gradient (known without its prediction)
-      use[u] = (p0 + u < run_end) && !(kind == MFB_LOSS_ADAPTIVE_HINGE && jj[u] >= b && jj[u] - b != jstar);
+      jj[u] = (p0 + u < run_end) ? (int)a.svals[a.base + p0 + u] : 0;
+      use[u] = (p0 + u < run_end) && !(KIND == MFB_LOSS_ADAPTIVE_HINGE && jj[u] >= b && jj[u] - b != jstar);
     }
-    if (p0 + 4 < run_end) j_next = (int)svals[base + p0 + 4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       dd[u] = 0.f;
       if (use[u]) {
         frag_load<VEC, NIT>(o[u], other + (long long)jj[u] * D, D, lane);
-        dd[u] = slot_dz(kind, jj[u], b, m_neg, pred, gmax, jstar);
+        dd[u] = slot_dz<KIND>(jj[u], b, m_neg, pred, gmax, jstar);
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (use[u] && dd[u] != 0.f) {
+      if (use[u]) {
 #pragma unroll
         for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fadd_rn(g.x[k], __fmul_rn(dd[u], o[u].x[k]));
         gb = __fadd_rn(gb, dd[u]);
@@ -695,28 +778,26 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_update(
     // piece of a long segment: publish the partial, take a ticket
     const int first_win = fl / UPD_WIN, last_win = (seg_end - 1) / UPD_WIN;
     const int npieces = last_win - first_win + 1;
-    const int nwin = (n + UPD_WIN - 1) / UPD_WIN;
+    const int nwin = (a.n + UPD_WIN - 1) / UPD_WIN;
     // partial slots: [0, nwin) pieces that start at a window boundary, [nwin, 2*nwin) pieces that start at a head
     const int pslot = head ? (nwin + ql / UPD_WIN) : (ql / UPD_WIN);
-    float *pp = partial + (long long)pslot * pstride;
+    float *pp = a.partial + (long long)pslot * a.pstride;
     frag_store<VEC, NIT>(g, pp, D, lane);
     if (lane == 0) pp[D] = gb;
     __threadfence();
     __syncwarp();
     int old = 0;
-    if (lane == 0) old = atomicAdd(tickets + fl, 1);
+    if (lane == 0) old = atomicAdd(a.tickets + fl, 1);
     old = __shfl_sync(0xffffffffu, old, 0);
     if (old != npieces - 1) return;
-    if (lane == 0) tickets[fl] = 0;  // self-cleaning for the next step
+    if (lane == 0) a.tickets[fl] = 0;  // self-cleaning for the next step
     __threadfence();
     // ordered sum: the head piece, then the window-aligned pieces in position order
-    const bool head_aligned = (fl % UPD_WIN) == 0;
-    const float *hp = partial + (long long)(nwin + first_win) * pstride;
+    const float *hp = a.partial + (long long)(nwin + first_win) * a.pstride;
     frag_load_cg<VEC, NIT>(g, hp, D, lane);
     gb = __ldcg(hp + D);
-    (void)head_aligned;
     for (int w = first_win + 1; w <= last_win; ++w) {
-      const float *wp = partial + (long long)w * pstride;
+      const float *wp = a.partial + (long long)w * a.pstride;
       Frag<VEC, NIT> o;
       frag_load_cg<VEC, NIT>(o, wp, D, lane);
 #pragma unroll
@@ -725,9 +806,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_update(
     }
     row_load<VEC, NIT>(r, T, row, D, lane, adam);
   }
-  apply_step<VEC, NIT, FAST>(r, g, gb, opt, t);
+  apply_step<VEC, NIT, FAST>(r, g, gb, a.opt, a.t);
+  // eager replay: the row is next used `gap` steps from now, so the zero-gradient dense updates of the
+  // steps in between are applied right here (no extra pass over the row later)
+  int upto = a.t;
+  const int gap = (int)raw.w;
+  if (gap > 1 && gap <= a.eager_max) {   // (every position of a segment carries the segment's gap)
+    upto = a.t + gap - 1;
+    row_replay<VEC, NIT, FAST>(r, a.t, upto, a.opt);
+  }
   row_store<VEC, NIT>(r, T, row, D, lane, adam);
-  if (lane == 0) T.last[row] = t;
+  if (lane == 0) T.last[row] = upto;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -748,7 +837,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_flush(TableView T, OptView op
 }
 
 // ---------------------------------------------------------------------------------------
-// dispatch on (vector width, iterations per lane, fast math)
+// dispatch on (vector width, iterations per lane, fast math, loss kind)
 // ---------------------------------------------------------------------------------------
 struct Shape {
   int vec, nit;
@@ -765,24 +854,21 @@ int pick_shape(int D, Shape *s) {
     s->nit = per <= 1 ? 1 : (per <= 2 ? 2 : 4);
   } else {
     s->vec = 1;
-    int per = (D + 31) / 32;
-    s->nit = per <= 2 ? 2 : (per <= 4 ? 4 : (per <= 8 ? 8 : 16));
+    s->nit = (D <= 128) ? 4 : 16;
   }
   return MFB_OK;
 }
 
-#define MFB_DISPATCH_SHAPE(SH, CALL)                       \
-  do {                                                     \
-    if ((SH).vec == 4) {                                   \
-      if ((SH).nit == 1) { CALL(4, 1); }                   \
-      else if ((SH).nit == 2) { CALL(4, 2); }              \
-      else { CALL(4, 4); }                                 \
-    } else {                                               \
-      if ((SH).nit == 2) { CALL(1, 2); }                   \
-      else if ((SH).nit == 4) { CALL(1, 4); }              \
-      else if ((SH).nit == 8) { CALL(1, 8); }              \
-      else { CALL(1, 16); }                                \
-    }                                                      \
+#define MFB_DISPATCH_SHAPE(SH, CALL)            \
+  do {                                          \
+    if ((SH).vec == 4) {                        \
+      if ((SH).nit == 1) { CALL(4, 1); }        \
+      else if ((SH).nit == 2) { CALL(4, 2); }   \
+      else { CALL(4, 4); }                      \
+    } else {                                    \
+      if ((SH).nit == 4) { CALL(1, 4); }        \
+      else { CALL(1, 16); }                     \
+    }                                           \
   } while (0)
 
 inline int grid_for_warps(long long warps) { return (int)((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK); }
@@ -939,29 +1025,28 @@ extern "C" int mfb_predict_user(mfb_model *m, int64_t user, float *d_out, mfb_st
 
 // ---------------------------------------------------------------------------------------
 // host pipeline
-//   stream P (planner): pack ids -> radix sort -> segment table, for chunk c+1 while chunk c trains
-//   stream A (caller's): per step  forward -> update ; per chunk  loss values
-//   stream S (side):     catch-up of the rows of step s+1 that are not in step s, during step s
 // ---------------------------------------------------------------------------------------
 struct StepGeom {
   int D, batch, m_neg, Lfull, rb, chunk, loss;
   int64_t n_pos, nsteps;
   bool train, fast, adaptive;
+  int eager_max = 0;   // longest next-use distance replayed eagerly inside k_update
+  int cu_blocks = 0;   // catch-up blocks prepended to every k_update launch
   // negatives: explicit per-epoch arrays, or drawn per chunk from the model's MT19937 stream
   const int64_t *pop_users = nullptr, *pop_items = nullptr;
   int64_t pop_len = 0;
 };
 
 static int ensure_streams(mfb_model *m) {
-  if (m->st_side) return MFB_OK;
-  MFB_CUDA(cudaStreamCreateWithFlags(&m->st_side, cudaStreamNonBlocking));
+  if (m->st_plan) return MFB_OK;
   MFB_CUDA(cudaStreamCreateWithFlags(&m->st_plan, cudaStreamNonBlocking));
   auto mk = [](cudaEvent_t *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
   for (auto &e : m->ev_plan) MFB_CUDA(mk(&e));
   for (auto &e : m->ev_done) MFB_CUDA(mk(&e));
-  for (auto &e : m->ev_upd) MFB_CUDA(mk(&e));
-  for (auto &e : m->ev_pc) MFB_CUDA(mk(&e));
   MFB_CUDA(mk(&m->ev_join));
+  int dev = 0;
+  MFB_CUDA(cudaGetDevice(&dev));
+  MFB_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, dev));
   return MFB_OK;
 }
 
@@ -988,7 +1073,12 @@ static int plan_chunk(mfb_model *m, PlanBuf &pb, const StepGeom &g, const int64_
   if (g.train) {
     MFB_CHECK(pb.keys_b.reserve(slots * 2 * sizeof(uint32_t)));
     MFB_CHECK(pb.vals_b.reserve(slots * 2 * sizeof(uint32_t)));
-    MFB_CHECK(pb.seg.reserve(slots * 2 * 2 * sizeof(uint32_t)));
+    MFB_CHECK(pb.keys_c.reserve(slots * 2 * sizeof(uint32_t)));
+    MFB_CHECK(pb.vals_c.reserve(slots * 2 * sizeof(uint32_t)));
+    MFB_CHECK(pb.seg.reserve(slots * 2 * 3 * sizeof(uint32_t)));
+    MFB_CHECK(pb.info.reserve(slots * 2 * sizeof(PosInfo)));
+    MFB_CHECK(pb.lazy_rows.reserve(slots * 2 * sizeof(uint32_t)));
+    MFB_CHECK(pb.lazy_cnt.reserve((size_t)g.chunk * sizeof(int)));
   }
   int *slot_u = pb.slots.as<int>();
   int *slot_i = slot_u + slots;
@@ -1019,32 +1109,65 @@ static int plan_chunk(mfb_model *m, PlanBuf &pb, const StepGeom &g, const int64_
   MFB_KERNEL_CHECK();
   if (g.adaptive) MFB_CUDA(cudaMemsetAsync(pb.gmax.ptr, 0, (size_t)ns * sizeof(unsigned long long), sp));
   if (g.train) {
-    int nbits = g.rb + 1 + (ns > 1 ? bits_for((uint32_t)(ns - 1)) : 0);
-    tk = m->prof.begin(PK_SORT, sp, 3 * ((nbits + 7) / 8) + 1);
+    const unsigned gk = (unsigned)((nkeys + 255) / 256);
+    const int step_bits = ns > 1 ? bits_for((uint32_t)(ns - 1)) : 0;
+    const int npass = (g.rb + 1 + step_bits + 7) / 8 + (g.rb + 1 + 7) / 8;
+    tk = m->prof.begin(PK_SORT, sp, 3 * npass + 4);
     MFB_CHECK(mfb_radix_sort_pairs(pb.keys_a.as<uint32_t>(), pb.vals_a.as<uint32_t>(), pb.keys_b.as<uint32_t>(),
-                                   pb.vals_b.as<uint32_t>(), nkeys, nbits, m->ws_hist, &pb.skeys, &pb.svals, sp));
+                                   pb.vals_b.as<uint32_t>(), nkeys, g.rb + 1 + step_bits, m->ws_hist, &pb.skeys,
+                                   &pb.svals, sp));
     uint32_t *seg_first = pb.seg.as<uint32_t>();
-    k_segments<<<(unsigned)((nkeys + 255) / 256), 256, 0, sp>>>(pb.skeys, nkeys, g.rb, g.Lfull, seg_first,
-                                                                seg_first + slots * 2);
+    uint32_t *seg_len = seg_first + slots * 2;
+    uint32_t *seg_gap = seg_len + slots * 2;
+    k_segments<<<gk, 256, 0, sp>>>(pb.skeys, nkeys, seg_first, seg_len);
+    MFB_KERNEL_CHECK();
+    // re-sort by (table,row): the free ping-pong pair holds the input, keys_c/vals_c the other side
+    uint32_t *fk = (pb.skeys == pb.keys_a.as<uint32_t>()) ? pb.keys_b.as<uint32_t>() : pb.keys_a.as<uint32_t>();
+    uint32_t *fv = (pb.svals == pb.vals_a.as<uint32_t>()) ? pb.vals_b.as<uint32_t>() : pb.vals_a.as<uint32_t>();
+    k_rowkeys<<<gk, 256, 0, sp>>>(pb.skeys, nkeys, g.rb, fk, fv);
+    MFB_KERNEL_CHECK();
+    uint32_t *rk = nullptr, *rv = nullptr;
+    MFB_CHECK(mfb_radix_sort_pairs(fk, fv, pb.keys_c.as<uint32_t>(), pb.vals_c.as<uint32_t>(), nkeys, g.rb + 1,
+                                   m->ws_hist, &rk, &rv, sp));
+    MFB_CUDA(cudaMemsetAsync(pb.lazy_cnt.ptr, 0, (size_t)ns * sizeof(int), sp));
+    k_next_use<<<gk, 256, 0, sp>>>(rk, rv, nkeys, g.rb, pb.skeys, seg_first, seg_len, seg_gap, g.eager_max,
+                                   pb.lazy_rows.as<uint32_t>(), pb.lazy_cnt.as<int>(), 2 * g.Lfull);
+    MFB_KERNEL_CHECK();
+    k_posinfo<<<gk, 256, 0, sp>>>(pb.skeys, nkeys, seg_first, seg_len, seg_gap, pb.info.as<PosInfo>());
     m->prof.end(tk, sp);
     MFB_KERNEL_CHECK();
   }
   return MFB_OK;
 }
 
-static int launch_catchup(mfb_model *m, const Shape &sh, const StepGeom &g, const uint32_t *k, const uint32_t *slen,
-                          int nk, int t, int skip_in_prev, cudaStream_t st) {
-  const int D = g.D;
-  int tk = m->prof.begin(PK_CATCHUP, st);
-#define CALL(V, N)                                                                                            \
-  if (g.fast)                                                                                                 \
-    k_catchup<V, N, true><<<(nk + CU_WARPS - 1) / CU_WARPS, CU_WARPS * 32, 0, st>>>(k, slen, nk, g.rb, m->users, \
-                                                                                    m->items, m->opt, D, t,   \
-                                                                                    skip_in_prev);            \
-  else                                                                                                        \
-    k_catchup<V, N, false><<<(nk + CU_WARPS - 1) / CU_WARPS, CU_WARPS * 32, 0, st>>>(k, slen, nk, g.rb, m->users, \
-                                                                                     m->items, m->opt, D, t,  \
-                                                                                     skip_in_prev)
+template <int V, int N, bool FAST>
+static void launch_update_kind(const UpdArgs &a, int loss, int grid, cudaStream_t st) {
+  switch (loss) {
+    case MFB_LOSS_POINTWISE:
+      k_update<V, N, FAST, MFB_LOSS_POINTWISE><<<grid, BLOCK_THREADS, 0, st>>>(a);
+      break;
+    case MFB_LOSS_BPR:
+      k_update<V, N, FAST, MFB_LOSS_BPR><<<grid, BLOCK_THREADS, 0, st>>>(a);
+      break;
+    case MFB_LOSS_HINGE:
+      k_update<V, N, FAST, MFB_LOSS_HINGE><<<grid, BLOCK_THREADS, 0, st>>>(a);
+      break;
+    default:
+      k_update<V, N, FAST, MFB_LOSS_ADAPTIVE_HINGE><<<grid, BLOCK_THREADS, 0, st>>>(a);
+      break;
+  }
+}
+
+static int launch_update(mfb_model *m, const Shape &sh, const StepGeom &g, const UpdArgs &a, int cls,
+                         cudaStream_t st) {
+  const int grid = a.cu_blocks + grid_for_warps(a.n);
+  if (grid == 0) return MFB_OK;
+  int tk = m->prof.begin(cls, st);
+#define CALL(V, N)                                        \
+  if (g.fast)                                             \
+    launch_update_kind<V, N, true>(a, g.loss, grid, st);  \
+  else                                                    \
+    launch_update_kind<V, N, false>(a, g.loss, grid, st)
   MFB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
   m->prof.end(tk, st);
@@ -1063,18 +1186,38 @@ static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom
   const int *slot_i = slot_u + slots;
   float *pred_chunk = pb.pred.as<float>();
   unsigned long long *gmax = pb.gmax.as<unsigned long long>();
-  const uint32_t *seg_first = g.train ? pb.seg.as<uint32_t>() : nullptr;
-  const uint32_t *seg_len = g.train ? seg_first + slots * 2 : nullptr;
   float *snap_u = g.train ? m->ws_rows.as<float>() : nullptr;
   float *snap_i = g.train ? snap_u + (size_t)Lfull * D : nullptr;
-  const int pstride = ((D + 1 + 31) / 32) * 32;  // partial rows own whole 128-byte lines
-  cudaStream_t side = m->st_side;
   int tk;
 
+  UpdArgs a;
   if (g.train) {
-    // the side stream may touch tables only after everything queued so far on the main stream
-    MFB_CUDA(cudaEventRecord(m->ev_join, st));
-    MFB_CUDA(cudaStreamWaitEvent(side, m->ev_join, 0));
+    a.info = pb.info.as<PosInfo>();
+    a.svals = pb.svals;
+    a.rb = g.rb;
+    a.D = D;
+    a.users = m->users;
+    a.items = m->items;
+    a.opt = m->opt;
+    a.snap_u = snap_u;
+    a.snap_i = snap_i;
+    a.m_neg = m_neg;
+    a.partial = m->ws_partial.as<float>();
+    a.pstride = ((D + 1 + 31) / 32) * 32;  // partial rows own whole 128-byte lines
+    a.tickets = m->ws_tickets.as<int>();
+    a.eager_max = g.eager_max;
+    // first step of the chunk: nothing has replayed its listed rows yet -> pure catch-up pass to t-1
+    a.base = 0;
+    a.n = 0;
+    a.pred = nullptr;
+    a.b = 0;
+    a.gmax_cell = nullptr;
+    a.t = (int)(m->step + 1);
+    a.cu_blocks = 4 * m->num_sms;
+    a.lazy_rows = pb.lazy_rows.as<uint32_t>();
+    a.lazy_cnt = pb.lazy_cnt.as<int>();
+    a.cu_target = (int)m->step;
+    MFB_CHECK(launch_update(m, sh, g, a, PK_CATCHUP, st));
   }
   for (int s = 0; s < ns; ++s) {
     const int b = (s == ns - 1) ? b_last : g.batch;
@@ -1083,57 +1226,33 @@ static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom
     const int *si = slot_i + (size_t)s * Lfull;
     float *pred = pred_chunk + (size_t)s * Lfull;
     const int neg_begin = g.adaptive ? b : -1;
-    if (g.train) {
-      const int t = (int)(m->step + 1);
-      const long long base = 2 * (long long)s * Lfull;
-      const int nk = 2 * L;
-      if (s == 0) {
-        // first step of a chunk: no look-ahead information, catch its rows up in line
-        MFB_CHECK(launch_catchup(m, sh, g, pb.skeys + base, seg_len + base, nk, t, 0, st));
-      } else {
-        MFB_CUDA(cudaStreamWaitEvent(st, m->ev_pc[s & 3], 0));
-      }
-      tk = m->prof.begin(PK_FORWARD, st);
+    tk = m->prof.begin(PK_FORWARD, st);
 #define CALL(V, N)                                                                                                 \
   k_forward<V, N><<<grid_for_warps(L), BLOCK_THREADS, 0, st>>>(su, si, L, m->users, m->items, D, snap_u, snap_i, pred, \
                                                                 neg_begin, gmax + s)
-      MFB_DISPATCH_SHAPE(sh, CALL);
+    MFB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
-      m->prof.end(tk, st);
-      // look-ahead: rows of step s+1 that are not in step s are replayed up to optimiser step t while this
-      // step runs (they are disjoint from everything forward/update of step s touch)
+    m->prof.end(tk, st);
+    MFB_KERNEL_CHECK();
+    if (g.train) {
+      const int t = (int)(m->step + 1);
+      a.base = 2 * (long long)s * Lfull;
+      a.n = 2 * L;
+      a.pred = pred;
+      a.b = b;
+      a.gmax_cell = gmax + s;
+      a.t = t;
+      // rows first needed by step s+1 (and not replayed by anyone) are brought to step t by extra blocks
       if (s + 1 < ns) {
-        const int b1 = (s + 1 == ns - 1) ? b_last : g.batch;
-        const long long base1 = 2 * (long long)(s + 1) * Lfull;
-        if (s >= 1) MFB_CUDA(cudaStreamWaitEvent(side, m->ev_upd[(s - 1) & 3], 0));
-        MFB_CHECK(launch_catchup(m, sh, g, pb.skeys + base1, seg_len + base1, 2 * (b1 + m_neg), t + 1, 1, side));
-        MFB_CUDA(cudaEventRecord(m->ev_pc[(s + 1) & 3], side));
+        a.cu_blocks = g.cu_blocks;
+        a.lazy_rows = pb.lazy_rows.as<uint32_t>() + (size_t)(s + 1) * 2 * Lfull;
+        a.lazy_cnt = pb.lazy_cnt.as<int>() + (s + 1);
+        a.cu_target = t;
+      } else {
+        a.cu_blocks = 0;
       }
-      tk = m->prof.begin(PK_UPDATE, st);
-#define CALL(V, N)                                                                                                    \
-  if (g.fast)                                                                                                         \
-    k_update<V, N, true><<<grid_for_warps(nk), BLOCK_THREADS, 0, st>>>(                                               \
-        pb.skeys, pb.svals, seg_first, seg_len, base, nk, g.rb, m->users, m->items, m->opt, D, snap_u, snap_i, pred,  \
-        g.loss, b, m_neg, gmax + s, m->ws_partial.as<float>(), pstride, m->ws_tickets.as<int>(), t);                  \
-  else                                                                                                                \
-    k_update<V, N, false><<<grid_for_warps(nk), BLOCK_THREADS, 0, st>>>(                                              \
-        pb.skeys, pb.svals, seg_first, seg_len, base, nk, g.rb, m->users, m->items, m->opt, D, snap_u, snap_i, pred,  \
-        g.loss, b, m_neg, gmax + s, m->ws_partial.as<float>(), pstride, m->ws_tickets.as<int>(), t)
-      MFB_DISPATCH_SHAPE(sh, CALL);
-#undef CALL
-      m->prof.end(tk, st);
-      MFB_KERNEL_CHECK();
-      MFB_CUDA(cudaEventRecord(m->ev_upd[s & 3], st));
+      MFB_CHECK(launch_update(m, sh, g, a, PK_UPDATE, st));
       m->step += 1;
-    } else {
-      tk = m->prof.begin(PK_FORWARD, st);
-#define CALL(V, N)                                                                                                   \
-  k_forward<V, N><<<grid_for_warps(L), BLOCK_THREADS, 0, st>>>(su, si, L, m->users, m->items, D, nullptr, nullptr, pred, \
-                                                                -1, nullptr)
-      MFB_DISPATCH_SHAPE(sh, CALL);
-#undef CALL
-      m->prof.end(tk, st);
-      MFB_KERNEL_CHECK();
     }
   }
   // loss values of the whole chunk in one launch (the predictions of every step were kept)
@@ -1161,6 +1280,7 @@ static int run_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const i
   }
   Shape sh;
   MFB_CHECK(pick_shape(m->desc.dim, &sh));
+  MFB_CHECK(ensure_streams(m));
   StepGeom g;
   g.D = m->desc.dim;
   const int64_t m_neg64 = (int64_t)n_neg * batch;
@@ -1177,6 +1297,8 @@ static int run_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const i
   g.train = train;
   g.fast = m->desc.fast_math != 0;
   g.adaptive = loss == MFB_LOSS_ADAPTIVE_HINGE;
+  g.eager_max = train ? m->tune_eager_max : 0;
+  g.cu_blocks = m->tune_cu_blocks_per_sm * m->num_sms;
   if (n_neg > 0 && from_stream) {
     g.pop_users = d_pop_users;
     g.pop_items = d_pop_items;
@@ -1189,9 +1311,9 @@ static int run_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const i
     mfb_set_error("tables too large for 32-bit planner keys");
     return MFB_ERR_UNSUPPORTED;
   }
-  g.chunk = 1 << (sb_max > 6 ? 6 : sb_max);
+  const int chunk_bits = m->tune_chunk_bits;
+  g.chunk = 1 << (sb_max > chunk_bits ? chunk_bits : sb_max);
   while (g.chunk > 1 && (int64_t)g.chunk * g.Lfull > (1ll << 25)) g.chunk >>= 1;  // bound workspace
-  MFB_CHECK(ensure_streams(m));
   if (!train) MFB_CHECK(launch_flush(m, st));
   if (train) MFB_CHECK(mfb_ensure_scalars(m, m->step + g.nsteps + 1));
 
