@@ -86,7 +86,10 @@ def load_library():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if _build.is_stale():
+    override = os.environ.get('MFB_LIB_PATH')
+    if override:
+        path = override
+    elif _build.is_stale():
         try:
             path = _build.build_library()
         except Exception as exc:  # no nvcc on this box and no prebuilt library

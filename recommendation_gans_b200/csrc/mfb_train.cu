@@ -634,6 +634,15 @@ __global__ void k_posinfo(const uint32_t *__restrict__ skeys, long long n, const
 // row current.  With n == 0 the kernel is a pure catch-up pass (first step of a chunk).
 // ---------------------------------------------------------------------------------------
 constexpr int UPD_WIN = 32;
+// Measured on B200 (cfg3): 4-warp blocks capped at ~51 registers beat 8-warp/64-register blocks by ~12%
+// (a block retires only when its slowest warp -- the longest eager replay -- is done).
+#ifndef MFB_UPD_WARPS
+#define MFB_UPD_WARPS 4
+#endif
+#ifndef MFB_UPD_MINB
+#define MFB_UPD_MINB 10
+#endif
+constexpr int UPD_WARPS = MFB_UPD_WARPS;   // warps per k_update block
 
 struct UpdArgs {
   const PosInfo *info;        // chunk-global
@@ -675,7 +684,7 @@ __device__ __forceinline__ void apply_step(RowState<VEC, NIT> &r, const Frag<VEC
 }
 
 template <int VEC, int NIT, bool FAST, int KIND>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_update(const UpdArgs a) {
+__global__ void __launch_bounds__(UPD_WARPS * 32, MFB_UPD_MINB) k_update(const UpdArgs a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int D = a.D;
   const bool adam = a.opt.kind == MFB_OPT_ADAM;
@@ -683,8 +692,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_update(const UpdArgs a) {
   if ((int)blockIdx.x < a.cu_blocks) {
     // ---- lazy catch-up role ------------------------------------------------------------
     const int cnt = *a.lazy_cnt;
-    const int stride = a.cu_blocks * WARPS_PER_BLOCK;
-    for (int i = blockIdx.x * WARPS_PER_BLOCK + wid; i < cnt; i += stride) {
+    const int stride = a.cu_blocks * UPD_WARPS;
+    for (int i = blockIdx.x * UPD_WARPS + wid; i < cnt; i += stride) {
       const uint32_t rk = a.lazy_rows[i];
       const long long row = rk & ((1u << a.rb) - 1u);
       const TableView &T = ((rk >> a.rb) & 1u) ? a.items : a.users;
@@ -700,7 +709,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_update(const UpdArgs a) {
   }
 
   // ---- update role -----------------------------------------------------------------------
-  const int ql = ((int)blockIdx.x - a.cu_blocks) * WARPS_PER_BLOCK + wid;  // position within the step
+  const int ql = ((int)blockIdx.x - a.cu_blocks) * UPD_WARPS + wid;  // position within the step
   if (ql >= a.n) return;
   const long long q = a.base + ql;
   // independent loads first: this kernel is bound by dependent-load latency, not bandwidth
@@ -1144,23 +1153,23 @@ template <int V, int N, bool FAST>
 static void launch_update_kind(const UpdArgs &a, int loss, int grid, cudaStream_t st) {
   switch (loss) {
     case MFB_LOSS_POINTWISE:
-      k_update<V, N, FAST, MFB_LOSS_POINTWISE><<<grid, BLOCK_THREADS, 0, st>>>(a);
+      k_update<V, N, FAST, MFB_LOSS_POINTWISE><<<grid, UPD_WARPS * 32, 0, st>>>(a);
       break;
     case MFB_LOSS_BPR:
-      k_update<V, N, FAST, MFB_LOSS_BPR><<<grid, BLOCK_THREADS, 0, st>>>(a);
+      k_update<V, N, FAST, MFB_LOSS_BPR><<<grid, UPD_WARPS * 32, 0, st>>>(a);
       break;
     case MFB_LOSS_HINGE:
-      k_update<V, N, FAST, MFB_LOSS_HINGE><<<grid, BLOCK_THREADS, 0, st>>>(a);
+      k_update<V, N, FAST, MFB_LOSS_HINGE><<<grid, UPD_WARPS * 32, 0, st>>>(a);
       break;
     default:
-      k_update<V, N, FAST, MFB_LOSS_ADAPTIVE_HINGE><<<grid, BLOCK_THREADS, 0, st>>>(a);
+      k_update<V, N, FAST, MFB_LOSS_ADAPTIVE_HINGE><<<grid, UPD_WARPS * 32, 0, st>>>(a);
       break;
   }
 }
 
 static int launch_update(mfb_model *m, const Shape &sh, const StepGeom &g, const UpdArgs &a, int cls,
                          cudaStream_t st) {
-  const int grid = a.cu_blocks + grid_for_warps(a.n);
+  const int grid = a.cu_blocks + (a.n + UPD_WARPS - 1) / UPD_WARPS;
   if (grid == 0) return MFB_OK;
   int tk = m->prof.begin(cls, st);
 #define CALL(V, N)                                        \
@@ -1213,7 +1222,7 @@ static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom
     a.b = 0;
     a.gmax_cell = nullptr;
     a.t = (int)(m->step + 1);
-    a.cu_blocks = 4 * m->num_sms;
+    a.cu_blocks = 4 * m->num_sms * (WARPS_PER_BLOCK / UPD_WARPS);
     a.lazy_rows = pb.lazy_rows.as<uint32_t>();
     a.lazy_cnt = pb.lazy_cnt.as<int>();
     a.cu_target = (int)m->step;
@@ -1244,7 +1253,7 @@ static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom
       a.t = t;
       // rows first needed by step s+1 (and not replayed by anyone) are brought to step t by extra blocks
       if (s + 1 < ns) {
-        a.cu_blocks = g.cu_blocks;
+        a.cu_blocks = g.cu_blocks * (WARPS_PER_BLOCK / UPD_WARPS);
         a.lazy_rows = pb.lazy_rows.as<uint32_t>() + (size_t)(s + 1) * 2 * Lfull;
         a.lazy_cnt = pb.lazy_cnt.as<int>() + (s + 1);
         a.cu_target = t;

@@ -6,6 +6,7 @@ training steps, validation losses, predict, top-k evaluation.  No torch ops run 
 torch supplies device memory and the current stream only.
 """
 import ctypes
+import os
 import random as _py_random
 
 import numpy as np
@@ -103,8 +104,13 @@ class MFEngine(object):
 
     optimizer=None gives a forward-only engine (predict / evaluate)."""
 
-    def __init__(self, net, optimizer=None, fast_math=False):
+    def __init__(self, net, optimizer=None, fast_math=None):
+        """fast_math: MUFU sqrt/rcp (flush-to-zero) in the Adam arithmetic instead of IEEE sqrt/div.  Both modes
+        pass the 1e-5 parity tests; the default (None) follows $MFB_FAST_MATH, which defaults to 1."""
         N.require_cuda()
+        if fast_math is None:
+            fast_math = os.environ.get('MFB_FAST_MATH', '1') != '0'
+        self.fast_math = bool(fast_math)
         self._lib = N.load_library()
         self._handle = ctypes.c_void_p(0)
         ue, ie = net.user_embeddings.weight, net.item_embeddings.weight

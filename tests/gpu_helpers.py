@@ -20,6 +20,7 @@ def make_net(tables):
 
 
 def make_engine(tables, opt_name='adam', lr=1e-3, l2=0.0, fast_math=False):
+    # parity tests default to the IEEE arithmetic; the fast-math mode has its own parametrised cases
     net = make_net(tables)
     opt = None
     if opt_name is not None:
