@@ -173,6 +173,12 @@ int mfb_train_epoch_host(mfb_model *m, int loss, const int64_t *h_pos_users, con
 int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
              const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
              mfb_stream stream);
+/* Users that the last mfb_topk call had to redo with the exact-fp32 kernel (tensor-core path bookkeeping). */
+int mfb_topk_last_redo(const mfb_model *m);
+/* Test hook: raw tensor-core scores (bf16 inputs, fp32 accumulate, + item bias), item-major
+ * [num_items][ceil(n_users/256)*256]; embedding_dim 64 or 128 only. */
+int mfb_debug_tc_scores(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, float *d_out, mfb_stream stream);
+
 /* _get_precision_recall (evaluation.py:108-113): hits[u*nk + j] = |topk[u,:ks[j]] ∩ test_row(u)|,
  * ntargets[u] = len(test_row(u)).  ks ascending, ks[nk-1] <= k. */
 int mfb_topk_hits(const int32_t *d_topk_ids, const int64_t *d_user_ids, int64_t n_users, int32_t k,

@@ -100,6 +100,8 @@ extern "C" int mfb_model_create(const mfb_model_desc *d, mfb_model **out) {
   m->desc = *d;
   if (const char *e = getenv("MFB_EAGER_MAX")) m->tune_eager_max = atoi(e);
   if (const char *e = getenv("MFB_CHUNK_BITS")) m->tune_chunk_bits = atoi(e) < 0 ? 0 : (atoi(e) > 12 ? 12 : atoi(e));
+  if (const char *e = getenv("MFB_TC")) m->tune_tc = atoi(e);
+  if (const char *e = getenv("MFB_TC_SAMPLE_STEP")) m->tune_tc_sample_step = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("MFB_CU_BLOCKS")) m->tune_cu_blocks_per_sm = atoi(e) < 1 ? 1 : atoi(e);
   auto bind = [&](TableView &T, int rows, float *p, float *pm, float *pv, float *b, float *bm, float *bv) {
     T.p = p; T.m = pm; T.v = pv; T.bp = b; T.bm = bm; T.bv = bv; T.rows = rows; T.last = nullptr;
@@ -162,6 +164,11 @@ extern "C" int mfb_model_destroy(mfb_model *m) {
     for (DevBuf *b : pbufs) b->release();
   }
   m->rng_state.release();
+  {
+    DevBuf *ebufs[] = {&m->eval.ub, &m->eval.vb, &m->eval.unorm, &m->eval.vnorm, &m->eval.gmax, &m->eval.thr,
+                       &m->eval.cand, &m->eval.cnt, &m->eval.redo, &m->eval.mcnt, &m->eval.mptr, &m->eval.mpairs};
+    for (DevBuf *b : ebufs) b->release();
+  }
   if (m->st_plan) cudaStreamDestroy(m->st_plan);
   for (cudaEvent_t e : m->ev_plan) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_done) if (e) cudaEventDestroy(e);

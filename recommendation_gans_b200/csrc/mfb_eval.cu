@@ -200,18 +200,9 @@ __global__ void k_topk_hits(const int *__restrict__ topk, const long long *__res
 
 }  // namespace
 
-extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
-                        const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
-                        mfb_stream stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if (!m || !d_user_ids || !d_out_ids || n_users < 0) return MFB_ERR_INVALID;
-  if (k <= 0 || k > MFB_MAX_TOPK || k > m->items.rows) {
-    mfb_set_error("topk: k=%d outside 1..min(%d, num_items)", k, MFB_MAX_TOPK);
-    return MFB_ERR_UNSUPPORTED;
-  }
-  if ((d_train_indptr == nullptr) != (d_train_indices == nullptr)) return MFB_ERR_INVALID;
-  if (n_users == 0) return MFB_OK;
-  MFB_CHECK(mfb_flush(m, stream));
+static int topk_exact_impl(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
+                           const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
+                           cudaStream_t st) {
   const int D = m->desc.dim;
   size_t smem = ((size_t)EV_ITEMS * (D + 1) + (size_t)EV_USERS * D + (size_t)EV_USERS * EV_ITEMS) * sizeof(float);
   if (smem > 220 * 1024) {
@@ -227,6 +218,40 @@ extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users
   m->prof.end(tk, st);
   MFB_KERNEL_CHECK();
   return MFB_OK;
+}
+
+extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
+                        const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
+                        mfb_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!m || !d_user_ids || !d_out_ids || n_users < 0) return MFB_ERR_INVALID;
+  if (k <= 0 || k > MFB_MAX_TOPK || k > m->items.rows) {
+    mfb_set_error("topk: k=%d outside 1..min(%d, num_items)", k, MFB_MAX_TOPK);
+    return MFB_ERR_UNSUPPORTED;
+  }
+  if ((d_train_indptr == nullptr) != (d_train_indices == nullptr)) return MFB_ERR_INVALID;
+  if (n_users == 0) return MFB_OK;
+  MFB_CHECK(mfb_flush(m, stream));
+  m->last_topk_redo = 0;
+  // large problems go through the tensor-core path (bf16 candidates + exact fp32 re-score: same ids as the
+  // exact kernel); small ones are not worth the extra passes
+  if (mfb_tc_supported(m, k) && n_users >= 64 && n_users < (1ll << 30))
+    return mfb_topk_tc(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st,
+                       topk_exact_impl, &m->last_topk_redo);
+  return topk_exact_impl(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st);
+}
+
+// Number of users the last mfb_topk call re-did with the exact kernel (tensor-core path only).
+extern "C" int mfb_topk_last_redo(const mfb_model *m) { return m ? m->last_topk_redo : -1; }
+
+// Test hook: raw tensor-core (bf16 x bf16 -> fp32, + item bias) scores of the listed users, item-major
+// [num_items][ceil(n_users/256)*256].
+extern "C" int mfb_debug_tc_scores(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, float *d_out,
+                                   mfb_stream stream) {
+  if (!m || !d_user_ids || !d_out || n_users <= 0) return MFB_ERR_INVALID;
+  if (!(m->desc.dim == 64 || m->desc.dim == 128)) return MFB_ERR_UNSUPPORTED;
+  MFB_CHECK(mfb_flush(m, stream));
+  return mfb_tc_dump_scores(m, d_user_ids, (int)n_users, d_out, (cudaStream_t)stream);
 }
 
 extern "C" int mfb_topk_hits(const int32_t *d_topk_ids, const int64_t *d_user_ids, int64_t n_users, int32_t k,

@@ -1,0 +1,901 @@
+// Tensor-core full-catalog scoring for evaluation (sm_100a: TMA + tcgen05.mma + TMEM).
+//
+// Replaces the score computation inside spotlight/evaluation.py:155-180 (model.predict(user) for every
+// user = users x items x D flops) for the top-k metrics.  The user x item score matrix is never
+// written to HBM:
+//
+//   1. k_tc_convert      bf16 copies of the user/item embedding rows (+ L2 norms for the error bound)
+//   2. k_tc_gemm<MAX>    scores of a SAMPLE of item tiles; epilogue keeps, per user, the maximum of each
+//                        32-item group  ->  k_tc_threshold: a per-user lower bound of the k-th best score
+//   3. k_tc_gemm<COLLECT> all item tiles; epilogue appends every (user, item) whose approximate score
+//                        reaches the bound to the user's candidate list (a guaranteed superset of the top-k)
+//   4. k_tc_rescore      exact fp32 re-scoring of the candidates (same sequential-FMA definition as
+//                        k_topk_exact), train mask, top-k (ties -> lower item id); users whose list
+//                        overflowed or cannot be certified are flagged and redone by k_topk_exact.
+//
+// GEMM mapping: A = item tile (M = 128 rows -> TMEM lanes), B = 256 users (N -> TMEM columns), K = D,
+// bf16 inputs, fp32 accumulation in TMEM.  One thread owns one ITEM, so a warp-wide ballot tests one
+// user's score against 32 items in a single instruction; the item bias is pre-stored into the
+// accumulator in fp32 (tcgen05.st) and the MMA accumulates on top of it.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2-5 =
+// epilogue (one TMEM lane quarter each).  Pipelines: smem full/empty (TMA <-> MMA, 4 stages), TMEM
+// full/empty (MMA <-> epilogue, 2 accumulators of 256 columns).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "mfb_internal.cuh"
+
+namespace {
+
+constexpr int TC_M = 128;          // items per tile (MMA M)
+constexpr int TC_N = 256;          // users per CTA (MMA N)
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int TC_KATOM = 64;       // bf16 elements per 128-byte swizzle atom
+constexpr int MODE_DUMP = 0, MODE_MAX = 1, MODE_COLLECT = 2;
+constexpr float MASKED_SCORE_TC = -3.402823466e38f;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+#define TC_LD32(r, taddr)                                                                                            \
+  asm volatile(                                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                      \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "   \
+      "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                                         \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),       \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                    \
+      : "r"(taddr)                                                                                                   \
+      : "memory")
+
+__device__ __forceinline__ void tc_st32_splat(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), leading byte offset >> 4 in [16,30) (unused for swizzled K-major: 1),
+// stride byte offset >> 4 in [32,46) (1024 B between 8-row groups), version 1 in [46,48), SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// order-preserving float -> int32 map (for integer redux max)
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+// ---------------------------------------------------------------------------------------------
+// 1. fp32 -> bf16 row conversion (+ row norms).  rows_out >= rows: padding rows are zero.
+//    `ids` (may be null) selects which source rows to convert (the evaluated users, in list order).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tc_convert(const float *__restrict__ src, const long long *__restrict__ ids, int rows, int rows_out,
+                             int D, __nv_bfloat16 *__restrict__ dst, float *__restrict__ norm) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows_out) return;
+  float ss = 0.f;
+  const long long srow = (r < rows) ? (ids ? ids[r] : r) : -1;
+  for (int d = lane; d < D; d += 32) {
+    float x = (srow >= 0) ? src[srow * D + d] : 0.f;
+    dst[(long long)r * D + d] = __float2bfloat16_rn(x);
+    ss = fmaf(x, x, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0 && norm) norm[r] = sqrtf(ss);
+}
+
+__global__ void k_tc_maxnorm(const float *__restrict__ norm, int n, float *__restrict__ out) {
+  __shared__ float sh[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, norm[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sh[w]);
+    *out = m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2/3. the GEMM kernel
+// ---------------------------------------------------------------------------------------------
+struct TcArgs {
+  int num_items, n_users;       // valid rows of A / B
+  int D;                        // multiple of 64, <= 256
+  int tile_begin, tile_step, n_tiles;   // item tiles processed: tile_begin + i*tile_step, i < n_tiles
+  const float *item_bias;       // [num_items]
+  // MODE_MAX: gmax[(i*4 + quarter) * n_users_pad + user]  (ordered-int encoded)
+  int *gmax;
+  int n_users_pad;
+  // MODE_COLLECT
+  const float *thr;             // [n_users_pad] collection threshold per user
+  unsigned long long *cand;     // [n_users][cap]: (score bits << 32) | item id
+  int *cand_cnt;                // [n_users_pad]
+  int cap;
+  // MODE_DUMP
+  float *dump;                  // [num_items_pad][n_users_pad]
+  // train mask (MODE_MAX / MODE_COLLECT; null = no mask): for CTA c, the (item, user-column) train pairs bucketed by
+  // 32-item group g: mask_pairs[mask_base[c] + mask_ptr[c*(ngroups+1) + g] ...), entry = (item & 31) | (column << 5)
+  const uint16_t *mask_pairs;
+  const int *mask_ptr;
+  const long long *mask_base;
+  int ngroups;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__ CUtensorMap map_users,
+          const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // carve shared memory (1024-byte aligned operand buffers for the 128B swizzle)
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int katoms = a.D / TC_KATOM;
+  const uint32_t b_bytes = (uint32_t)TC_N * 128u * katoms;       // users, resident
+  const uint32_t a_bytes = (uint32_t)TC_M * 128u * katoms;       // one item stage
+  uint8_t *sB = smem;
+  uint8_t *sA = sB + b_bytes;
+  uint8_t *tail = sA + (size_t)TC_STAGES * a_bytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(tail);           // [TC_STAGES]
+  uint64_t *empty = full + TC_STAGES;                            // [TC_STAGES]
+  uint64_t *tfull = empty + TC_STAGES;                           // [2]
+  uint64_t *tempty = tfull + 2;                                  // [2]
+  uint64_t *bfull = tempty + 2;                                  // [1]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 112);
+  float *thr_s = reinterpret_cast<float *>(tail + 128);          // [TC_N]   (16-byte aligned from here on)
+  int *cnt_s = reinterpret_cast<int *>(thr_s + TC_N);            // [TC_N]
+  uint32_t *mask_s = reinterpret_cast<uint32_t *>(cnt_s + TC_N); // [4 warps][32 lanes][8 words]: train-mask bits
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * TC_N;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1);
+      mbar_init(tempty + b, 4);   // one arrival per epilogue warp
+    }
+    mbar_init(bfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (MODE == MODE_COLLECT) {
+    for (int i = threadIdx.x; i < TC_N; i += TC_THREADS) {
+      thr_s[i] = (u0 + i < a.n_users) ? a.thr[u0 + i] : INFINITY;
+      cnt_s[i] = 0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(bfull, b_bytes);
+      for (int ka = 0; ka < katoms; ++ka)
+        tma_load_2d(sB + (size_t)ka * TC_N * 128, &map_users, bfull, ka * TC_KATOM, u0);
+      for (int i = 0; i < a.n_tiles; ++i) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+        mbar_wait(empty + s, ph ^ 1u);
+        mbar_expect_tx(full + s, a_bytes);
+        const int row0 = (a.tile_begin + i * a.tile_step) * TC_M;
+        for (int ka = 0; ka < katoms; ++ka)
+          tma_load_2d(sA + (size_t)s * a_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
+    // both K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    if (lane == 0) {
+      mbar_wait(bfull, 0);
+      tc_fence_after();
+      for (int i = 0; i < a.n_tiles; ++i) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+        const int b = i & 1;
+        const uint32_t bph = (uint32_t)(i >> 1) & 1u;
+        mbar_wait(tempty + b, bph);          // accumulator drained AND the item bias pre-stored by the epilogue
+        mbar_wait(full + s, ph);             // item tile landed
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * TC_N);
+        for (int ka = 0; ka < katoms; ++ka) {
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (size_t)s * a_bytes + (size_t)ka * TC_M * 128));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (size_t)ka * TC_N * 128));
+#pragma unroll
+          for (int k = 0; k < TC_KATOM / 16; ++k)   // 16 bf16 = 32 bytes per MMA along K: +2 in the (>>4) address field
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+        }
+        tc_commit(empty + s);    // smem stage reusable once these MMAs retire
+        tc_commit(tfull + b);    // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter q = warp % 4 =====
+    const int q = warp & 3;
+    const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+    // pre-store the item bias of tiles 0 and 1 into the two accumulators
+    for (int i = 0; i < 2 && i < a.n_tiles; ++i) {
+      const int item = (a.tile_begin + i * a.tile_step) * TC_M + q * 32 + lane;
+      const float bi = (item < a.num_items) ? a.item_bias[item] : 0.f;
+      for (int c0 = 0; c0 < TC_N; c0 += 32) tc_st32_splat(tmem_base + lane_addr + (uint32_t)(i * TC_N + c0), __float_as_uint(bi));
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + i);
+    }
+    if (a.n_tiles == 1) {  // second accumulator is never used; nothing else to release
+    }
+    for (int i = 0; i < a.n_tiles; ++i) {
+      const int b = i & 1;
+      const uint32_t bph = (uint32_t)(i >> 1) & 1u;
+      const int tile = a.tile_begin + i * a.tile_step;
+      const int item = tile * TC_M + q * 32 + lane;
+      const bool item_ok = item < a.num_items;
+      // train mask of this tile's 32 items (lane = item) x 256 user columns, built while the MMA runs
+      uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if (MODE != MODE_DUMP && a.mask_pairs != nullptr) {
+        uint32_t *mrow = mask_s + (q * 32 + lane) * 8;
+        *reinterpret_cast<uint4 *>(mrow) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(mrow + 4) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        const int g = tile * 4 + q;
+        if (g < a.ngroups) {
+          const int *mp = a.mask_ptr + (long long)blockIdx.x * (a.ngroups + 1) + g;
+          const int lo = mp[0], hi = mp[1];
+          const uint16_t *pairs = a.mask_pairs + a.mask_base[blockIdx.x];
+          for (int r = lo + lane; r < hi; r += 32) {
+            const uint32_t e = pairs[r];
+            atomicOr(mask_s + (q * 32 + (int)(e & 31u)) * 8 + (e >> 10), 1u << ((e >> 5) & 31u));
+          }
+        }
+        __syncwarp();
+        const uint4 m0 = *reinterpret_cast<const uint4 *>(mrow);
+        const uint4 m1 = *reinterpret_cast<const uint4 *>(mrow + 4);
+        mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
+        mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+      }
+      mbar_wait(tfull + b, bph);
+      tc_fence_after();
+      int keep = float_to_ordered(-INFINITY);   // MODE_MAX: lane c keeps the group max of column c0 + c
+      for (int c0 = 0; c0 < TC_N; c0 += 32) {
+        uint32_t r[32];
+        TC_LD32(r, tmem_base + lane_addr + (uint32_t)(b * TC_N + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (MODE == MODE_DUMP) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (item_ok) a.dump[(long long)item * a.n_users_pad + (u0 + c0 + c)] = __uint_as_float(r[c]);
+        } else if (MODE == MODE_MAX) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const bool usable = item_ok && !((mw[c0 >> 5] >> c) & 1u);   // train items do not count
+            const int v = usable ? float_to_ordered(__uint_as_float(r[c])) : float_to_ordered(-INFINITY);
+            const int mx = __reduce_max_sync(0xffffffffu, v);
+            if (lane == c) keep = mx;
+          }
+          a.gmax[(long long)(i * 4 + q) * a.n_users_pad + (u0 + c0 + lane)] = keep;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float sc = __uint_as_float(r[c]);
+            const bool hit = item_ok && (sc >= thr_s[c0 + c]);
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) {   // rare: append the hitting, unmasked items to this user's candidate list
+              const bool take = hit && !((mw[c0 >> 5] >> c) & 1u);
+              const unsigned tb = __ballot_sync(0xffffffffu, take);
+              if (tb) {
+                const int uu = c0 + c;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(cnt_s + uu, __popc(tb));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (take) {
+                  const int pos = base + __popc(tb & ((1u << lane) - 1u));
+                  if (pos < a.cap)
+                    a.cand[(long long)(u0 + uu) * a.cap + pos] = ((unsigned long long)r[c] << 32) | (unsigned)item;
+                }
+              }
+            }
+          }
+        }
+      }
+      // hand the accumulator back: pre-store the bias of the tile that will use it next
+      if (i + 2 < a.n_tiles) {
+        const int nitem = (a.tile_begin + (i + 2) * a.tile_step) * TC_M + q * 32 + lane;
+        const float bi = (nitem < a.num_items) ? a.item_bias[nitem] : 0.f;
+        for (int c0 = 0; c0 < TC_N; c0 += 32) tc_st32_splat(tmem_base + lane_addr + (uint32_t)(b * TC_N + c0), __float_as_uint(bi));
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty + b);
+      }
+    }
+  }
+  // teardown
+  tc_fence_before();
+  __syncthreads();
+  if (MODE == MODE_COLLECT) {
+    for (int i = threadIdx.x; i < TC_N; i += TC_THREADS)
+      if (u0 + i < a.n_users) a.cand_cnt[u0 + i] = cnt_s[i];
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// threshold from the sampled group maxima: the m-th largest group maximum is a lower bound of the m-th best
+// item score; m = k + (user's train items) so that at least k of the counted items are unmasked.
+// thr_collect = bound - 2*eps_u (eps_u bounds |bf16 score - fp32 score|), certified later by k_tc_rescore.
+// ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// train-mask structure for the GEMM epilogue, built on the device per mfb_topk call
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tc_user_counts(const long long *__restrict__ user_ids, const long long *__restrict__ indptr,
+                                 int n_users, int n_groups_u, long long *__restrict__ cta_cnt) {
+  // one thread per CTA-group of 256 users: total train entries of the group
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_groups_u) return;
+  long long tot = 0;
+  for (int p = c * TC_N; p < (c + 1) * TC_N && p < n_users; ++p) {
+    const long long uid = user_ids[p];
+    tot += indptr[uid + 1] - indptr[uid];
+  }
+  cta_cnt[c] = tot;
+}
+
+__global__ void k_tc_scan_ll(const long long *__restrict__ in, int n, long long *__restrict__ out) {
+  // tiny exclusive scan (n = number of CTAs, a few hundred): one thread
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    long long run = 0;
+    for (int i = 0; i < n; ++i) {
+      out[i] = run;
+      run += in[i];
+    }
+    out[n] = run;
+  }
+}
+
+// One block per CTA-group: counting sort of the group's (item, column) train pairs by 32-item group.
+// Dynamic smem: hist[ngroups + 1].
+__global__ void __launch_bounds__(256) k_tc_mask_build(const long long *__restrict__ user_ids,
+                                                       const long long *__restrict__ indptr,
+                                                       const int *__restrict__ indices, int n_users, int ngroups,
+                                                       const long long *__restrict__ base, int *__restrict__ mask_ptr,
+                                                       uint16_t *__restrict__ pairs) {
+  extern __shared__ int mb_smem[];
+  int *hist = mb_smem;   // [ngroups + 1]
+  __shared__ int carry_s, warp_tot[8];
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i <= ngroups; i += 256) hist[i] = 0;
+  __syncthreads();
+  const int p0 = c * TC_N;
+  // pass 1: histogram (warp per user, lanes over the user's entries)
+  for (int p = p0 + wid; p < p0 + TC_N && p < n_users; p += 8) {
+    const long long uid = user_ids[p];
+    const long long lo = indptr[uid], hi = indptr[uid + 1];
+    for (long long e = lo + lane; e < hi; e += 32) atomicAdd(hist + (indices[e] >> 5), 1);
+  }
+  __syncthreads();
+  // exclusive scan of hist[0..ngroups) in chunks of 256
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int start = 0; start < ngroups; start += 256) {
+    const int i = start + tid;
+    const int v = (i < ngroups) ? hist[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    int before = 0, all = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < wid) before += warp_tot[w];
+      all += warp_tot[w];
+    }
+    const int excl = carry_s + before + x - v;
+    __syncthreads();
+    if (i < ngroups) hist[i] = excl;
+    if (tid == 0) carry_s += all;
+    __syncthreads();
+  }
+  if (tid == 0) hist[ngroups] = carry_s;
+  __syncthreads();
+  int *mp = mask_ptr + (long long)c * (ngroups + 1);
+  for (int i = tid; i <= ngroups; i += 256) mp[i] = hist[i];
+  __syncthreads();
+  // pass 2: scatter (order inside a group is irrelevant); hist[] doubles as the running cursor
+  uint16_t *out = pairs + base[c];
+  for (int p = p0 + wid; p < p0 + TC_N && p < n_users; p += 8) {
+    const long long uid = user_ids[p];
+    const long long lo = indptr[uid], hi = indptr[uid + 1];
+    const uint32_t col = (uint32_t)(p - p0);
+    for (long long e = lo + lane; e < hi; e += 32) {
+      const int item = indices[e];
+      const int at = atomicAdd(hist + (item >> 5), 1);
+      out[at] = (uint16_t)((item & 31) | (col << 5));
+    }
+  }
+}
+
+constexpr int TH_VPL = 8;   // group maxima per lane -> up to 256 groups per user
+
+__global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gmax, int groups, int n_users,
+                                                      int n_users_pad, int k, const long long *__restrict__ user_ids,
+                                                      const long long *__restrict__ indptr,
+                                                      const float *__restrict__ unorm, const float *__restrict__ vmax,
+                                                      float *__restrict__ thr, float *__restrict__ eps_out,
+                                                      int masked_in_gemm) {
+  const int lane = threadIdx.x & 31;
+  const int u = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (u >= n_users) return;
+  long long ntrain = 0;
+  if (indptr && !masked_in_gemm) {   // group maxima already exclude train items when the GEMM applies the mask
+    const long long uid = user_ids[u];
+    ntrain = indptr[uid + 1] - indptr[uid];
+  }
+  // bf16 rounding: each operand within 2^-8 relative -> products within ~2^-7; Cauchy-Schwarz over the row
+  const float eps = 0.0084f * unorm[u] * vmax[0] + 1e-30f;
+  if (lane == 0) eps_out[u] = eps;
+  long long m = (long long)k + ntrain;
+  if (m > groups) {
+    if (lane == 0) thr[u] = -INFINITY;   // cannot bound: the user goes to the exact path
+    return;
+  }
+  // values as order-preserving unsigned keys; radix-select the m-th largest from the top bit down
+  uint32_t v[TH_VPL];
+#pragma unroll
+  for (int j = 0; j < TH_VPL; ++j) {
+    const int g = j * 32 + lane;
+    v[j] = (g < groups) ? ((uint32_t)gmax[(long long)g * n_users_pad + u] ^ 0x80000000u) : 0u;   // 0 = below everything
+  }
+  uint32_t prefix = 0, mask = 0;
+  int want = (int)m;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t test = prefix | (1u << bit);
+    const uint32_t tmask = mask | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < TH_VPL; ++j) c += ((v[j] & tmask) == test) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (c >= want) {
+      prefix = test;      // the m-th largest has this bit set
+    } else {
+      want -= c;          // skip the c values above
+    }
+    mask = tmask;
+  }
+  if (lane == 0) thr[u] = ordered_to_float((int)(prefix ^ 0x80000000u)) - 2.0f * eps;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. exact re-score of the candidates + mask + top-k.  One warp per user.
+//    Exact score = sequential fp32 FMA over d = 0..D-1, then (+ user bias) + item bias: bit-identical to k_topk_exact.
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_MAXC = 1024;   // candidates kept per user (cap)
+
+__global__ void __launch_bounds__(128) k_tc_rescore(const long long *__restrict__ user_ids, int n_users, TableView users,
+                                                    TableView items, int D, const unsigned long long *__restrict__ cand,
+                                                    const int *__restrict__ cand_cnt, int cap,
+                                                    const float *__restrict__ thr, const float *__restrict__ eps,
+                                                    const long long *__restrict__ indptr, const int *__restrict__ indices,
+                                                    int k, int *__restrict__ out_ids, float *__restrict__ out_scores,
+                                                    int *__restrict__ redo_flag) {
+  extern __shared__ float rs_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * 4 + wib;
+  float *urow = rs_smem + (size_t)wib * (D + 2 * RS_MAXC);
+  float *sc = urow + D;                       // exact scores
+  int *ids = reinterpret_cast<int *>(sc + RS_MAXC);
+  if (u >= n_users) return;
+  const long long uid = user_ids[u];
+  const int cnt = cand_cnt[u];
+  if (cnt > cap || cnt > RS_MAXC || !(thr[u] > -INFINITY)) {   // overflow or no bound: exact path
+    if (lane == 0) redo_flag[u] = 1;
+    return;
+  }
+  for (int d = lane; d < D; d += 32) urow[d] = users.p[uid * D + d];
+  __syncwarp();
+  const float ub = users.bp[uid];
+  long long tlo = 0, thi = 0;
+  if (indptr) {
+    tlo = indptr[uid];
+    thi = indptr[uid + 1];
+  }
+  const float certify = thr[u] + 2.0f * eps[u];
+  int good = 0;   // unmasked candidates whose approximate score certifies the bound
+  for (int c = lane; c < cnt; c += 32) {
+    const unsigned long long e = cand[(long long)u * cap + c];
+    const int item = (int)(e & 0xffffffffull);
+    const float approx = __uint_as_float((unsigned)(e >> 32));
+    const float *v = items.p + (long long)item * D;
+    float acc = 0.f;
+    for (int d = 0; d < D; d += 4) {
+      const float4 x = *reinterpret_cast<const float4 *>(v + d);
+      acc = fmaf(urow[d], x.x, acc);
+      acc = fmaf(urow[d + 1], x.y, acc);
+      acc = fmaf(urow[d + 2], x.z, acc);
+      acc = fmaf(urow[d + 3], x.w, acc);
+    }
+    float z = (acc + ub) + items.bp[item];
+    // train mask: binary search in the user's sorted CSR row
+    long long lo = tlo, hi = thi;
+    while (lo < hi) {
+      long long mid = (lo + hi) >> 1;
+      if (indices[mid] < item) lo = mid + 1; else hi = mid;
+    }
+    const bool masked = (lo < thi) && indices[lo] == item;
+    if (masked) z = MASKED_SCORE_TC;
+    else if (approx >= certify) ++good;
+    sc[c] = z;
+    ids[c] = item;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) good += __shfl_xor_sync(0xffffffffu, good, o);
+  if (good < k) {   // the collected set is not certified to contain the exact top-k
+    if (lane == 0) redo_flag[u] = 1;
+    return;
+  }
+  __syncwarp();
+  // k rounds of warp arg-max on (score desc, id asc); winners are removed
+  for (int r = 0; r < k; ++r) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff, bc = -1;
+    for (int c = lane; c < cnt; c += 32) {
+      const float z = sc[c];
+      const int id = ids[c];
+      if (id >= 0 && (z > bv || (z == bv && id < bi))) {
+        bv = z;
+        bi = id;
+        bc = c;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+        bc = oc;
+      }
+    }
+    if (lane == 0) {
+      out_ids[(long long)u * k + r] = bi;
+      if (out_scores) out_scores[(long long)u * k + r] = (bv == MASKED_SCORE_TC) ? 0.f : 1.0f / (1.0f + expf(-bv));
+      if (bc >= 0) ids[bc] = -1;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) redo_flag[u] = 0;
+}
+
+// compact the flagged users into a list for the exact kernel
+__global__ void k_tc_compact_redo(const int *__restrict__ redo_flag, const long long *__restrict__ user_ids,
+                                  int n_users, long long *__restrict__ redo_users, int *__restrict__ redo_pos,
+                                  int *__restrict__ redo_cnt) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_users) return;
+  if (redo_flag[u]) {
+    const int at = atomicAdd(redo_cnt, 1);
+    redo_users[at] = user_ids[u];
+    redo_pos[at] = u;
+  }
+}
+
+__global__ void k_tc_scatter_redo(const int *__restrict__ redo_pos, int n_redo, int k, const int *__restrict__ src_ids,
+                                  const float *__restrict__ src_scores, int *__restrict__ out_ids,
+                                  float *__restrict__ out_scores) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_redo * k) return;
+  const int r = i / k, j = i - r * k;
+  out_ids[(long long)redo_pos[r] * k + j] = src_ids[i];
+  if (out_scores) out_scores[(long long)redo_pos[r] * k + j] = src_scores[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+int make_tmap(CUtensorMap *map, void *base, int rows, int D, int box_rows) {
+  static PFN_tmapEncodeTiled encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      mfb_set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+      return MFB_ERR_CUDA;
+    }
+    encode = (PFN_tmapEncodeTiled)fn;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_KATOM, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mfb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return MFB_ERR_CUDA;
+  }
+  return MFB_OK;
+}
+
+size_t tc_smem_bytes(int D) {
+  const int katoms = D / TC_KATOM;
+  return 1024 + (size_t)TC_N * 128 * katoms + (size_t)TC_STAGES * TC_M * 128 * katoms + 256 + TC_N * 8 + 4 * 32 * 8 * 4;
+}
+
+template <int MODE>
+int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, int n_users, cudaStream_t st) {
+  const size_t smem = tc_smem_bytes(a.D);
+  MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (n_users + TC_N - 1) / TC_N;
+  k_tc_gemm<MODE><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
+  MFB_KERNEL_CHECK();
+  return MFB_OK;
+}
+
+}  // namespace
+
+bool mfb_tc_supported(const mfb_model *m, int k) {
+  const int D = m->desc.dim;
+  return (D == 64 || D == 128) && k <= MFB_MAX_TOPK && m->items.rows >= 8 * TC_M && m->tune_tc != 0;
+}
+
+// Top-k for the listed users through the tensor-core path.  d_out_* as in mfb_topk.
+// exact_topk: callback into the exact kernel for the (few) users that could not be certified.
+int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, const int64_t *d_train_indptr,
+                const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores, cudaStream_t st,
+                int (*exact_topk)(mfb_model *, const int64_t *, int64_t, const int64_t *, const int32_t *, int32_t,
+                                  int32_t *, float *, cudaStream_t),
+                int *h_n_redo) {
+  const int n_users = (int)n_users64;
+  const int D = m->desc.dim, I = m->items.rows;
+  const int n_users_pad = ((n_users + TC_N - 1) / TC_N) * TC_N;
+  const int i_tiles = (I + TC_M - 1) / TC_M;
+  const int items_pad = i_tiles * TC_M;
+  int sample_step = m->tune_tc_sample_step > 0 ? m->tune_tc_sample_step : 4;
+  while ((i_tiles + sample_step - 1) / sample_step > 8 * TH_VPL) ++sample_step;   // groups = 4*n_sample <= 32*TH_VPL
+  const int n_sample = (i_tiles + sample_step - 1) / sample_step;
+  const int groups = n_sample * 4;
+  const int cap = RS_MAXC;
+
+  EvalBuf &eb = m->eval;
+  MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__nv_bfloat16)));
+  MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__nv_bfloat16)));
+  MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
+  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * sizeof(float) + 16));
+  MFB_CHECK(eb.gmax.reserve((size_t)groups * n_users_pad * sizeof(int)));
+  MFB_CHECK(eb.thr.reserve((size_t)n_users_pad * 2 * sizeof(float)));
+  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * cap * sizeof(unsigned long long)));
+  MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * 3 + 64));
+  MFB_CHECK(eb.redo.reserve((size_t)n_users_pad * (sizeof(long long) + (size_t)k * (sizeof(int) + sizeof(float))) + 64));
+  __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
+  float *unorm = eb.unorm.as<float>(), *vnorm = eb.vnorm.as<float>();
+  float *vmax = vnorm + items_pad;
+  float *thr = eb.thr.as<float>(), *eps = thr + n_users_pad;
+  int *cand_cnt = eb.cnt.as<int>();
+  int *redo_flag = cand_cnt + n_users_pad;
+  int *redo_pos = redo_flag + n_users_pad;
+  int *redo_cnt = redo_pos + n_users_pad;
+
+  int tk = m->prof.begin(PK_TOPK, st, 8);
+  k_tc_convert<<<(n_users_pad + 7) / 8, 256, 0, st>>>(m->users.p, (const long long *)d_user_ids, n_users, n_users_pad, D,
+                                                     ub, unorm);
+  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, vnorm);
+  k_tc_maxnorm<<<1, 1024, 0, st>>>(vnorm, I, vmax);
+  MFB_KERNEL_CHECK();
+
+  CUtensorMap map_items, map_users;
+  MFB_CHECK(make_tmap(&map_items, vb, items_pad, D, TC_M));
+  MFB_CHECK(make_tmap(&map_users, ub, n_users_pad, D, TC_N));
+
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.num_items = I;
+  a.n_users = n_users;
+  a.D = D;
+  a.item_bias = m->items.bp;
+  a.n_users_pad = n_users_pad;
+  // train mask for the epilogue: per-CTA (item, column) pairs bucketed by 32-item group
+  const int ncta = n_users_pad / TC_N;
+  const int ngroups = (I + 31) / 32;
+  int masked_in_gemm = 0;
+  if (d_train_indptr != nullptr && (size_t)(ngroups + 1) * sizeof(int) <= 200 * 1024) {
+    MFB_CHECK(eb.mcnt.reserve((size_t)(2 * ncta + 2) * sizeof(long long)));
+    MFB_CHECK(eb.mptr.reserve((size_t)ncta * (ngroups + 1) * sizeof(int)));
+    long long *cta_cnt = eb.mcnt.as<long long>();
+    long long *cta_base = cta_cnt + ncta + 1;
+    k_tc_user_counts<<<(ncta + 127) / 128, 128, 0, st>>>((const long long *)d_user_ids,
+                                                         (const long long *)d_train_indptr, n_users, ncta, cta_cnt);
+    k_tc_scan_ll<<<1, 32, 0, st>>>(cta_cnt, ncta, cta_base);
+    MFB_KERNEL_CHECK();
+    long long total_pairs = 0;
+    MFB_CUDA(cudaMemcpyAsync(&total_pairs, cta_base + ncta, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    MFB_CUDA(cudaStreamSynchronize(st));
+    MFB_CHECK(eb.mpairs.reserve((size_t)total_pairs * sizeof(uint16_t) + 64));
+    const size_t mb_smem = (size_t)(ngroups + 1) * sizeof(int);
+    MFB_CUDA(cudaFuncSetAttribute(k_tc_mask_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb_smem));
+    k_tc_mask_build<<<ncta, 256, mb_smem, st>>>((const long long *)d_user_ids, (const long long *)d_train_indptr,
+                                                d_train_indices, n_users, ngroups, cta_base, eb.mptr.as<int>(),
+                                                eb.mpairs.as<uint16_t>());
+    MFB_KERNEL_CHECK();
+    a.mask_pairs = eb.mpairs.as<uint16_t>();
+    a.mask_ptr = eb.mptr.as<int>();
+    a.mask_base = cta_base;
+    a.ngroups = ngroups;
+    masked_in_gemm = 1;
+  }
+  // sample pass: group maxima of every sample_step-th item tile
+  a.tile_begin = 0;
+  a.tile_step = sample_step;
+  a.n_tiles = n_sample;
+  a.gmax = eb.gmax.as<int>();
+  MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st));
+  k_tc_threshold<<<(n_users + 3) / 4, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k,
+                                                        (const long long *)d_user_ids,
+                                                        (const long long *)d_train_indptr, unorm, vmax, thr, eps,
+                                                        masked_in_gemm);
+  MFB_KERNEL_CHECK();
+  // collect pass: all tiles
+  a.tile_begin = 0;
+  a.tile_step = 1;
+  a.n_tiles = i_tiles;
+  a.thr = thr;
+  a.cand = eb.cand.as<unsigned long long>();
+  a.cand_cnt = cand_cnt;
+  a.cap = cap;
+  MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st));
+  // exact re-score + mask + top-k
+  MFB_CUDA(cudaMemsetAsync(redo_cnt, 0, sizeof(int), st));
+  const size_t rs_smem = (size_t)4 * (D + 2 * RS_MAXC) * sizeof(float);
+  MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+  k_tc_rescore<<<(n_users + 3) / 4, 128, rs_smem, st>>>((const long long *)d_user_ids, n_users, m->users, m->items, D,
+                                                        eb.cand.as<unsigned long long>(), cand_cnt, cap, thr, eps,
+                                                        (const long long *)d_train_indptr, d_train_indices, k,
+                                                        d_out_ids, d_out_scores, redo_flag);
+  MFB_KERNEL_CHECK();
+  long long *redo_users = eb.redo.as<long long>();
+  k_tc_compact_redo<<<(n_users + 255) / 256, 256, 0, st>>>(redo_flag, (const long long *)d_user_ids, n_users, redo_users,
+                                                           redo_pos, redo_cnt);
+  MFB_KERNEL_CHECK();
+  m->prof.end(tk, st);
+  int n_redo = 0;
+  MFB_CUDA(cudaMemcpyAsync(&n_redo, redo_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  if (h_n_redo) *h_n_redo = n_redo;
+  if (n_redo > 0) {
+    int *tmp_ids = reinterpret_cast<int *>(redo_users + n_users_pad);
+    float *tmp_scores = reinterpret_cast<float *>(tmp_ids + (size_t)n_users_pad * k);
+    MFB_CHECK(exact_topk(m, (const int64_t *)redo_users, n_redo, d_train_indptr, d_train_indices, k, tmp_ids,
+                         d_out_scores ? tmp_scores : nullptr, st));
+    k_tc_scatter_redo<<<(n_redo * k + 255) / 256, 256, 0, st>>>(redo_pos, n_redo, k, tmp_ids, tmp_scores, d_out_ids,
+                                                                d_out_scores);
+    MFB_KERNEL_CHECK();
+  }
+  return MFB_OK;
+}
+
+// debug / test hook: dump the raw tensor-core scores (item-major) of the listed users
+int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, float *d_out, cudaStream_t st) {
+  const int D = m->desc.dim, I = m->items.rows;
+  const int n_users_pad = ((n_users + TC_N - 1) / TC_N) * TC_N;
+  const int i_tiles = (I + TC_M - 1) / TC_M;
+  const int items_pad = i_tiles * TC_M;
+  EvalBuf &eb = m->eval;
+  MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__nv_bfloat16)));
+  MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__nv_bfloat16)));
+  MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
+  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * sizeof(float) + 16));
+  __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
+  k_tc_convert<<<(n_users_pad + 7) / 8, 256, 0, st>>>(m->users.p, (const long long *)d_user_ids, n_users, n_users_pad, D,
+                                                     ub, eb.unorm.as<float>());
+  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, eb.vnorm.as<float>());
+  MFB_KERNEL_CHECK();
+  CUtensorMap map_items, map_users;
+  MFB_CHECK(make_tmap(&map_items, vb, items_pad, D, TC_M));
+  MFB_CHECK(make_tmap(&map_users, ub, n_users_pad, D, TC_N));
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.num_items = I;
+  a.n_users = n_users;
+  a.D = D;
+  a.item_bias = m->items.bp;
+  a.n_users_pad = n_users_pad;
+  a.tile_begin = 0;
+  a.tile_step = 1;
+  a.n_tiles = i_tiles;
+  a.dump = d_out;   // [I][n_users_pad]
+  return launch_gemm<MODE_DUMP>(map_items, map_users, a, n_users, st);
+}

@@ -119,9 +119,17 @@ struct PlanBuf {
   uint32_t *skeys = nullptr, *svals = nullptr;
 };
 
+// Workspaces of the tensor-core evaluation path (mfb_eval_tc.cu)
+struct EvalBuf {
+  DevBuf ub, vb, unorm, vnorm, gmax, thr, cand, cnt, redo, mcnt, mptr, mpairs;
+};
+
 struct mfb_model {
   mfb_model_desc desc;
   Profiler prof;
+  EvalBuf eval;
+  int tune_tc = 1, tune_tc_sample_step = 4;   // MFB_TC=0 forces the exact-fp32 evaluation kernel
+  int last_topk_redo = 0;                     // users re-done by the exact kernel in the last mfb_topk call
   PlanBuf plan[2];
   cudaStream_t st_plan = nullptr;   // planner stream
   cudaEvent_t ev_plan[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -146,6 +154,15 @@ struct mfb_model {
 };
 
 int mfb_ensure_scalars(mfb_model *m, int64_t upto);
+
+// ---- tensor-core evaluation (mfb_eval_tc.cu)
+bool mfb_tc_supported(const mfb_model *m, int k);
+int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
+                const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores, cudaStream_t st,
+                int (*exact_topk)(mfb_model *, const int64_t *, int64_t, const int64_t *, const int32_t *, int32_t,
+                                  int32_t *, float *, cudaStream_t),
+                int *h_n_redo);
+int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, float *d_out, cudaStream_t st);
 
 // ---- MT19937 (mfb_mt19937.cu)
 int mfb_mt_generate(uint32_t *h_state, int64_t nwords, uint32_t *d_words, cudaStream_t st);

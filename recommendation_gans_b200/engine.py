@@ -350,6 +350,19 @@ class MFEngine(object):
                    N.dptr(ids), N.dptr(scores), N.stream_ptr())
         return (ids, scores) if with_scores else ids
 
+    @property
+    def topk_last_redo(self):
+        return int(self._lib.mfb_topk_last_redo(self._handle))
+
+    def debug_tc_scores(self, user_ids):
+        """Raw tensor-core scores [num_items, n_users_padded] (test hook)."""
+        user_ids = _as_i64_cuda(user_ids, self.device)
+        n = user_ids.numel()
+        npad = (n + 255) // 256 * 256
+        out = torch.zeros((self.num_items, npad), dtype=torch.float32, device=self.device)
+        self._call('mfb_debug_tc_scores', N.dptr(user_ids), n, N.dptr(out), N.stream_ptr())
+        return out[:, :n]
+
     def topk_hits(self, topk_ids, user_ids, test_indptr, test_indices, ks):
         user_ids = _as_i64_cuda(user_ids, self.device)
         n, k = topk_ids.shape

@@ -143,3 +143,53 @@ def test_topk_random_fp32_respects_gaps():
             if gap_ok:
                 assert got[u, r] == order[r]
         np.testing.assert_allclose(scores[u], 1 / (1 + np.exp(-z[got[u]])), rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core evaluation path (TMA + tcgen05 GEMM -> candidates -> exact fp32 re-score)
+# ------------------------------------------------------------------------------------------------
+def _random_tables(rs, U, I, D, scale=0.3):
+    return (rs.normal(0, scale, (U, D)).astype(np.float32), rs.normal(0, scale, (I, D)).astype(np.float32),
+            rs.normal(0, 0.1, (U, 1)).astype(np.float32), rs.normal(0, 0.1, (I, 1)).astype(np.float32))
+
+
+@pytest.mark.parametrize('U,I,D', [(300, 1500, 128), (70, 1100, 64), (513, 2049, 128)])
+def test_tc_raw_scores_match_bf16_matmul(U, I, D):
+    """The tcgen05 GEMM (descriptors, swizzle, TMEM layout, bias pre-store) against torch on bf16-rounded inputs."""
+    from recommendation_gans_b200.engine import MFEngine
+    rs = np.random.RandomState(U)
+    tabs = _random_tables(rs, U, I, D)
+    eng = MFEngine(make_net(tabs))
+    users = np.arange(U, dtype=np.int64)[::-1].copy()
+    got = eng.debug_tc_scores(users).cpu().numpy()                       # [I, U]
+    ub = torch.from_numpy(tabs[0][users]).cuda().bfloat16().float()
+    vb = torch.from_numpy(tabs[1]).cuda().bfloat16().float()
+    ref = (vb.double() @ ub.double().T).float().cpu().numpy() + tabs[3]   # + item bias (fp32)
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('U,I,D,k,scale', [(600, 12000, 128, 20, 0.3), (300, 9000, 64, 5, 0.05), (1000, 20000, 128, 10, 1.0)])
+def test_tc_topk_equals_exact_kernel(U, I, D, k, scale, monkeypatch):
+    """Tensor-core path returns bit-identical ids to the exact fp32 kernel (same exact re-score definition)."""
+    from recommendation_gans_b200.engine import MFEngine
+    rs = np.random.RandomState(I)
+    tabs = _random_tables(rs, U, I, D, scale)
+    tu, ti = rs.randint(0, U, 12 * U), rs.randint(0, I, 12 * U)
+    tu[tu == 7] = 8                                                # a cold-start user
+    train = O.csr_from_pairs(tu, ti, U, I)
+    train.sort_indices()
+    indptr = torch.from_numpy(train.indptr.astype(np.int64)).cuda()
+    indices = torch.from_numpy(train.indices.astype(np.int32)).cuda()
+    users = rs.permutation(U).astype(np.int64)
+    monkeypatch.setenv('MFB_TC', '0')
+    exact = MFEngine(make_net(tabs))
+    monkeypatch.setenv('MFB_TC', '1')
+    tc = MFEngine(make_net(tabs))
+    for masked in (True, False):
+        args = (indptr, indices) if masked else (None, None)
+        ids_e, sc_e = exact.topk(users, k, *args, with_scores=True)
+        ids_t, sc_t = tc.topk(users, k, *args, with_scores=True)
+        assert (ids_e.cpu().numpy() == ids_t.cpu().numpy()).all()
+        np.testing.assert_array_equal(sc_e.cpu().numpy(), sc_t.cpu().numpy())
+        assert tc.topk_last_redo < U // 4, tc.topk_last_redo        # the fast path did most of the work
+    assert exact.topk_last_redo == 0

@@ -1,0 +1,32 @@
+# timing of the evaluation top-k pass at cfg4 shape: tensor-core path vs exact kernel
+import sys, os, numpy as np, torch, scipy.sparse as sp
+sys.path.insert(0, '.')
+import recommendation_gans_b200
+from tests.gpu_helpers import make_net
+from recommendation_gans_b200.engine import MFEngine
+U, I, D, k = 138493, 26744, 128, 20
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0 / 128
+rs = np.random.RandomState(0)
+tabs = [rs.normal(0, scale, (U, D)).astype(np.float32), rs.normal(0, scale, (I, D)).astype(np.float32),
+        rs.normal(0, scale, (U, 1)).astype(np.float32), rs.normal(0, scale, (I, 1)).astype(np.float32)]
+n_tr = 117 * U
+tu = np.sort(rs.randint(0, U, n_tr)); ti = rs.randint(0, I, n_tr)
+csr = sp.coo_matrix((np.ones(n_tr), (tu, ti)), shape=(U, I)).tocsr(); csr.sum_duplicates(); csr.sort_indices()
+indptr = torch.from_numpy(csr.indptr.astype(np.int64)).cuda(); indices = torch.from_numpy(csr.indices.astype(np.int32)).cuda()
+users = torch.arange(U, device='cuda', dtype=torch.int64)
+res = {}
+for mode in ('1', '0'):
+    os.environ['MFB_TC'] = mode
+    eng = MFEngine(make_net(tabs))
+    eng.profile(False)
+    ids = eng.topk(users, k, indptr, indices)
+    best = 1e9
+    for rep in range(3):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ids = eng.topk(users, k, indptr, indices); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    res[mode] = ids.cpu().numpy()
+    print('MFB_TC=%s: %.3f ms per pass -> %.2f M users/s, %.1f TFLOP/s algorithmic, redo %d' % (
+        mode, best, U / best / 1e3, 2.0 * U * I * D / best / 1e9, eng.topk_last_redo))
+print('ids identical:', (res['1'] == res['0']).all())
