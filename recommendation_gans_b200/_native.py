@@ -70,6 +70,7 @@ SIGNATURES = {
     'mfb_loss_epoch': (ctypes.c_int, [c_void, ctypes.c_int, c_void, c_void, ctypes.c_int64, ctypes.c_int32,
                                       ctypes.c_int32, c_void, c_void, ctypes.c_int64, c_void, c_void]),
     'mfb_topk_last_redo': (ctypes.c_int, [c_void]),
+    'mfb_debug_tc_stats': (ctypes.c_int, [c_void, ctypes.c_int64, c_void, c_void]),
     'mfb_debug_tc_scores': (ctypes.c_int, [c_void, c_void, ctypes.c_int64, c_void, c_void]),
     'mfb_profile_enable': (ctypes.c_int, [c_void, ctypes.c_int]),
     'mfb_profile_read': (ctypes.c_int, [c_void, c_void, c_void]),

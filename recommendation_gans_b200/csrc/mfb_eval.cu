@@ -244,6 +244,11 @@ extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users
 // Number of users the last mfb_topk call re-did with the exact kernel (tensor-core path only).
 extern "C" int mfb_topk_last_redo(const mfb_model *m) { return m ? m->last_topk_redo : -1; }
 
+extern "C" int mfb_debug_tc_stats(mfb_model *m, int64_t n_users, int64_t *h_out, mfb_stream stream) {
+  if (!m || !h_out || n_users <= 0) return MFB_ERR_INVALID;
+  return mfb_tc_stats(m, (int)n_users, (long long *)h_out, (cudaStream_t)stream);
+}
+
 // Test hook: raw tensor-core (bf16 x bf16 -> fp32, + item bias) scores of the listed users, item-major
 // [num_items][ceil(n_users/256)*256].
 extern "C" int mfb_debug_tc_scores(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, float *d_out,

@@ -17,12 +17,13 @@
 // bf16 inputs, fp32 accumulation in TMEM.  One thread owns one ITEM, so a warp-wide ballot tests one
 // user's score against 32 items in a single instruction; the item bias is pre-stored into the
 // accumulator in fp32 (tcgen05.st) and the MMA accumulates on top of it.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2-5 =
-// epilogue (one TMEM lane quarter each).  Pipelines: smem full/empty (TMA <-> MMA, 4 stages), TMEM
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2-9 =
+// epilogue (two per TMEM lane quarter, each owning 128 of the 256 user columns).  Pipelines: smem full/empty (TMA <-> MMA, 4 stages), TMEM
 // full/empty (MMA <-> epilogue, 2 accumulators of 256 columns).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "mfb_internal.cuh"
 
@@ -31,7 +32,8 @@ namespace {
 constexpr int TC_M = 128;          // items per tile (MMA M)
 constexpr int TC_N = 256;          // users per CTA (MMA N)
 constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;    // two per TMEM lane quarter, each owning half of the user columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_KATOM = 64;       // bf16 elements per 128-byte swizzle atom
 constexpr int MODE_DUMP = 0, MODE_MAX = 1, MODE_COLLECT = 2;
 constexpr float MASKED_SCORE_TC = -3.402823466e38f;
@@ -177,7 +179,7 @@ struct TcArgs {
   int n_users_pad;
   // MODE_COLLECT
   const float *thr;             // [n_users_pad] collection threshold per user
-  unsigned long long *cand;     // [n_users][cap]: (score bits << 32) | item id
+  int *cand;                    // [n_users][cap]: item ids
   int *cand_cnt;                // [n_users_pad]
   int cap;
   // MODE_DUMP
@@ -188,6 +190,7 @@ struct TcArgs {
   const int *mask_ptr;
   const long long *mask_base;
   int ngroups;
+  int dbg;   // experiment switches: 1 = skip score processing, 2 = skip appends, 4 = skip mask build, 8 = skip bias pre-store
 };
 
 template <int MODE>
@@ -223,7 +226,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull + b, 1);
-      mbar_init(tempty + b, 4);   // one arrival per epilogue warp
+      mbar_init(tempty + b, TC_EPI_WARPS);   // one arrival per epilogue warp
     }
     mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -288,104 +291,124 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       }
     }
   } else {
-    // ===== epilogue warps: TMEM lane quarter q = warp % 4 =====
+    // ===== epilogue warps: TMEM lane quarter q = warp % 4, column half h =====
     const int q = warp & 3;
+    const int h = (warp - 2) >> 2;                         // 0: user columns 0..127, 1: 128..255
+    const int col_lo = h * (TC_N / 2);
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
-    // pre-store the item bias of tiles 0 and 1 into the two accumulators
-    for (int i = 0; i < 2 && i < a.n_tiles; ++i) {
-      const int item = (a.tile_begin + i * a.tile_step) * TC_M + q * 32 + lane;
-      const float bi = (item < a.num_items) ? a.item_bias[item] : 0.f;
-      for (int c0 = 0; c0 < TC_N; c0 += 32) tc_st32_splat(tmem_base + lane_addr + (uint32_t)(i * TC_N + c0), __float_as_uint(bi));
+    const bool use_mask = (MODE != MODE_DUMP) && a.mask_pairs != nullptr;
+    uint32_t *mbase = mask_s + (warp - 2) * 32 * 4;         // this warp's [32 items][4 words] = 128 column bits
+    uint32_t *mrow = mbase + lane * 4;
+    const uint16_t *pairs = use_mask ? a.mask_pairs + a.mask_base[blockIdx.x] : nullptr;
+    const int *mp_row = use_mask ? a.mask_ptr + (long long)blockIdx.x * (a.ngroups + 1) : nullptr;
+    // group range and first 32 pairs of a tile, fetched one tile ahead of their use
+    int pf_lo = 0, pf_hi = 0;
+    uint32_t pf_e = 0;
+    auto prefetch_mask = [&](int tile_idx) {
+      pf_lo = pf_hi = 0;
+      if (use_mask && tile_idx < a.n_tiles) {
+        const int g = (a.tile_begin + tile_idx * a.tile_step) * 4 + q;
+        if (g < a.ngroups) {
+          pf_lo = mp_row[g];
+          pf_hi = mp_row[g + 1];
+          if (pf_lo + lane < pf_hi) pf_e = pairs[pf_lo + lane];
+        }
+      }
+    };
+    auto mask_set = [&](uint32_t e) {   // e = (item & 31) | (column << 5); keep this warp's column half only
+      const uint32_t col = e >> 5;
+      if ((int)(col >> 7) == h) atomicOr(mbase + (e & 31u) * 4 + ((col >> 5) & 3u), 1u << (col & 31u));
+    };
+    auto load_bias = [&](int tile_idx) {
+      const int it = (a.tile_begin + tile_idx * a.tile_step) * TC_M + q * 32 + lane;
+      return (tile_idx < a.n_tiles && it < a.num_items && !(a.dbg & 8)) ? a.item_bias[it] : 0.f;
+    };
+    auto prestore_bias = [&](float bi, int buf) {
+#pragma unroll
+      for (int c0 = 0; c0 < TC_N / 2; c0 += 32)
+        tc_st32_splat(tmem_base + lane_addr + (uint32_t)(buf * TC_N + col_lo + c0), __float_as_uint(bi));
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + i);
-    }
-    if (a.n_tiles == 1) {  // second accumulator is never used; nothing else to release
-    }
+      if (lane == 0) mbar_arrive(tempty + buf);
+    };
+    prefetch_mask(0);
+    for (int i = 0; i < 2 && i < a.n_tiles; ++i) prestore_bias(load_bias(i), i);
     for (int i = 0; i < a.n_tiles; ++i) {
       const int b = i & 1;
       const uint32_t bph = (uint32_t)(i >> 1) & 1u;
       const int tile = a.tile_begin + i * a.tile_step;
       const int item = tile * TC_M + q * 32 + lane;
       const bool item_ok = item < a.num_items;
-      // train mask of this tile's 32 items (lane = item) x 256 user columns, built while the MMA runs
-      uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      if (MODE != MODE_DUMP && a.mask_pairs != nullptr) {
-        uint32_t *mrow = mask_s + (q * 32 + lane) * 8;
+      const float bias_next = load_bias(i + 2);   // in flight while this tile is processed
+      // train mask of this tile's 32 items (lane = item) x this warp's 128 user columns, built while the MMA runs
+      if (use_mask && !(a.dbg & 4)) {
         *reinterpret_cast<uint4 *>(mrow) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4 *>(mrow + 4) = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
-        const int g = tile * 4 + q;
-        if (g < a.ngroups) {
-          const int *mp = a.mask_ptr + (long long)blockIdx.x * (a.ngroups + 1) + g;
-          const int lo = mp[0], hi = mp[1];
-          const uint16_t *pairs = a.mask_pairs + a.mask_base[blockIdx.x];
-          for (int r = lo + lane; r < hi; r += 32) {
-            const uint32_t e = pairs[r];
-            atomicOr(mask_s + (q * 32 + (int)(e & 31u)) * 8 + (e >> 10), 1u << ((e >> 5) & 31u));
-          }
-        }
+        const int lo = pf_lo, hi = pf_hi;
+        if (lo + lane < hi) mask_set(pf_e);
+        for (int r = lo + 32 + lane; r < hi; r += 32) mask_set(pairs[r]);
+        prefetch_mask(i + 1);   // loads complete while this tile's scores are processed
         __syncwarp();
-        const uint4 m0 = *reinterpret_cast<const uint4 *>(mrow);
-        const uint4 m1 = *reinterpret_cast<const uint4 *>(mrow + 4);
-        mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
-        mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
       }
       mbar_wait(tfull + b, bph);
       tc_fence_after();
-      int keep = float_to_ordered(-INFINITY);   // MODE_MAX: lane c keeps the group max of column c0 + c
-      for (int c0 = 0; c0 < TC_N; c0 += 32) {
+#pragma unroll 1
+      for (int cc0 = 0; cc0 < ((a.dbg & 1) ? 0 : TC_N / 2); cc0 += 32) {
+        const int c0 = col_lo + cc0;
         uint32_t r[32];
         TC_LD32(r, tmem_base + lane_addr + (uint32_t)(b * TC_N + c0));
+        // bit c = column c0+c is NOT usable for this lane's item (train item, or item beyond the catalog)
+        const uint32_t mword = item_ok ? (use_mask ? mrow[cc0 >> 5] : 0u) : 0xffffffffu;
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (MODE == MODE_DUMP) {
 #pragma unroll
           for (int c = 0; c < 32; ++c)
             if (item_ok) a.dump[(long long)item * a.n_users_pad + (u0 + c0 + c)] = __uint_as_float(r[c]);
         } else if (MODE == MODE_MAX) {
+          // per column: max over the warp's 32 items, train items excluded.  Butterfly transpose-reduce:
+          // after the 5 steps lane l holds the maximum of column c0 + l (31 shuffles for 32 columns).
+          float x[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const bool usable = item_ok && !((mw[c0 >> 5] >> c) & 1u);   // train items do not count
-            const int v = usable ? float_to_ordered(__uint_as_float(r[c])) : float_to_ordered(-INFINITY);
-            const int mx = __reduce_max_sync(0xffffffffu, v);
-            if (lane == c) keep = mx;
+          for (int c = 0; c < 32; ++c) x[c] = ((mword >> c) & 1u) ? -INFINITY : __uint_as_float(r[c]);
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+              const float give = upper ? x[j] : x[j + off];
+              const float keepv = upper ? x[j + off] : x[j];
+              x[j] = fmaxf(keepv, __shfl_xor_sync(0xffffffffu, give, off));
+            }
           }
-          a.gmax[(long long)(i * 4 + q) * a.n_users_pad + (u0 + c0 + lane)] = keep;
+          a.gmax[(long long)(i * 4 + q) * a.n_users_pad + (u0 + c0 + lane)] = float_to_ordered(x[0]);
         } else {
+          // bit c of hw = this lane's item reaches user (c0+c)'s threshold; branch-free, then one warp-wide test
+          const float4 *t4 = reinterpret_cast<const float4 *>(thr_s + c0);
+          uint32_t hw = 0u;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float sc = __uint_as_float(r[c]);
-            const bool hit = item_ok && (sc >= thr_s[c0 + c]);
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (bal) {   // rare: append the hitting, unmasked items to this user's candidate list
-              const bool take = hit && !((mw[c0 >> 5] >> c) & 1u);
-              const unsigned tb = __ballot_sync(0xffffffffu, take);
-              if (tb) {
-                const int uu = c0 + c;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(cnt_s + uu, __popc(tb));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (take) {
-                  const int pos = base + __popc(tb & ((1u << lane) - 1u));
-                  if (pos < a.cap)
-                    a.cand[(long long)(u0 + uu) * a.cap + pos] = ((unsigned long long)r[c] << 32) | (unsigned)item;
-                }
-              }
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 th = t4[c4];
+            hw |= (__uint_as_float(r[c4 * 4 + 0]) >= th.x ? 1u : 0u) << (c4 * 4 + 0);
+            hw |= (__uint_as_float(r[c4 * 4 + 1]) >= th.y ? 1u : 0u) << (c4 * 4 + 1);
+            hw |= (__uint_as_float(r[c4 * 4 + 2]) >= th.z ? 1u : 0u) << (c4 * 4 + 2);
+            hw |= (__uint_as_float(r[c4 * 4 + 3]) >= th.w ? 1u : 0u) << (c4 * 4 + 3);
+          }
+          hw &= ~mword;
+          if (!(a.dbg & 2) && __any_sync(0xffffffffu, hw != 0u)) {
+            // rare: each lane appends its own hits (usually one) to the users' candidate lists
+            while (hw) {
+              const int c = __ffs(hw) - 1;
+              hw &= hw - 1u;
+              const int uu = c0 + c;
+              const int pos = atomicAdd(cnt_s + uu, 1);
+              if (pos < a.cap) a.cand[(long long)(u0 + uu) * a.cap + pos] = item;
             }
           }
         }
       }
       // hand the accumulator back: pre-store the bias of the tile that will use it next
-      if (i + 2 < a.n_tiles) {
-        const int nitem = (a.tile_begin + (i + 2) * a.tile_step) * TC_M + q * 32 + lane;
-        const float bi = (nitem < a.num_items) ? a.item_bias[nitem] : 0.f;
-        for (int c0 = 0; c0 < TC_N; c0 += 32) tc_st32_splat(tmem_base + lane_addr + (uint32_t)(b * TC_N + c0), __float_as_uint(bi));
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty + b);
-      }
+      if (i + 2 < a.n_tiles) prestore_bias(bias_next, b);
     }
   }
   // teardown
@@ -548,7 +571,9 @@ __global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gm
     }
     mask = tmask;
   }
-  if (lane == 0) thr[u] = ordered_to_float((int)(prefix ^ 0x80000000u)) - 2.0f * eps;
+  // collect everything within 4 eps of the bound: the k sampled items behind the bound have exact scores >=
+  // bound - eps, which is what k_tc_rescore certifies against (thr + 3 eps)
+  if (lane == 0) thr[u] = ordered_to_float((int)(prefix ^ 0x80000000u)) - 4.0f * eps;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -558,7 +583,7 @@ __global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gm
 constexpr int RS_MAXC = 1024;   // candidates kept per user (cap)
 
 __global__ void __launch_bounds__(128) k_tc_rescore(const long long *__restrict__ user_ids, int n_users, TableView users,
-                                                    TableView items, int D, const unsigned long long *__restrict__ cand,
+                                                    TableView items, int D, const int *__restrict__ cand,
                                                     const int *__restrict__ cand_cnt, int cap,
                                                     const float *__restrict__ thr, const float *__restrict__ eps,
                                                     const long long *__restrict__ indptr, const int *__restrict__ indices,
@@ -585,12 +610,12 @@ __global__ void __launch_bounds__(128) k_tc_rescore(const long long *__restrict_
     tlo = indptr[uid];
     thi = indptr[uid + 1];
   }
-  const float certify = thr[u] + 2.0f * eps[u];
+  // any item outside the list has approx < thr, i.e. exact < thr + eps; k listed, unmasked items with
+  // exact >= thr + 3 eps (two spare eps for safety) prove the exact top-k lies inside the list
+  const float certify = thr[u] + 3.0f * eps[u];
   int good = 0;   // unmasked candidates whose approximate score certifies the bound
   for (int c = lane; c < cnt; c += 32) {
-    const unsigned long long e = cand[(long long)u * cap + c];
-    const int item = (int)(e & 0xffffffffull);
-    const float approx = __uint_as_float((unsigned)(e >> 32));
+    const int item = cand[(long long)u * cap + c];
     const float *v = items.p + (long long)item * D;
     float acc = 0.f;
     for (int d = 0; d < D; d += 4) {
@@ -600,7 +625,9 @@ __global__ void __launch_bounds__(128) k_tc_rescore(const long long *__restrict_
       acc = fmaf(urow[d + 2], x.z, acc);
       acc = fmaf(urow[d + 3], x.w, acc);
     }
-    float z = (acc + ub) + items.bp[item];
+    const float ib = items.bp[item];
+    float z = (acc + ub) + ib;
+    const float zc = acc + ib;   // the GEMM's score space has no user bias (constant per user: irrelevant for ranking)
     // train mask: binary search in the user's sorted CSR row
     long long lo = tlo, hi = thi;
     while (lo < hi) {
@@ -609,7 +636,7 @@ __global__ void __launch_bounds__(128) k_tc_rescore(const long long *__restrict_
     }
     const bool masked = (lo < thi) && indices[lo] == item;
     if (masked) z = MASKED_SCORE_TC;
-    else if (approx >= certify) ++good;
+    else if (zc >= certify) ++good;
     sc[c] = z;
     ids[c] = item;
   }
@@ -758,7 +785,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * sizeof(float) + 16));
   MFB_CHECK(eb.gmax.reserve((size_t)groups * n_users_pad * sizeof(int)));
   MFB_CHECK(eb.thr.reserve((size_t)n_users_pad * 2 * sizeof(float)));
-  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * cap * sizeof(unsigned long long)));
+  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * cap * sizeof(int)));
   MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * 3 + 64));
   MFB_CHECK(eb.redo.reserve((size_t)n_users_pad * (sizeof(long long) + (size_t)k * (sizeof(int) + sizeof(float))) + 64));
   __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
@@ -788,6 +815,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.D = D;
   a.item_bias = m->items.bp;
   a.n_users_pad = n_users_pad;
+  if (const char *e = getenv("MFB_TC_DBG")) a.dbg = atoi(e);
   // train mask for the epilogue: per-CTA (item, column) pairs bucketed by 32-item group
   const int ncta = n_users_pad / TC_N;
   const int ngroups = (I + 31) / 32;
@@ -833,7 +861,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.tile_step = 1;
   a.n_tiles = i_tiles;
   a.thr = thr;
-  a.cand = eb.cand.as<unsigned long long>();
+  a.cand = eb.cand.as<int>();
   a.cand_cnt = cand_cnt;
   a.cap = cap;
   MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st));
@@ -842,7 +870,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   const size_t rs_smem = (size_t)4 * (D + 2 * RS_MAXC) * sizeof(float);
   MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
   k_tc_rescore<<<(n_users + 3) / 4, 128, rs_smem, st>>>((const long long *)d_user_ids, n_users, m->users, m->items, D,
-                                                        eb.cand.as<unsigned long long>(), cand_cnt, cap, thr, eps,
+                                                        eb.cand.as<int>(), cand_cnt, cap, thr, eps,
                                                         (const long long *)d_train_indptr, d_train_indices, k,
                                                         d_out_ids, d_out_scores, redo_flag);
   MFB_KERNEL_CHECK();
@@ -864,6 +892,24 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
                                                                 d_out_scores);
     MFB_KERNEL_CHECK();
   }
+  return MFB_OK;
+}
+
+// debug: candidate-list statistics of the last tensor-core top-k call: {users, sum, max, over_cap}
+int mfb_tc_stats(mfb_model *m, int n_users, long long *h_out, cudaStream_t st) {
+  std::vector<int> cnt((size_t)n_users);
+  MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.ptr, (size_t)n_users * sizeof(int), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  long long sum = 0, mx = 0, over = 0;
+  for (int c : cnt) {
+    sum += c;
+    if (c > mx) mx = c;
+    if (c > RS_MAXC) ++over;
+  }
+  h_out[0] = n_users;
+  h_out[1] = sum;
+  h_out[2] = mx;
+  h_out[3] = over;
   return MFB_OK;
 }
 

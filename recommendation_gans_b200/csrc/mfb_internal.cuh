@@ -162,6 +162,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const 
                 int (*exact_topk)(mfb_model *, const int64_t *, int64_t, const int64_t *, const int32_t *, int32_t,
                                   int32_t *, float *, cudaStream_t),
                 int *h_n_redo);
+int mfb_tc_stats(mfb_model *m, int n_users, long long *h_out, cudaStream_t st);
 int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, float *d_out, cudaStream_t st);
 
 // ---- MT19937 (mfb_mt19937.cu)

@@ -354,6 +354,11 @@ class MFEngine(object):
     def topk_last_redo(self):
         return int(self._lib.mfb_topk_last_redo(self._handle))
 
+    def debug_tc_stats(self, n_users):
+        out = np.zeros(4, dtype=np.int64)
+        self._call('mfb_debug_tc_stats', int(n_users), N.hptr(out), N.stream_ptr())
+        return dict(users=int(out[0]), candidates=int(out[1]), max=int(out[2]), over_cap=int(out[3]))
+
     def debug_tc_scores(self, user_ids):
         """Raw tensor-core scores [num_items, n_users_padded] (test hook)."""
         user_ids = _as_i64_cuda(user_ids, self.device)
