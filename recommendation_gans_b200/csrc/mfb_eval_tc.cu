@@ -396,13 +396,37 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
           }
           hw &= ~mword;
           if (!(a.dbg & 2) && __any_sync(0xffffffffu, hw != 0u)) {
-            // rare: each lane appends its own hits (usually one) to the users' candidate lists
-            while (hw) {
-              const int c = __ffs(hw) - 1;
-              hw &= hw - 1u;
-              const int uu = c0 + c;
-              const int pos = atomicAdd(cnt_s + uu, 1);
-              if (pos < a.cap) a.cand[(long long)(u0 + uu) * a.cap + pos] = item;
+            const int item0 = tile * TC_M + q * 32;
+            if (!__any_sync(0xffffffffu, __popc(hw) > 2)) {
+              // sparse hits (the common case): each lane appends its own one or two
+              while (hw) {
+                const int c = __ffs(hw) - 1;
+                hw &= hw - 1u;
+                const int uu = c0 + c;
+                const int pos = atomicAdd(cnt_s + uu, 1);
+                if (pos < a.cap) a.cand[(long long)(u0 + uu) * a.cap + pos] = item;
+              }
+            } else {
+              // a popular item hits for many users of the chunk: transpose the 32x32 hit matrix with ballots so
+              // that lane c owns user column c0+c (`mine` = this warp's items that reached that user's threshold):
+              // one atomic per column, all columns in parallel
+              unsigned mine = 0u;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const unsigned bal = __ballot_sync(0xffffffffu, (hw >> c) & 1u);
+                mine = (lane == c) ? bal : mine;
+              }
+              if (mine) {
+                const int uu = c0 + lane;
+                int pos = atomicAdd(cnt_s + uu, __popc(mine));
+                int *dst = a.cand + (long long)(u0 + uu) * a.cap;
+                while (mine) {
+                  const int src = __ffs(mine) - 1;
+                  mine &= mine - 1u;
+                  if (pos < a.cap) dst[pos] = item0 + src;
+                  ++pos;
+                }
+              }
             }
           }
         }
@@ -580,20 +604,22 @@ __global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gm
 // 4. exact re-score of the candidates + mask + top-k.  One warp per user.
 //    Exact score = sequential fp32 FMA over d = 0..D-1, then (+ user bias) + item bias: bit-identical to k_topk_exact.
 // ---------------------------------------------------------------------------------------------
-constexpr int RS_MAXC = 1024;   // candidates kept per user (cap)
+constexpr int RS_MAXC = 768;    // candidates kept per user (cap)
+constexpr int RS_WARPS = 4;
 
-__global__ void __launch_bounds__(128) k_tc_rescore(const long long *__restrict__ user_ids, int n_users, TableView users,
-                                                    TableView items, int D, const int *__restrict__ cand,
-                                                    const int *__restrict__ cand_cnt, int cap,
-                                                    const float *__restrict__ thr, const float *__restrict__ eps,
-                                                    const long long *__restrict__ indptr, const int *__restrict__ indices,
-                                                    int k, int *__restrict__ out_ids, float *__restrict__ out_scores,
-                                                    int *__restrict__ redo_flag) {
-  extern __shared__ float rs_smem[];
+// smem per warp: user row [D] | exact scores [RS_MAXC] | ids [RS_MAXC]
+// (staging the candidate rows through shared memory with cp.async was measured 2x slower: the kernel is
+// latency-bound and the extra shared memory cuts the resident warps from 24 to 8 per SM)
+__global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
+    const long long *__restrict__ user_ids, int n_users, TableView users, TableView items, int D,
+    const int *__restrict__ cand, const int *__restrict__ cand_cnt, int cap, const float *__restrict__ thr,
+    const float *__restrict__ eps, const long long *__restrict__ indptr, const int *__restrict__ indices, int k,
+    int *__restrict__ out_ids, float *__restrict__ out_scores, int *__restrict__ redo_flag, int check_mask) {
+  extern __shared__ __align__(16) float rs_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u = blockIdx.x * 4 + wib;
+  const int u = blockIdx.x * RS_WARPS + wib;
   float *urow = rs_smem + (size_t)wib * (D + 2 * RS_MAXC);
-  float *sc = urow + D;                       // exact scores
+  float *sc = urow + D;                                    // exact scores
   int *ids = reinterpret_cast<int *>(sc + RS_MAXC);
   if (u >= n_users) return;
   const long long uid = user_ids[u];
@@ -602,43 +628,49 @@ __global__ void __launch_bounds__(128) k_tc_rescore(const long long *__restrict_
     if (lane == 0) redo_flag[u] = 1;
     return;
   }
-  for (int d = lane; d < D; d += 32) urow[d] = users.p[uid * D + d];
+  for (int d = lane * 4; d < D; d += 128) *reinterpret_cast<float4 *>(urow + d) = *reinterpret_cast<const float4 *>(users.p + uid * D + d);
   __syncwarp();
   const float ub = users.bp[uid];
   long long tlo = 0, thi = 0;
-  if (indptr) {
+  if (indptr && check_mask) {    // (the GEMM epilogue already dropped train items when it applied the mask itself)
     tlo = indptr[uid];
     thi = indptr[uid + 1];
   }
   // any item outside the list has approx < thr, i.e. exact < thr + eps; k listed, unmasked items with
   // exact >= thr + 3 eps (two spare eps for safety) prove the exact top-k lies inside the list
   const float certify = thr[u] + 3.0f * eps[u];
-  int good = 0;   // unmasked candidates whose approximate score certifies the bound
+  int good = 0;
   for (int c = lane; c < cnt; c += 32) {
-    const int item = cand[(long long)u * cap + c];
-    const float *v = items.p + (long long)item * D;
+    const int my_item = cand[(long long)u * cap + c];
+    const float *v = items.p + (long long)my_item * D;
+    const float ib = items.bp[my_item];
+    // exact score: sequential fp32 FMA over d = 0..D-1 (bit-identical to k_topk_exact); 8 row loads in flight
     float acc = 0.f;
-    for (int d = 0; d < D; d += 4) {
-      const float4 x = *reinterpret_cast<const float4 *>(v + d);
-      acc = fmaf(urow[d], x.x, acc);
-      acc = fmaf(urow[d + 1], x.y, acc);
-      acc = fmaf(urow[d + 2], x.z, acc);
-      acc = fmaf(urow[d + 3], x.w, acc);
+    for (int d0 = 0; d0 < D; d0 += 32) {
+      float4 x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float4 *>(v + d0 + 4 * j);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 y = *reinterpret_cast<const float4 *>(urow + d0 + 4 * j);
+        acc = fmaf(y.x, x[j].x, acc);
+        acc = fmaf(y.y, x[j].y, acc);
+        acc = fmaf(y.z, x[j].z, acc);
+        acc = fmaf(y.w, x[j].w, acc);
+      }
     }
-    const float ib = items.bp[item];
     float z = (acc + ub) + ib;
-    const float zc = acc + ib;   // the GEMM's score space has no user bias (constant per user: irrelevant for ranking)
-    // train mask: binary search in the user's sorted CSR row
+    const float zc = acc + ib;   // the GEMM's score space has no user bias (constant per user)
     long long lo = tlo, hi = thi;
-    while (lo < hi) {
+    while (lo < hi) {            // train mask: binary search in the user's sorted CSR row
       long long mid = (lo + hi) >> 1;
-      if (indices[mid] < item) lo = mid + 1; else hi = mid;
+      if (indices[mid] < my_item) lo = mid + 1; else hi = mid;
     }
-    const bool masked = (lo < thi) && indices[lo] == item;
+    const bool masked = (lo < thi) && indices[lo] == my_item;
     if (masked) z = MASKED_SCORE_TC;
     else if (zc >= certify) ++good;
     sc[c] = z;
-    ids[c] = item;
+    ids[c] = my_item;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) good += __shfl_xor_sync(0xffffffffu, good, o);
@@ -867,12 +899,12 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st));
   // exact re-score + mask + top-k
   MFB_CUDA(cudaMemsetAsync(redo_cnt, 0, sizeof(int), st));
-  const size_t rs_smem = (size_t)4 * (D + 2 * RS_MAXC) * sizeof(float);
+  const size_t rs_smem = (size_t)RS_WARPS * (D + 2 * RS_MAXC) * sizeof(float);
   MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
-  k_tc_rescore<<<(n_users + 3) / 4, 128, rs_smem, st>>>((const long long *)d_user_ids, n_users, m->users, m->items, D,
+  k_tc_rescore<<<(n_users + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>((const long long *)d_user_ids, n_users, m->users, m->items, D,
                                                         eb.cand.as<int>(), cand_cnt, cap, thr, eps,
                                                         (const long long *)d_train_indptr, d_train_indices, k,
-                                                        d_out_ids, d_out_scores, redo_flag);
+                                                        d_out_ids, d_out_scores, redo_flag, masked_in_gemm ? 0 : 1);
   MFB_KERNEL_CHECK();
   long long *redo_users = eb.redo.as<long long>();
   k_tc_compact_redo<<<(n_users + 255) / 256, 256, 0, st>>>(redo_flag, (const long long *)d_user_ids, n_users, redo_users,
