@@ -176,6 +176,8 @@ def native_bench(args, w, rank, world):
         import torch.distributed as dist_mod
         dist = dist_mod
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO'):
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     K, W = args.steps, args.warmup
@@ -322,7 +324,8 @@ def eval_bench(eng, w, rank, world, dev, rs):
     """cfg4: precision/recall top-k pass over the rank's shard of users (train mask on)."""
     import torch
     U, I = w['U'], w['I']
-    lo, hi = rank * U // world, (rank + 1) * U // world
+    from recommendation_gans_b200.sharding import shard_range
+    lo, hi = shard_range(U, rank, world)
     n_tr = 117 * (hi - lo)                          # ML-20M: ~117 train interactions per user
     tu = np.sort(rs.randint(lo, hi, n_tr))
     ti = rs.randint(0, I, n_tr)
@@ -344,7 +347,10 @@ def eval_bench(eng, w, rank, world, dev, rs):
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / 1e3
         best = t if best is None else min(best, t)
-    return dict(seconds=best, users=hi - lo, kernel='k_topk_exact (fp32 CUDA cores)')
+    redo = eng.topk_last_redo
+    kern = ('k_tc_gemm (TMA + tcgen05 bf16, TMEM accumulators) + exact fp32 re-score; %d users redone by k_topk_exact' % redo
+            if os.environ.get('MFB_TC', '1') != '0' else 'k_topk_exact (fp32 CUDA cores)')
+    return dict(seconds=best, users=hi - lo, kernel=kern)
 
 
 def main():

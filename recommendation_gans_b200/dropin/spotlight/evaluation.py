@@ -84,6 +84,43 @@ def precision_recall_score(model, test, train=None, k=10):
     return np.mean(precision.squeeze()), np.mean(recall.squeeze())
 
 
+def precision_recall_score_sharded(model, test, train=None, k=10):
+    """Multi-GPU variant (one process per GPU, torch.distributed initialised, the same model replicated on
+    every rank): the users with test items are split into contiguous blocks, each rank scores its block on its
+    own GPU and the per-k sums are all-reduced.  Returns the same two scalars as precision_recall_score."""
+    import torch.distributed as dist
+    from recommendation_gans_b200.sharding import allreduce_precision_recall, shard_range
+    eng = _native_engine(model)
+    test_csr = test.tocsr()
+    train_csr = train.tocsr() if train is not None else None
+    ks = np.array([k]) if np.isscalar(k) else np.asarray(k)
+    ks_sorted = np.unique(ks)
+    all_users = np.nonzero(np.diff(test_csr.indptr))[0].astype(np.int64)
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_range(len(all_users), rank, world)
+    user_ids = all_users[lo:hi]
+    t_indptr, t_indices = _csr_to_device(test_csr, eng.device)
+    m_indptr = m_indices = None
+    if train_csr is not None:
+        m_indptr, m_indices = _csr_to_device(train_csr, eng.device)
+    hits = np.zeros((len(user_ids), len(ks_sorted)), dtype=np.int64)
+    ntargets = np.zeros(len(user_ids), dtype=np.int64)
+    if len(user_ids):
+        d_users = torch.from_numpy(user_ids).to(eng.device)
+        topk = eng.topk(d_users, int(ks_sorted[-1]), m_indptr, m_indices)
+        for c0 in range(0, len(ks_sorted), 4):
+            chunk = ks_sorted[c0:c0 + 4]
+            h, nt = eng.topk_hits(topk, d_users, t_indptr, t_indices, chunk)
+            hits[:, c0:c0 + len(chunk)] = h.cpu().numpy()
+            ntargets = nt.cpu().numpy()
+    col = {int(kk): j for j, kk in enumerate(ks_sorted)}
+    cols = [col[int(kk)] for kk in ks]
+    prec, rec, _ = allreduce_precision_recall(hits[:, cols], ntargets, ks, dist=dist if world > 1 else None,
+                                              device=eng.device if (world > 1 and dist.get_backend() == 'nccl') else None)
+    return float(np.mean(prec)), float(np.mean(rec))
+
+
 def rmse_score(net, user_ids, item_ids):
     """Sum of squared (1 - prediction) over the batch (evaluation.py:187-190; logged as "BCE")."""
     predictions = net(user_ids, item_ids)
