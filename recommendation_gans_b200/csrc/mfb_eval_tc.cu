@@ -218,6 +218,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * TC_N;
+  // every CTA streams the same item tiles out of L2: start each CTA at a different tile so that concurrently
+  // running CTAs do not all hit the same L2 slices at the same moment
+  const int tile_off = (int)(((long long)blockIdx.x * 37) % (a.n_tiles > 0 ? a.n_tiles : 1));
+  auto logical = [&](int i) { int li = i + tile_off; return li >= a.n_tiles ? li - a.n_tiles : li; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -257,7 +261,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
         mbar_wait(empty + s, ph ^ 1u);
         mbar_expect_tx(full + s, a_bytes);
-        const int row0 = (a.tile_begin + i * a.tile_step) * TC_M;
+        const int row0 = (a.tile_begin + logical(i) * a.tile_step) * TC_M;
         for (int ka = 0; ka < katoms; ++ka)
           tma_load_2d(sA + (size_t)s * a_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
       }
@@ -303,15 +307,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     const int *mp_row = use_mask ? a.mask_ptr + (long long)blockIdx.x * (a.ngroups + 1) : nullptr;
     // group range and first 32 pairs of a tile, fetched one tile ahead of their use
     int pf_lo = 0, pf_hi = 0;
-    uint32_t pf_e = 0;
+    uint32_t pf_e = 0, pf_e2 = 0;
     auto prefetch_mask = [&](int tile_idx) {
       pf_lo = pf_hi = 0;
       if (use_mask && tile_idx < a.n_tiles) {
-        const int g = (a.tile_begin + tile_idx * a.tile_step) * 4 + q;
+        const int g = (a.tile_begin + logical(tile_idx) * a.tile_step) * 4 + q;
         if (g < a.ngroups) {
           pf_lo = mp_row[g];
           pf_hi = mp_row[g + 1];
           if (pf_lo + lane < pf_hi) pf_e = pairs[pf_lo + lane];
+          if (pf_lo + 32 + lane < pf_hi) pf_e2 = pairs[pf_lo + 32 + lane];
         }
       }
     };
@@ -320,14 +325,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       if ((int)(col >> 7) == h) atomicOr(mbase + (e & 31u) * 4 + ((col >> 5) & 3u), 1u << (col & 31u));
     };
     auto load_bias = [&](int tile_idx) {
-      const int it = (a.tile_begin + tile_idx * a.tile_step) * TC_M + q * 32 + lane;
+      const int it = (a.tile_begin + logical(tile_idx < a.n_tiles ? tile_idx : 0) * a.tile_step) * TC_M + q * 32 + lane;
       return (tile_idx < a.n_tiles && it < a.num_items && !(a.dbg & 8)) ? a.item_bias[it] : 0.f;
     };
     auto prestore_bias = [&](float bi, int buf) {
+      if (!(a.dbg & 16)) {
 #pragma unroll
-      for (int c0 = 0; c0 < TC_N / 2; c0 += 32)
-        tc_st32_splat(tmem_base + lane_addr + (uint32_t)(buf * TC_N + col_lo + c0), __float_as_uint(bi));
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        for (int c0 = 0; c0 < TC_N / 2; c0 += 32)
+          tc_st32_splat(tmem_base + lane_addr + (uint32_t)(buf * TC_N + col_lo + c0), __float_as_uint(bi));
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + buf);
@@ -337,7 +344,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     for (int i = 0; i < a.n_tiles; ++i) {
       const int b = i & 1;
       const uint32_t bph = (uint32_t)(i >> 1) & 1u;
-      const int tile = a.tile_begin + i * a.tile_step;
+      const int li = logical(i);
+      const int tile = a.tile_begin + li * a.tile_step;
       const int item = tile * TC_M + q * 32 + lane;
       const bool item_ok = item < a.num_items;
       const float bias_next = load_bias(i + 2);   // in flight while this tile is processed
@@ -347,7 +355,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
         __syncwarp();
         const int lo = pf_lo, hi = pf_hi;
         if (lo + lane < hi) mask_set(pf_e);
-        for (int r = lo + 32 + lane; r < hi; r += 32) mask_set(pairs[r]);
+        if (lo + 32 + lane < hi) mask_set(pf_e2);
+        for (int r = lo + 64 + lane; r < hi; r += 32) mask_set(pairs[r]);   // rare: more than 64 train pairs in the group
         prefetch_mask(i + 1);   // loads complete while this tile's scores are processed
         __syncwarp();
       }
@@ -381,7 +390,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
               x[j] = fmaxf(keepv, __shfl_xor_sync(0xffffffffu, give, off));
             }
           }
-          a.gmax[(long long)(i * 4 + q) * a.n_users_pad + (u0 + c0 + lane)] = float_to_ordered(x[0]);
+          a.gmax[(long long)(li * 4 + q) * a.n_users_pad + (u0 + c0 + lane)] = float_to_ordered(x[0]);
         } else {
           // bit c of hw = this lane's item reaches user (c0+c)'s threshold; branch-free, then one warp-wide test
           const float4 *t4 = reinterpret_cast<const float4 *>(thr_s + c0);
