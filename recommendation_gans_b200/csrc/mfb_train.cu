@@ -36,6 +36,12 @@ namespace {
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
 
+// Programmatic dependent launch: the per-step kernels are launched back to back on one stream with
+// programmatic stream serialization, so a kernel's CTAs start (and load their planner records) while the
+// previous kernel drains; everything that depends on the previous kernel's output comes after pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------
 // per-lane row fragments: element index e = (it*32 + lane)*VEC + k
 // ---------------------------------------------------------------------------------------
@@ -272,8 +278,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_forward(const int *__restrict
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * WARPS_PER_BLOCK + wid;
   unsigned long long mine = 0ull;
+  pdl_launch_dependents();
+  long long u = 0, i = 0;
   if (j < L) {
-    const long long u = slot_u[j], i = slot_i[j];
+    u = slot_u[j];       // planner output: independent of the previous kernel
+    i = slot_i[j];
+  }
+  pdl_wait();            // tables are written by the previous step's update
+  if (j < L) {
     Frag<VEC, NIT> fu, fi;
     frag_load<VEC, NIT>(fu, users.p + u * D, D, lane);
     frag_load<VEC, NIT>(fi, items.p + i * D, D, lane);
@@ -689,9 +701,11 @@ __global__ void __launch_bounds__(UPD_WARPS * 32, MFB_UPD_MINB) k_update(const U
   const int D = a.D;
   const bool adam = a.opt.kind == MFB_OPT_ADAM;
 
+  pdl_launch_dependents();
   if ((int)blockIdx.x < a.cu_blocks) {
     // ---- lazy catch-up role ------------------------------------------------------------
     const int cnt = *a.lazy_cnt;
+    pdl_wait();
     const int stride = a.cu_blocks * UPD_WARPS;
     for (int i = blockIdx.x * UPD_WARPS + wid; i < cnt; i += stride) {
       const uint32_t rk = a.lazy_rows[i];
@@ -715,6 +729,7 @@ __global__ void __launch_bounds__(UPD_WARPS * 32, MFB_UPD_MINB) k_update(const U
   // independent loads first: this kernel is bound by dependent-load latency, not bandwidth
   const uint4 raw = *reinterpret_cast<const uint4 *>(a.info + q);
   const int j0 = (int)a.svals[q];
+  pdl_wait();   // predictions, snapshots and the adaptive-hinge maximum come from this step's forward kernel
   unsigned long long gcell = 0ull;
   if (KIND == MFB_LOSS_ADAPTIVE_HINGE) gcell = *a.gmax_cell;
   const uint32_t key = raw.x;
@@ -881,6 +896,22 @@ int pick_shape(int D, Shape *s) {
   } while (0)
 
 inline int grid_for_warps(long long warps) { return (int)((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK); }
+
+// launch with programmatic stream serialization (see pdl_wait)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 int bits_for(uint32_t maxval) {
   int b = 1;
@@ -1153,16 +1184,16 @@ template <int V, int N, bool FAST>
 static void launch_update_kind(const UpdArgs &a, int loss, int grid, cudaStream_t st) {
   switch (loss) {
     case MFB_LOSS_POINTWISE:
-      k_update<V, N, FAST, MFB_LOSS_POINTWISE><<<grid, UPD_WARPS * 32, 0, st>>>(a);
+      launch_pdl(k_update<V, N, FAST, MFB_LOSS_POINTWISE>, grid, UPD_WARPS * 32, st, a);
       break;
     case MFB_LOSS_BPR:
-      k_update<V, N, FAST, MFB_LOSS_BPR><<<grid, UPD_WARPS * 32, 0, st>>>(a);
+      launch_pdl(k_update<V, N, FAST, MFB_LOSS_BPR>, grid, UPD_WARPS * 32, st, a);
       break;
     case MFB_LOSS_HINGE:
-      k_update<V, N, FAST, MFB_LOSS_HINGE><<<grid, UPD_WARPS * 32, 0, st>>>(a);
+      launch_pdl(k_update<V, N, FAST, MFB_LOSS_HINGE>, grid, UPD_WARPS * 32, st, a);
       break;
     default:
-      k_update<V, N, FAST, MFB_LOSS_ADAPTIVE_HINGE><<<grid, UPD_WARPS * 32, 0, st>>>(a);
+      launch_pdl(k_update<V, N, FAST, MFB_LOSS_ADAPTIVE_HINGE>, grid, UPD_WARPS * 32, st, a);
       break;
   }
 }
@@ -1236,9 +1267,9 @@ static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom
     float *pred = pred_chunk + (size_t)s * Lfull;
     const int neg_begin = g.adaptive ? b : -1;
     tk = m->prof.begin(PK_FORWARD, st);
-#define CALL(V, N)                                                                                                 \
-  k_forward<V, N><<<grid_for_warps(L), BLOCK_THREADS, 0, st>>>(su, si, L, m->users, m->items, D, snap_u, snap_i, pred, \
-                                                                neg_begin, gmax + s)
+#define CALL(V, N)                                                                                             \
+  launch_pdl(k_forward<V, N>, grid_for_warps(L), BLOCK_THREADS, st, su, si, L, m->users, m->items, D, snap_u, snap_i, \
+             pred, neg_begin, gmax + s)
     MFB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
     m->prof.end(tk, st);
