@@ -177,7 +177,8 @@ int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int
 int mfb_topk_last_redo(const mfb_model *m);
 /* Test hook: raw tensor-core scores (bf16 inputs, fp32 accumulate, + item bias), item-major
  * [num_items][ceil(n_users/256)*256]; embedding_dim 64 or 128 only. */
-/* Debug: candidate-list statistics of the last tensor-core mfb_topk call: {users, total, max, over capacity}. */
+/* Debug: candidate-list statistics of the last tensor-core mfb_topk call, h_out[5]:
+ * {users, listed items total, max per user, users over capacity, items re-scored exactly}. */
 int mfb_debug_tc_stats(mfb_model *m, int64_t n_users, int64_t *h_out, mfb_stream stream);
 int mfb_debug_tc_scores(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, float *d_out, mfb_stream stream);
 

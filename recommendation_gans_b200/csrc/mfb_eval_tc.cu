@@ -31,7 +31,8 @@ namespace {
 
 constexpr int TC_M = 128;          // items per tile (MMA M)
 constexpr int TC_N = 256;          // users per CTA (MMA N)
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 3;
+constexpr int TC_SROW = 36;        // row stride (floats) of an epilogue warp's 32x32 score tile: conflict-free 16-byte stores
 constexpr int TC_EPI_WARPS = 8;    // two per TMEM lane quarter, each owning half of the user columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_KATOM = 64;       // bf16 elements per 128-byte swizzle atom
@@ -64,6 +65,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// same, for the single-thread producer / MMA roles: back off between polls so the spinning thread does not
+// take issue slots from the epilogue warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
   asm volatile(
@@ -131,17 +150,38 @@ __device__ __forceinline__ int float_to_ordered(float f) {
 }
 __device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
+// Item layout of the GEMM's A operand.  Item ids correlate with popularity in real catalogs (and in Zipf-drawn
+// synthetic ones), which would put all of a user's best items into a handful of 32-item groups and make the
+// sampled group maxima useless as a bound.  Items are therefore dealt round-robin over the T tiles and, inside
+// a tile, spread over the four 32-lane quarters:  position = (item % T) * 128 + ((item / T) * 37 & 127).
+// 37 * 45 = 1 (mod 128), so  item = ((slot * 45) & 127) * T + tile.  Positions whose item >= num_items are padding.
+__device__ __forceinline__ int tc_item_of(int tile, int slot, int T) { return ((slot * 45) & 127) * T + tile; }
+__device__ __forceinline__ int tc_pos_of(int item, int T) {
+  const int j = item / T;
+  return (item - j * T) * TC_M + ((j * 37) & 127);
+}
+
 // ---------------------------------------------------------------------------------------------
 // 1. fp32 -> bf16 row conversion (+ row norms).  rows_out >= rows: padding rows are zero.
 //    `ids` (may be null) selects which source rows to convert (the evaluated users, in list order).
+//    perm_T > 0: destination row r is a tile position, the source row is tc_item_of(r); the item biases are
+//    copied into position order too.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_tc_convert(const float *__restrict__ src, const long long *__restrict__ ids, int rows, int rows_out,
-                             int D, __nv_bfloat16 *__restrict__ dst, float *__restrict__ norm) {
+                             int D, __nv_bfloat16 *__restrict__ dst, float *__restrict__ norm, float norm_scale,
+                             int perm_T, const float *__restrict__ bias_src, float *__restrict__ bias_dst) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows_out) return;
   float ss = 0.f;
-  const long long srow = (r < rows) ? (ids ? ids[r] : r) : -1;
+  long long srow;
+  if (perm_T > 0) {
+    const int it = tc_item_of(r >> 7, r & 127, perm_T);
+    srow = (it < rows) ? it : -1;
+    if (lane == 0 && bias_dst) bias_dst[r] = (srow >= 0) ? bias_src[srow] : 0.f;
+  } else {
+    srow = (r < rows) ? (ids ? ids[r] : r) : -1;
+  }
   for (int d = lane; d < D; d += 32) {
     float x = (srow >= 0) ? src[srow * D + d] : 0.f;
     dst[(long long)r * D + d] = __float2bfloat16_rn(x);
@@ -149,21 +189,7 @@ __global__ void k_tc_convert(const float *__restrict__ src, const long long *__r
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if (lane == 0 && norm) norm[r] = sqrtf(ss);
-}
-
-__global__ void k_tc_maxnorm(const float *__restrict__ norm, int n, float *__restrict__ out) {
-  __shared__ float sh[32];
-  float m = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, norm[i]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sh[w]);
-    *out = m;
-  }
+  if (lane == 0 && norm) norm[r] = norm_scale * sqrtf(ss);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,19 +199,23 @@ struct TcArgs {
   int num_items, n_users;       // valid rows of A / B
   int D;                        // multiple of 64, <= 256
   int tile_begin, tile_step, n_tiles;   // item tiles processed: tile_begin + i*tile_step, i < n_tiles
-  const float *item_bias;       // [num_items]
+  int total_tiles;              // T of the item layout (all tiles of the catalog)
+  const float *item_bias;       // [items_pad]  item biases in position order
+  const float *item_norm;       // [items_pad]  err_coeff * L2 norm of each fp32 item row, position order, where
+                                //              |bf16 score - fp32 score| <= err_coeff * |u| * |v|
+  const float *user_norm;       // [n_users_pad] L2 norm of each evaluated user's row
   // MODE_MAX: gmax[(i*4 + quarter) * n_users_pad + user]  (ordered-int encoded)
   int *gmax;
   int n_users_pad;
   // MODE_COLLECT
   const float *thr;             // [n_users_pad] collection threshold per user
-  int *cand;                    // [n_users][cap]: item ids
+  int2 *cand;                   // [n_users][cap]: (item id, bf16-GEMM score incl. item bias, as float bits)
   int *cand_cnt;                // [n_users_pad]
   int cap;
   // MODE_DUMP
   float *dump;                  // [num_items_pad][n_users_pad]
   // train mask (MODE_MAX / MODE_COLLECT; null = no mask): for CTA c, the (item, user-column) train pairs bucketed by
-  // 32-item group g: mask_pairs[mask_base[c] + mask_ptr[c*(ngroups+1) + g] ...), entry = (item & 31) | (column << 5)
+  // 32-position group g: mask_pairs[mask_base[c] + mask_ptr[c*(ngroups+1) + g] ...), entry = (position & 31) | (column << 5)
   const uint16_t *mask_pairs;
   const int *mask_ptr;
   const long long *mask_base;
@@ -199,7 +229,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
           const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // carve shared memory (1024-byte aligned operand buffers for the 128B swizzle)
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the shared-window address keeps every derived pointer a known shared-memory pointer,
+  // so the compiler emits LDS / STS / ATOMS instead of generic accesses)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int katoms = a.D / TC_KATOM;
   const uint32_t b_bytes = (uint32_t)TC_N * 128u * katoms;       // users, resident
   const uint32_t a_bytes = (uint32_t)TC_M * 128u * katoms;       // one item stage
@@ -214,7 +246,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 112);
   float *thr_s = reinterpret_cast<float *>(tail + 128);          // [TC_N]   (16-byte aligned from here on)
   int *cnt_s = reinterpret_cast<int *>(thr_s + TC_N);            // [TC_N]
-  uint32_t *mask_s = reinterpret_cast<uint32_t *>(cnt_s + TC_N); // [4 warps][32 lanes][8 words]: train-mask bits
+  uint32_t *mask_s = reinterpret_cast<uint32_t *>(cnt_s + TC_N); // [8 warps][32 lanes][4 words]: train-mask bits
+  float *nu_s = reinterpret_cast<float *>(mask_s + 4 * 32 * 8);  // [TC_N] user-row norms
+  float *sc_s = nu_s + TC_N;                                     // [8 warps][32][TC_SROW]: scores of the current chunk
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * TC_N;
@@ -245,6 +279,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       cnt_s[i] = 0;
     }
   }
+  if (MODE != MODE_DUMP) {
+    for (int i = threadIdx.x; i < TC_N; i += TC_THREADS) nu_s[i] = (u0 + i < a.n_users) ? a.user_norm[u0 + i] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -259,7 +296,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       for (int i = 0; i < a.n_tiles; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-        mbar_wait(empty + s, ph ^ 1u);
+        mbar_wait_backoff(empty + s, ph ^ 1u);
         mbar_expect_tx(full + s, a_bytes);
         const int row0 = (a.tile_begin + logical(i) * a.tile_step) * TC_M;
         for (int ka = 0; ka < katoms; ++ka)
@@ -272,15 +309,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     // both K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     if (lane == 0) {
-      mbar_wait(bfull, 0);
+      mbar_wait_backoff(bfull, 0);
       tc_fence_after();
       for (int i = 0; i < a.n_tiles; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
         const int b = i & 1;
         const uint32_t bph = (uint32_t)(i >> 1) & 1u;
-        mbar_wait(tempty + b, bph);          // accumulator drained AND the item bias pre-stored by the epilogue
-        mbar_wait(full + s, ph);             // item tile landed
+        mbar_wait_backoff(tempty + b, bph);  // accumulator drained AND the item bias pre-stored by the epilogue
+        mbar_wait_backoff(full + s, ph);     // item tile landed
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(b * TC_N);
         for (int ka = 0; ka < katoms; ++ka) {
@@ -305,29 +342,37 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     uint32_t *mrow = mbase + lane * 4;
     const uint16_t *pairs = use_mask ? a.mask_pairs + a.mask_base[blockIdx.x] : nullptr;
     const int *mp_row = use_mask ? a.mask_ptr + (long long)blockIdx.x * (a.ngroups + 1) : nullptr;
-    // group range and first 32 pairs of a tile, fetched one tile ahead of their use
-    int pf_lo = 0, pf_hi = 0;
-    uint32_t pf_e = 0, pf_e2 = 0;
-    auto prefetch_mask = [&](int tile_idx) {
-      pf_lo = pf_hi = 0;
+    // train pairs of a tile: the group's range is fetched two tiles ahead and its first 64 pairs one tile ahead,
+    // so that no load is issued with an address that is still in flight
+    int pf_lo = 0, pf_hi = 0, nx_lo = 0, nx_hi = 0;      // ranges of the current / next tile
+    uint32_t pf_e = 0, pf_e2 = 0;                         // pairs of the current tile
+    auto load_range = [&](int tile_idx, int &lo, int &hi) {
+      lo = hi = 0;
       if (use_mask && tile_idx < a.n_tiles) {
         const int g = (a.tile_begin + logical(tile_idx) * a.tile_step) * 4 + q;
         if (g < a.ngroups) {
-          pf_lo = mp_row[g];
-          pf_hi = mp_row[g + 1];
-          if (pf_lo + lane < pf_hi) pf_e = pairs[pf_lo + lane];
-          if (pf_lo + 32 + lane < pf_hi) pf_e2 = pairs[pf_lo + 32 + lane];
+          lo = mp_row[g];
+          hi = mp_row[g + 1];
         }
       }
+    };
+    auto load_pairs = [&](int lo, int hi, uint32_t &e, uint32_t &e2) {
+      if (lo + lane < hi) e = pairs[lo + lane];
+      if (lo + 32 + lane < hi) e2 = pairs[lo + 32 + lane];
     };
     auto mask_set = [&](uint32_t e) {   // e = (item & 31) | (column << 5); keep this warp's column half only
       const uint32_t col = e >> 5;
       if ((int)(col >> 7) == h) atomicOr(mbase + (e & 31u) * 4 + ((col >> 5) & 3u), 1u << (col & 31u));
     };
     auto load_bias = [&](int tile_idx) {
-      const int it = (a.tile_begin + logical(tile_idx < a.n_tiles ? tile_idx : 0) * a.tile_step) * TC_M + q * 32 + lane;
-      return (tile_idx < a.n_tiles && it < a.num_items && !(a.dbg & 8)) ? a.item_bias[it] : 0.f;
+      const int pos = (a.tile_begin + logical(tile_idx < a.n_tiles ? tile_idx : 0) * a.tile_step) * TC_M + q * 32 + lane;
+      return (tile_idx < a.n_tiles && !(a.dbg & 8)) ? a.item_bias[pos] : 0.f;
     };
+    auto load_norm = [&](int tile_idx) {   // error radius factor of this lane's item: err_coeff * |v_item| (pre-scaled)
+      const int pos = (a.tile_begin + logical(tile_idx < a.n_tiles ? tile_idx : 0) * a.tile_step) * TC_M + q * 32 + lane;
+      return (MODE != MODE_DUMP && tile_idx < a.n_tiles) ? a.item_norm[pos] : 0.f;
+    };
+    float nv = load_norm(0), nv_next = load_norm(1);
     auto prestore_bias = [&](float bi, int buf) {
       if (!(a.dbg & 16)) {
 #pragma unroll
@@ -339,16 +384,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + buf);
     };
-    prefetch_mask(0);
+    load_range(0, pf_lo, pf_hi);
+    load_range(1, nx_lo, nx_hi);
+    load_pairs(pf_lo, pf_hi, pf_e, pf_e2);
     for (int i = 0; i < 2 && i < a.n_tiles; ++i) prestore_bias(load_bias(i), i);
     for (int i = 0; i < a.n_tiles; ++i) {
       const int b = i & 1;
       const uint32_t bph = (uint32_t)(i >> 1) & 1u;
       const int li = logical(i);
-      const int tile = a.tile_begin + li * a.tile_step;
-      const int item = tile * TC_M + q * 32 + lane;
+      const int tile_id = a.tile_begin + li * a.tile_step;
+      const int item = tc_item_of(tile_id, q * 32 + lane, a.total_tiles);   // catalog id of this lane's row
       const bool item_ok = item < a.num_items;
       const float bias_next = load_bias(i + 2);   // in flight while this tile is processed
+      const float nv_next2 = load_norm(i + 2);
       // train mask of this tile's 32 items (lane = item) x this warp's 128 user columns, built while the MMA runs
       if (use_mask && !(a.dbg & 4)) {
         *reinterpret_cast<uint4 *>(mrow) = make_uint4(0u, 0u, 0u, 0u);
@@ -357,7 +405,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
         if (lo + lane < hi) mask_set(pf_e);
         if (lo + 32 + lane < hi) mask_set(pf_e2);
         for (int r = lo + 64 + lane; r < hi; r += 32) mask_set(pairs[r]);   // rare: more than 64 train pairs in the group
-        prefetch_mask(i + 1);   // loads complete while this tile's scores are processed
+        // loads for the coming tiles complete while this tile's scores are processed
+        pf_lo = nx_lo;
+        pf_hi = nx_hi;
+        load_pairs(pf_lo, pf_hi, pf_e, pf_e2);
+        load_range(i + 2, nx_lo, nx_hi);
         __syncwarp();
       }
       mbar_wait(tfull + b, bph);
@@ -378,8 +430,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
           // per column: max over the warp's 32 items, train items excluded.  Butterfly transpose-reduce:
           // after the 5 steps lane l holds the maximum of column c0 + l (31 shuffles for 32 columns).
           float x[32];
+          const float4 *n4 = reinterpret_cast<const float4 *>(nu_s + c0);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) x[c] = ((mword >> c) & 1u) ? -INFINITY : __uint_as_float(r[c]);
+          for (int c4 = 0; c4 < 8; ++c4) {   // approx - err <= exact: the group maximum of this is a certified lower bound
+            const float4 nu = n4[c4];
+            x[c4 * 4 + 0] = ((mword >> (c4 * 4 + 0)) & 1u) ? -INFINITY : fmaf(-nv, nu.x, __uint_as_float(r[c4 * 4 + 0]));
+            x[c4 * 4 + 1] = ((mword >> (c4 * 4 + 1)) & 1u) ? -INFINITY : fmaf(-nv, nu.y, __uint_as_float(r[c4 * 4 + 1]));
+            x[c4 * 4 + 2] = ((mword >> (c4 * 4 + 2)) & 1u) ? -INFINITY : fmaf(-nv, nu.z, __uint_as_float(r[c4 * 4 + 2]));
+            x[c4 * 4 + 3] = ((mword >> (c4 * 4 + 3)) & 1u) ? -INFINITY : fmaf(-nv, nu.w, __uint_as_float(r[c4 * 4 + 3]));
+          }
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) {
             const bool upper = (lane & off) != 0;
@@ -393,19 +452,30 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
           a.gmax[(long long)(li * 4 + q) * a.n_users_pad + (u0 + c0 + lane)] = float_to_ordered(x[0]);
         } else {
           // bit c of hw = this lane's item reaches user (c0+c)'s threshold; branch-free, then one warp-wide test
+          // approx + err >= exact: everything whose upper bound reaches the user's certified k-th-best bound
           const float4 *t4 = reinterpret_cast<const float4 *>(thr_s + c0);
+          const float4 *n4 = reinterpret_cast<const float4 *>(nu_s + c0);
           uint32_t hw = 0u;
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const float4 th = t4[c4];
-            hw |= (__uint_as_float(r[c4 * 4 + 0]) >= th.x ? 1u : 0u) << (c4 * 4 + 0);
-            hw |= (__uint_as_float(r[c4 * 4 + 1]) >= th.y ? 1u : 0u) << (c4 * 4 + 1);
-            hw |= (__uint_as_float(r[c4 * 4 + 2]) >= th.z ? 1u : 0u) << (c4 * 4 + 2);
-            hw |= (__uint_as_float(r[c4 * 4 + 3]) >= th.w ? 1u : 0u) << (c4 * 4 + 3);
+            const float4 nu = n4[c4];
+            hw |= (fmaf(nv, nu.x, __uint_as_float(r[c4 * 4 + 0])) >= th.x ? 1u : 0u) << (c4 * 4 + 0);
+            hw |= (fmaf(nv, nu.y, __uint_as_float(r[c4 * 4 + 1])) >= th.y ? 1u : 0u) << (c4 * 4 + 1);
+            hw |= (fmaf(nv, nu.z, __uint_as_float(r[c4 * 4 + 2])) >= th.z ? 1u : 0u) << (c4 * 4 + 2);
+            hw |= (fmaf(nv, nu.w, __uint_as_float(r[c4 * 4 + 3])) >= th.w ? 1u : 0u) << (c4 * 4 + 3);
           }
           hw &= ~mword;
           if (!(a.dbg & 2) && __any_sync(0xffffffffu, hw != 0u)) {
-            const int item0 = tile * TC_M + q * 32;
+            // the records carry the GEMM score (k_tc_rescore uses it to discard most of the list before the exact
+            // pass); a hit's column is only known at run time, so the chunk's scores go through shared memory
+            float *tile = sc_s + (warp - 2) * 32 * TC_SROW;
+            __syncwarp();
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4)
+              *reinterpret_cast<uint4 *>(tile + lane * TC_SROW + c4 * 4) =
+                  make_uint4(r[c4 * 4 + 0], r[c4 * 4 + 1], r[c4 * 4 + 2], r[c4 * 4 + 3]);
+            __syncwarp();
             if (!__any_sync(0xffffffffu, __popc(hw) > 2)) {
               // sparse hits (the common case): each lane appends its own one or two
               while (hw) {
@@ -413,7 +483,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
                 hw &= hw - 1u;
                 const int uu = c0 + c;
                 const int pos = atomicAdd(cnt_s + uu, 1);
-                if (pos < a.cap) a.cand[(long long)(u0 + uu) * a.cap + pos] = item;
+                if (pos < a.cap)
+                  a.cand[(long long)(u0 + uu) * a.cap + pos] = make_int2(item, __float_as_int(tile[lane * TC_SROW + c]));
               }
             } else {
               // a popular item hits for many users of the chunk: transpose the 32x32 hit matrix with ballots so
@@ -428,11 +499,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
               if (mine) {
                 const int uu = c0 + lane;
                 int pos = atomicAdd(cnt_s + uu, __popc(mine));
-                int *dst = a.cand + (long long)(u0 + uu) * a.cap;
+                int2 *dst = a.cand + (long long)(u0 + uu) * a.cap;
                 while (mine) {
                   const int src = __ffs(mine) - 1;
                   mine &= mine - 1u;
-                  if (pos < a.cap) dst[pos] = item0 + src;
+                  if (pos < a.cap)
+                    dst[pos] = make_int2(tc_item_of(tile_id, q * 32 + src, a.total_tiles),
+                                         __float_as_int(tile[src * TC_SROW + lane]));
                   ++pos;
                 }
               }
@@ -442,6 +515,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       }
       // hand the accumulator back: pre-store the bias of the tile that will use it next
       if (i + 2 < a.n_tiles) prestore_bias(bias_next, b);
+      nv = nv_next;
+      nv_next = nv_next2;
     }
   }
   // teardown
@@ -465,29 +540,58 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // train-mask structure for the GEMM epilogue, built on the device per mfb_topk call
 // ---------------------------------------------------------------------------------------------
-__global__ void k_tc_user_counts(const long long *__restrict__ user_ids, const long long *__restrict__ indptr,
-                                 int n_users, int n_groups_u, long long *__restrict__ cta_cnt) {
-  // one thread per CTA-group of 256 users: total train entries of the group
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_groups_u) return;
-  long long tot = 0;
-  for (int p = c * TC_N; p < (c + 1) * TC_N && p < n_users; ++p) {
+__global__ void __launch_bounds__(TC_N) k_tc_user_counts(const long long *__restrict__ user_ids,
+                                                         const long long *__restrict__ indptr, int n_users,
+                                                         long long *__restrict__ cta_cnt) {
+  // one block per CTA-group of 256 users (one thread per user): total train entries of the group
+  __shared__ long long wsum[TC_N / 32];
+  const int p = blockIdx.x * TC_N + threadIdx.x;
+  long long v = 0;
+  if (p < n_users) {
     const long long uid = user_ids[p];
-    tot += indptr[uid + 1] - indptr[uid];
+    v = indptr[uid + 1] - indptr[uid];
   }
-  cta_cnt[c] = tot;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tot = 0;
+    for (int w = 0; w < TC_N / 32; ++w) tot += wsum[w];
+    cta_cnt[blockIdx.x] = tot;
+  }
 }
 
-__global__ void k_tc_scan_ll(const long long *__restrict__ in, int n, long long *__restrict__ out) {
-  // tiny exclusive scan (n = number of CTAs, a few hundred): one thread
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    long long run = 0;
-    for (int i = 0; i < n; ++i) {
-      out[i] = run;
-      run += in[i];
+__global__ void __launch_bounds__(1024) k_tc_scan_ll(const long long *__restrict__ in, int n,
+                                                     long long *__restrict__ out) {
+  // exclusive scan of the per-CTA totals (a few hundred values), one block; out[n] = grand total
+  __shared__ long long wtot[32];
+  __shared__ long long carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += 1024) {
+    const int i = start + tid;
+    const long long v = (i < n) ? in[i] : 0;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
     }
-    out[n] = run;
+    if (lane == 31) wtot[wid] = x;
+    __syncthreads();
+    long long before = carry_s, all = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < wid) before += wtot[w];
+      all += wtot[w];
+    }
+    if (i < n) out[i] = before + x - v;
+    __syncthreads();
+    if (tid == 0) carry_s += all;
+    __syncthreads();
   }
+  if (tid == 0) out[n] = carry_s;
 }
 
 // One block per CTA-group: counting sort of the group's (item, column) train pairs by 32-item group.
@@ -495,8 +599,8 @@ __global__ void k_tc_scan_ll(const long long *__restrict__ in, int n, long long 
 __global__ void __launch_bounds__(256) k_tc_mask_build(const long long *__restrict__ user_ids,
                                                        const long long *__restrict__ indptr,
                                                        const int *__restrict__ indices, int n_users, int ngroups,
-                                                       const long long *__restrict__ base, int *__restrict__ mask_ptr,
-                                                       uint16_t *__restrict__ pairs) {
+                                                       int total_tiles, const long long *__restrict__ base,
+                                                       int *__restrict__ mask_ptr, uint16_t *__restrict__ pairs) {
   extern __shared__ int mb_smem[];
   int *hist = mb_smem;   // [ngroups + 1]
   __shared__ int carry_s, warp_tot[8];
@@ -509,7 +613,7 @@ __global__ void __launch_bounds__(256) k_tc_mask_build(const long long *__restri
   for (int p = p0 + wid; p < p0 + TC_N && p < n_users; p += 8) {
     const long long uid = user_ids[p];
     const long long lo = indptr[uid], hi = indptr[uid + 1];
-    for (long long e = lo + lane; e < hi; e += 32) atomicAdd(hist + (indices[e] >> 5), 1);
+    for (long long e = lo + lane; e < hi; e += 32) atomicAdd(hist + (tc_pos_of(indices[e], total_tiles) >> 5), 1);
   }
   __syncthreads();
   // exclusive scan of hist[0..ngroups) in chunks of 256
@@ -549,14 +653,57 @@ __global__ void __launch_bounds__(256) k_tc_mask_build(const long long *__restri
     const long long lo = indptr[uid], hi = indptr[uid + 1];
     const uint32_t col = (uint32_t)(p - p0);
     for (long long e = lo + lane; e < hi; e += 32) {
-      const int item = indices[e];
-      const int at = atomicAdd(hist + (item >> 5), 1);
-      out[at] = (uint16_t)((item & 31) | (col << 5));
+      const int pos = tc_pos_of(indices[e], total_tiles);
+      const int at = atomicAdd(hist + (pos >> 5), 1);
+      out[at] = (uint16_t)((pos & 31) | (col << 5));
     }
   }
 }
 
 constexpr int TH_VPL = 8;   // group maxima per lane -> up to 256 groups per user
+
+// m-th largest group maximum, one THREAD per user (m <= K): the K largest keys are kept sorted in registers
+// by a branch-free insertion (one max/min pair per slot); the loads of consecutive users coalesce.
+template <int K>
+__global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restrict__ gmax, int groups, int n_users,
+                                                            int n_users_pad, int m, float *__restrict__ thr,
+                                                            float *__restrict__ eps_out) {
+  const int u = blockIdx.x * 128 + threadIdx.x;
+  if (u >= n_users) return;
+  int top[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) top[j] = INT_MIN;
+  const int *col = gmax + u;
+  int g = 0;
+  for (; g + 4 <= groups; g += 4) {
+    int v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = col[(long long)(g + t) * n_users_pad];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int hi = max(top[j], v[t]);
+        v[t] = min(top[j], v[t]);
+        top[j] = hi;
+      }
+    }
+  }
+  for (; g < groups; ++g) {
+    int v = col[(long long)g * n_users_pad];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int hi = max(top[j], v);
+      v = min(top[j], v);
+      top[j] = hi;
+    }
+  }
+  int r = INT_MIN;
+#pragma unroll
+  for (int j = 0; j < K; ++j) r = (j == m - 1) ? top[j] : r;
+  thr[u] = (m <= groups && r != INT_MIN) ? ordered_to_float(r) : -INFINITY;   // -inf: the user goes to the exact path
+  eps_out[u] = 0.f;
+}
 
 __global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gmax, int groups, int n_users,
                                                       int n_users_pad, int k, const long long *__restrict__ user_ids,
@@ -572,9 +719,11 @@ __global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gm
     const long long uid = user_ids[u];
     ntrain = indptr[uid + 1] - indptr[uid];
   }
-  // bf16 rounding: each operand within 2^-8 relative -> products within ~2^-7; Cauchy-Schwarz over the row
-  const float eps = 0.0084f * unorm[u] * vmax[0] + 1e-30f;
-  if (lane == 0) eps_out[u] = eps;
+  // the group maxima are already lower bounds of exact scores (approx - err_coeff*|u|*|v|), so the m-th largest
+  // is a certified lower bound of the m-th best exact score: no further margin is needed
+  if (lane == 0) eps_out[u] = 0.f;
+  (void)unorm;
+  (void)vmax;
   long long m = (long long)k + ntrain;
   if (m > groups) {
     if (lane == 0) thr[u] = -INFINITY;   // cannot bound: the user goes to the exact path
@@ -604,53 +753,97 @@ __global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gm
     }
     mask = tmask;
   }
-  // collect everything within 4 eps of the bound: the k sampled items behind the bound have exact scores >=
-  // bound - eps, which is what k_tc_rescore certifies against (thr + 3 eps)
-  if (lane == 0) thr[u] = ordered_to_float((int)(prefix ^ 0x80000000u)) - 4.0f * eps;
+  if (lane == 0) thr[u] = ordered_to_float((int)(prefix ^ 0x80000000u));
 }
 
 // ---------------------------------------------------------------------------------------------
 // 4. exact re-score of the candidates + mask + top-k.  One warp per user.
 //    Exact score = sequential fp32 FMA over d = 0..D-1, then (+ user bias) + item bias: bit-identical to k_topk_exact.
 // ---------------------------------------------------------------------------------------------
-constexpr int RS_MAXC = 768;    // candidates kept per user (cap)
+constexpr int RS_MAXC = 512;    // candidates kept per user (cap)
 constexpr int RS_WARPS = 4;
 
-// smem per warp: user row [D] | exact scores [RS_MAXC] | ids [RS_MAXC]
+// smem per warp: user row [D] | scores [RS_MAXC] (upper bounds, then exact) | lower bounds [RS_MAXC] | ids [RS_MAXC]
 // (staging the candidate rows through shared memory with cp.async was measured 2x slower: the kernel is
-// latency-bound and the extra shared memory cuts the resident warps from 24 to 8 per SM)
+// latency-bound and the extra shared memory cuts the resident warps)
 __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     const long long *__restrict__ user_ids, int n_users, TableView users, TableView items, int D,
-    const int *__restrict__ cand, const int *__restrict__ cand_cnt, int cap, const float *__restrict__ thr,
-    const float *__restrict__ eps, const long long *__restrict__ indptr, const int *__restrict__ indices, int k,
-    int *__restrict__ out_ids, float *__restrict__ out_scores, int *__restrict__ redo_flag, int check_mask) {
+    const int2 *__restrict__ cand, const int *__restrict__ cand_cnt, int cap, const float *__restrict__ thr,
+    const float *__restrict__ unorm, const float *__restrict__ item_norm, int total_tiles,
+    const long long *__restrict__ indptr, const int *__restrict__ indices, int k, int *__restrict__ out_ids,
+    float *__restrict__ out_scores, int *__restrict__ redo_flag, int *__restrict__ surv_cnt, int check_mask) {
   extern __shared__ __align__(16) float rs_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u = blockIdx.x * RS_WARPS + wib;
-  float *urow = rs_smem + (size_t)wib * (D + 2 * RS_MAXC);
-  float *sc = urow + D;                                    // exact scores
-  int *ids = reinterpret_cast<int *>(sc + RS_MAXC);
+  float *urow = rs_smem + (size_t)wib * (D + 3 * RS_MAXC);
+  float *sc = urow + D;
+  float *lob = sc + RS_MAXC;
+  int *ids = reinterpret_cast<int *>(lob + RS_MAXC);
   if (u >= n_users) return;
   const long long uid = user_ids[u];
   const int cnt = cand_cnt[u];
-  if (cnt > cap || cnt > RS_MAXC || !(thr[u] > -INFINITY)) {   // overflow or no bound: exact path
-    if (lane == 0) redo_flag[u] = 1;
+  if (cnt > cap || cnt > RS_MAXC || cnt < k || !(thr[u] > -INFINITY)) {   // overflow or no bound: exact path
+    if (lane == 0) {
+      redo_flag[u] = 1;
+      surv_cnt[u] = 0;
+    }
     return;
   }
   for (int d = lane * 4; d < D; d += 128) *reinterpret_cast<float4 *>(urow + d) = *reinterpret_cast<const float4 *>(users.p + uid * D + d);
-  __syncwarp();
   const float ub = users.bp[uid];
   long long tlo = 0, thi = 0;
   if (indptr && check_mask) {    // (the GEMM epilogue already dropped train items when it applied the mask itself)
     tlo = indptr[uid];
     thi = indptr[uid + 1];
   }
-  // any item outside the list has approx < thr, i.e. exact < thr + eps; k listed, unmasked items with
-  // exact >= thr + 3 eps (two spare eps for safety) prove the exact top-k lies inside the list
-  const float certify = thr[u] + 3.0f * eps[u];
-  int good = 0;
+  // ---- 1. bounds of every listed item's exact score from its GEMM score: [s - e, s + e], e = err_coeff*|u|*|v|
+  const float nu = unorm[u];
   for (int c = lane; c < cnt; c += 32) {
-    const int my_item = cand[(long long)u * cap + c];
+    const int2 rec = cand[(long long)u * cap + c];
+    const float e = item_norm[tc_pos_of(rec.x, total_tiles)];
+    const float sg = __int_as_float(rec.y);
+    ids[c] = rec.x;
+    sc[c] = fmaf(e, nu, sg);
+    lob[c] = fmaf(-e, nu, sg);
+  }
+  __syncwarp();
+  // ---- 2. the k-th largest lower bound L: at least k listed items have exact score >= L, so an item whose upper
+  // bound is below L is strictly below the k-th best and cannot be in the top-k.  Radix select from the top bit.
+  int n_surv = cnt;
+  if (!check_mask) {   // (with the mask applied here instead of in the GEMM, listed items may be train items: no filter)
+    uint32_t prefix = 0, mask = 0;
+    int want = k;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t test = prefix | (1u << bit), tmask = mask | (1u << bit);
+      int c1 = 0;
+      for (int c = lane; c < cnt; c += 32)
+        c1 += ((((uint32_t)float_to_ordered(lob[c]) ^ 0x80000000u) & tmask) == test) ? 1 : 0;
+      c1 = __reduce_add_sync(0xffffffffu, c1);
+      if (c1 >= want) prefix = test; else want -= c1;
+      mask = tmask;
+    }
+    const float L = ordered_to_float((int)(prefix ^ 0x80000000u));
+    // compact the survivors (upper bound >= L) to the front, order preserved
+    n_surv = 0;
+    for (int base = 0; base < cnt; base += 32) {
+      const int c = base + lane;
+      const bool keep = c < cnt && sc[c] >= L;
+      const int id = c < cnt ? ids[c] : 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) ids[n_surv + __popc(bal & ((1u << lane) - 1u))] = id;
+      n_surv += __popc(bal);
+      __syncwarp();
+    }
+  }
+  if (lane == 0) surv_cnt[u] = n_surv;
+  // ---- 3. exact scores of the survivors
+  // every item outside the list has exact <= approx + err < thr; k listed, unmasked items with exact >= thr
+  // (guaranteed by construction: the sampled items behind the bound are listed) prove the top-k is inside the list
+  const float certify = thr[u];
+  int good = 0;
+  for (int c = lane; c < n_surv; c += 32) {
+    const int my_item = ids[c];
     const float *v = items.p + (long long)my_item * D;
     const float ib = items.bp[my_item];
     // exact score: sequential fp32 FMA over d = 0..D-1 (bit-identical to k_topk_exact); 8 row loads in flight
@@ -679,7 +872,6 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     if (masked) z = MASKED_SCORE_TC;
     else if (zc >= certify) ++good;
     sc[c] = z;
-    ids[c] = my_item;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) good += __shfl_xor_sync(0xffffffffu, good, o);
@@ -688,11 +880,11 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     return;
   }
   __syncwarp();
-  // k rounds of warp arg-max on (score desc, id asc); winners are removed
+  // ---- 4. k rounds of warp arg-max on (score desc, id asc); winners are removed
   for (int r = 0; r < k; ++r) {
     float bv = -INFINITY;
     int bi = 0x7fffffff, bc = -1;
-    for (int c = lane; c < cnt; c += 32) {
+    for (int c = lane; c < n_surv; c += 32) {
       const float z = sc[c];
       const int id = ids[c];
       if (id >= 0 && (z > bv || (z == bv && id < bi))) {
@@ -781,7 +973,8 @@ int make_tmap(CUtensorMap *map, void *base, int rows, int D, int box_rows) {
 
 size_t tc_smem_bytes(int D) {
   const int katoms = D / TC_KATOM;
-  return 1024 + (size_t)TC_N * 128 * katoms + (size_t)TC_STAGES * TC_M * 128 * katoms + 256 + TC_N * 8 + 4 * 32 * 8 * 4;
+  return 1024 + (size_t)TC_N * 128 * katoms + (size_t)TC_STAGES * TC_M * 128 * katoms + 256 + TC_N * 12 + 4 * 32 * 8 * 4 +
+         (size_t)TC_EPI_WARPS * 32 * TC_SROW * 4;
 }
 
 template <int MODE>
@@ -823,26 +1016,31 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__nv_bfloat16)));
   MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__nv_bfloat16)));
   MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
-  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * sizeof(float) + 16));
+  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * 2 * sizeof(float) + 16));
   MFB_CHECK(eb.gmax.reserve((size_t)groups * n_users_pad * sizeof(int)));
   MFB_CHECK(eb.thr.reserve((size_t)n_users_pad * 2 * sizeof(float)));
-  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * cap * sizeof(int)));
-  MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * 3 + 64));
+  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * cap * sizeof(int2)));
+  MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * 4 + 64));
   MFB_CHECK(eb.redo.reserve((size_t)n_users_pad * (sizeof(long long) + (size_t)k * (sizeof(int) + sizeof(float))) + 64));
   __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
   float *unorm = eb.unorm.as<float>(), *vnorm = eb.vnorm.as<float>();
-  float *vmax = vnorm + items_pad;
+  float *vbias = vnorm + items_pad;   // item biases in position order
   float *thr = eb.thr.as<float>(), *eps = thr + n_users_pad;
   int *cand_cnt = eb.cnt.as<int>();
   int *redo_flag = cand_cnt + n_users_pad;
   int *redo_pos = redo_flag + n_users_pad;
-  int *redo_cnt = redo_pos + n_users_pad;
+  int *surv_cnt = redo_pos + n_users_pad;
+  int *redo_cnt = surv_cnt + n_users_pad;
 
   int tk = m->prof.begin(PK_TOPK, st, 8);
   k_tc_convert<<<(n_users_pad + 7) / 8, 256, 0, st>>>(m->users.p, (const long long *)d_user_ids, n_users, n_users_pad, D,
-                                                     ub, unorm);
-  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, vnorm);
-  k_tc_maxnorm<<<1, 1024, 0, st>>>(vnorm, I, vmax);
+                                                     ub, unorm, 1.0f, 0, nullptr, nullptr);
+  // bf16 round-to-nearest: each operand within 2^-9 relative (8 significant bits), so each product within
+  // 2^-8 + 2^-18; sum over the row bounded by Cauchy-Schwarz; fp32 accumulation of 128 terms adds < 1e-5 relative.
+  // 0.0042 = 2^-8 * 1.075 leaves 7% slack.  The item norms are stored pre-multiplied by it.
+  const float err_coeff = 0.0042f;
+  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, vnorm, err_coeff, i_tiles,
+                                                    m->items.bp, vbias);
   MFB_KERNEL_CHECK();
 
   CUtensorMap map_items, map_users;
@@ -854,21 +1052,24 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.num_items = I;
   a.n_users = n_users;
   a.D = D;
-  a.item_bias = m->items.bp;
+  a.total_tiles = i_tiles;
+  a.item_bias = vbias;
+  a.item_norm = vnorm;
+  a.user_norm = unorm;
   a.n_users_pad = n_users_pad;
   if (const char *e = getenv("MFB_TC_DBG")) a.dbg = atoi(e);
   // train mask for the epilogue: per-CTA (item, column) pairs bucketed by 32-item group
   const int ncta = n_users_pad / TC_N;
-  const int ngroups = (I + 31) / 32;
+  const int ngroups = i_tiles * 4;
   int masked_in_gemm = 0;
   if (d_train_indptr != nullptr && (size_t)(ngroups + 1) * sizeof(int) <= 200 * 1024) {
     MFB_CHECK(eb.mcnt.reserve((size_t)(2 * ncta + 2) * sizeof(long long)));
     MFB_CHECK(eb.mptr.reserve((size_t)ncta * (ngroups + 1) * sizeof(int)));
     long long *cta_cnt = eb.mcnt.as<long long>();
     long long *cta_base = cta_cnt + ncta + 1;
-    k_tc_user_counts<<<(ncta + 127) / 128, 128, 0, st>>>((const long long *)d_user_ids,
-                                                         (const long long *)d_train_indptr, n_users, ncta, cta_cnt);
-    k_tc_scan_ll<<<1, 32, 0, st>>>(cta_cnt, ncta, cta_base);
+    k_tc_user_counts<<<ncta, TC_N, 0, st>>>((const long long *)d_user_ids, (const long long *)d_train_indptr, n_users,
+                                            cta_cnt);
+    k_tc_scan_ll<<<1, 1024, 0, st>>>(cta_cnt, ncta, cta_base);
     MFB_KERNEL_CHECK();
     long long total_pairs = 0;
     MFB_CUDA(cudaMemcpyAsync(&total_pairs, cta_base + ncta, sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -877,7 +1078,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
     const size_t mb_smem = (size_t)(ngroups + 1) * sizeof(int);
     MFB_CUDA(cudaFuncSetAttribute(k_tc_mask_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb_smem));
     k_tc_mask_build<<<ncta, 256, mb_smem, st>>>((const long long *)d_user_ids, (const long long *)d_train_indptr,
-                                                d_train_indices, n_users, ngroups, cta_base, eb.mptr.as<int>(),
+                                                d_train_indices, n_users, ngroups, i_tiles, cta_base, eb.mptr.as<int>(),
                                                 eb.mpairs.as<uint16_t>());
     MFB_KERNEL_CHECK();
     a.mask_pairs = eb.mpairs.as<uint16_t>();
@@ -892,28 +1093,37 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.n_tiles = n_sample;
   a.gmax = eb.gmax.as<int>();
   MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st));
-  k_tc_threshold<<<(n_users + 3) / 4, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k,
-                                                        (const long long *)d_user_ids,
-                                                        (const long long *)d_train_indptr, unorm, vmax, thr, eps,
-                                                        masked_in_gemm);
+  if (masked_in_gemm && k <= 32) {   // group maxima already exclude train items: the bound is the k-th largest
+    const int tb = (n_users + 127) / 128;
+    if (k <= 8) k_tc_threshold_small<8><<<tb, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k, thr, eps);
+    else if (k <= 16) k_tc_threshold_small<16><<<tb, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k, thr, eps);
+    else if (k <= 24) k_tc_threshold_small<24><<<tb, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k, thr, eps);
+    else k_tc_threshold_small<32><<<tb, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k, thr, eps);
+  } else {
+    k_tc_threshold<<<(n_users + 3) / 4, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k,
+                                                      (const long long *)d_user_ids,
+                                                      (const long long *)d_train_indptr, unorm, nullptr, thr, eps,
+                                                      masked_in_gemm);
+  }
   MFB_KERNEL_CHECK();
   // collect pass: all tiles
   a.tile_begin = 0;
   a.tile_step = 1;
   a.n_tiles = i_tiles;
   a.thr = thr;
-  a.cand = eb.cand.as<int>();
+  a.cand = eb.cand.as<int2>();
   a.cand_cnt = cand_cnt;
   a.cap = cap;
   MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st));
   // exact re-score + mask + top-k
   MFB_CUDA(cudaMemsetAsync(redo_cnt, 0, sizeof(int), st));
-  const size_t rs_smem = (size_t)RS_WARPS * (D + 2 * RS_MAXC) * sizeof(float);
+  const size_t rs_smem = (size_t)RS_WARPS * (D + 3 * RS_MAXC) * sizeof(float);
   MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
   k_tc_rescore<<<(n_users + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>((const long long *)d_user_ids, n_users, m->users, m->items, D,
-                                                        eb.cand.as<int>(), cand_cnt, cap, thr, eps,
+                                                        eb.cand.as<int2>(), cand_cnt, cap, thr, unorm, vnorm, i_tiles,
                                                         (const long long *)d_train_indptr, d_train_indices, k,
-                                                        d_out_ids, d_out_scores, redo_flag, masked_in_gemm ? 0 : 1);
+                                                        d_out_ids, d_out_scores, redo_flag, surv_cnt,
+                                                        masked_in_gemm ? 0 : 1);
   MFB_KERNEL_CHECK();
   long long *redo_users = eb.redo.as<long long>();
   k_tc_compact_redo<<<(n_users + 255) / 256, 256, 0, st>>>(redo_flag, (const long long *)d_user_ids, n_users, redo_users,
@@ -936,7 +1146,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   return MFB_OK;
 }
 
-// debug: candidate-list statistics of the last tensor-core top-k call: {users, sum, max, over_cap}
+// debug: candidate-list statistics of the last tensor-core top-k call: {users, sum, max, over_cap, re-scored}
 int mfb_tc_stats(mfb_model *m, int n_users, long long *h_out, cudaStream_t st) {
   std::vector<int> cnt((size_t)n_users);
   MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.ptr, (size_t)n_users * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -951,6 +1161,14 @@ int mfb_tc_stats(mfb_model *m, int n_users, long long *h_out, cudaStream_t st) {
   h_out[1] = sum;
   h_out[2] = mx;
   h_out[3] = over;
+  // listed items that survived the bound filter and were re-scored exactly
+  const int n_users_pad = ((n_users + TC_N - 1) / TC_N) * TC_N;
+  MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.as<int>() + 3 * (size_t)n_users_pad, (size_t)n_users * sizeof(int),
+                           cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  long long surv = 0;
+  for (int c : cnt) surv += c;
+  h_out[4] = surv;
   return MFB_OK;
 }
 
@@ -964,11 +1182,12 @@ int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, flo
   MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__nv_bfloat16)));
   MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__nv_bfloat16)));
   MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
-  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * sizeof(float) + 16));
+  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * 2 * sizeof(float) + 16));
   __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
   k_tc_convert<<<(n_users_pad + 7) / 8, 256, 0, st>>>(m->users.p, (const long long *)d_user_ids, n_users, n_users_pad, D,
-                                                     ub, eb.unorm.as<float>());
-  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, eb.vnorm.as<float>());
+                                                     ub, eb.unorm.as<float>(), 1.0f, 0, nullptr, nullptr);
+  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, eb.vnorm.as<float>(), 1.0f,
+                                                    i_tiles, m->items.bp, eb.vnorm.as<float>() + items_pad);
   MFB_KERNEL_CHECK();
   CUtensorMap map_items, map_users;
   MFB_CHECK(make_tmap(&map_items, vb, items_pad, D, TC_M));
@@ -978,7 +1197,8 @@ int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, flo
   a.num_items = I;
   a.n_users = n_users;
   a.D = D;
-  a.item_bias = m->items.bp;
+  a.total_tiles = i_tiles;
+  a.item_bias = eb.vnorm.as<float>() + items_pad;
   a.n_users_pad = n_users_pad;
   a.tile_begin = 0;
   a.tile_step = 1;

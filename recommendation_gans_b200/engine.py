@@ -355,9 +355,10 @@ class MFEngine(object):
         return int(self._lib.mfb_topk_last_redo(self._handle))
 
     def debug_tc_stats(self, n_users):
-        out = np.zeros(4, dtype=np.int64)
+        out = np.zeros(5, dtype=np.int64)
         self._call('mfb_debug_tc_stats', int(n_users), N.hptr(out), N.stream_ptr())
-        return dict(users=int(out[0]), candidates=int(out[1]), max=int(out[2]), over_cap=int(out[3]))
+        return dict(users=int(out[0]), candidates=int(out[1]), max=int(out[2]), over_cap=int(out[3]),
+                    rescored=int(out[4]))
 
     def debug_tc_scores(self, user_ids):
         """Raw tensor-core scores [num_items, n_users_padded] (test hook)."""
