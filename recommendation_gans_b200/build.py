@@ -39,18 +39,24 @@ def is_stale():
     return any(os.path.getmtime(p) > built for p in deps)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, out=None, defines=()):
+    """Compile csrc/*.cu into lib/libmfb200.so.  `out` / `defines` build an experiment variant elsewhere
+    (e.g. defines=['MFB_TC_EPI_WARPS=8']); load it with $MFB_LIB_PATH."""
+    if out is None and not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + sources()
+    target = out or LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + \
+        ['-o', target] + sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError('nvcc failed:\n%s\n%s' % (' '.join(cmd), proc.stderr[-4000:]))
     if verbose:
         sys.stderr.write(proc.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == '__main__':
-    print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    _out = sys.argv[sys.argv.index('--out') + 1] if '--out' in sys.argv else None
+    _defs = [a[2:] for a in sys.argv if a.startswith('-D')]
+    print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv, out=_out, defines=_defs))

@@ -31,9 +31,19 @@ namespace {
 
 constexpr int TC_M = 128;          // items per tile (MMA M)
 constexpr int TC_N = 256;          // users per CTA (MMA N)
-constexpr int TC_STAGES = 3;
+#ifndef MFB_TC_STAGES
+#define MFB_TC_STAGES 2
+#endif
+#ifndef MFB_TC_EPI_WARPS
+#define MFB_TC_EPI_WARPS 16
+#endif
+constexpr int TC_STAGES = MFB_TC_STAGES;
 constexpr int TC_SROW = 36;        // row stride (floats) of an epilogue warp's 32x32 score tile: conflict-free 16-byte stores
-constexpr int TC_EPI_WARPS = 8;    // two per TMEM lane quarter, each owning half of the user columns
+constexpr int TC_EPI_WARPS = MFB_TC_EPI_WARPS;   // TC_NH per TMEM lane quarter, each owning TC_SPAN user columns
+constexpr int TC_NH = TC_EPI_WARPS / 4;
+constexpr int TC_SPAN = TC_N / TC_NH;            // user columns per epilogue warp
+constexpr int TC_WPL = TC_SPAN / 32;             // train-mask words per item row of a warp
+static_assert(TC_SPAN % 64 == 0, "the bias pre-store writes 64 columns at a time");
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_KATOM = 64;       // bf16 elements per 128-byte swizzle atom
 constexpr int MODE_DUMP = 0, MODE_MAX = 1, MODE_COLLECT = 2;
@@ -130,6 +140,24 @@ __device__ __forceinline__ void tc_st32_splat(uint32_t taddr, uint32_t v) {
       : "memory");
 }
 
+// two adjacent 32-column blocks from ONE register vector (a single asm statement, so the 32 splat registers are
+// materialised once instead of once per store)
+__device__ __forceinline__ void tc_st32_splat2(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 t2;\n\t"
+      "add.u32 t2, %0, 32;\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1};\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [t2], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1};\n\t"
+      "}" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
+
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start address >> 4 in [0,14), leading byte offset >> 4 in [16,30) (unused for swizzled K-major: 1),
 // stride byte offset >> 4 in [32,46) (1024 B between 8-row groups), version 1 in [46,48), SWIZZLE_128B = 2 in [61,64).
@@ -156,8 +184,9 @@ __device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float
 // a tile, spread over the four 32-lane quarters:  position = (item % T) * 128 + ((item / T) * 37 & 127).
 // 37 * 45 = 1 (mod 128), so  item = ((slot * 45) & 127) * T + tile.  Positions whose item >= num_items are padding.
 __device__ __forceinline__ int tc_item_of(int tile, int slot, int T) { return ((slot * 45) & 127) * T + tile; }
-__device__ __forceinline__ int tc_pos_of(int item, int T) {
-  const int j = item / T;
+// magic = ceil(2^32 / T) gives item / T = umulhi(item, magic) exactly while item * T < 2^32 (the host passes 0 otherwise)
+__device__ __forceinline__ int tc_pos_of(int item, int T, uint32_t magic) {
+  const int j = magic ? (int)__umulhi((uint32_t)item, magic) : item / T;
   return (item - j * T) * TC_M + ((j * 37) & 127);
 }
 
@@ -169,7 +198,8 @@ __device__ __forceinline__ int tc_pos_of(int item, int T) {
 // ---------------------------------------------------------------------------------------------
 __global__ void k_tc_convert(const float *__restrict__ src, const long long *__restrict__ ids, int rows, int rows_out,
                              int D, __nv_bfloat16 *__restrict__ dst, float *__restrict__ norm, float norm_scale,
-                             int perm_T, const float *__restrict__ bias_src, float *__restrict__ bias_dst) {
+                             int perm_T, const float *__restrict__ bias_src, float *__restrict__ bias_dst,
+                             float *__restrict__ norm_by_src) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows_out) return;
@@ -190,6 +220,7 @@ __global__ void k_tc_convert(const float *__restrict__ src, const long long *__r
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   if (lane == 0 && norm) norm[r] = norm_scale * sqrtf(ss);
+  if (lane == 0 && norm_by_src && srow >= 0) norm_by_src[srow] = norm_scale * sqrtf(ss);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -247,7 +278,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   float *thr_s = reinterpret_cast<float *>(tail + 128);          // [TC_N]   (16-byte aligned from here on)
   int *cnt_s = reinterpret_cast<int *>(thr_s + TC_N);            // [TC_N]
   uint32_t *mask_s = reinterpret_cast<uint32_t *>(cnt_s + TC_N); // [8 warps][32 lanes][4 words]: train-mask bits
-  float *nu_s = reinterpret_cast<float *>(mask_s + 4 * 32 * 8);  // [TC_N] user-row norms
+  float *nu_s = reinterpret_cast<float *>(mask_s + 4 * 32 * 8);  // [TC_N] user-row norms   (mask: 128 rows x 256 bits)
   float *sc_s = nu_s + TC_N;                                     // [8 warps][32][TC_SROW]: scores of the current chunk
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -334,12 +365,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   } else {
     // ===== epilogue warps: TMEM lane quarter q = warp % 4, column half h =====
     const int q = warp & 3;
-    const int h = (warp - 2) >> 2;                         // 0: user columns 0..127, 1: 128..255
-    const int col_lo = h * (TC_N / 2);
+    const int h = (warp - 2) >> 2;                         // column group: user columns [h*TC_SPAN, (h+1)*TC_SPAN)
+    const int col_lo = h * TC_SPAN;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
     const bool use_mask = (MODE != MODE_DUMP) && a.mask_pairs != nullptr;
-    uint32_t *mbase = mask_s + (warp - 2) * 32 * 4;         // this warp's [32 items][4 words] = 128 column bits
-    uint32_t *mrow = mbase + lane * 4;
+    uint32_t *mbase = mask_s + (warp - 2) * 32 * TC_WPL;    // this warp's [32 items][TC_WPL words] of column bits
+    uint32_t *mrow = mbase + lane * TC_WPL;
     const uint16_t *pairs = use_mask ? a.mask_pairs + a.mask_base[blockIdx.x] : nullptr;
     const int *mp_row = use_mask ? a.mask_ptr + (long long)blockIdx.x * (a.ngroups + 1) : nullptr;
     // train pairs of a tile: the group's range is fetched two tiles ahead and its first 64 pairs one tile ahead,
@@ -362,7 +393,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     };
     auto mask_set = [&](uint32_t e) {   // e = (item & 31) | (column << 5); keep this warp's column half only
       const uint32_t col = e >> 5;
-      if ((int)(col >> 7) == h) atomicOr(mbase + (e & 31u) * 4 + ((col >> 5) & 3u), 1u << (col & 31u));
+      if ((int)(col / TC_SPAN) == h)
+        atomicOr(mbase + (e & 31u) * TC_WPL + ((col % TC_SPAN) >> 5), 1u << (col & 31u));
     };
     auto load_bias = [&](int tile_idx) {
       const int pos = (a.tile_begin + logical(tile_idx < a.n_tiles ? tile_idx : 0) * a.tile_step) * TC_M + q * 32 + lane;
@@ -376,8 +408,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     auto prestore_bias = [&](float bi, int buf) {
       if (!(a.dbg & 16)) {
 #pragma unroll
-        for (int c0 = 0; c0 < TC_N / 2; c0 += 32)
-          tc_st32_splat(tmem_base + lane_addr + (uint32_t)(buf * TC_N + col_lo + c0), __float_as_uint(bi));
+        for (int c0 = 0; c0 < TC_SPAN; c0 += 64)
+          tc_st32_splat2(tmem_base + lane_addr + (uint32_t)(buf * TC_N + col_lo + c0), __float_as_uint(bi));
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       tc_fence_before();
@@ -399,7 +431,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       const float nv_next2 = load_norm(i + 2);
       // train mask of this tile's 32 items (lane = item) x this warp's 128 user columns, built while the MMA runs
       if (use_mask && !(a.dbg & 4)) {
-        *reinterpret_cast<uint4 *>(mrow) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int w = 0; w < TC_WPL; ++w) mrow[w] = 0u;
         __syncwarp();
         const int lo = pf_lo, hi = pf_hi;
         if (lo + lane < hi) mask_set(pf_e);
@@ -415,7 +448,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       mbar_wait(tfull + b, bph);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc0 = 0; cc0 < ((a.dbg & 1) ? 0 : TC_N / 2); cc0 += 32) {
+      for (int cc0 = 0; cc0 < ((a.dbg & 1) ? 0 : TC_SPAN); cc0 += 32) {
         const int c0 = col_lo + cc0;
         uint32_t r[32];
         TC_LD32(r, tmem_base + lane_addr + (uint32_t)(b * TC_N + c0));
@@ -429,42 +462,46 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
         } else if (MODE == MODE_MAX) {
           // per column: max over the warp's 32 items, train items excluded.  Butterfly transpose-reduce:
           // after the 5 steps lane l holds the maximum of column c0 + l (31 shuffles for 32 columns).
-          float x[32];
+          // The 32x32 block (lane = item, register = column) is transposed through the warp's shared-memory tile;
+          // lane l then reduces column c0 + l over the 32 items with 3-input max instructions.
+          float *tile = sc_s + (warp - 2) * 32 * TC_SROW;
           const float4 *n4 = reinterpret_cast<const float4 *>(nu_s + c0);
+          __syncwarp();
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {   // approx - err <= exact: the group maximum of this is a certified lower bound
             const float4 nu = n4[c4];
-            x[c4 * 4 + 0] = ((mword >> (c4 * 4 + 0)) & 1u) ? -INFINITY : fmaf(-nv, nu.x, __uint_as_float(r[c4 * 4 + 0]));
-            x[c4 * 4 + 1] = ((mword >> (c4 * 4 + 1)) & 1u) ? -INFINITY : fmaf(-nv, nu.y, __uint_as_float(r[c4 * 4 + 1]));
-            x[c4 * 4 + 2] = ((mword >> (c4 * 4 + 2)) & 1u) ? -INFINITY : fmaf(-nv, nu.z, __uint_as_float(r[c4 * 4 + 2]));
-            x[c4 * 4 + 3] = ((mword >> (c4 * 4 + 3)) & 1u) ? -INFINITY : fmaf(-nv, nu.w, __uint_as_float(r[c4 * 4 + 3]));
+            float4 x;
+            x.x = ((mword >> (c4 * 4 + 0)) & 1u) ? -INFINITY : fmaf(-nv, nu.x, __uint_as_float(r[c4 * 4 + 0]));
+            x.y = ((mword >> (c4 * 4 + 1)) & 1u) ? -INFINITY : fmaf(-nv, nu.y, __uint_as_float(r[c4 * 4 + 1]));
+            x.z = ((mword >> (c4 * 4 + 2)) & 1u) ? -INFINITY : fmaf(-nv, nu.z, __uint_as_float(r[c4 * 4 + 2]));
+            x.w = ((mword >> (c4 * 4 + 3)) & 1u) ? -INFINITY : fmaf(-nv, nu.w, __uint_as_float(r[c4 * 4 + 3]));
+            *reinterpret_cast<float4 *>(tile + lane * TC_SROW + c4 * 4) = x;
           }
+          __syncwarp();
+          float mx = -INFINITY;
 #pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int j = 0; j < off; ++j) {
-              const float give = upper ? x[j] : x[j + off];
-              const float keepv = upper ? x[j + off] : x[j];
-              x[j] = fmaxf(keepv, __shfl_xor_sync(0xffffffffu, give, off));
-            }
-          }
-          a.gmax[(long long)(li * 4 + q) * a.n_users_pad + (u0 + c0 + lane)] = float_to_ordered(x[0]);
+          for (int it = 0; it < 32; it += 2)
+            mx = fmaxf(mx, fmaxf(tile[it * TC_SROW + lane], tile[(it + 1) * TC_SROW + lane]));
+          a.gmax[(long long)(li * 4 + q) * a.n_users_pad + (u0 + c0 + lane)] = float_to_ordered(mx);
         } else {
           // bit c of hw = this lane's item reaches user (c0+c)'s threshold; branch-free, then one warp-wide test
           // approx + err >= exact: everything whose upper bound reaches the user's certified k-th-best bound
           const float4 *t4 = reinterpret_cast<const float4 *>(thr_s + c0);
           const float4 *n4 = reinterpret_cast<const float4 *>(nu_s + c0);
-          uint32_t hw = 0u;
+          // margin = (score + err) - threshold on the FMA pipe; its sign bit (1 = below the threshold) is funnel-
+          // shifted into one of four byte accumulators, columns taken from high to low so that column c lands on bit c
+          uint32_t wb[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
+          for (int c4 = 7; c4 >= 0; --c4) {
             const float4 th = t4[c4];
             const float4 nu = n4[c4];
-            hw |= (fmaf(nv, nu.x, __uint_as_float(r[c4 * 4 + 0])) >= th.x ? 1u : 0u) << (c4 * 4 + 0);
-            hw |= (fmaf(nv, nu.y, __uint_as_float(r[c4 * 4 + 1])) >= th.y ? 1u : 0u) << (c4 * 4 + 1);
-            hw |= (fmaf(nv, nu.z, __uint_as_float(r[c4 * 4 + 2])) >= th.z ? 1u : 0u) << (c4 * 4 + 2);
-            hw |= (fmaf(nv, nu.w, __uint_as_float(r[c4 * 4 + 3])) >= th.w ? 1u : 0u) << (c4 * 4 + 3);
+            uint32_t &w = wb[c4 >> 1];
+            w = __funnelshift_l(__float_as_uint(fmaf(nv, nu.w, __uint_as_float(r[c4 * 4 + 3])) - th.w), w, 1);
+            w = __funnelshift_l(__float_as_uint(fmaf(nv, nu.z, __uint_as_float(r[c4 * 4 + 2])) - th.z), w, 1);
+            w = __funnelshift_l(__float_as_uint(fmaf(nv, nu.y, __uint_as_float(r[c4 * 4 + 1])) - th.y), w, 1);
+            w = __funnelshift_l(__float_as_uint(fmaf(nv, nu.x, __uint_as_float(r[c4 * 4 + 0])) - th.x), w, 1);
           }
+          uint32_t hw = ~(wb[0] | (wb[1] << 8) | (wb[2] << 16) | (wb[3] << 24));
           hw &= ~mword;
           if (!(a.dbg & 2) && __any_sync(0xffffffffu, hw != 0u)) {
             // the records carry the GEMM score (k_tc_rescore uses it to discard most of the list before the exact
@@ -599,8 +636,9 @@ __global__ void __launch_bounds__(1024) k_tc_scan_ll(const long long *__restrict
 __global__ void __launch_bounds__(256) k_tc_mask_build(const long long *__restrict__ user_ids,
                                                        const long long *__restrict__ indptr,
                                                        const int *__restrict__ indices, int n_users, int ngroups,
-                                                       int total_tiles, const long long *__restrict__ base,
-                                                       int *__restrict__ mask_ptr, uint16_t *__restrict__ pairs) {
+                                                       int total_tiles, uint32_t magic,
+                                                       const long long *__restrict__ base, int *__restrict__ mask_ptr,
+                                                       uint16_t *__restrict__ pairs) {
   extern __shared__ int mb_smem[];
   int *hist = mb_smem;   // [ngroups + 1]
   __shared__ int carry_s, warp_tot[8];
@@ -613,7 +651,7 @@ __global__ void __launch_bounds__(256) k_tc_mask_build(const long long *__restri
   for (int p = p0 + wid; p < p0 + TC_N && p < n_users; p += 8) {
     const long long uid = user_ids[p];
     const long long lo = indptr[uid], hi = indptr[uid + 1];
-    for (long long e = lo + lane; e < hi; e += 32) atomicAdd(hist + (tc_pos_of(indices[e], total_tiles) >> 5), 1);
+    for (long long e = lo + lane; e < hi; e += 32) atomicAdd(hist + (tc_pos_of(indices[e], total_tiles, magic) >> 5), 1);
   }
   __syncthreads();
   // exclusive scan of hist[0..ngroups) in chunks of 256
@@ -653,7 +691,7 @@ __global__ void __launch_bounds__(256) k_tc_mask_build(const long long *__restri
     const long long lo = indptr[uid], hi = indptr[uid + 1];
     const uint32_t col = (uint32_t)(p - p0);
     for (long long e = lo + lane; e < hi; e += 32) {
-      const int pos = tc_pos_of(indices[e], total_tiles);
+      const int pos = tc_pos_of(indices[e], total_tiles, magic);
       const int at = atomicAdd(hist + (pos >> 5), 1);
       out[at] = (uint16_t)((pos & 31) | (col << 5));
     }
@@ -674,28 +712,25 @@ __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restric
 #pragma unroll
   for (int j = 0; j < K; ++j) top[j] = INT_MIN;
   const int *col = gmax + u;
-  int g = 0;
-  for (; g + 4 <= groups; g += 4) {
-    int v[4];
+  constexpr int NB = 8;          // loads in flight per thread; the next batch is issued before this one is inserted
+  int nxt[NB];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) v[t] = col[(long long)(g + t) * n_users_pad];
+  for (int t = 0; t < NB; ++t) nxt[t] = (t < groups) ? col[(long long)t * n_users_pad] : INT_MIN;
+  for (int g = 0; g < groups; g += NB) {
+    int v[NB];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < NB; ++t) v[t] = nxt[t];
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+      nxt[t] = (g + NB + t < groups) ? col[(long long)(g + NB + t) * n_users_pad] : INT_MIN;   // INT_MIN never enters
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
 #pragma unroll
       for (int j = 0; j < K; ++j) {
         const int hi = max(top[j], v[t]);
         v[t] = min(top[j], v[t]);
         top[j] = hi;
       }
-    }
-  }
-  for (; g < groups; ++g) {
-    int v = col[(long long)g * n_users_pad];
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      const int hi = max(top[j], v);
-      v = min(top[j], v);
-      top[j] = hi;
     }
   }
   int r = INT_MIN;
@@ -769,7 +804,7 @@ constexpr int RS_WARPS = 4;
 __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     const long long *__restrict__ user_ids, int n_users, TableView users, TableView items, int D,
     const int2 *__restrict__ cand, const int *__restrict__ cand_cnt, int cap, const float *__restrict__ thr,
-    const float *__restrict__ unorm, const float *__restrict__ item_norm, int total_tiles,
+    const float *__restrict__ unorm, const float *__restrict__ item_norm,
     const long long *__restrict__ indptr, const int *__restrict__ indices, int k, int *__restrict__ out_ids,
     float *__restrict__ out_scores, int *__restrict__ redo_flag, int *__restrict__ surv_cnt, int check_mask) {
   extern __shared__ __align__(16) float rs_smem[];
@@ -800,7 +835,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
   const float nu = unorm[u];
   for (int c = lane; c < cnt; c += 32) {
     const int2 rec = cand[(long long)u * cap + c];
-    const float e = item_norm[tc_pos_of(rec.x, total_tiles)];
+    const float e = item_norm[rec.x];   // err_coeff * |v|, indexed by item id
     const float sg = __int_as_float(rec.y);
     ids[c] = rec.x;
     sc[c] = fmaf(e, nu, sg);
@@ -811,13 +846,27 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
   // bound is below L is strictly below the k-th best and cannot be in the top-k.  Radix select from the top bit.
   int n_surv = cnt;
   if (!check_mask) {   // (with the mask applied here instead of in the GEMM, listed items may be train items: no filter)
+    // Only the top 20 key bits are resolved: the result is the k-th largest key with its low bits cleared, a
+    // slightly smaller -- still valid -- bound.  Lists of up to 128 items (the usual case) sit in registers.
     uint32_t prefix = 0, mask = 0;
     int want = k;
-    for (int bit = 31; bit >= 0; --bit) {
+    const bool small = cnt <= 128;
+    uint32_t kreg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = j * 32 + lane;
+      kreg[j] = (small && c < cnt) ? ((uint32_t)float_to_ordered(lob[c]) ^ 0x80000000u) : 0u;   // 0 never matches
+    }
+    for (int bit = 31; bit >= 12; --bit) {
       const uint32_t test = prefix | (1u << bit), tmask = mask | (1u << bit);
       int c1 = 0;
-      for (int c = lane; c < cnt; c += 32)
-        c1 += ((((uint32_t)float_to_ordered(lob[c]) ^ 0x80000000u) & tmask) == test) ? 1 : 0;
+      if (small) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c1 += ((kreg[j] & tmask) == test) ? 1 : 0;
+      } else {
+        for (int c = lane; c < cnt; c += 32)
+          c1 += ((((uint32_t)float_to_ordered(lob[c]) ^ 0x80000000u) & tmask) == test) ? 1 : 0;
+      }
       c1 = __reduce_add_sync(0xffffffffu, c1);
       if (c1 >= want) prefix = test; else want -= c1;
       mask = tmask;
@@ -880,7 +929,33 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     return;
   }
   __syncwarp();
-  // ---- 4. k rounds of warp arg-max on (score desc, id asc); winners are removed
+  // ---- 4. top-k by (score desc, id asc)
+  if (n_surv <= 32) {
+    // one survivor per lane: bitonic sort of 64-bit keys (ordered score : inverted id), largest first
+    unsigned long long key = 0ull;
+    if (lane < n_surv)
+      key = ((unsigned long long)((uint32_t)float_to_ordered(sc[lane]) ^ 0x80000000u) << 32) |
+            (unsigned long long)(uint32_t)(0x7fffffff - ids[lane]);
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+        const bool desc = (lane & k2) == 0;            // this block ends up largest-first (k2 == 32: everyone)
+        const bool lower = (lane & j) == 0;            // this lane keeps the block's "first" element of the pair
+        const bool take_max = (desc == lower);
+        key = take_max ? (key > other ? key : other) : (key < other ? key : other);
+      }
+    }
+    if (lane < k) {
+      const float bv = ordered_to_float((int)((uint32_t)(key >> 32) ^ 0x80000000u));
+      out_ids[(long long)u * k + lane] = 0x7fffffff - (int)(uint32_t)(key & 0xffffffffull);
+      if (out_scores) out_scores[(long long)u * k + lane] = (bv == MASKED_SCORE_TC) ? 0.f : 1.0f / (1.0f + expf(-bv));
+    }
+    if (lane == 0) redo_flag[u] = 0;
+    return;
+  }
+  // longer lists: k rounds of warp arg-max; winners are removed
   for (int r = 0; r < k; ++r) {
     float bv = -INFINITY;
     int bi = 0x7fffffff, bc = -1;
@@ -1016,7 +1091,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__nv_bfloat16)));
   MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__nv_bfloat16)));
   MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
-  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * 2 * sizeof(float) + 16));
+  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * 3 * sizeof(float) + 16));
   MFB_CHECK(eb.gmax.reserve((size_t)groups * n_users_pad * sizeof(int)));
   MFB_CHECK(eb.thr.reserve((size_t)n_users_pad * 2 * sizeof(float)));
   MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * cap * sizeof(int2)));
@@ -1025,6 +1100,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
   float *unorm = eb.unorm.as<float>(), *vnorm = eb.vnorm.as<float>();
   float *vbias = vnorm + items_pad;   // item biases in position order
+  float *vnorm_item = vbias + items_pad;   // scaled norms again, indexed by item id (for k_tc_rescore)
   float *thr = eb.thr.as<float>(), *eps = thr + n_users_pad;
   int *cand_cnt = eb.cnt.as<int>();
   int *redo_flag = cand_cnt + n_users_pad;
@@ -1034,13 +1110,13 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
 
   int tk = m->prof.begin(PK_TOPK, st, 8);
   k_tc_convert<<<(n_users_pad + 7) / 8, 256, 0, st>>>(m->users.p, (const long long *)d_user_ids, n_users, n_users_pad, D,
-                                                     ub, unorm, 1.0f, 0, nullptr, nullptr);
+                                                     ub, unorm, 1.0f, 0, nullptr, nullptr, nullptr);
   // bf16 round-to-nearest: each operand within 2^-9 relative (8 significant bits), so each product within
   // 2^-8 + 2^-18; sum over the row bounded by Cauchy-Schwarz; fp32 accumulation of 128 terms adds < 1e-5 relative.
   // 0.0042 = 2^-8 * 1.075 leaves 7% slack.  The item norms are stored pre-multiplied by it.
   const float err_coeff = 0.0042f;
   k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, vnorm, err_coeff, i_tiles,
-                                                    m->items.bp, vbias);
+                                                    m->items.bp, vbias, vnorm_item);
   MFB_KERNEL_CHECK();
 
   CUtensorMap map_items, map_users;
@@ -1061,6 +1137,9 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   // train mask for the epilogue: per-CTA (item, column) pairs bucketed by 32-item group
   const int ncta = n_users_pad / TC_N;
   const int ngroups = i_tiles * 4;
+  const uint32_t magic = ((uint64_t)items_pad * (uint64_t)i_tiles < (1ull << 32) && i_tiles > 1)
+                             ? (uint32_t)(((1ull << 32) + (uint64_t)i_tiles - 1) / (uint64_t)i_tiles)
+                             : 0u;
   int masked_in_gemm = 0;
   if (d_train_indptr != nullptr && (size_t)(ngroups + 1) * sizeof(int) <= 200 * 1024) {
     MFB_CHECK(eb.mcnt.reserve((size_t)(2 * ncta + 2) * sizeof(long long)));
@@ -1078,7 +1157,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
     const size_t mb_smem = (size_t)(ngroups + 1) * sizeof(int);
     MFB_CUDA(cudaFuncSetAttribute(k_tc_mask_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb_smem));
     k_tc_mask_build<<<ncta, 256, mb_smem, st>>>((const long long *)d_user_ids, (const long long *)d_train_indptr,
-                                                d_train_indices, n_users, ngroups, i_tiles, cta_base, eb.mptr.as<int>(),
+                                                d_train_indices, n_users, ngroups, i_tiles, magic, cta_base, eb.mptr.as<int>(),
                                                 eb.mpairs.as<uint16_t>());
     MFB_KERNEL_CHECK();
     a.mask_pairs = eb.mpairs.as<uint16_t>();
@@ -1120,7 +1199,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   const size_t rs_smem = (size_t)RS_WARPS * (D + 3 * RS_MAXC) * sizeof(float);
   MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
   k_tc_rescore<<<(n_users + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>((const long long *)d_user_ids, n_users, m->users, m->items, D,
-                                                        eb.cand.as<int2>(), cand_cnt, cap, thr, unorm, vnorm, i_tiles,
+                                                        eb.cand.as<int2>(), cand_cnt, cap, thr, unorm, vnorm_item,
                                                         (const long long *)d_train_indptr, d_train_indices, k,
                                                         d_out_ids, d_out_scores, redo_flag, surv_cnt,
                                                         masked_in_gemm ? 0 : 1);
@@ -1182,12 +1261,12 @@ int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, flo
   MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__nv_bfloat16)));
   MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__nv_bfloat16)));
   MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
-  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * 2 * sizeof(float) + 16));
+  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * 3 * sizeof(float) + 16));
   __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
   k_tc_convert<<<(n_users_pad + 7) / 8, 256, 0, st>>>(m->users.p, (const long long *)d_user_ids, n_users, n_users_pad, D,
-                                                     ub, eb.unorm.as<float>(), 1.0f, 0, nullptr, nullptr);
+                                                     ub, eb.unorm.as<float>(), 1.0f, 0, nullptr, nullptr, nullptr);
   k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, eb.vnorm.as<float>(), 1.0f,
-                                                    i_tiles, m->items.bp, eb.vnorm.as<float>() + items_pad);
+                                                    i_tiles, m->items.bp, eb.vnorm.as<float>() + items_pad, nullptr);
   MFB_KERNEL_CHECK();
   CUtensorMap map_items, map_users;
   MFB_CHECK(make_tmap(&map_items, vb, items_pad, D, TC_M));
