@@ -29,21 +29,14 @@
 
 namespace {
 
-constexpr int TC_M = 128;          // items per tile (MMA M)
-constexpr int TC_N = 256;          // users per CTA (MMA N)
+constexpr int TC_M = 128;          // items per tile (the MMA's N: 128 TMEM columns per user block)
+constexpr int TC_N = 256;          // users per CTA (two MMA M-blocks of 128 = the 128 TMEM lanes, twice)
 #ifndef MFB_TC_STAGES
 #define MFB_TC_STAGES 2
 #endif
-#ifndef MFB_TC_EPI_WARPS
-#define MFB_TC_EPI_WARPS 16
-#endif
 constexpr int TC_STAGES = MFB_TC_STAGES;
 constexpr int TC_SROW = 36;        // row stride (floats) of an epilogue warp's 32x32 score tile: conflict-free 16-byte stores
-constexpr int TC_EPI_WARPS = MFB_TC_EPI_WARPS;   // TC_NH per TMEM lane quarter, each owning TC_SPAN user columns
-constexpr int TC_NH = TC_EPI_WARPS / 4;
-constexpr int TC_SPAN = TC_N / TC_NH;            // user columns per epilogue warp
-constexpr int TC_WPL = TC_SPAN / 32;             // train-mask words per item row of a warp
-static_assert(TC_SPAN % 64 == 0, "the bias pre-store writes 64 columns at a time");
+constexpr int TC_EPI_WARPS = 16;   // (TMEM lane quarter) x (user block) x (half of the tile's item columns)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_KATOM = 64;       // bf16 elements per 128-byte swizzle atom
 constexpr int MODE_DUMP = 0, MODE_MAX = 1, MODE_COLLECT = 2;
@@ -131,32 +124,16 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       : "r"(taddr)                                                                                                   \
       : "memory")
 
-__device__ __forceinline__ void tc_st32_splat(uint32_t taddr, uint32_t v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
-      "%1, %1, %1, %1, %1};" ::"r"(taddr),
-      "r"(v)
-      : "memory");
-}
-
-// two adjacent 32-column blocks from ONE register vector (a single asm statement, so the 32 splat registers are
-// materialised once instead of once per store)
-__device__ __forceinline__ void tc_st32_splat2(uint32_t taddr, uint32_t v) {
-  asm volatile(
-      "{\n\t"
-      ".reg .b32 t2;\n\t"
-      "add.u32 t2, %0, 32;\n\t"
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
-      "%1, %1, %1, %1, %1};\n\t"
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [t2], "
-      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
-      "%1, %1, %1, %1, %1};\n\t"
-      "}" ::"r"(taddr),
-      "r"(v)
-      : "memory");
-}
+#define TC_ST32(r, taddr)                                                                                              \
+  asm volatile(                                                                                                        \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                                  \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "  \
+      "%24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),                                                    \
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),  \
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),     \
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),     \
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                                   \
+      : "memory")
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start address >> 4 in [0,14), leading byte offset >> 4 in [16,30) (unused for swizzled K-major: 1),
@@ -208,7 +185,8 @@ __global__ void k_tc_convert(const float *__restrict__ src, const long long *__r
   if (perm_T > 0) {
     const int it = tc_item_of(r >> 7, r & 127, perm_T);
     srow = (it < rows) ? it : -1;
-    if (lane == 0 && bias_dst) bias_dst[r] = (srow >= 0) ? bias_src[srow] : 0.f;
+    // padding positions get a hugely negative bias: their scores can neither be a maximum nor reach a threshold
+    if (lane == 0 && bias_dst) bias_dst[r] = (srow >= 0) ? bias_src[srow] : MASKED_SCORE_TC;
   } else {
     srow = (r < rows) ? (ids ? ids[r] : r) : -1;
   }
@@ -223,28 +201,44 @@ __global__ void k_tc_convert(const float *__restrict__ src, const long long *__r
   if (lane == 0 && norm_by_src && srow >= 0) norm_by_src[srow] = norm_scale * sqrtf(ss);
 }
 
+// per item tile: the largest (pre-scaled) row norm, one warp per tile
+__global__ void k_tc_tile_maxnorm(const float *__restrict__ norm_pos, int tiles, float *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= tiles) return;
+  float m = 0.f;
+  for (int j = lane; j < TC_M; j += 32) m = fmaxf(m, norm_pos[(long long)t * TC_M + j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) out[t] = m;
+}
+
 // ---------------------------------------------------------------------------------------------
-// 2/3. the GEMM kernel
+// 2/3. the GEMM kernel.  D[user][item] = sum_k U[user][k] * V[item][k]: the CTA's 256 users are the M side (two
+// 128-row blocks = the 128 TMEM lanes, twice), a tile of 128 items is the N side (128 TMEM columns per block).
+// An epilogue thread therefore owns ONE USER: its threshold, error radius and candidate counter are registers,
+// the reduction over items is a chain of 3-input maxima inside the thread, and appends need no atomics.
 // ---------------------------------------------------------------------------------------------
 struct TcArgs {
-  int num_items, n_users;       // valid rows of A / B
+  int num_items, n_users;       // valid rows of the item / user operand
   int D;                        // multiple of 64, <= 256
   int tile_begin, tile_step, n_tiles;   // item tiles processed: tile_begin + i*tile_step, i < n_tiles
   int total_tiles;              // T of the item layout (all tiles of the catalog)
-  const float *item_bias;       // [items_pad]  item biases in position order
-  const float *item_norm;       // [items_pad]  err_coeff * L2 norm of each fp32 item row, position order, where
+  const float *item_bias;       // [items_pad]  item biases in position order; padding positions hold MASKED_SCORE_TC
+  const float *tile_nmax;       // [total_tiles] max over the tile's items of err_coeff * |v|, where
                                 //              |bf16 score - fp32 score| <= err_coeff * |u| * |v|
   const float *user_norm;       // [n_users_pad] L2 norm of each evaluated user's row
-  // MODE_MAX: gmax[(i*4 + quarter) * n_users_pad + user]  (ordered-int encoded)
+  // MODE_MAX: gmax[(i*4 + column group) * n_users_pad + user]  (ordered-int encoded)
   int *gmax;
   int n_users_pad;
   // MODE_COLLECT
   const float *thr;             // [n_users_pad] collection threshold per user
-  int2 *cand;                   // [n_users][cap]: (item id, bf16-GEMM score incl. item bias, as float bits)
-  int *cand_cnt;                // [n_users_pad]
-  int cap;
+  int2 *cand;                   // [n_users_pad][2][cap2]: (item id, bf16-GEMM score incl. item bias, as float bits);
+                                // the two sub-lists of a user belong to the two epilogue warps that share its columns
+  int *cand_cnt;                // [n_users_pad][2]
+  int cap2;
   // MODE_DUMP
-  float *dump;                  // [num_items_pad][n_users_pad]
+  float *dump;                  // [num_items][n_users_pad]
   // train mask (MODE_MAX / MODE_COLLECT; null = no mask): for CTA c, the (item, user-column) train pairs bucketed by
   // 32-position group g: mask_pairs[mask_base[c] + mask_ptr[c*(ngroups+1) + g] ...), entry = (position & 31) | (column << 5)
   const uint16_t *mask_pairs;
@@ -264,22 +258,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   // so the compiler emits LDS / STS / ATOMS instead of generic accesses)
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int katoms = a.D / TC_KATOM;
-  const uint32_t b_bytes = (uint32_t)TC_N * 128u * katoms;       // users, resident
-  const uint32_t a_bytes = (uint32_t)TC_M * 128u * katoms;       // one item stage
-  uint8_t *sB = smem;
-  uint8_t *sA = sB + b_bytes;
-  uint8_t *tail = sA + (size_t)TC_STAGES * a_bytes;
+  const uint32_t u_bytes = (uint32_t)TC_N * 128u * katoms;       // users, resident: [katom][256 rows][128 B]
+  const uint32_t v_bytes = (uint32_t)TC_M * 128u * katoms;       // one item stage:  [katom][128 rows][128 B]
+  uint8_t *sU = smem;
+  uint8_t *sV = sU + u_bytes;
+  uint8_t *tail = sV + (size_t)TC_STAGES * v_bytes;
   uint64_t *full = reinterpret_cast<uint64_t *>(tail);           // [TC_STAGES]
   uint64_t *empty = full + TC_STAGES;                            // [TC_STAGES]
   uint64_t *tfull = empty + TC_STAGES;                           // [2]
   uint64_t *tempty = tfull + 2;                                  // [2]
-  uint64_t *bfull = tempty + 2;                                  // [1]
+  uint64_t *ufull = tempty + 2;                                  // [1]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 112);
-  float *thr_s = reinterpret_cast<float *>(tail + 128);          // [TC_N]   (16-byte aligned from here on)
-  int *cnt_s = reinterpret_cast<int *>(thr_s + TC_N);            // [TC_N]
-  uint32_t *mask_s = reinterpret_cast<uint32_t *>(cnt_s + TC_N); // [8 warps][32 lanes][4 words]: train-mask bits
-  float *nu_s = reinterpret_cast<float *>(mask_s + 4 * 32 * 8);  // [TC_N] user-row norms   (mask: 128 rows x 256 bits)
-  float *sc_s = nu_s + TC_N;                                     // [8 warps][32][TC_SROW]: scores of the current chunk
+  uint32_t *mask_s = reinterpret_cast<uint32_t *>(tail + 128);   // [16 warps][32 users][2 words]: train-mask bits
+  float *sc_s = reinterpret_cast<float *>(mask_s + TC_EPI_WARPS * 32 * 2);   // [16 warps][32][TC_SROW]: chunk scores
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * TC_N;
@@ -297,21 +288,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       mbar_init(tfull + b, 1);
       mbar_init(tempty + b, TC_EPI_WARPS);   // one arrival per epilogue warp
     }
-    mbar_init(bfull, 1);
+    mbar_init(ufull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulators)
+  if (warp == 1) {  // TMEM: all 512 columns = 2 buffers x 2 user blocks x 128 item columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (MODE == MODE_COLLECT) {
-    for (int i = threadIdx.x; i < TC_N; i += TC_THREADS) {
-      thr_s[i] = (u0 + i < a.n_users) ? a.thr[u0 + i] : INFINITY;
-      cnt_s[i] = 0;
-    }
-  }
-  if (MODE != MODE_DUMP) {
-    for (int i = threadIdx.x; i < TC_N; i += TC_THREADS) nu_s[i] = (u0 + i < a.n_users) ? a.user_norm[u0 + i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -321,248 +303,208 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_expect_tx(bfull, b_bytes);
+      mbar_expect_tx(ufull, u_bytes);
       for (int ka = 0; ka < katoms; ++ka)
-        tma_load_2d(sB + (size_t)ka * TC_N * 128, &map_users, bfull, ka * TC_KATOM, u0);
+        tma_load_2d(sU + (size_t)ka * TC_N * 128, &map_users, ufull, ka * TC_KATOM, u0);
       for (int i = 0; i < a.n_tiles; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
         mbar_wait_backoff(empty + s, ph ^ 1u);
-        mbar_expect_tx(full + s, a_bytes);
+        mbar_expect_tx(full + s, v_bytes);
         const int row0 = (a.tile_begin + logical(i) * a.tile_step) * TC_M;
         for (int ka = 0; ka < katoms; ++ka)
-          tma_load_2d(sA + (size_t)s * a_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
+          tma_load_2d(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
-    // both K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    // both K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28.  M = 128 users, N = 128 items.
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     if (lane == 0) {
-      mbar_wait_backoff(bfull, 0);
+      mbar_wait_backoff(ufull, 0);
       tc_fence_after();
       for (int i = 0; i < a.n_tiles; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
         const int b = i & 1;
         const uint32_t bph = (uint32_t)(i >> 1) & 1u;
-        mbar_wait_backoff(tempty + b, bph);  // accumulator drained AND the item bias pre-stored by the epilogue
+        mbar_wait_backoff(tempty + b, bph);  // accumulators drained AND the item biases pre-stored by the epilogue
         mbar_wait_backoff(full + s, ph);     // item tile landed
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(b * TC_N);
-        for (int ka = 0; ka < katoms; ++ka) {
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (size_t)s * a_bytes + (size_t)ka * TC_M * 128));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (size_t)ka * TC_N * 128));
 #pragma unroll
-          for (int k = 0; k < TC_KATOM / 16; ++k)   // 16 bf16 = 32 bytes per MMA along K: +2 in the (>>4) address field
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+        for (int ub = 0; ub < 2; ++ub) {     // the two 128-user blocks share the item tile
+          const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256 + ub * 128);
+          for (int ka = 0; ka < katoms; ++ka) {
+            const uint64_t udesc = umma_desc_sw128(smem_u32(sU + (size_t)ka * TC_N * 128 + (size_t)ub * 128 * 128));
+            const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128));
+#pragma unroll
+            for (int k = 0; k < TC_KATOM / 16; ++k)   // 16 bf16 = 32 bytes per MMA along K: +2 in the (>>4) address field
+              tc_mma_bf16(d_tmem, udesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc, 1u);
+          }
         }
         tc_commit(empty + s);    // smem stage reusable once these MMAs retire
-        tc_commit(tfull + b);    // accumulator ready for the epilogue
+        tc_commit(tfull + b);    // accumulators ready for the epilogue
       }
     }
   } else {
-    // ===== epilogue warps: TMEM lane quarter q = warp % 4, column half h =====
+    // ===== epilogue warps: TMEM lane quarter q = warp % 4 (32 users), user block ub, item-column half ch =====
     const int q = warp & 3;
-    const int h = (warp - 2) >> 2;                         // column group: user columns [h*TC_SPAN, (h+1)*TC_SPAN)
-    const int col_lo = h * TC_SPAN;
+    const int e = (warp - 2) >> 2;                         // 0..3
+    const int ub = e & 1, ch = e >> 1;
+    const int ucol = ub * 128 + q * 32 + lane;             // this thread's user, as a column of the CTA
+    const int gu = u0 + ucol;
+    const bool user_ok = gu < a.n_users;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+    const uint32_t col_base = (uint32_t)(ub * 128 + ch * 64);     // + buffer * 256
     const bool use_mask = (MODE != MODE_DUMP) && a.mask_pairs != nullptr;
-    uint32_t *mbase = mask_s + (warp - 2) * 32 * TC_WPL;    // this warp's [32 items][TC_WPL words] of column bits
-    uint32_t *mrow = mbase + lane * TC_WPL;
+    uint32_t *mbase = mask_s + (warp - 2) * 32 * 2;         // this warp's [32 users][2 words] of item-column bits
+    uint32_t *mrow = mbase + lane * 2;
+    float *tile = sc_s + (warp - 2) * 32 * TC_SROW;
     const uint16_t *pairs = use_mask ? a.mask_pairs + a.mask_base[blockIdx.x] : nullptr;
     const int *mp_row = use_mask ? a.mask_ptr + (long long)blockIdx.x * (a.ngroups + 1) : nullptr;
-    // train pairs of a tile: the group's range is fetched two tiles ahead and its first 64 pairs one tile ahead,
-    // so that no load is issued with an address that is still in flight
-    int pf_lo = 0, pf_hi = 0, nx_lo = 0, nx_hi = 0;      // ranges of the current / next tile
-    uint32_t pf_e = 0, pf_e2 = 0;                         // pairs of the current tile
-    auto load_range = [&](int tile_idx, int &lo, int &hi) {
-      lo = hi = 0;
+    const uint32_t my_ucol32 = (uint32_t)(ub * 4 + q);      // the pairs of my 32 users have (column >> 5) == this
+    const float nu = (MODE != MODE_DUMP && user_ok) ? a.user_norm[gu] : 0.f;
+    const float thr_u = (MODE == MODE_COLLECT && user_ok) ? a.thr[gu] : INFINITY;
+    int my_cnt = 0;
+    int2 *my_cand = (MODE == MODE_COLLECT) ? a.cand + ((long long)gu * 2 + ch) * a.cap2 : nullptr;
+
+    // train pairs of a tile: the two position groups of this warp's 64 columns are adjacent in the bucketed list;
+    // their range is fetched two tiles ahead and the first 96 pairs one tile ahead, so that no load is issued with
+    // an address that is still in flight
+    int pf_lo = 0, pf_mid = 0, pf_hi = 0, nx_lo = 0, nx_mid = 0, nx_hi = 0;
+    uint32_t pf_e0 = 0, pf_e1 = 0, pf_e2 = 0;
+    auto load_range = [&](int tile_idx, int &lo, int &mid, int &hi) {
+      lo = mid = hi = 0;
       if (use_mask && tile_idx < a.n_tiles) {
-        const int g = (a.tile_begin + logical(tile_idx) * a.tile_step) * 4 + q;
-        if (g < a.ngroups) {
+        const int g = (a.tile_begin + logical(tile_idx) * a.tile_step) * 4 + ch * 2;
+        if (g + 1 < a.ngroups) {
           lo = mp_row[g];
-          hi = mp_row[g + 1];
+          mid = mp_row[g + 1];
+          hi = mp_row[g + 2];
         }
       }
     };
-    auto load_pairs = [&](int lo, int hi, uint32_t &e, uint32_t &e2) {
-      if (lo + lane < hi) e = pairs[lo + lane];
-      if (lo + 32 + lane < hi) e2 = pairs[lo + 32 + lane];
+    auto load_pairs = [&](int lo, int hi, uint32_t &e0, uint32_t &e1, uint32_t &e2) {
+      if (lo + lane < hi) e0 = pairs[lo + lane];
+      if (lo + 32 + lane < hi) e1 = pairs[lo + 32 + lane];
+      if (lo + 64 + lane < hi) e2 = pairs[lo + 64 + lane];
     };
-    auto mask_set = [&](uint32_t e) {   // e = (item & 31) | (column << 5); keep this warp's column half only
-      const uint32_t col = e >> 5;
-      if ((int)(col / TC_SPAN) == h)
-        atomicOr(mbase + (e & 31u) * TC_WPL + ((col % TC_SPAN) >> 5), 1u << (col & 31u));
+    auto mask_set = [&](uint32_t en, int word) {   // en = (position & 31) | (user column << 5)
+      const uint32_t col = en >> 5;
+      if ((col >> 5) == my_ucol32) atomicOr(mbase + (col & 31u) * 2 + word, 1u << (en & 31u));
     };
-    auto load_bias = [&](int tile_idx) {
-      const int pos = (a.tile_begin + logical(tile_idx < a.n_tiles ? tile_idx : 0) * a.tile_step) * TC_M + q * 32 + lane;
-      return (tile_idx < a.n_tiles && !(a.dbg & 8)) ? a.item_bias[pos] : 0.f;
-    };
-    auto load_norm = [&](int tile_idx) {   // error radius factor of this lane's item: err_coeff * |v_item| (pre-scaled)
-      const int pos = (a.tile_begin + logical(tile_idx < a.n_tiles ? tile_idx : 0) * a.tile_step) * TC_M + q * 32 + lane;
-      return (MODE != MODE_DUMP && tile_idx < a.n_tiles) ? a.item_norm[pos] : 0.f;
-    };
-    float nv = load_norm(0), nv_next = load_norm(1);
-    auto prestore_bias = [&](float bi, int buf) {
+    // item biases of a tile's 64 columns -> both accumulators' next use (they differ per column, not per user)
+    auto prestore_bias = [&](int tile_idx, int buf) {
       if (!(a.dbg & 16)) {
+        const int tile_id = a.tile_begin + logical(tile_idx) * a.tile_step;
+        const float4 *bsrc = reinterpret_cast<const float4 *>(a.item_bias + (long long)tile_id * TC_M + ch * 64);
 #pragma unroll
-        for (int c0 = 0; c0 < TC_SPAN; c0 += 64)
-          tc_st32_splat2(tmem_base + lane_addr + (uint32_t)(buf * TC_N + col_lo + c0), __float_as_uint(bi));
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t r[32];
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 bv = (a.dbg & 8) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(bsrc + (c0 >> 2) + c4);
+            r[c4 * 4 + 0] = __float_as_uint(bv.x);
+            r[c4 * 4 + 1] = __float_as_uint(bv.y);
+            r[c4 * 4 + 2] = __float_as_uint(bv.z);
+            r[c4 * 4 + 3] = __float_as_uint(bv.w);
+          }
+          TC_ST32(r, tmem_base + lane_addr + (uint32_t)(buf * 256) + col_base + (uint32_t)c0);
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + buf);
     };
-    load_range(0, pf_lo, pf_hi);
-    load_range(1, nx_lo, nx_hi);
-    load_pairs(pf_lo, pf_hi, pf_e, pf_e2);
-    for (int i = 0; i < 2 && i < a.n_tiles; ++i) prestore_bias(load_bias(i), i);
+    load_range(0, pf_lo, pf_mid, pf_hi);
+    load_range(1, nx_lo, nx_mid, nx_hi);
+    load_pairs(pf_lo, pf_hi, pf_e0, pf_e1, pf_e2);
+    for (int i = 0; i < 2 && i < a.n_tiles; ++i) prestore_bias(i, i);
     for (int i = 0; i < a.n_tiles; ++i) {
       const int b = i & 1;
       const uint32_t bph = (uint32_t)(i >> 1) & 1u;
       const int li = logical(i);
       const int tile_id = a.tile_begin + li * a.tile_step;
-      const int item = tc_item_of(tile_id, q * 32 + lane, a.total_tiles);   // catalog id of this lane's row
-      const bool item_ok = item < a.num_items;
-      const float bias_next = load_bias(i + 2);   // in flight while this tile is processed
-      const float nv_next2 = load_norm(i + 2);
-      // train mask of this tile's 32 items (lane = item) x this warp's 128 user columns, built while the MMA runs
+      // error radius of every score of this tile for this user: |u| * max over the tile of err_coeff * |v|
+      const float rad = (MODE != MODE_DUMP) ? nu * __ldg(a.tile_nmax + tile_id) : 0.f;
+      // train mask of this warp's 32 users x 64 item columns, built while the MMA runs
       if (use_mask && !(a.dbg & 4)) {
-#pragma unroll
-        for (int w = 0; w < TC_WPL; ++w) mrow[w] = 0u;
+        mrow[0] = 0u;
+        mrow[1] = 0u;
         __syncwarp();
-        const int lo = pf_lo, hi = pf_hi;
-        if (lo + lane < hi) mask_set(pf_e);
-        if (lo + 32 + lane < hi) mask_set(pf_e2);
-        for (int r = lo + 64 + lane; r < hi; r += 32) mask_set(pairs[r]);   // rare: more than 64 train pairs in the group
+        const int lo = pf_lo, mid = pf_mid, hi = pf_hi;
+        if (lo + lane < hi) mask_set(pf_e0, lo + lane >= mid);
+        if (lo + 32 + lane < hi) mask_set(pf_e1, lo + 32 + lane >= mid);
+        if (lo + 64 + lane < hi) mask_set(pf_e2, lo + 64 + lane >= mid);
+        for (int r = lo + 96 + lane; r < hi; r += 32) mask_set(pairs[r], r >= mid);   // rare: more than 96 pairs
         // loads for the coming tiles complete while this tile's scores are processed
         pf_lo = nx_lo;
+        pf_mid = nx_mid;
         pf_hi = nx_hi;
-        load_pairs(pf_lo, pf_hi, pf_e, pf_e2);
-        load_range(i + 2, nx_lo, nx_hi);
+        load_pairs(pf_lo, pf_hi, pf_e0, pf_e1, pf_e2);
+        load_range(i + 2, nx_lo, nx_mid, nx_hi);
         __syncwarp();
       }
       mbar_wait(tfull + b, bph);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc0 = 0; cc0 < ((a.dbg & 1) ? 0 : TC_SPAN); cc0 += 32) {
-        const int c0 = col_lo + cc0;
+      for (int cc0 = 0; cc0 < ((a.dbg & 1) ? 0 : 64); cc0 += 32) {
         uint32_t r[32];
-        TC_LD32(r, tmem_base + lane_addr + (uint32_t)(b * TC_N + c0));
-        // bit c = column c0+c is NOT usable for this lane's item (train item, or item beyond the catalog)
-        const uint32_t mword = item_ok ? (use_mask ? mrow[cc0 >> 5] : 0u) : 0xffffffffu;
+        TC_LD32(r, tmem_base + lane_addr + (uint32_t)(b * 256) + col_base + (uint32_t)cc0);
+        const uint32_t mword = use_mask ? mrow[cc0 >> 5] : 0u;   // bit c: item column cc0+c is a train item of my user
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int slot0 = ch * 64 + cc0;                         // tile slot of r[0]
         if (MODE == MODE_DUMP) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (item_ok) a.dump[(long long)item * a.n_users_pad + (u0 + c0 + c)] = __uint_as_float(r[c]);
-        } else if (MODE == MODE_MAX) {
-          // per column: max over the warp's 32 items, train items excluded.  Butterfly transpose-reduce:
-          // after the 5 steps lane l holds the maximum of column c0 + l (31 shuffles for 32 columns).
-          // The 32x32 block (lane = item, register = column) is transposed through the warp's shared-memory tile;
-          // lane l then reduces column c0 + l over the 32 items with 3-input max instructions.
-          float *tile = sc_s + (warp - 2) * 32 * TC_SROW;
-          const float4 *n4 = reinterpret_cast<const float4 *>(nu_s + c0);
-          __syncwarp();
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {   // approx - err <= exact: the group maximum of this is a certified lower bound
-            const float4 nu = n4[c4];
-            float4 x;
-            x.x = ((mword >> (c4 * 4 + 0)) & 1u) ? -INFINITY : fmaf(-nv, nu.x, __uint_as_float(r[c4 * 4 + 0]));
-            x.y = ((mword >> (c4 * 4 + 1)) & 1u) ? -INFINITY : fmaf(-nv, nu.y, __uint_as_float(r[c4 * 4 + 1]));
-            x.z = ((mword >> (c4 * 4 + 2)) & 1u) ? -INFINITY : fmaf(-nv, nu.z, __uint_as_float(r[c4 * 4 + 2]));
-            x.w = ((mword >> (c4 * 4 + 3)) & 1u) ? -INFINITY : fmaf(-nv, nu.w, __uint_as_float(r[c4 * 4 + 3]));
-            *reinterpret_cast<float4 *>(tile + lane * TC_SROW + c4 * 4) = x;
+          for (int c = 0; c < 32; ++c) {
+            const int item = tc_item_of(tile_id, slot0 + c, a.total_tiles);
+            if (item < a.num_items) a.dump[(long long)item * a.n_users_pad + gu] = __uint_as_float(r[c]);
           }
-          __syncwarp();
-          float mx = -INFINITY;
+        } else if (MODE == MODE_MAX) {
+          // maximum over the 32 items, inside the thread.  A group that contains one of the user's train items is
+          // dropped (-inf) rather than masked score by score; the bound only needs k clean groups.
+          float mx = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
 #pragma unroll
-          for (int it = 0; it < 32; it += 2)
-            mx = fmaxf(mx, fmaxf(tile[it * TC_SROW + lane], tile[(it + 1) * TC_SROW + lane]));
-          a.gmax[(long long)(li * 4 + q) * a.n_users_pad + (u0 + c0 + lane)] = float_to_ordered(mx);
+          for (int c = 2; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[c]), __uint_as_float(r[c + 1])));
+          mx = (mword != 0u) ? -INFINITY : mx - rad;   // approx - err <= exact: a certified lower bound
+          a.gmax[(long long)(li * 4 + ch * 2 + (cc0 >> 5)) * a.n_users_pad + gu] = float_to_ordered(mx);
         } else {
-          // bit c of hw = this lane's item reaches user (c0+c)'s threshold; branch-free, then one warp-wide test
-          // approx + err >= exact: everything whose upper bound reaches the user's certified k-th-best bound
-          const float4 *t4 = reinterpret_cast<const float4 *>(thr_s + c0);
-          const float4 *n4 = reinterpret_cast<const float4 *>(nu_s + c0);
-          // margin = (score + err) - threshold on the FMA pipe; its sign bit (1 = below the threshold) is funnel-
-          // shifted into one of four byte accumulators, columns taken from high to low so that column c lands on bit c
+          // margin = score - (threshold - radius) on the FMA pipe; its sign bit (1 = below) is funnel-shifted into
+          // one of four byte accumulators, columns taken from high to low so that column c lands on bit c
+          const float t = thr_u - rad;    // approx + err >= exact: collect everything whose upper bound reaches thr
           uint32_t wb[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-          for (int c4 = 7; c4 >= 0; --c4) {
-            const float4 th = t4[c4];
-            const float4 nu = n4[c4];
-            uint32_t &w = wb[c4 >> 1];
-            w = __funnelshift_l(__float_as_uint(fmaf(nv, nu.w, __uint_as_float(r[c4 * 4 + 3])) - th.w), w, 1);
-            w = __funnelshift_l(__float_as_uint(fmaf(nv, nu.z, __uint_as_float(r[c4 * 4 + 2])) - th.z), w, 1);
-            w = __funnelshift_l(__float_as_uint(fmaf(nv, nu.y, __uint_as_float(r[c4 * 4 + 1])) - th.y), w, 1);
-            w = __funnelshift_l(__float_as_uint(fmaf(nv, nu.x, __uint_as_float(r[c4 * 4 + 0])) - th.x), w, 1);
-          }
-          uint32_t hw = ~(wb[0] | (wb[1] << 8) | (wb[2] << 16) | (wb[3] << 24));
-          hw &= ~mword;
-          if (!(a.dbg & 2) && __any_sync(0xffffffffu, hw != 0u)) {
+          for (int c = 31; c >= 0; --c)
+            wb[c >> 3] = __funnelshift_l(__float_as_uint(__uint_as_float(r[c]) - t), wb[c >> 3], 1);
+          uint32_t hw = ~(wb[0] | (wb[1] << 8) | (wb[2] << 16) | (wb[3] << 24)) & ~mword;
+          if (!(a.dbg & 2) && hw != 0u) {
             // the records carry the GEMM score (k_tc_rescore uses it to discard most of the list before the exact
-            // pass); a hit's column is only known at run time, so the chunk's scores go through shared memory
-            float *tile = sc_s + (warp - 2) * 32 * TC_SROW;
-            __syncwarp();
+            // pass); a hit's column is only known at run time, so the thread's 32 scores go through shared memory
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4)
               *reinterpret_cast<uint4 *>(tile + lane * TC_SROW + c4 * 4) =
                   make_uint4(r[c4 * 4 + 0], r[c4 * 4 + 1], r[c4 * 4 + 2], r[c4 * 4 + 3]);
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, __popc(hw) > 2)) {
-              // sparse hits (the common case): each lane appends its own one or two
-              while (hw) {
-                const int c = __ffs(hw) - 1;
-                hw &= hw - 1u;
-                const int uu = c0 + c;
-                const int pos = atomicAdd(cnt_s + uu, 1);
-                if (pos < a.cap)
-                  a.cand[(long long)(u0 + uu) * a.cap + pos] = make_int2(item, __float_as_int(tile[lane * TC_SROW + c]));
-              }
-            } else {
-              // a popular item hits for many users of the chunk: transpose the 32x32 hit matrix with ballots so
-              // that lane c owns user column c0+c (`mine` = this warp's items that reached that user's threshold):
-              // one atomic per column, all columns in parallel
-              unsigned mine = 0u;
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const unsigned bal = __ballot_sync(0xffffffffu, (hw >> c) & 1u);
-                mine = (lane == c) ? bal : mine;
-              }
-              if (mine) {
-                const int uu = c0 + lane;
-                int pos = atomicAdd(cnt_s + uu, __popc(mine));
-                int2 *dst = a.cand + (long long)(u0 + uu) * a.cap;
-                while (mine) {
-                  const int src = __ffs(mine) - 1;
-                  mine &= mine - 1u;
-                  if (pos < a.cap)
-                    dst[pos] = make_int2(tc_item_of(tile_id, q * 32 + src, a.total_tiles),
-                                         __float_as_int(tile[src * TC_SROW + lane]));
-                  ++pos;
-                }
-              }
+            while (hw) {
+              const int c = __ffs(hw) - 1;
+              hw &= hw - 1u;
+              if (my_cnt < a.cap2)
+                my_cand[my_cnt] = make_int2(tc_item_of(tile_id, slot0 + c, a.total_tiles),
+                                            __float_as_int(tile[lane * TC_SROW + c]));
+              ++my_cnt;
             }
           }
         }
       }
-      // hand the accumulator back: pre-store the bias of the tile that will use it next
-      if (i + 2 < a.n_tiles) prestore_bias(bias_next, b);
-      nv = nv_next;
-      nv_next = nv_next2;
+      // hand the accumulators back: pre-store the biases of the tile that will use them next
+      if (i + 2 < a.n_tiles) prestore_bias(i + 2, b);
     }
+    if (MODE == MODE_COLLECT && user_ok) a.cand_cnt[(long long)gu * 2 + ch] = my_cnt;
   }
   // teardown
   tc_fence_before();
   __syncthreads();
-  if (MODE == MODE_COLLECT) {
-    for (int i = threadIdx.x; i < TC_N; i += TC_THREADS)
-      if (u0 + i < a.n_users) a.cand_cnt[u0 + i] = cnt_s[i];
-  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
@@ -803,7 +745,7 @@ constexpr int RS_WARPS = 4;
 // latency-bound and the extra shared memory cuts the resident warps)
 __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     const long long *__restrict__ user_ids, int n_users, TableView users, TableView items, int D,
-    const int2 *__restrict__ cand, const int *__restrict__ cand_cnt, int cap, const float *__restrict__ thr,
+    const int2 *__restrict__ cand, const int *__restrict__ cand_cnt, int cap2, const float *__restrict__ thr,
     const float *__restrict__ unorm, const float *__restrict__ item_norm,
     const long long *__restrict__ indptr, const int *__restrict__ indices, int k, int *__restrict__ out_ids,
     float *__restrict__ out_scores, int *__restrict__ redo_flag, int *__restrict__ surv_cnt, int check_mask) {
@@ -816,8 +758,9 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
   int *ids = reinterpret_cast<int *>(lob + RS_MAXC);
   if (u >= n_users) return;
   const long long uid = user_ids[u];
-  const int cnt = cand_cnt[u];
-  if (cnt > cap || cnt > RS_MAXC || cnt < k || !(thr[u] > -INFINITY)) {   // overflow or no bound: exact path
+  const int cnt0 = cand_cnt[2 * u], cnt1 = cand_cnt[2 * u + 1];   // the user's two sub-lists (item-column halves)
+  const int cnt = cnt0 + cnt1;
+  if (cnt0 > cap2 || cnt1 > cap2 || cnt > RS_MAXC || cnt < k || !(thr[u] > -INFINITY)) {   // overflow / no bound: exact path
     if (lane == 0) {
       redo_flag[u] = 1;
       surv_cnt[u] = 0;
@@ -834,7 +777,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
   // ---- 1. bounds of every listed item's exact score from its GEMM score: [s - e, s + e], e = err_coeff*|u|*|v|
   const float nu = unorm[u];
   for (int c = lane; c < cnt; c += 32) {
-    const int2 rec = cand[(long long)u * cap + c];
+    const int2 rec = (c < cnt0) ? cand[(long long)(2 * u) * cap2 + c] : cand[(long long)(2 * u + 1) * cap2 + (c - cnt0)];
     const float e = item_norm[rec.x];   // err_coeff * |v|, indexed by item id
     const float sg = __int_as_float(rec.y);
     ids[c] = rec.x;
@@ -1048,8 +991,8 @@ int make_tmap(CUtensorMap *map, void *base, int rows, int D, int box_rows) {
 
 size_t tc_smem_bytes(int D) {
   const int katoms = D / TC_KATOM;
-  return 1024 + (size_t)TC_N * 128 * katoms + (size_t)TC_STAGES * TC_M * 128 * katoms + 256 + TC_N * 12 + 4 * 32 * 8 * 4 +
-         (size_t)TC_EPI_WARPS * 32 * TC_SROW * 4;
+  return 1024 + (size_t)TC_N * 128 * katoms + (size_t)TC_STAGES * TC_M * 128 * katoms + 128 +
+         (size_t)TC_EPI_WARPS * 32 * 2 * 4 + (size_t)TC_EPI_WARPS * 32 * TC_SROW * 4;
 }
 
 template <int MODE>
@@ -1085,25 +1028,26 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   while ((i_tiles + sample_step - 1) / sample_step > 8 * TH_VPL) ++sample_step;   // groups = 4*n_sample <= 32*TH_VPL
   const int n_sample = (i_tiles + sample_step - 1) / sample_step;
   const int groups = n_sample * 4;
-  const int cap = RS_MAXC;
+  const int cap2 = RS_MAXC / 2;
 
   EvalBuf &eb = m->eval;
   MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__nv_bfloat16)));
   MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__nv_bfloat16)));
   MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
-  MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * 3 * sizeof(float) + 16));
+  MFB_CHECK(eb.vnorm.reserve(((size_t)items_pad * 3 + i_tiles) * sizeof(float) + 16));
   MFB_CHECK(eb.gmax.reserve((size_t)groups * n_users_pad * sizeof(int)));
   MFB_CHECK(eb.thr.reserve((size_t)n_users_pad * 2 * sizeof(float)));
-  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * cap * sizeof(int2)));
-  MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * 4 + 64));
+  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * 2 * cap2 * sizeof(int2)));
+  MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * 5 + 64));
   MFB_CHECK(eb.redo.reserve((size_t)n_users_pad * (sizeof(long long) + (size_t)k * (sizeof(int) + sizeof(float))) + 64));
   __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
   float *unorm = eb.unorm.as<float>(), *vnorm = eb.vnorm.as<float>();
   float *vbias = vnorm + items_pad;   // item biases in position order
   float *vnorm_item = vbias + items_pad;   // scaled norms again, indexed by item id (for k_tc_rescore)
+  float *tile_nmax = vnorm_item + items_pad;   // per tile: largest scaled norm
   float *thr = eb.thr.as<float>(), *eps = thr + n_users_pad;
   int *cand_cnt = eb.cnt.as<int>();
-  int *redo_flag = cand_cnt + n_users_pad;
+  int *redo_flag = cand_cnt + 2 * (size_t)n_users_pad;
   int *redo_pos = redo_flag + n_users_pad;
   int *surv_cnt = redo_pos + n_users_pad;
   int *redo_cnt = surv_cnt + n_users_pad;
@@ -1117,6 +1061,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   const float err_coeff = 0.0042f;
   k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, vnorm, err_coeff, i_tiles,
                                                     m->items.bp, vbias, vnorm_item);
+  k_tc_tile_maxnorm<<<(i_tiles + 7) / 8, 256, 0, st>>>(vnorm, i_tiles, tile_nmax);
   MFB_KERNEL_CHECK();
 
   CUtensorMap map_items, map_users;
@@ -1130,7 +1075,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.D = D;
   a.total_tiles = i_tiles;
   a.item_bias = vbias;
-  a.item_norm = vnorm;
+  a.tile_nmax = tile_nmax;
   a.user_norm = unorm;
   a.n_users_pad = n_users_pad;
   if (const char *e = getenv("MFB_TC_DBG")) a.dbg = atoi(e);
@@ -1192,14 +1137,14 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.thr = thr;
   a.cand = eb.cand.as<int2>();
   a.cand_cnt = cand_cnt;
-  a.cap = cap;
+  a.cap2 = cap2;
   MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st));
   // exact re-score + mask + top-k
   MFB_CUDA(cudaMemsetAsync(redo_cnt, 0, sizeof(int), st));
   const size_t rs_smem = (size_t)RS_WARPS * (D + 3 * RS_MAXC) * sizeof(float);
   MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
   k_tc_rescore<<<(n_users + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>((const long long *)d_user_ids, n_users, m->users, m->items, D,
-                                                        eb.cand.as<int2>(), cand_cnt, cap, thr, unorm, vnorm_item,
+                                                        eb.cand.as<int2>(), cand_cnt, cap2, thr, unorm, vnorm_item,
                                                         (const long long *)d_train_indptr, d_train_indices, k,
                                                         d_out_ids, d_out_scores, redo_flag, surv_cnt,
                                                         masked_in_gemm ? 0 : 1);
@@ -1227,26 +1172,27 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
 
 // debug: candidate-list statistics of the last tensor-core top-k call: {users, sum, max, over_cap, re-scored}
 int mfb_tc_stats(mfb_model *m, int n_users, long long *h_out, cudaStream_t st) {
-  std::vector<int> cnt((size_t)n_users);
-  MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.ptr, (size_t)n_users * sizeof(int), cudaMemcpyDeviceToHost, st));
+  const int n_users_pad = ((n_users + TC_N - 1) / TC_N) * TC_N;
+  std::vector<int> cnt((size_t)n_users * 2);
+  MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.ptr, (size_t)n_users * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
   long long sum = 0, mx = 0, over = 0;
-  for (int c : cnt) {
-    sum += c;
-    if (c > mx) mx = c;
-    if (c > RS_MAXC) ++over;
+  for (int u = 0; u < n_users; ++u) {
+    const int c0 = cnt[2 * (size_t)u], c1 = cnt[2 * (size_t)u + 1];
+    sum += c0 + c1;
+    if (c0 + c1 > mx) mx = c0 + c1;
+    if (c0 > RS_MAXC / 2 || c1 > RS_MAXC / 2) ++over;
   }
   h_out[0] = n_users;
   h_out[1] = sum;
   h_out[2] = mx;
   h_out[3] = over;
   // listed items that survived the bound filter and were re-scored exactly
-  const int n_users_pad = ((n_users + TC_N - 1) / TC_N) * TC_N;
-  MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.as<int>() + 3 * (size_t)n_users_pad, (size_t)n_users * sizeof(int),
+  MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.as<int>() + 4 * (size_t)n_users_pad, (size_t)n_users * sizeof(int),
                            cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
   long long surv = 0;
-  for (int c : cnt) surv += c;
+  for (int u = 0; u < n_users; ++u) surv += cnt[(size_t)u];
   h_out[4] = surv;
   return MFB_OK;
 }
