@@ -35,7 +35,12 @@ constexpr int TC_N = 256;          // users per CTA (two MMA M-blocks of 128 = t
 #define MFB_TC_STAGES 2
 #endif
 constexpr int TC_STAGES = MFB_TC_STAGES;
-constexpr int TC_SROW = 36;        // row stride (floats) of an epilogue warp's 32x32 score tile: conflict-free 16-byte stores
+constexpr int TC_SROW = 36;        // row stride (floats) of an epilogue warp's score scratch: conflict-free 16-byte stores
+#ifndef MFB_TC_SCR_ROWS
+#define MFB_TC_SCR_ROWS 32
+#endif
+constexpr int TC_SCR_ROWS = MFB_TC_SCR_ROWS;   // scratch rows per epilogue warp: lanes with a hit in the chunk take one each
+                                               // (32 = a private row per lane, no rounds)
 constexpr int TC_EPI_WARPS = 16;   // (TMEM lane quarter) x (user block) x (half of the tile's item columns)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_KATOM = 64;       // bf16 elements per 128-byte swizzle atom
@@ -249,7 +254,7 @@ struct TcArgs {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)   // 18 warps (allocated as 20): 96 registers per thread
 k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__ CUtensorMap map_users,
           const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -270,7 +275,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   uint64_t *ufull = tempty + 2;                                  // [1]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 112);
   uint32_t *mask_s = reinterpret_cast<uint32_t *>(tail + 128);   // [16 warps][32 users][2 words]: train-mask bits
-  float *sc_s = reinterpret_cast<float *>(mask_s + TC_EPI_WARPS * 32 * 2);   // [16 warps][32][TC_SROW]: chunk scores
+  float *sc_s = reinterpret_cast<float *>(mask_s + TC_EPI_WARPS * 32 * 2);   // [16 warps][TC_SCR_ROWS][TC_SROW]
+  float *bias_s = sc_s + TC_EPI_WARPS * TC_SCR_ROWS * TC_SROW;               // [16 warps][64]: item biases, prefetched
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * TC_N;
@@ -360,7 +366,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     const bool use_mask = (MODE != MODE_DUMP) && a.mask_pairs != nullptr;
     uint32_t *mbase = mask_s + (warp - 2) * 32 * 2;         // this warp's [32 users][2 words] of item-column bits
     uint32_t *mrow = mbase + lane * 2;
-    float *tile = sc_s + (warp - 2) * 32 * TC_SROW;
+    float *scratch = sc_s + (warp - 2) * TC_SCR_ROWS * TC_SROW;
+    float *my_bias = bias_s + (warp - 2) * 64;
     const uint16_t *pairs = use_mask ? a.mask_pairs + a.mask_base[blockIdx.x] : nullptr;
     const int *mp_row = use_mask ? a.mask_ptr + (long long)blockIdx.x * (a.ngroups + 1) : nullptr;
     const uint32_t my_ucol32 = (uint32_t)(ub * 4 + q);      // the pairs of my 32 users have (column >> 5) == this
@@ -394,17 +401,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       const uint32_t col = en >> 5;
       if ((col >> 5) == my_ucol32) atomicOr(mbase + (col & 31u) * 2 + word, 1u << (en & 31u));
     };
-    // item biases of a tile's 64 columns -> both accumulators' next use (they differ per column, not per user)
-    auto prestore_bias = [&](int tile_idx, int buf) {
-      if (!(a.dbg & 16)) {
+    // item biases of a tile's 64 columns (they differ per column, not per user): fetched into this warp's slot with
+    // cp.async at the top of the tile loop, written into the accumulator's next use at the bottom
+    auto prefetch_bias = [&](int tile_idx) {
+      if (tile_idx < a.n_tiles && lane < 16) {
         const int tile_id = a.tile_begin + logical(tile_idx) * a.tile_step;
-        const float4 *bsrc = reinterpret_cast<const float4 *>(a.item_bias + (long long)tile_id * TC_M + ch * 64);
+        const float *src = a.item_bias + (long long)tile_id * TC_M + ch * 64 + lane * 4;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_bias + lane * 4)), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto prestore_bias = [&](int buf) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      if (!(a.dbg & 16)) {
 #pragma unroll
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t r[32];
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 bv = (a.dbg & 8) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(bsrc + (c0 >> 2) + c4);
+            const float4 bv = *reinterpret_cast<const float4 *>(my_bias + c0 + c4 * 4);
             r[c4 * 4 + 0] = __float_as_uint(bv.x);
             r[c4 * 4 + 1] = __float_as_uint(bv.y);
             r[c4 * 4 + 2] = __float_as_uint(bv.z);
@@ -421,7 +437,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     load_range(0, pf_lo, pf_mid, pf_hi);
     load_range(1, nx_lo, nx_mid, nx_hi);
     load_pairs(pf_lo, pf_hi, pf_e0, pf_e1, pf_e2);
-    for (int i = 0; i < 2 && i < a.n_tiles; ++i) prestore_bias(i, i);
+    for (int i = 0; i < 2 && i < a.n_tiles; ++i) {
+      prefetch_bias(i);
+      prestore_bias(i);
+      __syncwarp();
+    }
     for (int i = 0; i < a.n_tiles; ++i) {
       const int b = i & 1;
       const uint32_t bph = (uint32_t)(i >> 1) & 1u;
@@ -429,6 +449,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       const int tile_id = a.tile_begin + li * a.tile_step;
       // error radius of every score of this tile for this user: |u| * max over the tile of err_coeff * |v|
       const float rad = (MODE != MODE_DUMP) ? nu * __ldg(a.tile_nmax + tile_id) : 0.f;
+      prefetch_bias(i + 2);   // consumed by the pre-store at the bottom of this iteration
       // train mask of this warp's 32 users x 64 item columns, built while the MMA runs
       if (use_mask && !(a.dbg & 4)) {
         mrow[0] = 0u;
@@ -479,26 +500,48 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
           for (int c = 31; c >= 0; --c)
             wb[c >> 3] = __funnelshift_l(__float_as_uint(__uint_as_float(r[c]) - t), wb[c >> 3], 1);
           uint32_t hw = ~(wb[0] | (wb[1] << 8) | (wb[2] << 16) | (wb[3] << 24)) & ~mword;
-          if (!(a.dbg & 2) && hw != 0u) {
+          if (!(a.dbg & 2)) {
             // the records carry the GEMM score (k_tc_rescore uses it to discard most of the list before the exact
-            // pass); a hit's column is only known at run time, so the thread's 32 scores go through shared memory
+            // pass); a hit's column is only known at run time, so a thread with hits copies its 32 scores to a
+            // scratch row (the few lanes with hits take a row each, in rounds if there are more than TC_SCR_ROWS)
+            if (TC_SCR_ROWS == 32) {
+              if (hw != 0u) {
+                float *row = scratch + lane * TC_SROW;
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4)
-              *reinterpret_cast<uint4 *>(tile + lane * TC_SROW + c4 * 4) =
-                  make_uint4(r[c4 * 4 + 0], r[c4 * 4 + 1], r[c4 * 4 + 2], r[c4 * 4 + 3]);
-            while (hw) {
-              const int c = __ffs(hw) - 1;
-              hw &= hw - 1u;
-              if (my_cnt < a.cap2)
-                my_cand[my_cnt] = make_int2(tc_item_of(tile_id, slot0 + c, a.total_tiles),
-                                            __float_as_int(tile[lane * TC_SROW + c]));
-              ++my_cnt;
+                for (int c4 = 0; c4 < 8; ++c4)
+                  *reinterpret_cast<uint4 *>(row + c4 * 4) = make_uint4(r[c4 * 4 + 0], r[c4 * 4 + 1], r[c4 * 4 + 2], r[c4 * 4 + 3]);
+                while (hw) {
+                  const int c = __ffs(hw) - 1;
+                  hw &= hw - 1u;
+                  if (my_cnt < a.cap2)
+                    my_cand[my_cnt] = make_int2(tc_item_of(tile_id, slot0 + c, a.total_tiles), __float_as_int(row[c]));
+                  ++my_cnt;
+                }
+              }
+            }
+            unsigned pend = (TC_SCR_ROWS == 32) ? 0u : __ballot_sync(0xffffffffu, hw != 0u);
+            while (pend) {
+              const int rank = __popc(pend & ((1u << lane) - 1u));
+              if (hw != 0u && rank < TC_SCR_ROWS) {
+                float *row = scratch + rank * TC_SROW;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4)
+                  *reinterpret_cast<uint4 *>(row + c4 * 4) = make_uint4(r[c4 * 4 + 0], r[c4 * 4 + 1], r[c4 * 4 + 2], r[c4 * 4 + 3]);
+                while (hw) {
+                  const int c = __ffs(hw) - 1;
+                  hw &= hw - 1u;
+                  if (my_cnt < a.cap2)
+                    my_cand[my_cnt] = make_int2(tc_item_of(tile_id, slot0 + c, a.total_tiles), __float_as_int(row[c]));
+                  ++my_cnt;
+                }
+              }
+              pend = __ballot_sync(0xffffffffu, hw != 0u);
             }
           }
         }
       }
       // hand the accumulators back: pre-store the biases of the tile that will use them next
-      if (i + 2 < a.n_tiles) prestore_bias(i + 2, b);
+      if (i + 2 < a.n_tiles) prestore_bias(b);
     }
     if (MODE == MODE_COLLECT && user_ok) a.cand_cnt[(long long)gu * 2 + ch] = my_cnt;
   }
@@ -647,9 +690,30 @@ constexpr int TH_VPL = 8;   // group maxima per lane -> up to 256 groups per use
 template <int K>
 __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restrict__ gmax, int groups, int n_users,
                                                             int n_users_pad, int m, float *__restrict__ thr,
-                                                            float *__restrict__ eps_out) {
+                                                            const long long *__restrict__ user_ids,
+                                                            const long long *__restrict__ indptr,
+                                                            const int *__restrict__ indices, int total_tiles,
+                                                            uint32_t magic, int sample_step) {
+  // The MAX pass does not look at the train mask: a sampled 32-item group that contains one of the user's train
+  // items is dropped here instead (its maximum may belong to that item).  dirty[w][thread]: bit g of the user's set.
+  __shared__ uint32_t dirty[8][128];
   const int u = blockIdx.x * 128 + threadIdx.x;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) dirty[w][threadIdx.x] = 0u;
   if (u >= n_users) return;
+  if (indptr != nullptr) {
+    const long long uid = user_ids[u];
+    const long long lo = indptr[uid], hi = indptr[uid + 1];
+    for (long long e = lo; e < hi; ++e) {
+      const int pos = tc_pos_of(indices[e], total_tiles, magic);
+      const int tile = pos >> 7;
+      const int li = tile / sample_step;
+      if (li * sample_step == tile) {
+        const int g = li * 4 + ((pos & 127) >> 5);
+        dirty[g >> 5][threadIdx.x] |= 1u << (g & 31);
+      }
+    }
+  }
   int top[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) top[j] = INT_MIN;
@@ -660,11 +724,12 @@ __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restric
   for (int t = 0; t < NB; ++t) nxt[t] = (t < groups) ? col[(long long)t * n_users_pad] : INT_MIN;
   for (int g = 0; g < groups; g += NB) {
     int v[NB];
+    const uint32_t dw = dirty[g >> 5][threadIdx.x] >> (g & 31);   // NB divides 32: the batch sits in one word
 #pragma unroll
-    for (int t = 0; t < NB; ++t) v[t] = nxt[t];
+    for (int t = 0; t < NB; ++t) v[t] = ((dw >> t) & 1u) ? INT_MIN : nxt[t];   // INT_MIN never enters the top list
 #pragma unroll
     for (int t = 0; t < NB; ++t)
-      nxt[t] = (g + NB + t < groups) ? col[(long long)(g + NB + t) * n_users_pad] : INT_MIN;   // INT_MIN never enters
+      nxt[t] = (g + NB + t < groups) ? col[(long long)(g + NB + t) * n_users_pad] : INT_MIN;
 #pragma unroll
     for (int t = 0; t < NB; ++t) {
 #pragma unroll
@@ -679,7 +744,6 @@ __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restric
 #pragma unroll
   for (int j = 0; j < K; ++j) r = (j == m - 1) ? top[j] : r;
   thr[u] = (m <= groups && r != INT_MIN) ? ordered_to_float(r) : -INFINITY;   // -inf: the user goes to the exact path
-  eps_out[u] = 0.f;
 }
 
 __global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gmax, int groups, int n_users,
@@ -992,7 +1056,8 @@ int make_tmap(CUtensorMap *map, void *base, int rows, int D, int box_rows) {
 size_t tc_smem_bytes(int D) {
   const int katoms = D / TC_KATOM;
   return 1024 + (size_t)TC_N * 128 * katoms + (size_t)TC_STAGES * TC_M * 128 * katoms + 128 +
-         (size_t)TC_EPI_WARPS * 32 * 2 * 4 + (size_t)TC_EPI_WARPS * 32 * TC_SROW * 4;
+         (size_t)TC_EPI_WARPS * 32 * 2 * 4 + (size_t)TC_EPI_WARPS * TC_SCR_ROWS * TC_SROW * 4 +
+         (size_t)TC_EPI_WARPS * 64 * 4;
 }
 
 template <int MODE>
@@ -1111,18 +1176,26 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
     a.ngroups = ngroups;
     masked_in_gemm = 1;
   }
-  // sample pass: group maxima of every sample_step-th item tile
+  // sample pass: group maxima of every sample_step-th item tile.  With the small-k threshold kernel the MAX pass
+  // ignores the train mask (that kernel drops the groups that contain a train item of the user).
+  const bool small_thr = masked_in_gemm && k <= 32 && groups <= 256;
   a.tile_begin = 0;
   a.tile_step = sample_step;
   a.n_tiles = n_sample;
   a.gmax = eb.gmax.as<int>();
-  MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st));
-  if (masked_in_gemm && k <= 32) {   // group maxima already exclude train items: the bound is the k-th largest
+  {
+    TcArgs amax = a;
+    if (small_thr) amax.mask_pairs = nullptr;
+    MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, amax, n_users, st));
+  }
+  if (small_thr) {
     const int tb = (n_users + 127) / 128;
-    if (k <= 8) k_tc_threshold_small<8><<<tb, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k, thr, eps);
-    else if (k <= 16) k_tc_threshold_small<16><<<tb, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k, thr, eps);
-    else if (k <= 24) k_tc_threshold_small<24><<<tb, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k, thr, eps);
-    else k_tc_threshold_small<32><<<tb, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k, thr, eps);
+    const long long *uids = (const long long *)d_user_ids, *ip = (const long long *)d_train_indptr;
+    int *gm = eb.gmax.as<int>();
+    if (k <= 8) k_tc_threshold_small<8><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, uids, ip, d_train_indices, i_tiles, magic, sample_step);
+    else if (k <= 16) k_tc_threshold_small<16><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, uids, ip, d_train_indices, i_tiles, magic, sample_step);
+    else if (k <= 24) k_tc_threshold_small<24><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, uids, ip, d_train_indices, i_tiles, magic, sample_step);
+    else k_tc_threshold_small<32><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, uids, ip, d_train_indices, i_tiles, magic, sample_step);
   } else {
     k_tc_threshold<<<(n_users + 3) / 4, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k,
                                                       (const long long *)d_user_ids,
