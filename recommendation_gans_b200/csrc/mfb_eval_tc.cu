@@ -244,12 +244,10 @@ struct TcArgs {
   int cap2;
   // MODE_DUMP
   float *dump;                  // [num_items][n_users_pad]
-  // train mask (MODE_MAX / MODE_COLLECT; null = no mask): for CTA c, the (item, user-column) train pairs bucketed by
-  // 32-position group g: mask_pairs[mask_base[c] + mask_ptr[c*(ngroups+1) + g] ...), entry = (position & 31) | (column << 5)
-  const uint16_t *mask_pairs;
-  const int *mask_ptr;
-  const long long *mask_base;
-  int ngroups;
+  // train mask (null = no mask): a dense bitmap in exactly the order the epilogue threads consume it,
+  // mask_bits[((cta * total_tiles + tile) * 16 + (q + 4*(ub + 2*ch))) * 32 + lane] = the 64 item-column bits of that
+  // thread's user in that tile (x: columns 0..31 of the warp's half, y: 32..63); built by k_tc_mask_bitmap
+  const uint2 *mask_bits;
   int dbg;   // experiment switches: 1 = skip score processing, 2 = skip appends, 4 = skip mask build, 8 = skip bias pre-store
 };
 
@@ -274,8 +272,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   uint64_t *tempty = tfull + 2;                                  // [2]
   uint64_t *ufull = tempty + 2;                                  // [1]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 112);
-  uint32_t *mask_s = reinterpret_cast<uint32_t *>(tail + 128);   // [16 warps][32 users][2 words]: train-mask bits
-  float *sc_s = reinterpret_cast<float *>(mask_s + TC_EPI_WARPS * 32 * 2);   // [16 warps][TC_SCR_ROWS][TC_SROW]
+  float *sc_s = reinterpret_cast<float *>(tail + 128);                       // [16 warps][TC_SCR_ROWS][TC_SROW]
   float *bias_s = sc_s + TC_EPI_WARPS * TC_SCR_ROWS * TC_SROW;               // [16 warps][64]: item biases, prefetched
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -363,44 +360,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     const bool user_ok = gu < a.n_users;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
     const uint32_t col_base = (uint32_t)(ub * 128 + ch * 64);     // + buffer * 256
-    const bool use_mask = (MODE != MODE_DUMP) && a.mask_pairs != nullptr;
-    uint32_t *mbase = mask_s + (warp - 2) * 32 * 2;         // this warp's [32 users][2 words] of item-column bits
-    uint32_t *mrow = mbase + lane * 2;
+    const bool use_mask = (MODE == MODE_COLLECT) && a.mask_bits != nullptr;
     float *scratch = sc_s + (warp - 2) * TC_SCR_ROWS * TC_SROW;
     float *my_bias = bias_s + (warp - 2) * 64;
-    const uint16_t *pairs = use_mask ? a.mask_pairs + a.mask_base[blockIdx.x] : nullptr;
-    const int *mp_row = use_mask ? a.mask_ptr + (long long)blockIdx.x * (a.ngroups + 1) : nullptr;
-    const uint32_t my_ucol32 = (uint32_t)(ub * 4 + q);      // the pairs of my 32 users have (column >> 5) == this
+    // this thread's mask words, one 8-byte load per tile, fetched one tile ahead of its use
+    const uint2 *my_mask = use_mask ? a.mask_bits + ((long long)blockIdx.x * a.total_tiles * 16 + (q + 4 * e)) * 32 + lane
+                                    : nullptr;
+    auto load_mask = [&](int tile_idx) {
+      if (!use_mask || tile_idx >= a.n_tiles || (a.dbg & 4)) return make_uint2(0u, 0u);
+      const int tile_id = a.tile_begin + logical(tile_idx) * a.tile_step;
+      return __ldg(my_mask + (long long)tile_id * 16 * 32);
+    };
+    uint2 mw_next = load_mask(0);
     const float nu = (MODE != MODE_DUMP && user_ok) ? a.user_norm[gu] : 0.f;
     const float thr_u = (MODE == MODE_COLLECT && user_ok) ? a.thr[gu] : INFINITY;
     int my_cnt = 0;
     int2 *my_cand = (MODE == MODE_COLLECT) ? a.cand + ((long long)gu * 2 + ch) * a.cap2 : nullptr;
 
-    // train pairs of a tile: the two position groups of this warp's 64 columns are adjacent in the bucketed list;
-    // their range is fetched two tiles ahead and the first 96 pairs one tile ahead, so that no load is issued with
-    // an address that is still in flight
-    int pf_lo = 0, pf_mid = 0, pf_hi = 0, nx_lo = 0, nx_mid = 0, nx_hi = 0;
-    uint32_t pf_e0 = 0, pf_e1 = 0, pf_e2 = 0;
-    auto load_range = [&](int tile_idx, int &lo, int &mid, int &hi) {
-      lo = mid = hi = 0;
-      if (use_mask && tile_idx < a.n_tiles) {
-        const int g = (a.tile_begin + logical(tile_idx) * a.tile_step) * 4 + ch * 2;
-        if (g + 1 < a.ngroups) {
-          lo = mp_row[g];
-          mid = mp_row[g + 1];
-          hi = mp_row[g + 2];
-        }
-      }
-    };
-    auto load_pairs = [&](int lo, int hi, uint32_t &e0, uint32_t &e1, uint32_t &e2) {
-      if (lo + lane < hi) e0 = pairs[lo + lane];
-      if (lo + 32 + lane < hi) e1 = pairs[lo + 32 + lane];
-      if (lo + 64 + lane < hi) e2 = pairs[lo + 64 + lane];
-    };
-    auto mask_set = [&](uint32_t en, int word) {   // en = (position & 31) | (user column << 5)
-      const uint32_t col = en >> 5;
-      if ((col >> 5) == my_ucol32) atomicOr(mbase + (col & 31u) * 2 + word, 1u << (en & 31u));
-    };
     // item biases of a tile's 64 columns (they differ per column, not per user): fetched into this warp's slot with
     // cp.async at the top of the tile loop, written into the accumulator's next use at the bottom
     auto prefetch_bias = [&](int tile_idx) {
@@ -434,9 +410,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + buf);
     };
-    load_range(0, pf_lo, pf_mid, pf_hi);
-    load_range(1, nx_lo, nx_mid, nx_hi);
-    load_pairs(pf_lo, pf_hi, pf_e0, pf_e1, pf_e2);
     for (int i = 0; i < 2 && i < a.n_tiles; ++i) {
       prefetch_bias(i);
       prestore_bias(i);
@@ -450,31 +423,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       // error radius of every score of this tile for this user: |u| * max over the tile of err_coeff * |v|
       const float rad = (MODE != MODE_DUMP) ? nu * __ldg(a.tile_nmax + tile_id) : 0.f;
       prefetch_bias(i + 2);   // consumed by the pre-store at the bottom of this iteration
-      // train mask of this warp's 32 users x 64 item columns, built while the MMA runs
-      if (use_mask && !(a.dbg & 4)) {
-        mrow[0] = 0u;
-        mrow[1] = 0u;
-        __syncwarp();
-        const int lo = pf_lo, mid = pf_mid, hi = pf_hi;
-        if (lo + lane < hi) mask_set(pf_e0, lo + lane >= mid);
-        if (lo + 32 + lane < hi) mask_set(pf_e1, lo + 32 + lane >= mid);
-        if (lo + 64 + lane < hi) mask_set(pf_e2, lo + 64 + lane >= mid);
-        for (int r = lo + 96 + lane; r < hi; r += 32) mask_set(pairs[r], r >= mid);   // rare: more than 96 pairs
-        // loads for the coming tiles complete while this tile's scores are processed
-        pf_lo = nx_lo;
-        pf_mid = nx_mid;
-        pf_hi = nx_hi;
-        load_pairs(pf_lo, pf_hi, pf_e0, pf_e1, pf_e2);
-        load_range(i + 2, nx_lo, nx_mid, nx_hi);
-        __syncwarp();
-      }
+      const uint2 mw = mw_next;
+      mw_next = load_mask(i + 1);
       mbar_wait(tfull + b, bph);
       tc_fence_after();
 #pragma unroll 1
       for (int cc0 = 0; cc0 < ((a.dbg & 1) ? 0 : 64); cc0 += 32) {
         uint32_t r[32];
         TC_LD32(r, tmem_base + lane_addr + (uint32_t)(b * 256) + col_base + (uint32_t)cc0);
-        const uint32_t mword = use_mask ? mrow[cc0 >> 5] : 0u;   // bit c: item column cc0+c is a train item of my user
+        const uint32_t mword = cc0 ? mw.y : mw.x;   // bit c: item column cc0+c is a train item of my user
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int slot0 = ch * 64 + cc0;                         // tile slot of r[0]
         if (MODE == MODE_DUMP) {
@@ -484,12 +441,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
             if (item < a.num_items) a.dump[(long long)item * a.n_users_pad + gu] = __uint_as_float(r[c]);
           }
         } else if (MODE == MODE_MAX) {
-          // maximum over the 32 items, inside the thread.  A group that contains one of the user's train items is
-          // dropped (-inf) rather than masked score by score; the bound only needs k clean groups.
+          // maximum over the 32 items, inside the thread.  The train mask is not applied here: the threshold kernel
+          // drops every group that contains one of the user's train items; the bound only needs k clean groups.
           float mx = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
 #pragma unroll
           for (int c = 2; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[c]), __uint_as_float(r[c + 1])));
-          mx = (mword != 0u) ? -INFINITY : mx - rad;   // approx - err <= exact: a certified lower bound
+          mx -= rad;   // approx - err <= exact: a certified lower bound (train items: see k_tc_threshold_small)
           a.gmax[(long long)(li * 4 + ch * 2 + (cc0 >> 5)) * a.n_users_pad + gu] = float_to_ordered(mx);
         } else {
           // margin = score - (threshold - radius) on the FMA pipe; its sign bit (1 = below) is funnel-shifted into
@@ -560,127 +517,75 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
 // thr_collect = bound - 2*eps_u (eps_u bounds |bf16 score - fp32 score|), certified later by k_tc_rescore.
 // ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
-// train-mask structure for the GEMM epilogue, built on the device per mfb_topk call
+// train mask for the COLLECT epilogue: a dense bitmap, built on the device per mfb_topk call.
+// Block (c, s) owns 32 users of CTA-group c -- the users of the epilogue warps (q, ub) = (s & 3, s >> 2) -- and all
+// item tiles (in ranges of MB_TILES): it assembles the 512 bytes per tile that those users' two epilogue warps
+// (item-column halves) will read, in shared memory, from the users' CSR rows, and streams them out.  It also marks,
+// per user, the sampled 32-item groups that contain a train item (`dirty`, 8 words per user) for
+// k_tc_threshold_small.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_N) k_tc_user_counts(const long long *__restrict__ user_ids,
-                                                         const long long *__restrict__ indptr, int n_users,
-                                                         long long *__restrict__ cta_cnt) {
-  // one block per CTA-group of 256 users (one thread per user): total train entries of the group
-  __shared__ long long wsum[TC_N / 32];
-  const int p = blockIdx.x * TC_N + threadIdx.x;
-  long long v = 0;
-  if (p < n_users) {
-    const long long uid = user_ids[p];
-    v = indptr[uid + 1] - indptr[uid];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    long long tot = 0;
-    for (int w = 0; w < TC_N / 32; ++w) tot += wsum[w];
-    cta_cnt[blockIdx.x] = tot;
-  }
-}
+constexpr int MB_TILES = 400;     // 200 KB of bit images per range
+constexpr int MB_THREADS = 256;
 
-__global__ void __launch_bounds__(1024) k_tc_scan_ll(const long long *__restrict__ in, int n,
-                                                     long long *__restrict__ out) {
-  // exclusive scan of the per-CTA totals (a few hundred values), one block; out[n] = grand total
-  __shared__ long long wtot[32];
-  __shared__ long long carry_s;
+__global__ void __launch_bounds__(MB_THREADS) k_tc_mask_bitmap(const long long *__restrict__ user_ids,
+                                                              const long long *__restrict__ indptr,
+                                                              const int *__restrict__ indices, int n_users,
+                                                              int total_tiles, uint32_t magic, int sample_step,
+                                                              uint32_t *__restrict__ mask_bits,
+                                                              uint32_t *__restrict__ dirty) {
+  extern __shared__ uint32_t mb_bits[];          // [tiles of the range][2 halves][32 users][2 words]
+  __shared__ uint32_t dirty_s[32][8];
+  const int c = blockIdx.x, s = blockIdx.y;
+  const int q = s & 3, ub = s >> 2;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  for (int start = 0; start < n; start += 1024) {
-    const int i = start + tid;
-    const long long v = (i < n) ? in[i] : 0;
-    long long x = v;
+  for (int i = tid; i < 32 * 8; i += MB_THREADS) (&dirty_s[0][0])[i] = 0u;
+  for (int t0 = 0; t0 < total_tiles; t0 += MB_TILES) {
+    const int nt = min(MB_TILES, total_tiles - t0);
+    __syncthreads();
+    for (int i = tid; i < nt * 128; i += MB_THREADS) mb_bits[i] = 0u;
+    __syncthreads();
+    for (int ul = wid; ul < 32; ul += MB_THREADS / 32) {   // warp per user, lanes over the user's entries
+      const int p = c * TC_N + ub * 128 + q * 32 + ul;
+      if (p >= n_users) continue;
+      const long long uid = user_ids[p];
+      const long long lo = indptr[uid], hi = indptr[uid + 1];
+      for (long long base = lo; base < hi; base += 128) {
+        int it[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) wtot[wid] = x;
-    __syncthreads();
-    long long before = carry_s, all = 0;
-    for (int w = 0; w < 32; ++w) {
-      if (w < wid) before += wtot[w];
-      all += wtot[w];
-    }
-    if (i < n) out[i] = before + x - v;
-    __syncthreads();
-    if (tid == 0) carry_s += all;
-    __syncthreads();
-  }
-  if (tid == 0) out[n] = carry_s;
-}
-
-// One block per CTA-group: counting sort of the group's (item, column) train pairs by 32-item group.
-// Dynamic smem: hist[ngroups + 1].
-__global__ void __launch_bounds__(256) k_tc_mask_build(const long long *__restrict__ user_ids,
-                                                       const long long *__restrict__ indptr,
-                                                       const int *__restrict__ indices, int n_users, int ngroups,
-                                                       int total_tiles, uint32_t magic,
-                                                       const long long *__restrict__ base, int *__restrict__ mask_ptr,
-                                                       uint16_t *__restrict__ pairs) {
-  extern __shared__ int mb_smem[];
-  int *hist = mb_smem;   // [ngroups + 1]
-  __shared__ int carry_s, warp_tot[8];
-  const int c = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int i = tid; i <= ngroups; i += 256) hist[i] = 0;
-  __syncthreads();
-  const int p0 = c * TC_N;
-  // pass 1: histogram (warp per user, lanes over the user's entries)
-  for (int p = p0 + wid; p < p0 + TC_N && p < n_users; p += 8) {
-    const long long uid = user_ids[p];
-    const long long lo = indptr[uid], hi = indptr[uid + 1];
-    for (long long e = lo + lane; e < hi; e += 32) atomicAdd(hist + (tc_pos_of(indices[e], total_tiles, magic) >> 5), 1);
-  }
-  __syncthreads();
-  // exclusive scan of hist[0..ngroups) in chunks of 256
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  for (int start = 0; start < ngroups; start += 256) {
-    const int i = start + tid;
-    const int v = (i < ngroups) ? hist[i] : 0;
-    int x = v;
+        for (int j = 0; j < 4; ++j) {                       // four loads in flight per lane
+          const long long e = base + j * 32 + lane;
+          it[j] = (e < hi) ? indices[e] : -1;
+        }
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+        for (int j = 0; j < 4; ++j) {
+          if (it[j] < 0) continue;
+          const int pos = tc_pos_of(it[j], total_tiles, magic);
+          const int tile = pos >> 7, col = pos & 127;
+          if (tile >= t0 && tile < t0 + nt)
+            atomicOr(mb_bits + (((tile - t0) * 2 + (col >> 6)) * 32 + ul) * 2 + ((col >> 5) & 1), 1u << (col & 31));
+          if (t0 == 0) {
+            const int li = tile / sample_step;
+            if (li * sample_step == tile) {
+              const int g = li * 4 + (col >> 5);
+              if (g < 256) atomicOr(&dirty_s[ul][g >> 5], 1u << (g & 31));
+            }
+          }
+        }
+      }
     }
-    if (lane == 31) warp_tot[wid] = x;
     __syncthreads();
-    int before = 0, all = 0;
-    for (int w = 0; w < 8; ++w) {
-      if (w < wid) before += warp_tot[w];
-      all += warp_tot[w];
-    }
-    const int excl = carry_s + before + x - v;
-    __syncthreads();
-    if (i < ngroups) hist[i] = excl;
-    if (tid == 0) carry_s += all;
-    __syncthreads();
-  }
-  if (tid == 0) hist[ngroups] = carry_s;
-  __syncthreads();
-  int *mp = mask_ptr + (long long)c * (ngroups + 1);
-  for (int i = tid; i <= ngroups; i += 256) mp[i] = hist[i];
-  __syncthreads();
-  // pass 2: scatter (order inside a group is irrelevant); hist[] doubles as the running cursor
-  uint16_t *out = pairs + base[c];
-  for (int p = p0 + wid; p < p0 + TC_N && p < n_users; p += 8) {
-    const long long uid = user_ids[p];
-    const long long lo = indptr[uid], hi = indptr[uid + 1];
-    const uint32_t col = (uint32_t)(p - p0);
-    for (long long e = lo + lane; e < hi; e += 32) {
-      const int pos = tc_pos_of(indices[e], total_tiles, magic);
-      const int at = atomicAdd(hist + (pos >> 5), 1);
-      out[at] = (uint16_t)((pos & 31) | (col << 5));
+    // the 256 bytes of (tile, half) go to epilogue warp q + 4*(ub + 2*half) of that tile's 4 KB image
+    const uint4 *src = reinterpret_cast<const uint4 *>(mb_bits);
+    for (int i = tid; i < nt * 32; i += MB_THREADS) {
+      const int run = i >> 4, k16 = i & 15;
+      const int t = t0 + (run >> 1), half = run & 1;
+      uint4 *dst = reinterpret_cast<uint4 *>(mask_bits + (((long long)c * total_tiles + t) * 16 + (q + 4 * (ub + 2 * half))) * 64);
+      dst[k16] = src[i];
     }
   }
+  __syncthreads();
+  for (int i = tid; i < 32 * 8; i += MB_THREADS)
+    dirty[((long long)c * TC_N + ub * 128 + q * 32) * 8 + i] = (&dirty_s[0][0])[i];
 }
 
 constexpr int TH_VPL = 8;   // group maxima per lane -> up to 256 groups per user
@@ -690,29 +595,21 @@ constexpr int TH_VPL = 8;   // group maxima per lane -> up to 256 groups per use
 template <int K>
 __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restrict__ gmax, int groups, int n_users,
                                                             int n_users_pad, int m, float *__restrict__ thr,
-                                                            const long long *__restrict__ user_ids,
-                                                            const long long *__restrict__ indptr,
-                                                            const int *__restrict__ indices, int total_tiles,
-                                                            uint32_t magic, int sample_step) {
+                                                            const uint32_t *__restrict__ dirty_g) {
   // The MAX pass does not look at the train mask: a sampled 32-item group that contains one of the user's train
-  // items is dropped here instead (its maximum may belong to that item).  dirty[w][thread]: bit g of the user's set.
-  __shared__ uint32_t dirty[8][128];
+  // items is dropped here instead (its maximum may belong to that item).  dirty_g[user][8]: bit g of the user's
+  // set (k_tc_mask_bitmap); null = no train mask.
   const int u = blockIdx.x * 128 + threadIdx.x;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) dirty[w][threadIdx.x] = 0u;
   if (u >= n_users) return;
-  if (indptr != nullptr) {
-    const long long uid = user_ids[u];
-    const long long lo = indptr[uid], hi = indptr[uid + 1];
-    for (long long e = lo; e < hi; ++e) {
-      const int pos = tc_pos_of(indices[e], total_tiles, magic);
-      const int tile = pos >> 7;
-      const int li = tile / sample_step;
-      if (li * sample_step == tile) {
-        const int g = li * 4 + ((pos & 127) >> 5);
-        dirty[g >> 5][threadIdx.x] |= 1u << (g & 31);
-      }
-    }
+  uint32_t dirty[8];
+  if (dirty_g != nullptr) {
+    const uint4 d0 = *reinterpret_cast<const uint4 *>(dirty_g + (long long)u * 8);
+    const uint4 d1 = *reinterpret_cast<const uint4 *>(dirty_g + (long long)u * 8 + 4);
+    dirty[0] = d0.x; dirty[1] = d0.y; dirty[2] = d0.z; dirty[3] = d0.w;
+    dirty[4] = d1.x; dirty[5] = d1.y; dirty[6] = d1.z; dirty[7] = d1.w;
+  } else {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) dirty[w] = 0u;
   }
   int top[K];
 #pragma unroll
@@ -724,7 +621,10 @@ __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restric
   for (int t = 0; t < NB; ++t) nxt[t] = (t < groups) ? col[(long long)t * n_users_pad] : INT_MIN;
   for (int g = 0; g < groups; g += NB) {
     int v[NB];
-    const uint32_t dw = dirty[g >> 5][threadIdx.x] >> (g & 31);   // NB divides 32: the batch sits in one word
+    uint32_t dsel = 0u;           // dirty[g >> 5] without a dynamically indexed register array
+#pragma unroll
+    for (int w = 0; w < 8; ++w) dsel = ((g >> 5) == w) ? dirty[w] : dsel;
+    const uint32_t dw = dsel >> (g & 31);   // NB divides 32: the batch sits in one word
 #pragma unroll
     for (int t = 0; t < NB; ++t) v[t] = ((dw >> t) & 1u) ? INT_MIN : nxt[t];   // INT_MIN never enters the top list
 #pragma unroll
@@ -1056,7 +956,7 @@ int make_tmap(CUtensorMap *map, void *base, int rows, int D, int box_rows) {
 size_t tc_smem_bytes(int D) {
   const int katoms = D / TC_KATOM;
   return 1024 + (size_t)TC_N * 128 * katoms + (size_t)TC_STAGES * TC_M * 128 * katoms + 128 +
-         (size_t)TC_EPI_WARPS * 32 * 2 * 4 + (size_t)TC_EPI_WARPS * TC_SCR_ROWS * TC_SROW * 4 +
+         (size_t)TC_EPI_WARPS * TC_SCR_ROWS * TC_SROW * 4 +
          (size_t)TC_EPI_WARPS * 64 * 4;
 }
 
@@ -1144,63 +1044,48 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.user_norm = unorm;
   a.n_users_pad = n_users_pad;
   if (const char *e = getenv("MFB_TC_DBG")) a.dbg = atoi(e);
-  // train mask for the epilogue: per-CTA (item, column) pairs bucketed by 32-item group
+  // train mask for the COLLECT epilogue (dense bitmap) + per-user dirty sampled groups for the threshold kernel
   const int ncta = n_users_pad / TC_N;
-  const int ngroups = i_tiles * 4;
   const uint32_t magic = ((uint64_t)items_pad * (uint64_t)i_tiles < (1ull << 32) && i_tiles > 1)
                              ? (uint32_t)(((1ull << 32) + (uint64_t)i_tiles - 1) / (uint64_t)i_tiles)
                              : 0u;
   int masked_in_gemm = 0;
-  if (d_train_indptr != nullptr && (size_t)(ngroups + 1) * sizeof(int) <= 200 * 1024) {
-    MFB_CHECK(eb.mcnt.reserve((size_t)(2 * ncta + 2) * sizeof(long long)));
-    MFB_CHECK(eb.mptr.reserve((size_t)ncta * (ngroups + 1) * sizeof(int)));
-    long long *cta_cnt = eb.mcnt.as<long long>();
-    long long *cta_base = cta_cnt + ncta + 1;
-    k_tc_user_counts<<<ncta, TC_N, 0, st>>>((const long long *)d_user_ids, (const long long *)d_train_indptr, n_users,
-                                            cta_cnt);
-    k_tc_scan_ll<<<1, 1024, 0, st>>>(cta_cnt, ncta, cta_base);
+  const size_t bitmap_bytes = (size_t)ncta * i_tiles * 4096;
+  uint32_t *dirty = nullptr;
+  if (d_train_indptr != nullptr && bitmap_bytes <= ((size_t)8 << 30) && groups <= 256 && k <= 32) {
+    MFB_CHECK(eb.mpairs.reserve(bitmap_bytes));
+    MFB_CHECK(eb.mptr.reserve((size_t)n_users_pad * 8 * sizeof(uint32_t)));
+    dirty = eb.mptr.as<uint32_t>();
+    const size_t mb_smem = (size_t)(i_tiles < MB_TILES ? i_tiles : MB_TILES) * 512;
+    MFB_CUDA(cudaFuncSetAttribute(k_tc_mask_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb_smem));
+    dim3 mgrid(ncta, 8);
+    k_tc_mask_bitmap<<<mgrid, MB_THREADS, mb_smem, st>>>((const long long *)d_user_ids,
+                                                         (const long long *)d_train_indptr, d_train_indices, n_users,
+                                                         i_tiles, magic, sample_step, eb.mpairs.as<uint32_t>(), dirty);
     MFB_KERNEL_CHECK();
-    long long total_pairs = 0;
-    MFB_CUDA(cudaMemcpyAsync(&total_pairs, cta_base + ncta, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    MFB_CUDA(cudaStreamSynchronize(st));
-    MFB_CHECK(eb.mpairs.reserve((size_t)total_pairs * sizeof(uint16_t) + 64));
-    const size_t mb_smem = (size_t)(ngroups + 1) * sizeof(int);
-    MFB_CUDA(cudaFuncSetAttribute(k_tc_mask_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb_smem));
-    k_tc_mask_build<<<ncta, 256, mb_smem, st>>>((const long long *)d_user_ids, (const long long *)d_train_indptr,
-                                                d_train_indices, n_users, ngroups, i_tiles, magic, cta_base, eb.mptr.as<int>(),
-                                                eb.mpairs.as<uint16_t>());
-    MFB_KERNEL_CHECK();
-    a.mask_pairs = eb.mpairs.as<uint16_t>();
-    a.mask_ptr = eb.mptr.as<int>();
-    a.mask_base = cta_base;
-    a.ngroups = ngroups;
+    a.mask_bits = eb.mpairs.as<uint2>();
     masked_in_gemm = 1;
   }
-  // sample pass: group maxima of every sample_step-th item tile.  With the small-k threshold kernel the MAX pass
-  // ignores the train mask (that kernel drops the groups that contain a train item of the user).
-  const bool small_thr = masked_in_gemm && k <= 32 && groups <= 256;
+  // sample pass: group maxima of every sample_step-th item tile (no train mask: the small-k threshold kernel drops
+  // the groups that contain a train item of the user; the general one counts k + ntrain maxima instead)
+  const bool small_thr = k <= 32 && groups <= 256 && (d_train_indptr == nullptr || masked_in_gemm);
   a.tile_begin = 0;
   a.tile_step = sample_step;
   a.n_tiles = n_sample;
   a.gmax = eb.gmax.as<int>();
-  {
-    TcArgs amax = a;
-    if (small_thr) amax.mask_pairs = nullptr;
-    MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, amax, n_users, st));
-  }
+  MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st));
   if (small_thr) {
     const int tb = (n_users + 127) / 128;
-    const long long *uids = (const long long *)d_user_ids, *ip = (const long long *)d_train_indptr;
     int *gm = eb.gmax.as<int>();
-    if (k <= 8) k_tc_threshold_small<8><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, uids, ip, d_train_indices, i_tiles, magic, sample_step);
-    else if (k <= 16) k_tc_threshold_small<16><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, uids, ip, d_train_indices, i_tiles, magic, sample_step);
-    else if (k <= 24) k_tc_threshold_small<24><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, uids, ip, d_train_indices, i_tiles, magic, sample_step);
-    else k_tc_threshold_small<32><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, uids, ip, d_train_indices, i_tiles, magic, sample_step);
+    if (k <= 8) k_tc_threshold_small<8><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, dirty);
+    else if (k <= 16) k_tc_threshold_small<16><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, dirty);
+    else if (k <= 24) k_tc_threshold_small<24><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, dirty);
+    else k_tc_threshold_small<32><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, dirty);
   } else {
     k_tc_threshold<<<(n_users + 3) / 4, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k,
                                                       (const long long *)d_user_ids,
                                                       (const long long *)d_train_indptr, unorm, nullptr, thr, eps,
-                                                      masked_in_gemm);
+                                                      0);
   }
   MFB_KERNEL_CHECK();
   // collect pass: all tiles
