@@ -335,6 +335,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
         mbar_wait_backoff(tempty + b, bph);  // accumulators drained AND the item biases pre-stored by the epilogue
         mbar_wait_backoff(full + s, ph);     // item tile landed
         tc_fence_after();
+        if (a.dbg & 32) {   // timing experiment only (results are garbage): one M=128 x N=256 MMA shape per K step
+          const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256);
+          for (int ka = 0; ka < katoms; ++ka) {
+            const uint64_t udesc = umma_desc_sw128(smem_u32(sU + (size_t)ka * TC_N * 128));
+            const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (size_t)ka * TC_M * 128));
+#pragma unroll
+            for (int k = 0; k < TC_KATOM / 16; ++k)
+              tc_mma_bf16(d_tmem, vdesc + (uint64_t)(2 * k), udesc + (uint64_t)(2 * k), idesc2, 1u);
+          }
+        } else
 #pragma unroll
         for (int ub = 0; ub < 2; ++ub) {     // the two 128-user blocks share the item tile
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256 + ub * 128);
@@ -740,13 +751,26 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
   }
   // ---- 1. bounds of every listed item's exact score from its GEMM score: [s - e, s + e], e = err_coeff*|u|*|v|
   const float nu = unorm[u];
-  for (int c = lane; c < cnt; c += 32) {
-    const int2 rec = (c < cnt0) ? cand[(long long)(2 * u) * cap2 + c] : cand[(long long)(2 * u + 1) * cap2 + (c - cnt0)];
-    const float e = item_norm[rec.x];   // err_coeff * |v|, indexed by item id
-    const float sg = __int_as_float(rec.y);
-    ids[c] = rec.x;
-    sc[c] = fmaf(e, nu, sg);
-    lob[c] = fmaf(-e, nu, sg);
+  constexpr int KR = 8;                       // lists of up to 32*KR items keep their lower-bound keys in registers
+  const bool small = cnt <= 32 * KR;
+  uint32_t kreg[KR];
+#pragma unroll
+  for (int j = 0; j < KR; ++j) kreg[j] = 0u;  // 0 never matches a radix-select test
+  for (int c0 = 0; c0 < cnt; c0 += 32 * KR) {
+#pragma unroll
+    for (int j = 0; j < KR; ++j) {
+      const int c = c0 + j * 32 + lane;
+      if (c < cnt) {
+        const int2 rec = (c < cnt0) ? cand[(long long)(2 * u) * cap2 + c] : cand[(long long)(2 * u + 1) * cap2 + (c - cnt0)];
+        const float e = item_norm[rec.x];   // err_coeff * |v|, indexed by item id
+        const float sg = __int_as_float(rec.y);
+        const float lo = fmaf(-e, nu, sg);
+        ids[c] = rec.x;
+        sc[c] = fmaf(e, nu, sg);
+        lob[c] = lo;
+        if (c0 == 0) kreg[j] = (uint32_t)float_to_ordered(lo) ^ 0x80000000u;
+      }
+    }
   }
   __syncwarp();
   // ---- 2. the k-th largest lower bound L: at least k listed items have exact score >= L, so an item whose upper
@@ -754,22 +778,17 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
   int n_surv = cnt;
   if (!check_mask) {   // (with the mask applied here instead of in the GEMM, listed items may be train items: no filter)
     // Only the top 20 key bits are resolved: the result is the k-th largest key with its low bits cleared, a
-    // slightly smaller -- still valid -- bound.  Lists of up to 128 items (the usual case) sit in registers.
+    // slightly smaller -- still valid -- bound.  Lists of up to 256 items (the usual case) sit in registers.
     uint32_t prefix = 0, mask = 0;
     int want = k;
-    const bool small = cnt <= 128;
-    uint32_t kreg[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = j * 32 + lane;
-      kreg[j] = (small && c < cnt) ? ((uint32_t)float_to_ordered(lob[c]) ^ 0x80000000u) : 0u;   // 0 never matches
-    }
+    const int nv = (cnt + 31) >> 5;           // key registers in use (warp-uniform)
     for (int bit = 31; bit >= 12; --bit) {
       const uint32_t test = prefix | (1u << bit), tmask = mask | (1u << bit);
       int c1 = 0;
       if (small) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) c1 += ((kreg[j] & tmask) == test) ? 1 : 0;
+        for (int j = 0; j < KR; ++j)
+          if (j < nv) c1 += ((kreg[j] & tmask) == test) ? 1 : 0;
       } else {
         for (int c = lane; c < cnt; c += 32)
           c1 += ((((uint32_t)float_to_ordered(lob[c]) ^ 0x80000000u) & tmask) == test) ? 1 : 0;
