@@ -39,20 +39,44 @@ def is_stale():
     return any(os.path.getmtime(p) > built for p in deps)
 
 
+def _compile_one(args):
+    src, obj, defines, verbose = args
+    cmd = [_nvcc(), '-c', '-Xcompiler', '-fPIC'] + NVCC_FLAGS[3:] + ['-D' + d for d in defines] + \
+        (['-Xptxas', '-v'] if verbose else []) + ['-o', obj, src]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError('nvcc failed:\n%s\n%s' % (' '.join(cmd), proc.stderr[-4000:]))
+    return proc.stderr
+
+
 def build_library(force=False, verbose=False, out=None, defines=()):
-    """Compile csrc/*.cu into lib/libmfb200.so.  `out` / `defines` build an experiment variant elsewhere
-    (e.g. defines=['MFB_TC_EPI_WARPS=8']); load it with $MFB_LIB_PATH."""
+    """Compile csrc/*.cu into lib/libmfb200.so (one object per source, compiled in parallel, only the stale ones).
+    `out` / `defines` build an experiment variant elsewhere (e.g. defines=['MFB_TC_EPI_WARPS=8']); load it with
+    $MFB_LIB_PATH."""
     if out is None and not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     target = out or LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + \
-        ['-o', target] + sources()
+    obj_dir = os.path.join(LIB_DIR, 'obj' if out is None else 'obj_' + os.path.basename(target))
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, '*.cuh')) + [os.path.join(HERE, '..', 'include', 'mfb200.h')]
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + '.o')
+        objs.append(obj)
+        fresh = os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time)
+        if force or defines or verbose or not fresh:
+            jobs.append((src, obj, list(defines), verbose))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        logs = list(pool.map(_compile_one, jobs))
+    cmd = [_nvcc()] + NVCC_FLAGS[:5] + ['-o', target] + objs
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError('nvcc failed:\n%s\n%s' % (' '.join(cmd), proc.stderr[-4000:]))
+        raise RuntimeError('link failed:\n%s\n%s' % (' '.join(cmd), proc.stderr[-4000:]))
     if verbose:
-        sys.stderr.write(proc.stderr)
+        sys.stderr.write(''.join(logs))
     return target
 
 
