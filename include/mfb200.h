@@ -188,6 +188,50 @@ int mfb_topk_hits(const int32_t *d_topk_ids, const int64_t *d_user_ids, int64_t 
                   const int64_t *d_test_indptr, const int32_t *d_test_indices, const int32_t *h_ks, int32_t nk,
                   int32_t *d_hits, int32_t *d_ntargets, mfb_stream stream);
 
+/* ---- row-sharded training (scaled catalog: tables split over the GPUs of one box) ------------- */
+/* No counterpart exists in the reference (one process, one set of tables, implicit.py:163-199); the
+ * arithmetic of a step is run_train_iteration's (implicit.py:347-364), distributed as follows.  Rank r of
+ * `world` OWNS the rows {g : g mod world == r} of the four tables (local index g / world) -- `local` is an
+ * mfb_model bound to those local tables, moments included -- and COMPUTES a contiguous block of every
+ * minibatch's positives and of its negatives (blocks as sharding.shard_range).  All ranks pass the SAME ids
+ * (positives replicated, negatives drawn from the same MT19937 stream), so ids are never exchanged.
+ * Exchange buffers hold rows of mfb_shard_row_stride() floats: dim values (padded to a multiple of 4), the
+ * bias, 3 pad floats.  One step s of a planned chunk:
+ *   mfb_shard_gather   -> all-to-all (rows to the computing ranks; counts from mfb_shard_plan)
+ *   mfb_shard_forward  -> [adaptive hinge: all-reduce MAX of the int64 cell]
+ *   mfb_shard_backward -> all-to-all back (gradient rows to the owners, mirrored counts)
+ *   mfb_shard_update.
+ * The host side (recommendation_gans_b200/sharded.py) runs the collectives with torch.distributed (NCCL). */
+typedef struct mfb_shard mfb_shard;
+int mfb_shard_create(mfb_model *local, int32_t rank, int32_t world, int64_t global_users, int64_t global_items,
+                     mfb_shard **out);
+int mfb_shard_destroy(mfb_shard *sh);
+int32_t mfb_shard_row_stride(const mfb_shard *sh);
+int64_t mfb_shard_launches(const mfb_shard *sh);
+/* Plans steps [step0, step0+nsteps) of the epoch over the n_pos positives (minibatches as mfb_train_steps).
+ * d_neg_*: the n_neg*batch negative pairs of each planned step, step-major, starting at step0's.
+ * h_counts[(s*world + o)*world + c] = rows owner o sends to computing rank c in step s (and receives back as
+ * gradients).  Synchronises the stream once. */
+int mfb_shard_plan(mfb_shard *sh, const int64_t *d_pos_users, const int64_t *d_pos_items, int64_t n_pos,
+                   int32_t batch, int32_t n_neg, const int64_t *d_neg_users, const int64_t *d_neg_items,
+                   int64_t step0, int32_t nsteps, int64_t *h_counts, mfb_stream stream);
+/* Owner: brings the step's requested rows up to date (dense-optimiser replay) and packs them into d_send,
+ * grouped by computing rank in rank order (sum_c counts[s][rank][c] rows). */
+int mfb_shard_gather(mfb_shard *sh, int32_t s, float *d_send, mfb_stream stream);
+/* Computing rank: d_recv holds the rows received from owner 0, 1, ... in that order.  BilinearNet.forward
+ * (representations.py:80-91) on this rank's slots; for MFB_LOSS_ADAPTIVE_HINGE *d_gmax_cell receives the
+ * packed (probability, first index) maximum of this rank's negatives -- all-reduce it with MAX as int64. */
+int mfb_shard_forward(mfb_shard *sh, int loss, int32_t s, const float *d_recv, int64_t *d_gmax_cell,
+                      mfb_stream stream);
+/* Computing rank: gradient rows (dLoss/drow contributions per slot, bias gradient in the bias position) into
+ * d_gsend, same layout as d_recv; d_loss_partial[2] receives this rank's partial loss sums (positive/pairwise
+ * sum, pointwise negative sum) -- the loss of the step is sum_ranks(p[0])/b (+ sum_ranks(p[1])/m). */
+int mfb_shard_backward(mfb_shard *sh, int loss, int32_t s, const float *d_recv, const int64_t *d_gmax_cell,
+                       float *d_gsend, double *d_loss_partial, mfb_stream stream);
+/* Owner: d_grecv holds the gradient rows in d_send's layout.  Ordered segment reduction per unique row and one
+ * dense-optimiser step (torch Adam / SGD) of the local model; advances its step counter. */
+int mfb_shard_update(mfb_shard *sh, int32_t s, const float *d_grecv, mfb_stream stream);
+
 /* ---- in-situ kernel timing (measurement only) ---------------------------------------------- */
 /* When enabled, every kernel launched for this model is bracketed by CUDA events on the launch
  * stream.  mfb_profile_read synchronises, then reports per kernel class the summed device time

@@ -72,6 +72,18 @@ SIGNATURES = {
     'mfb_topk_last_redo': (ctypes.c_int, [c_void]),
     'mfb_debug_tc_stats': (ctypes.c_int, [c_void, ctypes.c_int64, c_void, c_void]),
     'mfb_debug_tc_scores': (ctypes.c_int, [c_void, c_void, ctypes.c_int64, c_void, c_void]),
+    'mfb_shard_create': (ctypes.c_int, [c_void, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                                        ctypes.POINTER(c_void)]),
+    'mfb_shard_destroy': (ctypes.c_int, [c_void]),
+    'mfb_shard_row_stride': (ctypes.c_int32, [c_void]),
+    'mfb_shard_launches': (ctypes.c_int64, [c_void]),
+    'mfb_shard_plan': (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_void,
+                                      c_void, ctypes.c_int64, ctypes.c_int32, c_void, c_void]),
+    'mfb_shard_gather': (ctypes.c_int, [c_void, ctypes.c_int32, c_void, c_void]),
+    'mfb_shard_forward': (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int32, c_void, c_void, c_void]),
+    'mfb_shard_backward': (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int32, c_void, c_void, c_void, c_void,
+                                          c_void]),
+    'mfb_shard_update': (ctypes.c_int, [c_void, ctypes.c_int32, c_void, c_void]),
     'mfb_profile_enable': (ctypes.c_int, [c_void, ctypes.c_int]),
     'mfb_profile_read': (ctypes.c_int, [c_void, c_void, c_void]),
     'mfb_profile_name': (ctypes.c_char_p, [ctypes.c_int]),

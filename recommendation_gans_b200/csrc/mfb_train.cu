@@ -362,37 +362,6 @@ __device__ __forceinline__ float slot_dz(int j, int b, int m, const float *__res
 // ---------------------------------------------------------------------------------------
 // planner kernels (model-independent integer work, bulk per chunk)
 // ---------------------------------------------------------------------------------------
-// After the sort, equal keys (same step, table, row) are adjacent: seg_first[q] = first position of
-// q's segment, seg_len[head] = its length.
-__global__ void k_segments(const uint32_t *__restrict__ skeys, long long n, uint32_t *__restrict__ seg_first,
-                           uint32_t *__restrict__ seg_len) {
-  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  const uint32_t key = skeys[q];
-  if (q == 0 || skeys[q - 1] != key) {  // head: upper bound of key in (q, n)
-    long long lo = q + 1, hi = n;
-    if (lo < n && skeys[lo] == key) {    // (most segments have length 1 and skip the search)
-      while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
-        if (skeys[mid] <= key) lo = mid + 1; else hi = mid;
-      }
-    }
-    seg_first[q] = (uint32_t)q;
-    seg_len[q] = (uint32_t)(lo - q);
-  } else {                               // inside a segment: lower bound of key in [0, q)
-    long long lo = 0, hi = q - 1;        // skeys[q-1] == key, so the answer is <= q-1
-    if (q >= 2 && skeys[q - 2] != key) {
-      lo = q - 1;
-    } else {
-      while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
-        if (skeys[mid] < key) lo = mid + 1; else hi = mid;
-      }
-    }
-    seg_first[q] = (uint32_t)lo;
-  }
-}
-
 // Keys for the second, row-major sort: (table,row) only, payload = step-major position.
 __global__ void k_rowkeys(const uint32_t *__restrict__ skeys, long long n, int rb, uint32_t *__restrict__ rkeys,
                           uint32_t *__restrict__ rvals) {
@@ -431,28 +400,6 @@ __global__ void k_next_use(const uint32_t *__restrict__ rkeys, const uint32_t *_
     const int at = atomicAdd(lazy_cnt + step, 1);
     lazy_rows[(long long)step * lazy_cap + at] = rk;
   }
-}
-
-// One 16-byte record per sorted position, so k_update needs a single load for its bookkeeping.
-struct __align__(16) PosInfo {
-  uint32_t key;    // step | table | row
-  uint32_t first;  // chunk-global position of the segment head
-  uint32_t len;    // segment length
-  uint32_t gap;    // steps to the row's next use in the chunk (0: none)
-};
-
-__global__ void k_posinfo(const uint32_t *__restrict__ skeys, long long n, const uint32_t *__restrict__ seg_first,
-                          const uint32_t *__restrict__ seg_len, const uint32_t *__restrict__ seg_gap,
-                          PosInfo *__restrict__ info) {
-  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  const uint32_t first = seg_first[q];
-  PosInfo p;
-  p.key = skeys[q];
-  p.first = first;
-  p.len = seg_len[first];
-  p.gap = seg_gap ? seg_gap[first] : 0u;
-  info[q] = p;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -690,12 +637,6 @@ inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
-int bits_for(uint32_t maxval) {
-  int b = 1;
-  while (b < 32 && (maxval >> b) != 0) ++b;
-  return b;
 }
 
 int check_err_flag(int *d_flag, cudaStream_t st, const char *what) {
