@@ -258,6 +258,12 @@ def native_bench(args, w, rank, world):
     # ---- evaluation: full-catalog top-k with train mask, users sharded across ranks
     ev = eval_bench(eng, w, rank, world, dev, rs)
 
+    # ---- cfg5: scaled catalog, tables row-sharded over the ranks (all-to-all of rows over NVLink); strong scaling
+    sh = None
+    if not args.no_sharded:
+        from tools.shard_bench import run as shard_run
+        sh = shard_run(steps=args.sharded_steps, warmup=10, zipf=w['zipf'], fast_math=bool(args.fast_math))
+
     # ---- reduce over ranks: max time, summed work
     t_train, t_e2e, t_eval, n_eval = ms / 1e3, e2e_s, ev['seconds'], ev['users']
     if dist:
@@ -311,6 +317,12 @@ def native_bench(args, w, rank, world):
                               'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                               'frac': 2.0 * n_eval * w['I'] * D / t_eval / 1e12 / peaks['bf16_tflops']}},
     }
+    if sh is not None:
+        sh['roofline'] = {'bound': 'hbm', 'achieved': sh['hbm_gbs_algorithmic_total'], 'peak': peaks['hbm_gbs'] * world,
+                          'unit': 'GB/s', 'frac': sh['hbm_gbs_algorithmic_total'] / (peaks['hbm_gbs'] * world),
+                          'note': 'algorithmic bytes of the whole step over all GPUs; the step is bound by the '
+                                  'dense-optimiser replay arithmetic (MUFU), see DESIGN.md'}
+        out['sharded_train'] = sh
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_steps(w, steps=args.cpu_steps, warmup=1)
         out['cpu_baseline'] = {'value': cb['value'], 'unit': 'interactions/s', 'cores': cb['cores'], 'kind': 'port',
@@ -365,6 +377,8 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=120)
     ap.add_argument('--repeats', type=int, default=3, help='timed region repeated; best reported')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sharded', action='store_true', help='skip the cfg5 row-sharded training object')
+    ap.add_argument('--sharded-steps', type=int, default=100)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = dict(WORKLOADS[args.workload])

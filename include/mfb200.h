@@ -232,6 +232,27 @@ int mfb_shard_backward(mfb_shard *sh, int loss, int32_t s, const float *d_recv, 
  * dense-optimiser step (torch Adam / SGD) of the local model; advances its step counter. */
 int mfb_shard_update(mfb_shard *sh, int32_t s, const float *d_grecv, mfb_stream stream);
 
+/* Direct exchange over peer memory (NVLink): the collectives above are replaced by stores into the peers' exchange
+ * buffers from inside the gather / forward / backward kernels plus flag kernels (release/acquire at system scope),
+ * so a step needs no collective call and no host synchronisation.
+ *   mfb_shard_xbuf_alloc     allocates this rank's exchange buffer for minibatches of `batch` positives and
+ *                            n_neg*batch negatives (cudaMalloc: exportable with CUDA IPC)
+ *   mfb_ipc_export/open/close  64-byte CUDA IPC handle of a device pointer / mapping of a peer's handle
+ *   mfb_shard_xbuf_set_peers peer_ptrs[world]: every rank's exchange buffer as mapped in THIS process
+ *                            (entry `rank` = the pointer mfb_shard_xbuf_alloc returned); all ranks must have
+ *                            allocated before any rank runs steps
+ *   mfb_shard_run_steps      steps [s_begin, s_end) of the planned chunk, fully asynchronous;
+ *                            d_loss_partial: 2 doubles per step as mfb_shard_backward
+ *   mfb_shard_direct_check   synchronises the stream; error if a wait on a peer timed out (~3 s) */
+int mfb_shard_xbuf_alloc(mfb_shard *sh, int32_t batch, int32_t n_neg, void **d_ptr, int64_t *bytes);
+int mfb_shard_xbuf_set_peers(mfb_shard *sh, void *const *peer_ptrs);
+int mfb_ipc_export(void *d_ptr, void *h_handle64);
+int mfb_ipc_open(const void *h_handle64, void **d_ptr);
+int mfb_ipc_close(void *d_ptr);
+int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int32_t s_end, double *d_loss_partial,
+                        mfb_stream stream);
+int mfb_shard_direct_check(mfb_shard *sh, mfb_stream stream);
+
 /* ---- in-situ kernel timing (measurement only) ---------------------------------------------- */
 /* When enabled, every kernel launched for this model is bracketed by CUDA events on the launch
  * stream.  mfb_profile_read synchronises, then reports per kernel class the summed device time

@@ -84,6 +84,14 @@ SIGNATURES = {
     'mfb_shard_backward': (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int32, c_void, c_void, c_void, c_void,
                                           c_void]),
     'mfb_shard_update': (ctypes.c_int, [c_void, ctypes.c_int32, c_void, c_void]),
+    'mfb_shard_xbuf_alloc': (ctypes.c_int, [c_void, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(c_void),
+                                            ctypes.POINTER(ctypes.c_int64)]),
+    'mfb_shard_xbuf_set_peers': (ctypes.c_int, [c_void, c_void]),
+    'mfb_ipc_export': (ctypes.c_int, [c_void, c_void]),
+    'mfb_ipc_open': (ctypes.c_int, [c_void, ctypes.POINTER(c_void)]),
+    'mfb_ipc_close': (ctypes.c_int, [c_void]),
+    'mfb_shard_run_steps': (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int32, ctypes.c_int32, c_void, c_void]),
+    'mfb_shard_direct_check': (ctypes.c_int, [c_void, c_void]),
     'mfb_profile_enable': (ctypes.c_int, [c_void, ctypes.c_int]),
     'mfb_profile_read': (ctypes.c_int, [c_void, c_void, c_void]),
     'mfb_profile_name': (ctypes.c_char_p, [ctypes.c_int]),

@@ -49,6 +49,15 @@ struct Geom {
   int batch, m_neg, ns, Lfull, G, rank, gb, GP, rb, Lloc_cap;
 };
 
+constexpr int MAX_PEERS = 16;
+struct Peers {
+  char *base[MAX_PEERS];
+};
+struct XLayout {
+  size_t recv_off, grecv_off, cells_off, flags_off, err_off, total;
+};
+enum { FLAG_ROWS = 0, FLAG_MAX = 1, FLAG_GRADS = 2 };
+
 __device__ __forceinline__ int step_batch(const Geom &g, int s) {
   const long long first = (g.step0 + s) * g.batch;
   return (int)((g.n_pos - first < g.batch) ? (g.n_pos - first) : g.batch);
@@ -133,7 +142,8 @@ __global__ void k_shard_layout(const uint32_t *__restrict__ skeys, const uint32_
                                Geom g, const int *__restrict__ ids_u, const int *__restrict__ ids_i,
                                const uint32_t *__restrict__ start, const uint32_t *__restrict__ own_off,
                                const uint32_t *__restrict__ rbase, uint32_t *__restrict__ ent,
-                               uint32_t *__restrict__ keys2, uint32_t *__restrict__ vals2, int *__restrict__ rpos) {
+                               uint32_t *__restrict__ keys2, uint32_t *__restrict__ vals2, int *__restrict__ rpos,
+                               uint32_t *__restrict__ sdst, uint32_t *__restrict__ gdst) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
   const uint32_t key = skeys[q], val = svals[q];
@@ -148,13 +158,19 @@ __global__ void k_shard_layout(const uint32_t *__restrict__ skeys, const uint32_
     ent[at] = ((uint32_t)t << 31) | lrow;
     keys2[at] = ((uint32_t)s << (g.rb + 1)) | ((uint32_t)t << g.rb) | lrow;
     vals2[at] = p;
+    // direct exchange: where this row lands in computing rank c's receive buffer (blocks of owners 0..r-1 first)
+    uint32_t rb_c = 0;
+    for (int o2 = 0; o2 < r; ++o2) rb_c += start[(s * GP + o2) * GP + c + 1] - start[(s * GP + o2) * GP + c];
+    sdst[at] = ((uint32_t)c << 26) | (rb_c + ((uint32_t)q - start[(s * GP + r) * GP + c]));
   }
   if (c == r) {
     const int b = step_batch(g, s);
     const int b_lo = part_lo(r, b, g.G), b_loc = part_lo(r + 1, b, g.G) - b_lo;
     const int jl = (j < b) ? (j - b_lo) : (b_loc + (j - b - part_lo(r, g.m_neg, g.G)));
-    rpos[((long long)t * g.ns + s) * g.Lloc_cap + jl] =
-        (int)(rbase[s * GP + o] + ((uint32_t)q - start[(s * GP + o) * GP + r]));
+    const long long at = ((long long)t * g.ns + s) * g.Lloc_cap + jl;
+    rpos[at] = (int)(rbase[s * GP + o] + ((uint32_t)q - start[(s * GP + o) * GP + r]));
+    // direct exchange: the row's gradient goes to owner o, at the row's position in o's serve order
+    gdst[at] = ((uint32_t)o << 26) | ((uint32_t)q - start[(s * GP + o) * GP]);
   }
 }
 
@@ -212,13 +228,13 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_forward(const int *__restr
   if (jl < Lloc) {
     const float *ru = recv + (long long)rpos_u[jl] * stride, *ri = recv + (long long)rpos_i[jl] * stride;
     Frag<VEC, NIT> fu, fi;
-    frag_load<VEC, NIT>(fu, ru, D, lane);
-    frag_load<VEC, NIT>(fi, ri, D, lane);
+    frag_load_cg<VEC, NIT>(fu, ru, D, lane);   // exchange buffers are written by peers: L2-only loads
+    frag_load_cg<VEC, NIT>(fi, ri, D, lane);
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < NIT * VEC; ++k) acc = fmaf(fu.x[k], fi.x[k], acc);
     acc = warp_sum(acc);
-    const float y = sigmoidf_acc((acc + ru[Dp]) + ri[Dp]);
+    const float y = sigmoidf_acc((acc + __ldcg(ru + Dp)) + __ldcg(ri + Dp));
     if (lane == 0) pred[jl] = y;
     if (adaptive && jl >= b_loc) mine = pack_max(y, neg_lo + (jl - b_loc));
   }
@@ -269,7 +285,10 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_backward(const int *__rest
                                                                const float *__restrict__ recv, int D, int Dp, int stride,
                                                                const float *__restrict__ pred,
                                                                const unsigned long long *__restrict__ gmax_cell,
-                                                               float *__restrict__ gsend) {
+                                                               float *__restrict__ gsend,
+                                                               const uint32_t *__restrict__ gdst_u,
+                                                               const uint32_t *__restrict__ gdst_i, Peers peers,
+                                                               size_t grecv_off) {
   const int lane = threadIdx.x & 31;
   const int jl = blockIdx.x * SH_WARPS + (threadIdx.x >> 5);
   if (jl >= Lloc) return;
@@ -278,7 +297,15 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_backward(const int *__rest
   const float gmax = unpack_max_val(gcell);
   const int jstar = (KIND == MFB_LOSS_ADAPTIVE_HINGE) ? unpack_max_idx(gcell) : -1;
   const long long pu = rpos_u[jl], pi = rpos_i[jl];
-  float *gu = gsend + pu * stride, *gi = gsend + pi * stride;
+  float *gu, *gi;
+  if (gdst_u != nullptr) {   // direct exchange: straight into the owners' gradient buffers
+    const uint32_t du = gdst_u[jl], di = gdst_i[jl];
+    gu = reinterpret_cast<float *>(peers.base[du >> 26] + grecv_off) + (long long)(du & 0x3ffffffu) * stride;
+    gi = reinterpret_cast<float *>(peers.base[di >> 26] + grecv_off) + (long long)(di & 0x3ffffffu) * stride;
+  } else {
+    gu = gsend + pu * stride;
+    gi = gsend + pi * stride;
+  }
   Frag<VEC, NIT> fu, fi;
   // adaptive hinge: only the first maximal negative carries gradient; the others send zero rows
   const bool zero = KIND == MFB_LOSS_ADAPTIVE_HINGE && jl >= b_loc && (neg_lo + (jl - b_loc)) != jstar;
@@ -287,8 +314,8 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_backward(const int *__rest
 #pragma unroll
     for (int k = 0; k < NIT * VEC; ++k) fu.x[k] = fi.x[k] = 0.f;
   } else {
-    frag_load<VEC, NIT>(fu, recv + pu * stride, D, lane);
-    frag_load<VEC, NIT>(fi, recv + pi * stride, D, lane);
+    frag_load_cg<VEC, NIT>(fu, recv + pu * stride, D, lane);
+    frag_load_cg<VEC, NIT>(fi, recv + pi * stride, D, lane);
     d = shard_dz<KIND>(jl, b_loc, b_glob, m_glob, neg_lo, pred, gmax, jstar);
 #pragma unroll
     for (int k = 0; k < NIT * VEC; ++k) {
@@ -302,6 +329,83 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_backward(const int *__rest
   if (lane == 0) {
     gu[Dp] = d;
     gi[Dp] = d;
+  }
+}
+
+
+// ---- direct exchange over peer memory (NVLink): no collective call on the step's critical path -----------
+// Every rank owns one exchange buffer (xbuf) that its peers map (CUDA IPC across processes): [receive rows]
+// [gradient rows][adaptive-hinge cells, one per peer][flags: 3 kinds x one 64-bit sequence number per peer].
+// Producers store straight into the consumer's buffer; a one-thread-per-peer signal kernel publishes the step's
+// sequence number after the producing kernel (stream order + release.sys), and a one-warp wait kernel holds the
+// consumer's stream until all peers have signalled (acquire.sys).  Buffers are reused every step: a peer can only
+// overwrite a region after this rank signalled the phase that read it last.
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int VEC, int NIT>
+__global__ void __launch_bounds__(SH_THREADS) k_shard_gather_direct(const uint32_t *__restrict__ ent,
+                                                                    const uint32_t *__restrict__ sdst, int n,
+                                                                    TableView users, TableView items, int D, int Dp,
+                                                                    int stride, Peers peers, size_t recv_off) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * SH_WARPS + (threadIdx.x >> 5);
+  if (p >= n) return;
+  const uint32_t e = ent[p], d = sdst[p];
+  const TableView &T = (e >> 31) ? items : users;
+  const long long row = e & 0x7fffffffu;
+  Frag<VEC, NIT> f;
+  frag_load<VEC, NIT>(f, T.p + row * D, D, lane);
+  float *dst = reinterpret_cast<float *>(peers.base[d >> 26] + recv_off) + (long long)(d & 0x3ffffffu) * stride;
+  frag_store<VEC, NIT>(f, dst, D, lane);
+  if (lane == 0) dst[Dp] = T.bp[row];
+}
+
+// one thread per peer: [optionally copy this rank's adaptive-hinge cell into the peer's cell array, then] publish seq
+__global__ void k_shard_signal(Peers peers, int G, int me, size_t flags_off, int kind, unsigned long long seq,
+                               size_t cells_off, const unsigned long long *__restrict__ local_cell) {
+  const int c = threadIdx.x;
+  if (c >= G) return;
+  if (local_cell != nullptr) {
+    reinterpret_cast<unsigned long long *>(peers.base[c] + cells_off)[me] = *local_cell;
+  }
+  __threadfence_system();
+  st_release_sys(reinterpret_cast<unsigned long long *>(peers.base[c] + flags_off) + kind * MAX_PEERS + me, seq);
+}
+
+// one thread per peer spins until that peer's flag reaches seq (bounded: a dead peer must not hang the GPU);
+// with reduce_cells, thread 0 then folds the peers' adaptive-hinge cells into *out_cell.
+__global__ void k_shard_wait(const char *__restrict__ xbuf, int G, size_t flags_off, int kind, unsigned long long seq,
+                             size_t cells_off, unsigned long long *__restrict__ out_cell, int *__restrict__ err,
+                             long long timeout_clocks) {
+  const int c = threadIdx.x;
+  if (c < G) {
+    const unsigned long long *f = reinterpret_cast<const unsigned long long *>(xbuf + flags_off) + kind * MAX_PEERS + c;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < seq) {
+      if (clock64() - t0 > timeout_clocks) {
+        atomicExch(err, 1 + kind);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (out_cell != nullptr && threadIdx.x == 0) {
+    const unsigned long long *cells = reinterpret_cast<const unsigned long long *>(xbuf + cells_off);
+    unsigned long long best = 0ull;
+    for (int k = 0; k < G; ++k) {
+      const unsigned long long v = ld_acquire_sys(cells + k);
+      best = v > best ? v : best;
+    }
+    *out_cell = best;
   }
 }
 
@@ -387,17 +491,17 @@ __global__ void __launch_bounds__(SH_UPD_WARPS * 32) k_shard_update(const ShUpdA
   float gb;
   {
     const float *src = a.grecv + (long long)a.svals[q] * a.stride;
-    frag_load<VEC, NIT>(g, src, D, lane);
-    gb = src[a.Dp];
+    frag_load_cg<VEC, NIT>(g, src, D, lane);
+    gb = __ldcg(src + a.Dp);
   }
   for (int p0 = ql + 1; p0 < run_end; p0 += 2) {   // remaining rows of the run, two in flight, added in order
     const bool has2 = p0 + 1 < run_end;
     const float *s0 = a.grecv + (long long)a.svals[a.base + p0] * a.stride;
     const float *s1 = a.grecv + (long long)a.svals[a.base + (has2 ? p0 + 1 : p0)] * a.stride;
     Frag<VEC, NIT> o0, o1;
-    frag_load<VEC, NIT>(o0, s0, D, lane);
-    frag_load<VEC, NIT>(o1, s1, D, lane);
-    const float b0 = s0[a.Dp], b1 = s1[a.Dp];
+    frag_load_cg<VEC, NIT>(o0, s0, D, lane);
+    frag_load_cg<VEC, NIT>(o1, s1, D, lane);
+    const float b0 = __ldcg(s0 + a.Dp), b1 = __ldcg(s1 + a.Dp);
 #pragma unroll
     for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fadd_rn(g.x[k], o0.x[k]);
     gb = __fadd_rn(gb, b0);
@@ -457,8 +561,15 @@ struct mfb_shard {
   std::vector<uint32_t> h_start, h_own_off;
   uint32_t *skeys2 = nullptr, *svals2 = nullptr;
   DevBuf ids_u, ids_i, keys_a, keys_b, vals_a, vals_b, hist, start, own_off, rbase, ent, k2a, k2b, v2a, v2b, segf, segl,
-      info, rpos, pred, err, partial, tickets;
+      info, rpos, pred, err, partial, tickets, sdst, gdst, gcell;
   int64_t launches = 0;
+  // direct exchange over peer memory
+  void *xbuf = nullptr;
+  XLayout xl = {};
+  Peers peers = {};
+  bool peers_set = false;
+  unsigned long long seq = 0;
+  int x_batch = 0, x_m_neg = 0;
 };
 
 extern "C" int mfb_shard_create(mfb_model *local, int32_t rank, int32_t world, int64_t global_users,
@@ -498,8 +609,10 @@ extern "C" int mfb_shard_destroy(mfb_shard *sh) {
   cudaDeviceSynchronize();
   DevBuf *bufs[] = {&sh->ids_u, &sh->ids_i, &sh->keys_a, &sh->keys_b, &sh->vals_a, &sh->vals_b, &sh->hist, &sh->start,
                     &sh->own_off, &sh->rbase, &sh->ent, &sh->k2a, &sh->k2b, &sh->v2a, &sh->v2b, &sh->segf, &sh->segl,
-                    &sh->info, &sh->rpos, &sh->pred, &sh->err, &sh->partial, &sh->tickets};
+                    &sh->info, &sh->rpos, &sh->pred, &sh->err, &sh->partial, &sh->tickets, &sh->sdst, &sh->gdst,
+                    &sh->gcell};
   for (DevBuf *b : bufs) b->release();
+  if (sh->xbuf) cudaFree(sh->xbuf);
   delete sh;
   return MFB_OK;
 }
@@ -561,6 +674,11 @@ extern "C" int mfb_shard_plan(mfb_shard *sh, const int64_t *d_pos_users, const i
   MFB_CHECK(sh->rbase.reserve((size_t)nsteps * g.GP * 4));
   MFB_CHECK(sh->rpos.reserve((size_t)2 * nsteps * g.Lloc_cap * sizeof(int)));
   MFB_CHECK(sh->pred.reserve((size_t)nsteps * g.Lloc_cap * sizeof(float)));
+  MFB_CHECK(sh->gdst.reserve((size_t)2 * nsteps * g.Lloc_cap * 4));
+  if (2ll * g.Lfull >= (1ll << 26) || g.G > 64) {
+    mfb_set_error("shard_plan: batch too large for the packed exchange positions");
+    return MFB_ERR_UNSUPPORTED;
+  }
   MFB_CUDA(cudaMemsetAsync(sh->err.ptr, 0, sizeof(int), st));
   {
     const long long nthreads = (long long)nsteps * g.Lfull;
@@ -605,10 +723,11 @@ extern "C" int mfb_shard_plan(mfb_shard *sh, const int64_t *d_pos_users, const i
   MFB_CHECK(sh->segf.reserve(own_cap * 4));
   MFB_CHECK(sh->segl.reserve(own_cap * 4));
   MFB_CHECK(sh->info.reserve(own_cap * sizeof(PosInfo)));
+  MFB_CHECK(sh->sdst.reserve(own_cap * 4));
   k_shard_layout<<<(unsigned)((n_e + 255) / 256), 256, 0, st>>>(
       sk, sv, n_e, g, sh->ids_u.as<int>(), sh->ids_i.as<int>(), sh->start.as<uint32_t>(), sh->own_off.as<uint32_t>(),
       sh->rbase.as<uint32_t>(), sh->ent.as<uint32_t>(), sh->k2a.as<uint32_t>(), sh->v2a.as<uint32_t>(),
-      sh->rpos.as<int>());
+      sh->rpos.as<int>(), sh->sdst.as<uint32_t>(), sh->gdst.as<uint32_t>());
   MFB_KERNEL_CHECK();
   sh->skeys2 = sh->k2a.as<uint32_t>();
   sh->svals2 = sh->v2a.as<uint32_t>();
@@ -729,25 +848,27 @@ extern "C" int mfb_shard_forward(mfb_shard *sh, int loss, int32_t s, const float
   return MFB_OK;
 }
 
-extern "C" int mfb_shard_backward(mfb_shard *sh, int loss, int32_t s, const float *d_recv, const int64_t *d_gmax_cell,
-                                  float *d_gsend, double *d_loss_partial, mfb_stream stream) {
+static int shard_backward_impl(mfb_shard *sh, int loss, int32_t s, const float *d_recv, const int64_t *d_gmax_cell,
+                               float *d_gsend, bool direct, double *d_loss_partial, cudaStream_t st) {
   StepView v;
   MFB_CHECK(step_view(sh, s, &v));
   if (loss < MFB_LOSS_POINTWISE || loss > MFB_LOSS_ADAPTIVE_HINGE || !d_loss_partial) return MFB_ERR_INVALID;
   if (loss == MFB_LOSS_ADAPTIVE_HINGE && !d_gmax_cell) return MFB_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
   const Geom &g = sh->g;
   const int *rpu = sh->rpos.as<int>() + (long long)s * g.Lloc_cap;
   const int *rpi = sh->rpos.as<int>() + ((long long)g.ns + s) * g.Lloc_cap;
   const float *pred = sh->pred.as<float>() + (long long)s * g.Lloc_cap;
   const int D = sh->m->desc.dim;
   const unsigned long long *cell = (const unsigned long long *)d_gmax_cell;
+  const uint32_t *gdu = direct ? sh->gdst.as<uint32_t>() + (long long)s * g.Lloc_cap : nullptr;
+  const uint32_t *gdi = direct ? sh->gdst.as<uint32_t>() + ((long long)g.ns + s) * g.Lloc_cap : nullptr;
   if (v.Lloc > 0) {
-    if (!d_recv || !d_gsend) return MFB_ERR_INVALID;
+    if (!d_recv || (!d_gsend && !direct)) return MFB_ERR_INVALID;
     const int grid = grid_warps(v.Lloc, SH_WARPS);
 #define CALLK(V, N, K)                                                                                          \
   k_shard_backward<V, N, K><<<grid, SH_THREADS, 0, st>>>(rpu, rpi, v.Lloc, v.b_loc, v.b, g.m_neg, v.m_lo, d_recv, D, \
-                                                         sh->Dp, sh->stride, pred, cell, d_gsend)
+                                                         sh->Dp, sh->stride, pred, cell, d_gsend, gdu, gdi,  \
+                                                         sh->peers, sh->xl.grecv_off)
 #define CALL(V, N)                                                          \
   switch (loss) {                                                           \
     case MFB_LOSS_POINTWISE: CALLK(V, N, MFB_LOSS_POINTWISE); break;        \
@@ -765,6 +886,11 @@ extern "C" int mfb_shard_backward(mfb_shard *sh, int loss, int32_t s, const floa
   MFB_KERNEL_CHECK();
   sh->launches += 1;
   return MFB_OK;
+}
+
+extern "C" int mfb_shard_backward(mfb_shard *sh, int loss, int32_t s, const float *d_recv, const int64_t *d_gmax_cell,
+                                  float *d_gsend, double *d_loss_partial, mfb_stream stream) {
+  return shard_backward_impl(sh, loss, s, d_recv, d_gmax_cell, d_gsend, false, d_loss_partial, (cudaStream_t)stream);
 }
 
 extern "C" int mfb_shard_update(mfb_shard *sh, int32_t s, const float *d_grecv, mfb_stream stream) {
@@ -804,5 +930,168 @@ extern "C" int mfb_shard_update(mfb_shard *sh, int32_t s, const float *d_grecv, 
     sh->launches += 1;
   }
   m->step = t;   // the dense optimiser stepped every row; rows not served here catch up lazily
+  return MFB_OK;
+}
+
+// ---- direct exchange over peer memory ---------------------------------------------------------------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int mfb_shard_xbuf_alloc(mfb_shard *sh, int32_t batch, int32_t n_neg, void **d_ptr, int64_t *bytes) {
+  if (!sh || batch <= 0 || n_neg < 0 || !d_ptr || !bytes) return MFB_ERR_INVALID;
+  if (sh->world > MAX_PEERS) {
+    mfb_set_error("direct exchange supports up to %d ranks", MAX_PEERS);
+    return MFB_ERR_UNSUPPORTED;
+  }
+  const int G = sh->world;
+  const long long m_neg = (long long)n_neg * batch, Lfull = batch + m_neg;
+  const long long Lloc_cap = (batch + G - 1) / G + (m_neg + G - 1) / G;
+  XLayout x;
+  x.recv_off = 0;
+  x.grecv_off = align_up((size_t)(2 * Lloc_cap) * sh->stride * sizeof(float), 256);
+  x.cells_off = x.grecv_off + align_up((size_t)(2 * Lfull) * sh->stride * sizeof(float), 256);
+  x.flags_off = x.cells_off + align_up(MAX_PEERS * 8, 256);
+  x.err_off = x.flags_off + align_up(3 * MAX_PEERS * 8, 256);
+  x.total = x.err_off + 256;
+  if (sh->xbuf) {
+    MFB_CUDA(cudaDeviceSynchronize());
+    cudaFree(sh->xbuf);
+    sh->xbuf = nullptr;
+  }
+  cudaError_t e = cudaMalloc(&sh->xbuf, x.total);
+  if (e != cudaSuccess) {
+    mfb_set_error("cudaMalloc(%zu) for the exchange buffer failed: %s", x.total, cudaGetErrorString(e));
+    return MFB_ERR_NOMEM;
+  }
+  MFB_CUDA(cudaMemset((char *)sh->xbuf + x.cells_off, 0, x.total - x.cells_off));
+  MFB_CHECK(sh->gcell.reserve(2 * sizeof(unsigned long long)));
+  MFB_CUDA(cudaMemset(sh->gcell.ptr, 0, 2 * sizeof(unsigned long long)));
+  MFB_CUDA(cudaDeviceSynchronize());
+  sh->xl = x;
+  sh->peers_set = false;
+  sh->seq = 0;
+  sh->x_batch = batch;
+  sh->x_m_neg = (int)m_neg;
+  *d_ptr = sh->xbuf;
+  *bytes = (int64_t)x.total;
+  return MFB_OK;
+}
+
+extern "C" int mfb_shard_xbuf_set_peers(mfb_shard *sh, void *const *peer_ptrs) {
+  if (!sh || !sh->xbuf || !peer_ptrs) return MFB_ERR_INVALID;
+  for (int c = 0; c < sh->world; ++c) {
+    if (!peer_ptrs[c]) return MFB_ERR_INVALID;
+    sh->peers.base[c] = (char *)peer_ptrs[c];
+  }
+  if (sh->peers.base[sh->rank] != (char *)sh->xbuf) {
+    mfb_set_error("xbuf_set_peers: entry %d must be this rank's own buffer", sh->rank);
+    return MFB_ERR_INVALID;
+  }
+  sh->peers_set = true;
+  return MFB_OK;
+}
+
+extern "C" int mfb_ipc_export(void *d_ptr, void *h_handle64) {
+  if (!d_ptr || !h_handle64) return MFB_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  MFB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)h_handle64, d_ptr));
+  return MFB_OK;
+}
+
+extern "C" int mfb_ipc_open(const void *h_handle64, void **d_ptr) {
+  if (!d_ptr || !h_handle64) return MFB_ERR_INVALID;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, h_handle64, sizeof(h));
+  MFB_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MFB_OK;
+}
+
+extern "C" int mfb_ipc_close(void *d_ptr) {
+  if (!d_ptr) return MFB_OK;
+  MFB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return MFB_OK;
+}
+
+// Steps [s_begin, s_end) of the planned chunk with the direct exchange: everything is enqueued on `stream`, no host
+// synchronisation and no collective call.  d_loss_partial: 2 doubles per step (as mfb_shard_backward).
+extern "C" int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int32_t s_end, double *d_loss_partial,
+                                   mfb_stream stream) {
+  if (!sh || !sh->planned || !sh->peers_set || !d_loss_partial || s_begin < 0 || s_end > sh->g.ns || s_begin > s_end) {
+    mfb_set_error("shard_run_steps: needs a plan, an exchange buffer with peers, and a step range inside the plan");
+    return MFB_ERR_INVALID;
+  }
+  if (sh->g.batch != sh->x_batch || sh->g.m_neg != sh->x_m_neg) {
+    mfb_set_error("shard_run_steps: the exchange buffer was sized for batch %d / %d negatives, the plan has %d / %d",
+                  sh->x_batch, sh->x_m_neg, sh->g.batch, sh->g.m_neg);
+    return MFB_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  mfb_model *m = sh->m;
+  const int G = sh->world, D = m->desc.dim;
+  const bool fast = m->desc.fast_math != 0, adaptive = loss == MFB_LOSS_ADAPTIVE_HINGE;
+  const XLayout &x = sh->xl;
+  char *xb = (char *)sh->xbuf;
+  float *recv = (float *)(xb + x.recv_off), *grecv = (float *)(xb + x.grecv_off);
+  int *err = (int *)(xb + x.err_off);
+  unsigned long long *local_cell = sh->gcell.as<unsigned long long>(), *global_cell = local_cell + 1;
+  const long long timeout = 6000000000ll;   // ~3 s of SM clocks: a dead peer ends in an error, not in a hung GPU
+  for (int s = s_begin; s < s_end; ++s) {
+    StepView v;
+    MFB_CHECK(step_view(sh, s, &v));
+    const unsigned long long seq = ++sh->seq;
+    // owner: catch-up, rows straight into the computing ranks' receive buffers, signal
+    if (v.n_serve > 0) {
+      const int grid = grid_warps(v.n_serve, SH_WARPS);
+      const int target = (int)m->step;
+#define CALL(V, N)                                                                                                   \
+  if (fast)                                                                                                          \
+    k_shard_catchup<V, N, true><<<grid, SH_THREADS, 0, st>>>(sh->info.as<PosInfo>(), v.base, v.n_serve, sh->g.rb,    \
+                                                             m->users, m->items, m->opt, D, target);                 \
+  else                                                                                                               \
+    k_shard_catchup<V, N, false><<<grid, SH_THREADS, 0, st>>>(sh->info.as<PosInfo>(), v.base, v.n_serve, sh->g.rb,   \
+                                                              m->users, m->items, m->opt, D, target);                \
+  k_shard_gather_direct<V, N><<<grid, SH_THREADS, 0, st>>>(sh->ent.as<uint32_t>() + v.base,                          \
+                                                           sh->sdst.as<uint32_t>() + v.base, v.n_serve, m->users,    \
+                                                           m->items, D, sh->Dp, sh->stride, sh->peers, x.recv_off);
+      MFB_DISPATCH_SHAPE(sh->shape, CALL);
+#undef CALL
+      MFB_KERNEL_CHECK();
+      sh->launches += 2;
+    }
+    k_shard_signal<<<1, 32, 0, st>>>(sh->peers, G, sh->rank, x.flags_off, FLAG_ROWS, seq, x.cells_off, nullptr);
+    // computing rank: wait for every owner's rows, forward, publish the local maximum
+    k_shard_wait<<<1, 32, 0, st>>>(xb, G, x.flags_off, FLAG_ROWS, seq, x.cells_off, nullptr, err, timeout);
+    MFB_KERNEL_CHECK();
+    MFB_CHECK(mfb_shard_forward(sh, loss, s, recv, (int64_t *)local_cell, stream));
+    if (adaptive) {
+      k_shard_signal<<<1, 32, 0, st>>>(sh->peers, G, sh->rank, x.flags_off, FLAG_MAX, seq, x.cells_off, local_cell);
+      k_shard_wait<<<1, 32, 0, st>>>(xb, G, x.flags_off, FLAG_MAX, seq, x.cells_off, global_cell, err, timeout);
+      MFB_KERNEL_CHECK();
+      sh->launches += 2;
+    }
+    // gradient rows straight into the owners' buffers, signal; owner waits for all of them, then steps
+    MFB_CHECK(shard_backward_impl(sh, loss, s, recv, (const int64_t *)global_cell, nullptr, true,
+                                  d_loss_partial + 2 * (s - s_begin), st));
+    k_shard_signal<<<1, 32, 0, st>>>(sh->peers, G, sh->rank, x.flags_off, FLAG_GRADS, seq, x.cells_off, nullptr);
+    k_shard_wait<<<1, 32, 0, st>>>(xb, G, x.flags_off, FLAG_GRADS, seq, x.cells_off, nullptr, err, timeout);
+    MFB_KERNEL_CHECK();
+    sh->launches += 4;
+    MFB_CHECK(mfb_shard_update(sh, s, grecv, stream));
+  }
+  return MFB_OK;
+}
+
+// Synchronises the stream and reports whether a wait on a peer timed out since the last check.
+extern "C" int mfb_shard_direct_check(mfb_shard *sh, mfb_stream stream) {
+  if (!sh || !sh->xbuf) return MFB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int h = 0;
+  MFB_CUDA(cudaMemcpyAsync(&h, (char *)sh->xbuf + sh->xl.err_off, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  if (h) {
+    MFB_CUDA(cudaMemsetAsync((char *)sh->xbuf + sh->xl.err_off, 0, sizeof(int), st));
+    mfb_set_error("direct exchange: timed out waiting for a peer (%s)",
+                  h == 1 ? "rows" : (h == 2 ? "adaptive-hinge maximum" : "gradient rows"));
+    return MFB_ERR_CUDA;
+  }
   return MFB_OK;
 }

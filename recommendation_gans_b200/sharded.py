@@ -74,6 +74,16 @@ class DistComm(object):
     def all_reduce_sum(self, t):
         self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
 
+    same_process = False
+
+    def all_gather_object(self, obj):
+        out = [None] * self.world
+        self._dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def barrier(self):
+        self._dist.barrier(group=self.group)
+
 
 class LocalGroup(object):
     """Shared state of `world` virtual ranks running as threads of one process on one device."""
@@ -92,6 +102,8 @@ class LocalComm(object):
         self.g, self.rank, self.world = group, rank, group.world
 
     def _exchange(self, item):
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()    # virtual ranks run on their own streams
         self.g.slots[self.rank] = item
         self.g.barrier.wait()
         items = list(self.g.slots)
@@ -108,6 +120,8 @@ class LocalComm(object):
             assert n == int(out_counts[src]), 'all_to_all counts disagree between ranks'
             out[at:at + n].copy_(sbuf[off:off + n])
             at += n
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()
         self.g.barrier.wait()    # nobody reuses its input buffer before every rank has copied from it
 
     def all_reduce_max(self, t):
@@ -120,6 +134,14 @@ class LocalComm(object):
         for x in items[1:]:
             acc += x
         t.copy_(acc)
+
+    same_process = True
+
+    def all_gather_object(self, obj):
+        return self._exchange(obj)
+
+    def barrier(self):
+        self.g.barrier.wait()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -213,6 +235,49 @@ class CudaShardBackend(object):
     def update(self, s, grecv):
         self._call('mfb_shard_update', int(s), N.dptr(grecv), N.stream_ptr())
 
+    # -- direct exchange over peer memory (no collective on the step's critical path) ----------------
+    def enable_direct(self, batch, n_neg, comm):
+        """Allocates this rank's exchange buffer for the minibatch geometry and maps every peer's (CUDA IPC across
+        processes, plain pointers between virtual ranks of one process).  Collective: all ranks call it together."""
+        self._close_peers()
+        ptr, nbytes = ctypes.c_void_p(0), ctypes.c_int64(0)
+        self._call('mfb_shard_xbuf_alloc', int(batch), int(n_neg), ctypes.byref(ptr), ctypes.byref(nbytes))
+        if comm.same_process:
+            ptrs = comm.all_gather_object(int(ptr.value))
+        else:
+            handle = (ctypes.c_ubyte * 64)()
+            with torch.cuda.device(self.device):
+                N.check(self._lib.mfb_ipc_export(ptr, ctypes.cast(handle, ctypes.c_void_p)), 'ipc_export')
+            handles = comm.all_gather_object(bytes(handle))
+            ptrs = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(int(ptr.value))
+                    continue
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                peer = ctypes.c_void_p(0)
+                with torch.cuda.device(self.device):
+                    N.check(self._lib.mfb_ipc_open(ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(peer)), 'ipc_open')
+                self._peer_maps.append(peer)
+                ptrs.append(int(peer.value))
+        arr = (ctypes.c_void_p * self.world)(*ptrs)
+        self._call('mfb_shard_xbuf_set_peers', ctypes.cast(arr, ctypes.c_void_p))
+        self.direct_geometry = (int(batch), int(n_neg))
+        comm.barrier()        # every rank's flags are zeroed and mapped before anyone signals
+
+    def run_steps(self, loss, s_begin, s_end, partial):
+        self._call('mfb_shard_run_steps', N.LOSS[loss], int(s_begin), int(s_end), ctypes.c_void_p(partial.data_ptr()),
+                   N.stream_ptr())
+
+    def direct_check(self):
+        self._call('mfb_shard_direct_check', N.stream_ptr())
+
+    def _close_peers(self):
+        for peer in getattr(self, '_peer_maps', []):
+            self._lib.mfb_ipc_close(peer)
+        self._peer_maps = []
+        self.direct_geometry = None
+
     def flush(self):
         self.engine.flush()
 
@@ -227,6 +292,8 @@ class CudaShardBackend(object):
 
     def close(self):
         if getattr(self, '_shard', None):
+            torch.cuda.synchronize(self.device)
+            self._close_peers()
             self._lib.mfb_shard_destroy(self._shard)
             self._shard = ctypes.c_void_p(0)
         self.engine.close()
@@ -243,13 +310,15 @@ class ShardedMF(object):
     LOSS_KERNEL = {'pointwise': 'pointwise', 'bpr': 'adaptive_hinge', 'adaptive_hinge': 'adaptive_hinge',
                    'hinge': 'hinge', 'bpr_pairwise': 'bpr'}
 
-    def __init__(self, backend, comm, chunk_steps=64):
+    def __init__(self, backend, comm, chunk_steps=64, direct=False):
         if backend.rank != comm.rank or backend.world != comm.world:
             raise ValueError('backend is rank %d of %d, transport is rank %d of %d'
                              % (backend.rank, backend.world, comm.rank, comm.world))
         self.backend, self.comm = backend, comm
         self.rank, self.world = comm.rank, comm.world
         self.chunk_steps = int(chunk_steps)
+        # direct=True: rows and gradients move by peer-memory stores inside the kernels (NVLink), no collective per step
+        self.direct = bool(direct)
         self.stride = backend.stride
         self._bufs = {}
 
@@ -275,6 +344,8 @@ class ShardedMF(object):
             raise ValueError('need %d negative pairs, got %d' % (nsteps * m, neg_users.numel()))
         losses = np.zeros(nsteps, dtype=np.float64)
         cell = be.zeros(1, torch.int64)
+        if self.direct and getattr(be, 'direct_geometry', None) != (int(batch), int(n_neg)):
+            be.enable_direct(batch, n_neg, comm)
         for c0 in range(0, nsteps, self.chunk_steps):
             ns = min(self.chunk_steps, nsteps - c0)
             counts = be.plan(pos_users, pos_items, batch, n_neg, neg_users[c0 * m:(c0 + ns) * m],
@@ -285,7 +356,12 @@ class ShardedMF(object):
             send, grecv = self._buf('send', n_send.max()), self._buf('grecv', n_send.max())
             recv, gsend = self._buf('recv', n_recv.max()), self._buf('gsend', n_recv.max())
             partial = be.zeros(2 * ns, torch.float64)
-            for s in range(ns):
+            if self.direct:
+                if comm.same_process:
+                    comm.barrier()     # one device: nobody spins on a peer that is still planning (device-wide syncs)
+                be.run_steps(kind, 0, ns, partial)
+                be.direct_check()
+            for s in range(ns if not self.direct else 0):
                 be.gather(s, send)
                 comm.all_to_all(recv[:n_recv[s]], recv_counts[s], send[:n_send[s]], send_counts[s])
                 be.forward(kind, s, recv, cell)
@@ -335,8 +411,14 @@ def run_local_ranks(world, make_rank, work):
 
     def body(rank):
         try:
-            shard = make_rank(rank, group.comm(rank))
-            results[rank] = work(shard)
+            if torch.cuda.is_available():
+                with torch.cuda.stream(torch.cuda.Stream()):
+                    shard = make_rank(rank, group.comm(rank))
+                    results[rank] = work(shard)
+                    torch.cuda.current_stream().synchronize()
+            else:
+                shard = make_rank(rank, group.comm(rank))
+                results[rank] = work(shard)
         except BaseException as exc:   # noqa: BLE001 -- re-raised in the caller; abort the barrier so peers stop
             errors.append(exc)
             group.barrier.abort()

@@ -30,12 +30,12 @@ def _case(path):
                 init=[g['init%d' % i] for i in range(4)])
 
 
-def _make_rank(c, world, fast_math, chunk_steps):
+def _make_rank(c, world, fast_math, chunk_steps, direct=False):
     def make(rank, comm):
         be = sharded.CudaShardBackend(rank, world, c['U'], c['I'], c['D'],
                                       local_tables=sharded.slice_tables(c['init'], rank, world), optimizer=c['opt'],
                                       lr=c['lr'], l2=c['l2'], fast_math=fast_math)
-        return sharded.ShardedMF(be, comm, chunk_steps=chunk_steps)
+        return sharded.ShardedMF(be, comm, chunk_steps=chunk_steps, direct=direct)
     return make
 
 
@@ -69,6 +69,15 @@ def test_sharded_steps_match_reference(path, world):
     _check(c, results, world)
 
 
+@pytest.mark.parametrize('path', STEP_FILES, ids=[os.path.basename(p)[6:-4] for p in STEP_FILES])
+@pytest.mark.parametrize('world', [1, 2, 3])
+def test_sharded_direct_exchange_matches_reference(path, world):
+    """Peer-memory exchange (stores into the peers' buffers + flag kernels) instead of collectives."""
+    c = _case(path)
+    results = sharded.run_local_ranks(world, _make_rank(c, world, False, 5, direct=True), _work(c))
+    _check(c, results, world)
+
+
 def test_sharded_fast_math_and_single_chunk():
     c = _case([p for p in STEP_FILES if p.endswith('steps_bpr_adam.npz')][0])
     results = sharded.run_local_ranks(4, _make_rank(c, 4, True, 64), _work(c))
@@ -86,14 +95,14 @@ def test_sharded_rejects_out_of_range_ids():
     shard.close()
 
 
-def _nccl_worker(rank, world, port, path, out_dir):
+def _nccl_worker(rank, world, port, path, out_dir, direct=False):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     c = _case(path)
-    shard = _make_rank(c, world, False, 7)(rank, sharded.DistComm())
+    shard = _make_rank(c, world, False, 7, direct=direct)(rank, sharded.DistComm())
     losses, tables = _work(c)(shard)
     np.savez(os.path.join(out_dir, 'r%d.npz' % rank), losses=losses, t0=tables[0], t1=tables[1], t2=tables[2],
              t3=tables[3])
@@ -102,14 +111,15 @@ def _nccl_worker(rank, world, port, path, out_dir):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
 @pytest.mark.parametrize('name', ['steps_bpr_adam.npz', 'steps_pointwise_adam.npz'])
-def test_sharded_nccl_two_gpus(name, tmp_path):
+@pytest.mark.parametrize('direct', [False, True], ids=['nccl', 'peer_memory'])
+def test_sharded_nccl_two_gpus(name, direct, tmp_path):
     import torch.multiprocessing as mp
     path = [p for p in STEP_FILES if p.endswith(name)][0]
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_nccl_worker, args=(2, port, path, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, port, path, str(tmp_path), direct), nprocs=2, join=True)
     res = []
     for r in range(2):
         z = np.load(tmp_path / ('r%d.npz' % r))

@@ -23,7 +23,7 @@ if ROOT not in sys.path:
 
 
 def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=200, warmup=20, loss='bpr',
-        zipf=False, chunk_steps=32, fast_math=True, pop_len=4_000_000, comm=None, phase_times=False):
+        zipf=False, chunk_steps=32, fast_math=True, pop_len=4_000_000, comm=None, phase_times=False, direct=True):
     import recommendation_gans_b200  # noqa: F401
     from recommendation_gans_b200 import sharded
     import torch.distributed as dist
@@ -33,7 +33,7 @@ def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=
     dev = torch.device('cuda', torch.cuda.current_device())
     be = sharded.CudaShardBackend(rank, world, users, items, dim, optimizer='adam', lr=1e-3, l2=1e-5,
                                   fast_math=fast_math, device=dev, seed=0)
-    shard = sharded.ShardedMF(be, comm, chunk_steps=chunk_steps)
+    shard = sharded.ShardedMF(be, comm, chunk_steps=chunk_steps, direct=direct)
     rs = np.random.RandomState(0)                       # same ids on every rank
     n_pos = (steps + warmup) * batch
 
@@ -83,13 +83,15 @@ def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=
                                'n_neg %d, Adam(0.5,0.999) lr 1e-3 l2 1e-5, rows sharded by id %% %d'
                                % (users, items, dim, loss, batch, n_neg, world),
                    'items': 'zipf(1.05)' if zipf else 'uniform', 'chunk_steps': chunk_steps,
-                   'transport': type(comm).__name__},
+                   'transport': type(comm).__name__,
+                   'exchange': 'peer-memory stores + flag kernels (NVLink), no collective per step' if direct else
+                               'all_to_all_single + all_reduce per step'},
         'exchange_bytes_per_step_per_gpu_each_way': rows_per_step / world * stride * 4 * (world - 1) / world,
         'algorithmic_bytes_per_step': (6 * 2 * (1 + n_neg) * (dim + 1) * 4 + 16) * batch,
         'gpu_launches': be.launches - l0, 'final_loss': float(losses[-1]),
     }
     out['hbm_gbs_algorithmic_total'] = out['algorithmic_bytes_per_step'] / (out['ms_per_step'] * 1e-3) / 1e9
-    if phase_times:
+    if phase_times and not direct:
         out['phase_us_per_step'] = phase_breakdown(shard, loss, pos_u, pos_i, batch, n_neg, neg_u, neg_i, warmup, m)
     shard.close()
     return out
@@ -163,6 +165,7 @@ def main():
     ap.add_argument('--chunk-steps', type=int, default=32)
     ap.add_argument('--zipf', action='store_true')
     ap.add_argument('--phases', action='store_true')
+    ap.add_argument('--collectives', action='store_true', help='use all_to_all_single/all_reduce instead of peer memory')
     args = ap.parse_args()
     import torch.distributed as dist
     if 'RANK' in os.environ and int(os.environ.get('WORLD_SIZE', '1')) > 1:
@@ -170,7 +173,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     out = run(args.users, args.items, args.dim, args.batch, args.n_neg, args.steps, args.warmup, zipf=args.zipf,
-              chunk_steps=args.chunk_steps, phase_times=args.phases)
+              chunk_steps=args.chunk_steps, phase_times=args.phases, direct=not args.collectives)
     if not dist.is_initialized() or dist.get_rank() == 0:
         print(json.dumps(out))
     if dist.is_initialized():
