@@ -262,7 +262,7 @@ def native_bench(args, w, rank, world):
     sh = None
     if not args.no_sharded:
         from tools.shard_bench import run as shard_run
-        sh = shard_run(steps=args.sharded_steps, warmup=10, zipf=w['zipf'], fast_math=bool(args.fast_math))
+        sh = shard_run(steps=args.sharded_steps, warmup=32, zipf=w['zipf'], fast_math=bool(args.fast_math))
 
     # ---- reduce over ranks: max time, summed work
     t_train, t_e2e, t_eval, n_eval = ms / 1e3, e2e_s, ev['seconds'], ev['users']
@@ -378,7 +378,7 @@ def main():
     ap.add_argument('--repeats', type=int, default=3, help='timed region repeated; best reported')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sharded', action='store_true', help='skip the cfg5 row-sharded training object')
-    ap.add_argument('--sharded-steps', type=int, default=100)
+    ap.add_argument('--sharded-steps', type=int, default=96)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = dict(WORKLOADS[args.workload])

@@ -287,8 +287,8 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_backward(const int *__rest
                                                                const unsigned long long *__restrict__ gmax_cell,
                                                                float *__restrict__ gsend,
                                                                const uint32_t *__restrict__ gdst_u,
-                                                               const uint32_t *__restrict__ gdst_i, Peers peers,
-                                                               size_t grecv_off) {
+                                                               const uint32_t *__restrict__ gdst_i,
+                                                               char *const *__restrict__ peers, size_t grecv_off) {
   const int lane = threadIdx.x & 31;
   const int jl = blockIdx.x * SH_WARPS + (threadIdx.x >> 5);
   if (jl >= Lloc) return;
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_backward(const int *__rest
   float *gu, *gi;
   if (gdst_u != nullptr) {   // direct exchange: straight into the owners' gradient buffers
     const uint32_t du = gdst_u[jl], di = gdst_i[jl];
-    gu = reinterpret_cast<float *>(peers.base[du >> 26] + grecv_off) + (long long)(du & 0x3ffffffu) * stride;
-    gi = reinterpret_cast<float *>(peers.base[di >> 26] + grecv_off) + (long long)(di & 0x3ffffffu) * stride;
+    gu = reinterpret_cast<float *>(peers[du >> 26] + grecv_off) + (long long)(du & 0x3ffffffu) * stride;
+    gi = reinterpret_cast<float *>(peers[di >> 26] + grecv_off) + (long long)(di & 0x3ffffffu) * stride;
   } else {
     gu = gsend + pu * stride;
     gi = gsend + pi * stride;
@@ -354,7 +354,8 @@ template <int VEC, int NIT>
 __global__ void __launch_bounds__(SH_THREADS) k_shard_gather_direct(const uint32_t *__restrict__ ent,
                                                                     const uint32_t *__restrict__ sdst, int n,
                                                                     TableView users, TableView items, int D, int Dp,
-                                                                    int stride, Peers peers, size_t recv_off) {
+                                                                    int stride, char *const *__restrict__ peers,
+                                                                    size_t recv_off) {
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * SH_WARPS + (threadIdx.x >> 5);
   if (p >= n) return;
@@ -363,30 +364,27 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_gather_direct(const uint32
   const long long row = e & 0x7fffffffu;
   Frag<VEC, NIT> f;
   frag_load<VEC, NIT>(f, T.p + row * D, D, lane);
-  float *dst = reinterpret_cast<float *>(peers.base[d >> 26] + recv_off) + (long long)(d & 0x3ffffffu) * stride;
+  float *dst = reinterpret_cast<float *>(peers[d >> 26] + recv_off) + (long long)(d & 0x3ffffffu) * stride;
   frag_store<VEC, NIT>(f, dst, D, lane);
   if (lane == 0) dst[Dp] = T.bp[row];
 }
 
-// one thread per peer: [optionally copy this rank's adaptive-hinge cell into the peer's cell array, then] publish seq
-__global__ void k_shard_signal(Peers peers, int G, int me, size_t flags_off, int kind, unsigned long long seq,
-                               size_t cells_off, const unsigned long long *__restrict__ local_cell) {
-  const int c = threadIdx.x;
-  if (c >= G) return;
-  if (local_cell != nullptr) {
-    reinterpret_cast<unsigned long long *>(peers.base[c] + cells_off)[me] = *local_cell;
-  }
-  __threadfence_system();
-  st_release_sys(reinterpret_cast<unsigned long long *>(peers.base[c] + flags_off) + kind * MAX_PEERS + me, seq);
-}
-
-// one thread per peer spins until that peer's flag reaches seq (bounded: a dead peer must not hang the GPU);
-// with reduce_cells, thread 0 then folds the peers' adaptive-hinge cells into *out_cell.
-__global__ void k_shard_wait(const char *__restrict__ xbuf, int G, size_t flags_off, int kind, unsigned long long seq,
-                             size_t cells_off, unsigned long long *__restrict__ out_cell, int *__restrict__ err,
-                             long long timeout_clocks) {
+// One thread per peer c.  Publishes this rank's sequence number for `kind` in peer c's flag array (after copying
+// the local adaptive-hinge cell into c's cell array when local_cell != nullptr) -- everything this rank stored into
+// c's buffer earlier in the stream is ordered before it (kernel boundary + fence + release.sys) -- and then spins
+// until peer c's own flag for `kind` arrives here (bounded: a dead peer must end in an error, not in a hung GPU).
+// With out_cell, thread 0 finally folds the peers' cells into *out_cell.
+__global__ void k_shard_signal_wait(char *const *__restrict__ peers, char *__restrict__ xbuf, int G, int me,
+                                    size_t flags_off, int kind, unsigned long long seq, size_t cells_off,
+                                    const unsigned long long *__restrict__ local_cell,
+                                    unsigned long long *__restrict__ out_cell, int *__restrict__ err,
+                                    long long timeout_clocks) {
   const int c = threadIdx.x;
   if (c < G) {
+    char *pb = peers[c];
+    if (local_cell != nullptr) reinterpret_cast<unsigned long long *>(pb + cells_off)[me] = *local_cell;
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned long long *>(pb + flags_off) + kind * MAX_PEERS + me, seq);
     const unsigned long long *f = reinterpret_cast<const unsigned long long *>(xbuf + flags_off) + kind * MAX_PEERS + c;
     const long long t0 = clock64();
     while (ld_acquire_sys(f) < seq) {
@@ -394,7 +392,7 @@ __global__ void k_shard_wait(const char *__restrict__ xbuf, int G, size_t flags_
         atomicExch(err, 1 + kind);
         break;
       }
-      __nanosleep(64);
+      __nanosleep(32);
     }
   }
   __syncthreads();
@@ -567,6 +565,7 @@ struct mfb_shard {
   void *xbuf = nullptr;
   XLayout xl = {};
   Peers peers = {};
+  DevBuf peers_dev;
   bool peers_set = false;
   unsigned long long seq = 0;
   int x_batch = 0, x_m_neg = 0;
@@ -610,7 +609,7 @@ extern "C" int mfb_shard_destroy(mfb_shard *sh) {
   DevBuf *bufs[] = {&sh->ids_u, &sh->ids_i, &sh->keys_a, &sh->keys_b, &sh->vals_a, &sh->vals_b, &sh->hist, &sh->start,
                     &sh->own_off, &sh->rbase, &sh->ent, &sh->k2a, &sh->k2b, &sh->v2a, &sh->v2b, &sh->segf, &sh->segl,
                     &sh->info, &sh->rpos, &sh->pred, &sh->err, &sh->partial, &sh->tickets, &sh->sdst, &sh->gdst,
-                    &sh->gcell};
+                    &sh->gcell, &sh->peers_dev};
   for (DevBuf *b : bufs) b->release();
   if (sh->xbuf) cudaFree(sh->xbuf);
   delete sh;
@@ -868,7 +867,7 @@ static int shard_backward_impl(mfb_shard *sh, int loss, int32_t s, const float *
 #define CALLK(V, N, K)                                                                                          \
   k_shard_backward<V, N, K><<<grid, SH_THREADS, 0, st>>>(rpu, rpi, v.Lloc, v.b_loc, v.b, g.m_neg, v.m_lo, d_recv, D, \
                                                          sh->Dp, sh->stride, pred, cell, d_gsend, gdu, gdi,  \
-                                                         sh->peers, sh->xl.grecv_off)
+                                                         sh->peers_dev.as<char *>(), sh->xl.grecv_off)
 #define CALL(V, N)                                                          \
   switch (loss) {                                                           \
     case MFB_LOSS_POINTWISE: CALLK(V, N, MFB_LOSS_POINTWISE); break;        \
@@ -986,6 +985,8 @@ extern "C" int mfb_shard_xbuf_set_peers(mfb_shard *sh, void *const *peer_ptrs) {
     mfb_set_error("xbuf_set_peers: entry %d must be this rank's own buffer", sh->rank);
     return MFB_ERR_INVALID;
   }
+  MFB_CHECK(sh->peers_dev.reserve(MAX_PEERS * sizeof(char *)));
+  MFB_CUDA(cudaMemcpy(sh->peers_dev.ptr, sh->peers.base, MAX_PEERS * sizeof(char *), cudaMemcpyHostToDevice));
   sh->peers_set = true;
   return MFB_OK;
 }
@@ -1033,6 +1034,7 @@ extern "C" int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int
   float *recv = (float *)(xb + x.recv_off), *grecv = (float *)(xb + x.grecv_off);
   int *err = (int *)(xb + x.err_off);
   unsigned long long *local_cell = sh->gcell.as<unsigned long long>(), *global_cell = local_cell + 1;
+  char *const *pd = sh->peers_dev.as<char *>();
   const long long timeout = 6000000000ll;   // ~3 s of SM clocks: a dead peer ends in an error, not in a hung GPU
   for (int s = s_begin; s < s_end; ++s) {
     StepView v;
@@ -1051,30 +1053,31 @@ extern "C" int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int
                                                               m->users, m->items, m->opt, D, target);                \
   k_shard_gather_direct<V, N><<<grid, SH_THREADS, 0, st>>>(sh->ent.as<uint32_t>() + v.base,                          \
                                                            sh->sdst.as<uint32_t>() + v.base, v.n_serve, m->users,    \
-                                                           m->items, D, sh->Dp, sh->stride, sh->peers, x.recv_off);
+                                                           m->items, D, sh->Dp, sh->stride, pd, x.recv_off);
       MFB_DISPATCH_SHAPE(sh->shape, CALL);
 #undef CALL
       MFB_KERNEL_CHECK();
       sh->launches += 2;
     }
-    k_shard_signal<<<1, 32, 0, st>>>(sh->peers, G, sh->rank, x.flags_off, FLAG_ROWS, seq, x.cells_off, nullptr);
-    // computing rank: wait for every owner's rows, forward, publish the local maximum
-    k_shard_wait<<<1, 32, 0, st>>>(xb, G, x.flags_off, FLAG_ROWS, seq, x.cells_off, nullptr, err, timeout);
+    // computing rank: signal the rows this rank stored, wait for every owner's, forward
+    k_shard_signal_wait<<<1, 32, 0, st>>>(pd, xb, G, sh->rank, x.flags_off, FLAG_ROWS, seq, x.cells_off, nullptr, nullptr,
+                                          err, timeout);
     MFB_KERNEL_CHECK();
     MFB_CHECK(mfb_shard_forward(sh, loss, s, recv, (int64_t *)local_cell, stream));
     if (adaptive) {
-      k_shard_signal<<<1, 32, 0, st>>>(sh->peers, G, sh->rank, x.flags_off, FLAG_MAX, seq, x.cells_off, local_cell);
-      k_shard_wait<<<1, 32, 0, st>>>(xb, G, x.flags_off, FLAG_MAX, seq, x.cells_off, global_cell, err, timeout);
+      // publish the local maximum to every peer, wait for theirs, fold
+      k_shard_signal_wait<<<1, 32, 0, st>>>(pd, xb, G, sh->rank, x.flags_off, FLAG_MAX, seq, x.cells_off, local_cell,
+                                            global_cell, err, timeout);
       MFB_KERNEL_CHECK();
-      sh->launches += 2;
+      sh->launches += 1;
     }
     // gradient rows straight into the owners' buffers, signal; owner waits for all of them, then steps
     MFB_CHECK(shard_backward_impl(sh, loss, s, recv, (const int64_t *)global_cell, nullptr, true,
                                   d_loss_partial + 2 * (s - s_begin), st));
-    k_shard_signal<<<1, 32, 0, st>>>(sh->peers, G, sh->rank, x.flags_off, FLAG_GRADS, seq, x.cells_off, nullptr);
-    k_shard_wait<<<1, 32, 0, st>>>(xb, G, x.flags_off, FLAG_GRADS, seq, x.cells_off, nullptr, err, timeout);
+    k_shard_signal_wait<<<1, 32, 0, st>>>(pd, xb, G, sh->rank, x.flags_off, FLAG_GRADS, seq, x.cells_off, nullptr,
+                                          nullptr, err, timeout);
     MFB_KERNEL_CHECK();
-    sh->launches += 4;
+    sh->launches += 2;
     MFB_CHECK(mfb_shard_update(sh, s, grecv, stream));
   }
   return MFB_OK;

@@ -22,7 +22,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=200, warmup=20, loss='bpr',
+def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=192, warmup=32, loss='bpr',
         zipf=False, chunk_steps=32, fast_math=True, pop_len=4_000_000, comm=None, phase_times=False, direct=True):
     import recommendation_gans_b200  # noqa: F401
     from recommendation_gans_b200 import sharded
@@ -64,10 +64,19 @@ def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    losses = shard.train_steps(loss, pos_u, pos_i, batch, n_neg, neg_u[warmup * m:], neg_i[warmup * m:], step0=warmup,
-                               nsteps=steps)
+    chunk_ms, marks, losses = [], [e0], []
+    for c0 in range(0, steps, chunk_steps):          # one call per chunk so every chunk's device time is on record
+        ns = min(chunk_steps, steps - c0)
+        lo = (warmup + c0) * m
+        losses.append(shard.train_steps(loss, pos_u, pos_i, batch, n_neg, neg_u[lo:lo + ns * m], neg_i[lo:lo + ns * m],
+                                        step0=warmup + c0, nsteps=ns))
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
+    losses = np.concatenate(losses)
     e1.record()
     barrier()
+    chunk_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - 1)]
     wall = time.perf_counter() - t0
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if dist.is_initialized():
@@ -89,6 +98,7 @@ def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=
         'exchange_bytes_per_step_per_gpu_each_way': rows_per_step / world * stride * 4 * (world - 1) / world,
         'algorithmic_bytes_per_step': (6 * 2 * (1 + n_neg) * (dim + 1) * 4 + 16) * batch,
         'gpu_launches': be.launches - l0, 'final_loss': float(losses[-1]),
+        'chunk_ms': [round(x, 2) for x in chunk_ms],
     }
     out['hbm_gbs_algorithmic_total'] = out['algorithmic_bytes_per_step'] / (out['ms_per_step'] * 1e-3) / 1e9
     if phase_times and not direct:
@@ -160,8 +170,8 @@ def main():
     ap.add_argument('--dim', type=int, default=128)
     ap.add_argument('--batch', type=int, default=65536)
     ap.add_argument('--n-neg', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=192)
+    ap.add_argument('--warmup', type=int, default=32)
     ap.add_argument('--chunk-steps', type=int, default=32)
     ap.add_argument('--zipf', action='store_true')
     ap.add_argument('--phases', action='store_true')
