@@ -57,24 +57,35 @@ def bilinear_forward(user_emb, item_emb, user_bias, item_bias, user_ids, item_id
 # ----------------------------------------------------------------------------------------
 # losses: spotlight/losses.py:20-172 (all operate on probabilities)
 # ----------------------------------------------------------------------------------------
-def pointwise_loss(pos, neg=None):
+def _masked_mean(loss, mask):
+    """losses.py:51-55 (and :91-95, :124-128): `mask` zeroes entries; the mean runs over mask.sum()."""
+    if mask is not None:
+        mask = mask.float()
+        return (loss * mask).sum() / mask.sum()
+    return loss.mean()
+
+
+def pointwise_loss(pos, neg=None, mask=None):
     loss = F.binary_cross_entropy(pos, torch.ones_like(pos))          # losses.py:42-44
     if neg is not None:
         loss = loss + F.binary_cross_entropy(neg, torch.zeros_like(neg))  # losses.py:48-50
+    if mask is not None:                                              # losses.py:51-55: scalar loss times mask
+        mask = mask.float()
+        return (loss * mask).sum() / mask.sum()
     return loss
 
 
-def bpr_loss(pos, neg):
-    return (1.0 - torch.sigmoid(pos - neg)).mean()                    # losses.py:88-96
+def bpr_loss(pos, neg, mask=None):
+    return _masked_mean(1.0 - torch.sigmoid(pos - neg), mask)         # losses.py:88-96
 
 
-def hinge_loss(pos, neg):
-    return torch.clamp(neg - pos + 1.0, 0.0).mean()                   # losses.py:121-130
+def hinge_loss(pos, neg, mask=None):
+    return _masked_mean(torch.clamp(neg - pos + 1.0, 0.0), mask)      # losses.py:121-130
 
 
-def adaptive_hinge_loss(pos, neg):
-    highest, _ = torch.max(neg, 0)                                    # losses.py:170
-    return hinge_loss(pos, highest.squeeze())                         # losses.py:172
+def adaptive_hinge_loss(pos, neg, mask=None):
+    highest, _ = torch.max(neg, 0)                                    # losses.py:170 (neg [n, b] -> per-positive max)
+    return hinge_loss(pos, highest.squeeze(), mask)                   # losses.py:172
 
 
 def loss_for_model(name):

@@ -52,6 +52,8 @@ SIGNATURES = {
     'mfb_predict_user': (ctypes.c_int, [c_void, ctypes.c_int64, c_void, c_void]),
     'mfb_loss_forward_backward': (ctypes.c_int, [ctypes.c_int, c_void, ctypes.c_int64, c_void, ctypes.c_int64,
                                                  c_void, c_void, c_void, c_void]),
+    'mfb_loss_forward_backward_ex': (ctypes.c_int, [ctypes.c_int, c_void, ctypes.c_int64, c_void, ctypes.c_int64,
+                                                    ctypes.c_int64, c_void, c_void, c_void, c_void, c_void]),
     'mfb_train_steps': (ctypes.c_int, [c_void, ctypes.c_int, c_void, c_void, ctypes.c_int64, ctypes.c_int32,
                                        ctypes.c_int32, c_void, c_void, c_void, c_void]),
     'mfb_loss_steps': (ctypes.c_int, [c_void, ctypes.c_int, c_void, c_void, ctypes.c_int64, ctypes.c_int32,

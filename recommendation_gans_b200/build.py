@@ -30,13 +30,32 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
 
 
+def _dependencies():
+    return sources() + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + [os.path.join(HERE, '..', 'include', 'mfb200.h')]
+
+
+def source_hash():
+    """Content hash of everything the library is built from.  Staleness is decided by content, not by mtime: the
+    snapshot that carries the prebuilt .so to a GPU box does not preserve a meaningful mtime order, and a spurious
+    rebuild there would have N ranks rewriting the library under each other."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(' '.join(NVCC_FLAGS).encode())
+    for path in _dependencies():
+        h.update(os.path.basename(path).encode())
+        with open(path, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+HASH_PATH = LIB_PATH + '.srchash'
+
+
 def is_stale():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    built = os.path.getmtime(LIB_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, '*.cuh')) + \
-        [os.path.join(HERE, '..', 'include', 'mfb200.h')]
-    return any(os.path.getmtime(p) > built for p in deps)
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def _compile_one(args):
@@ -56,6 +75,18 @@ def build_library(force=False, verbose=False, out=None, defines=()):
     if out is None and not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(LIB_DIR, '.build.lock'), 'w') as lock:      # one builder at a time (ranks of one box)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if out is None and not force and not is_stale():           # another process built it while we waited
+                return LIB_PATH
+            return _build_locked(force, verbose, out, defines)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose, out, defines):
     target = out or LIB_PATH
     obj_dir = os.path.join(LIB_DIR, 'obj' if out is None else 'obj_' + os.path.basename(target))
     os.makedirs(obj_dir, exist_ok=True)
@@ -71,10 +102,16 @@ def build_library(force=False, verbose=False, out=None, defines=()):
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
         logs = list(pool.map(_compile_one, jobs))
-    cmd = [_nvcc()] + NVCC_FLAGS[:5] + ['-o', target] + objs
+    tmp = target + '.tmp.%d' % os.getpid()
+    cmd = [_nvcc()] + NVCC_FLAGS[:5] + ['-o', tmp] + objs
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (' '.join(cmd), proc.stderr[-4000:]))
+    os.replace(tmp, target)                                            # readers never see a half-written library
+    if out is None:
+        with open(HASH_PATH + '.tmp', 'w') as f:
+            f.write(source_hash())
+        os.replace(HASH_PATH + '.tmp', HASH_PATH)
     if verbose:
         sys.stderr.write(''.join(logs))
     return target

@@ -314,6 +314,123 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_loss(int kind, const float *__
   loss_block(kind, pos, b, neg, m, loss_out, dpos, dneg, to_logit);
 }
 
+// ---------------------------------------------------------------------------------------
+// k_loss_ex: the function-level forms the model driver never produces (spotlight/losses.py): a `mask` over the b
+// pairs (loss*mask summed, divided by mask.sum(), losses.py:51-55,91-95,124-128) and adaptive hinge on 2-D negatives
+// [n_rows, b] (per-positive maximum over dim 0, first maximal row, losses.py:170).  neg is row-major [n_rows, b];
+// n_rows == 0 means 1-D negatives of length m (adaptive hinge: the global maximum, as k_loss).  One CTA.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LOSS_THREADS) k_loss_ex(int kind, const float *__restrict__ pos, int b,
+                                                          const float *__restrict__ neg, int n_rows, int m,
+                                                          const float *__restrict__ mask, float *__restrict__ loss_out,
+                                                          float *__restrict__ dpos, float *__restrict__ dneg) {
+  __shared__ double sh[LOSS_THREADS / 32];
+  __shared__ float sh_max[LOSS_THREADS / 32];
+  __shared__ int sh_arg[LOSS_THREADS / 32];
+  const int tid = threadIdx.x;
+  const bool grad = dpos != nullptr;
+  double wsum = 0.0;
+  for (int j = tid; j < b; j += LOSS_THREADS) wsum += mask ? (double)mask[j] : 1.0;
+  wsum = block_sum(wsum, sh);
+  const float W = (float)wsum;                        // mask.sum() (or b): fp32 like the reference's tensor
+  if (kind == MFB_LOSS_POINTWISE) {
+    // scalar BCE sum, then (loss*mask).sum()/mask.sum(): the mask cancels unless it is all zero (-> nan, as torch)
+    double sp = 0.0, sn = 0.0;
+    for (int j = tid; j < b; j += LOSS_THREADS) sp += (double)(-fmaxf(logf(pos[j]), -100.0f));
+    for (int j = tid; j < m; j += LOSS_THREADS) sn += (double)(-fmaxf(logf(1.0f - neg[j]), -100.0f));
+    sp = block_sum(sp, sh);
+    sn = block_sum(sn, sh);
+    float l = (float)(sp / (double)b);
+    if (m > 0) l = l + (float)(sn / (double)m);
+    const float scale = mask ? __fdiv_rn(W, W) : 1.0f;            // d/dl of (l*mask).sum()/mask.sum()
+    if (tid == 0) *loss_out = mask ? __fdiv_rn(l * W, W) : l;
+    if (grad) {
+      for (int j = tid; j < b; j += LOSS_THREADS) {
+        const float x = pos[j];
+        dpos[j] = scale * __fdiv_rn(__fdiv_rn(x - 1.0f, fmaxf((1.0f - x) * x, 1e-12f)), (float)b);
+      }
+      for (int j = tid; j < m; j += LOSS_THREADS) {
+        const float x = neg[j];
+        dneg[j] = scale * __fdiv_rn(__fdiv_rn(x, fmaxf((1.0f - x) * x, 1e-12f)), (float)m);
+      }
+    }
+    return;
+  }
+  // pairwise losses over the b positives; the negative of pair j is neg[j] (1-D), the column maximum (2-D) or the
+  // global maximum (adaptive hinge on 1-D negatives)
+  float gbest = -INFINITY;
+  int garg = 0x7fffffff;
+  const bool adaptive = kind == MFB_LOSS_ADAPTIVE_HINGE;
+  if (adaptive && n_rows == 0) {
+    for (int j = tid; j < m; j += LOSS_THREADS) {
+      const float x = neg[j];
+      if (x > gbest) { gbest = x; garg = j; }
+    }
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, gbest, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, garg, o);
+      if (ob > gbest || (ob == gbest && oa < garg)) { gbest = ob; garg = oa; }
+    }
+    if (lane == 0) { sh_max[wid] = gbest; sh_arg[wid] = garg; }
+    __syncthreads();
+    gbest = sh_max[0];
+    garg = sh_arg[0];
+    for (int w = 1; w < LOSS_THREADS / 32; ++w)
+      if (sh_max[w] > gbest || (sh_max[w] == gbest && sh_arg[w] < garg)) { gbest = sh_max[w]; garg = sh_arg[w]; }
+    if (grad)
+      for (int j = tid; j < m; j += LOSS_THREADS) dneg[j] = 0.0f;
+    __syncthreads();
+  } else if (adaptive && grad) {
+    for (long long j = tid; j < (long long)n_rows * b; j += LOSS_THREADS) dneg[j] = 0.0f;
+    __syncthreads();
+  }
+  double s = 0.0, gsum = 0.0;
+  for (int j = tid; j < b; j += LOSS_THREADS) {
+    const float xp = pos[j], w = mask ? mask[j] : 1.0f;
+    float xn;
+    int arg = j;
+    if (!adaptive) {
+      xn = neg[j];
+    } else if (n_rows == 0) {
+      xn = gbest;
+    } else {
+      xn = neg[j];
+      arg = j;
+      for (int r = 1; r < n_rows; ++r) {
+        const float x = neg[(long long)r * b + j];
+        if (x > xn) { xn = x; arg = r * b + j; }
+      }
+    }
+    float dp, dn;
+    if (kind == MFB_LOSS_BPR) {
+      const float sg = sigmoidf_acc(xp - xn);
+      s += (double)((1.0f - sg) * w);
+      const float g = ((-__fdiv_rn(w, W)) * (1.0f - sg)) * sg;
+      dp = g;
+      dn = -g;
+    } else {
+      const float d = (xn - xp) + 1.0f;
+      s += (double)(fmaxf(d, 0.0f) * w);
+      const float a = (d >= 0.0f) ? __fdiv_rn(w, W) : 0.0f;
+      dp = -a;
+      dn = a;
+    }
+    if (grad) {
+      dpos[j] = dp;
+      if (adaptive && n_rows == 0) gsum += (double)dn;     // every pair feeds the one global maximum
+      else dneg[arg] = dn;
+    }
+  }
+  s = block_sum(s, sh);
+  gsum = block_sum(gsum, sh);
+  if (tid == 0) {
+    *loss_out = (float)(s / wsum);
+    if (grad && adaptive && n_rows == 0) dneg[garg] = (float)gsum;
+  }
+}
+
 // Loss values of a whole chunk of steps in one launch (block s <-> step step0+s): the per-step
 // predictions are kept until the chunk ends, so loss.item() costs nothing on the step's critical path.
 __global__ void __launch_bounds__(LOSS_THREADS) k_loss_steps(int kind, const float *__restrict__ pred_chunk,
@@ -723,6 +840,29 @@ extern "C" int mfb_loss_forward_backward(int loss, const float *d_pos, int64_t n
   mfb_count_library_launch(1);
   k_loss<<<1, LOSS_THREADS, 0, (cudaStream_t)stream>>>(loss, d_pos, (int)n_pos, d_neg, (int)n_neg, d_loss, d_dpos,
                                                        d_dneg, 0);
+  MFB_KERNEL_CHECK();
+  return MFB_OK;
+}
+
+extern "C" int mfb_loss_forward_backward_ex(int loss, const float *d_pos, int64_t n_pos, const float *d_neg,
+                                            int64_t neg_rows, int64_t neg_cols, const float *d_mask, float *d_loss,
+                                            float *d_dpos, float *d_dneg, mfb_stream stream) {
+  if (!d_pos || !d_loss || n_pos <= 0 || neg_rows < 0 || neg_cols < 0 || (neg_cols > 0 && !d_neg)) return MFB_ERR_INVALID;
+  if (loss < MFB_LOSS_POINTWISE || loss > MFB_LOSS_ADAPTIVE_HINGE) return MFB_ERR_INVALID;
+  if (neg_cols == 0 && loss != MFB_LOSS_POINTWISE) return MFB_ERR_SHAPE;
+  if (neg_rows > 0 && loss != MFB_LOSS_ADAPTIVE_HINGE) {
+    mfb_set_error("2-D negatives are supported by adaptive_hinge_loss only");
+    return MFB_ERR_UNSUPPORTED;
+  }
+  const bool pairwise = loss == MFB_LOSS_HINGE || loss == MFB_LOSS_BPR || neg_rows > 0;
+  if (pairwise && neg_cols != n_pos) {
+    mfb_set_error("pairwise loss: negatives have %lld columns, positives %lld", (long long)neg_cols, (long long)n_pos);
+    return MFB_ERR_SHAPE;
+  }
+  if ((d_dpos == nullptr) != (d_dneg == nullptr) && neg_cols > 0) return MFB_ERR_INVALID;
+  mfb_count_library_launch(1);
+  k_loss_ex<<<1, LOSS_THREADS, 0, (cudaStream_t)stream>>>(loss, d_pos, (int)n_pos, d_neg, (int)neg_rows, (int)neg_cols,
+                                                          d_mask, d_loss, d_dpos, d_dneg);
   MFB_KERNEL_CHECK();
   return MFB_OK;
 }

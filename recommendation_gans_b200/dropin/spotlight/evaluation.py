@@ -163,6 +163,36 @@ def map_at_k(model, test, k=5):
     return np.mean(apk_)
 
 
+def hit_ratio(model, test, k=10):
+    """Fraction of users with test items whose target is among the top-k recommendations (evaluation.py:192-213; no
+    train mask).  The reference evaluates `target in predictions[:k]` on numpy arrays: with one test item per user
+    (leave-one-out, its intended use) that is membership; with exactly k targets numpy compares position by position;
+    any other count makes numpy raise ValueError -- reproduced here."""
+    eng = _native_engine(model)
+    test_csr = test.tocsr()
+    user_ids = np.nonzero(np.diff(test_csr.indptr))[0].astype(np.int64)
+    if len(user_ids) == 0:
+        raise ZeroDivisionError('division by zero')            # num_hits / num_users with no test users
+    kk = min(int(k), eng.num_items)
+    counts = np.diff(test_csr.indptr)[user_ids]
+    bad = (counts != 1) & (counts != kk)
+    if bad.any():
+        raise ValueError('operands could not be broadcast together with shapes (%d,) (%d,) '
+                         % (kk, counts[np.argmax(bad)]))
+    d_users = torch.from_numpy(user_ids).to(eng.device)
+    topk = eng.topk(d_users, kk)
+    t_indptr, t_indices = _csr_to_device(test_csr, eng.device)
+    hits, _ = eng.topk_hits(topk, d_users, t_indptr, t_indices, np.array([kk]))
+    hit = hits.cpu().numpy().reshape(-1) > 0
+    multi = np.nonzero(counts == kk)[0] if kk != 1 else np.array([], dtype=np.int64)
+    if len(multi):                                              # k targets: numpy's elementwise comparison
+        top_h = topk.cpu().numpy()
+        for r in multi:
+            u = user_ids[r]
+            hit[r] = bool((top_h[r] == test_csr.indices[test_csr.indptr[u]:test_csr.indptr[u + 1]]).any())
+    return hit.sum() / len(user_ids)
+
+
 def evaluate_popItems(item_popularity, test, k=10):
     """Most-popular-items baseline (evaluation.py:215-243).  Host-side by nature: no model involved."""
     test_csr = test.tocsr()

@@ -83,8 +83,9 @@ def mt_words_device(state625, nwords, device=None):
     return out
 
 
-def loss_forward_backward(kind, pos, neg, need_grad):
-    """spotlight/losses.py on 1-D probability tensors -> (loss, dpos, dneg)."""
+def loss_forward_backward(kind, pos, neg, need_grad, mask=None):
+    """spotlight/losses.py on probability tensors -> (loss, dpos, dneg).  pos is 1-D [b]; neg is 1-D, or [n, b] for
+    adaptive_hinge (per-positive maximum over dim 0); mask is None or [b] (loss*mask summed over mask.sum())."""
     N.require_cuda()
     lib = N.load_library()
     pos = pos.detach().contiguous().float()
@@ -93,9 +94,19 @@ def loss_forward_backward(kind, pos, neg, need_grad):
     dpos = torch.empty_like(pos) if need_grad else None
     dneg = (torch.empty_like(neg_c) if need_grad else None) if neg_c is not None else None
     with torch.cuda.device(pos.device):
-        N.check(lib.mfb_loss_forward_backward(N.LOSS[kind], N.dptr(pos), pos.numel(), N.dptr(neg_c),
-                                              0 if neg_c is None else neg_c.numel(), N.dptr(loss), N.dptr(dpos),
-                                              N.dptr(dneg), N.stream_ptr()), kind + '_loss')
+        if mask is None and (neg_c is None or neg_c.dim() <= 1):
+            N.check(lib.mfb_loss_forward_backward(N.LOSS[kind], N.dptr(pos), pos.numel(), N.dptr(neg_c),
+                                                  0 if neg_c is None else neg_c.numel(), N.dptr(loss), N.dptr(dpos),
+                                                  N.dptr(dneg), N.stream_ptr()), kind + '_loss')
+        else:
+            mask_c = None if mask is None else mask.detach().to(device=pos.device, dtype=torch.float32).contiguous()
+            if mask_c is not None and mask_c.shape != pos.shape:
+                raise RuntimeError('%s_loss: mask of shape %s does not match the %d positive predictions'
+                                   % (kind, tuple(mask_c.shape), pos.numel()))
+            rows, cols = (0, 0) if neg_c is None else ((0, neg_c.numel()) if neg_c.dim() <= 1 else neg_c.shape)
+            N.check(lib.mfb_loss_forward_backward_ex(N.LOSS[kind], N.dptr(pos), pos.numel(), N.dptr(neg_c), int(rows),
+                                                     int(cols), N.dptr(mask_c), N.dptr(loss), N.dptr(dpos),
+                                                     N.dptr(dneg), N.stream_ptr()), kind + '_loss')
     return loss, dpos, dneg
 
 

@@ -203,3 +203,28 @@ def test_tc_topk_equals_exact_kernel(U, I, D, k, scale, skew, monkeypatch):
         np.testing.assert_array_equal(sc_e.cpu().numpy(), sc_t.cpu().numpy())
         assert tc.topk_last_redo < U // 20, tc.topk_last_redo       # the fast path did the work
     assert exact.topk_last_redo == 0
+
+
+def test_hit_ratio_matches_reference_loop():
+    """evaluation.hit_ratio (evaluation.py:192-213) on a leave-one-out test set: membership of the single target in the
+    top-k of the stable ranking (dyadic tables: every score exact, so the ranking is well defined)."""
+    from spotlight.evaluation import hit_ratio
+    from oracle import mf_oracle as O
+    rs = np.random.RandomState(3)
+    U, I, D, k = 300, 500, 16, 10
+    tabs = _dyadic_tables(rs, U, I, D)
+    net = make_net(tabs)
+
+    class _Model(object):          # the only thing evaluation needs from a fitted model
+        _net = net
+        _num_items = I
+    users = np.arange(0, U, 2)     # every second user has one test item
+    targets = rs.randint(0, I, len(users))
+    test = _interactions(users, targets, U, I)
+    logits = tabs[0] @ tabs[1].T + tabs[2] + tabs[3].T
+    expect = np.mean([targets[j] in O.topk_stable(logits[u], np.array([], dtype=np.int64), k)
+                      for j, u in enumerate(users)])
+    assert hit_ratio(_Model(), test, k=k) == pytest.approx(expect, abs=1e-12)
+    two = _interactions(np.repeat(users[:5], 2), rs.randint(0, I, 10), U, I)      # 2 targets, k=10: numpy raises
+    with pytest.raises(ValueError):
+        hit_ratio(_Model(), two, k=k)

@@ -100,6 +100,42 @@ def test_losses_match_reference(golden_dir):
             np.testing.assert_allclose(neg.grad.cpu().numpy(), g['dneg_' + key], rtol=2e-6, atol=1e-9)
 
 
+def test_losses_with_mask_and_2d_negatives_match_reference(golden_dir):
+    """`mask=` and adaptive_hinge_loss on [n, b] negatives (losses.py:51-55,91-95,124-128,170) vs vectors frozen from
+    the reference by oracle/make_golden_losses_ex.py; also checked against the oracle on fresh random inputs."""
+    import spotlight.losses as L
+    from oracle import mf_oracle as O
+    g = np.load(os.path.join(golden_dir, 'losses_ex.npz'))
+    for case in g['cases']:
+        name, negkey, use_mask = str(case).split('|')
+        pos = torch.from_numpy(g['pos'].copy()).cuda().requires_grad_(True)
+        neg = torch.from_numpy(g[negkey].copy()).cuda().requires_grad_(True)
+        mask = torch.from_numpy(g['mask']).cuda() if use_mask == '1' else None
+        val = getattr(L, name + '_loss')(pos, neg, mask=mask)
+        val.backward()
+        tag = '%s_%s_%s' % (name, negkey, 'mask' if use_mask == '1' else 'nomask')
+        np.testing.assert_allclose(val.item(), g['loss_' + tag], rtol=2e-6)
+        np.testing.assert_allclose(pos.grad.cpu().numpy(), g['dpos_' + tag], rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(neg.grad.cpu().numpy(), g['dneg_' + tag], rtol=2e-6, atol=1e-9)
+    rs = np.random.RandomState(5)
+    for b, n in ((1, 1), (33, 7), (4097, 3)):                 # sizes around the block size; a single pair
+        pos_h = rs.uniform(0.01, 0.99, b).astype(np.float32)
+        neg_h = rs.uniform(0.01, 0.99, (n, b)).astype(np.float32)
+        mask_h = (rs.uniform(0, 1, b) < 0.5).astype(np.float32)
+        mask_h[0] = 1.0
+        pc, nc = torch.from_numpy(pos_h).requires_grad_(True), torch.from_numpy(neg_h).requires_grad_(True)
+        ref = O.adaptive_hinge_loss(pc, nc, mask=torch.from_numpy(mask_h))
+        ref.backward()
+        pg, ng = torch.from_numpy(pos_h).cuda().requires_grad_(True), torch.from_numpy(neg_h).cuda().requires_grad_(True)
+        val = L.adaptive_hinge_loss(pg, ng, mask=torch.from_numpy(mask_h).cuda())
+        val.backward()
+        np.testing.assert_allclose(val.item(), ref.item(), rtol=2e-6)
+        np.testing.assert_allclose(pg.grad.cpu().numpy(), pc.grad.numpy(), rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(ng.grad.cpu().numpy(), nc.grad.numpy(), rtol=2e-6, atol=1e-9)
+    with pytest.raises(NotImplementedError):                   # 2-D negatives elsewhere are outside the path
+        L.hinge_loss(torch.rand(4).cuda(), torch.rand(2, 4).cuda())
+
+
 def test_forward_matches_reference(golden_dir):
     from tests.gpu_helpers import make_net
     g = np.load(os.path.join(golden_dir, 'forward_losses.npz'))

@@ -123,3 +123,22 @@ def test_fit_predict_evaluate(golden_dir, name):
         np.testing.assert_allclose([p2, r2], g['pr_masked_k%d' % k], atol=2e-3)
     p, r, _, _ = O.precision_recall_score(model, test, train, np.array([5, 10, 20]), ranking='reference')
     np.testing.assert_allclose([p, r], g['pr_masked_karray'], rtol=1e-9)
+
+
+def test_losses_with_mask_and_2d_negatives_match_reference(golden_dir):
+    """spotlight/losses.py `mask=` and adaptive_hinge_loss on [n, b] negatives (tests/golden/losses_ex.npz, frozen
+    from the reference by oracle/make_golden_losses_ex.py)."""
+    import torch
+    from oracle import mf_oracle as O
+    g = np.load(os.path.join(golden_dir, 'losses_ex.npz'))
+    for case in g['cases']:
+        name, negkey, use_mask = str(case).split('|')
+        pos = torch.from_numpy(g['pos'].copy()).requires_grad_(True)
+        neg = torch.from_numpy(g[negkey].copy()).requires_grad_(True)
+        mask = torch.from_numpy(g['mask']) if use_mask == '1' else None
+        val = O.LOSS_FUNCTIONS[name](pos, neg, mask=mask)
+        val.backward()
+        tag = '%s_%s_%s' % (name, negkey, 'mask' if use_mask == '1' else 'nomask')
+        np.testing.assert_allclose(val.detach().numpy(), g['loss_' + tag], rtol=1e-6)
+        np.testing.assert_allclose(pos.grad.numpy(), g['dpos_' + tag], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(neg.grad.numpy(), g['dneg_' + tag], rtol=1e-6, atol=1e-9)
