@@ -314,8 +314,8 @@ def native_bench(args, w, rank, world):
         'eval': {'metric': 'top-k eval users/s (k=20, train mask, full catalog)', 'value': n_eval / t_eval,
                  'unit': 'users/s', 'users': n_eval, 'seconds': t_eval, 'kernel': ev['kernel'],
                  'roofline': {'bound': 'tensor', 'achieved': 2.0 * n_eval * w['I'] * D / t_eval / 1e12,
-                              'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                              'frac': 2.0 * n_eval * w['I'] * D / t_eval / 1e12 / peaks['bf16_tflops']}},
+                              'peak': peaks['bf16_tflops'] * world, 'unit': 'TFLOP/s',
+                              'frac': 2.0 * n_eval * w['I'] * D / t_eval / 1e12 / (peaks['bf16_tflops'] * world)}},
     }
     if sh is not None:
         sh['roofline'] = {'bound': 'hbm', 'achieved': sh['hbm_gbs_algorithmic_total'], 'peak': peaks['hbm_gbs'] * world,
@@ -401,9 +401,19 @@ def main():
                         'd2h_bytes_per_step': 0}}
         print(json.dumps(line))
         return 0
-    out = native_bench(args, w, rank, world)
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = native_bench(args, w, rank, world)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if out is not None:
         print(json.dumps(out))
+        sys.stdout.flush()
     return 0
 
 
