@@ -262,7 +262,7 @@ def native_bench(args, w, rank, world):
     sh = None
     if not args.no_sharded:
         from tools.shard_bench import run as shard_run
-        sh = shard_run(steps=args.sharded_steps, warmup=32, zipf=w['zipf'], fast_math=bool(args.fast_math))
+        sh = shard_run(steps=args.sharded_steps, warmup=64, zipf=w['zipf'], fast_math=bool(args.fast_math))
 
     # ---- reduce over ranks: max time, summed work
     t_train, t_e2e, t_eval, n_eval = ms / 1e3, e2e_s, ev['seconds'], ev['users']

@@ -548,18 +548,29 @@ inline int grid_warps(long long warps, int per) { return (int)((warps + per - 1)
 
 }  // namespace
 
+struct PlanSet {
+  Geom g = {};
+  bool planned = false;
+  std::vector<uint32_t> h_own_off;
+  uint32_t *skeys2 = nullptr, *svals2 = nullptr;
+  DevBuf ent, k2a, k2b, v2a, v2b, segf, segl, info, rpos, pred, sdst, gdst;
+  cudaEvent_t ev_planned = nullptr;   // recorded on the planning stream when the set is complete
+  cudaEvent_t ev_used = nullptr;      // recorded on the step stream after the last kernel that reads the set
+  bool wait_planned = false, was_used = false;
+};
+
 struct mfb_shard {
   mfb_model *m = nullptr;
   int rank = 0, world = 1, gb = 1, GP = 2;
   long long g_users = 0, g_items = 0;
-  Geom g = {};
-  bool planned = false;
   Shape shape = {4, 1};
   int Dp = 0, stride = 0;
-  std::vector<uint32_t> h_start, h_own_off;
-  uint32_t *skeys2 = nullptr, *svals2 = nullptr;
-  DevBuf ids_u, ids_i, keys_a, keys_b, vals_a, vals_b, hist, start, own_off, rbase, ent, k2a, k2b, v2a, v2b, segf, segl,
-      info, rpos, pred, err, partial, tickets, sdst, gdst, gcell;
+  // Planner output is double-buffered: chunk c+1 is planned (on the caller's planning stream) into the set that chunk
+  // c-1 used while chunk c executes from the other one.  `active` = the set the step functions read.
+  PlanSet sets[2];
+  int active = 0;
+  std::vector<uint32_t> h_start;
+  DevBuf ids_u, ids_i, keys_a, keys_b, vals_a, vals_b, hist, start, own_off, rbase, err, partial, tickets, gcell;
   int64_t launches = 0;
   // direct exchange over peer memory
   void *xbuf = nullptr;
@@ -599,6 +610,10 @@ extern "C" int mfb_shard_create(mfb_model *local, int32_t rank, int32_t world, i
   }
   sh->Dp = (local->desc.dim + 3) / 4 * 4;
   sh->stride = sh->Dp + 4;
+  for (PlanSet &ps : sh->sets) {
+    cudaEventCreateWithFlags(&ps.ev_planned, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ps.ev_used, cudaEventDisableTiming);
+  }
   *out = sh;
   return MFB_OK;
 }
@@ -607,10 +622,15 @@ extern "C" int mfb_shard_destroy(mfb_shard *sh) {
   if (!sh) return MFB_OK;
   cudaDeviceSynchronize();
   DevBuf *bufs[] = {&sh->ids_u, &sh->ids_i, &sh->keys_a, &sh->keys_b, &sh->vals_a, &sh->vals_b, &sh->hist, &sh->start,
-                    &sh->own_off, &sh->rbase, &sh->ent, &sh->k2a, &sh->k2b, &sh->v2a, &sh->v2b, &sh->segf, &sh->segl,
-                    &sh->info, &sh->rpos, &sh->pred, &sh->err, &sh->partial, &sh->tickets, &sh->sdst, &sh->gdst,
-                    &sh->gcell, &sh->peers_dev};
+                    &sh->own_off, &sh->rbase, &sh->err, &sh->partial, &sh->tickets, &sh->gcell, &sh->peers_dev};
   for (DevBuf *b : bufs) b->release();
+  for (PlanSet &ps : sh->sets) {
+    DevBuf *pbufs[] = {&ps.ent, &ps.k2a, &ps.k2b, &ps.v2a, &ps.v2b, &ps.segf, &ps.segl, &ps.info, &ps.rpos, &ps.pred,
+                       &ps.sdst, &ps.gdst};
+    for (DevBuf *b : pbufs) b->release();
+    if (ps.ev_planned) cudaEventDestroy(ps.ev_planned);
+    if (ps.ev_used) cudaEventDestroy(ps.ev_used);
+  }
   if (sh->xbuf) cudaFree(sh->xbuf);
   delete sh;
   return MFB_OK;
@@ -634,8 +654,10 @@ extern "C" int mfb_shard_plan(mfb_shard *sh, const int64_t *d_pos_users, const i
     return MFB_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  sh->planned = false;
-  Geom &g = sh->g;
+  PlanSet &ps = sh->sets[1 - sh->active];   // the set the previous-but-one chunk used; the active one may be executing
+  if (ps.was_used) MFB_CUDA(cudaStreamWaitEvent(st, ps.ev_used, 0));
+  ps.planned = false;
+  Geom &g = ps.g;
   g.n_pos = n_pos;
   g.step0 = step0;
   g.batch = batch;
@@ -671,9 +693,9 @@ extern "C" int mfb_shard_plan(mfb_shard *sh, const int64_t *d_pos_users, const i
   MFB_CHECK(sh->start.reserve((size_t)(nkeys + 1) * 4));
   MFB_CHECK(sh->own_off.reserve((size_t)(nsteps + 1) * 4));
   MFB_CHECK(sh->rbase.reserve((size_t)nsteps * g.GP * 4));
-  MFB_CHECK(sh->rpos.reserve((size_t)2 * nsteps * g.Lloc_cap * sizeof(int)));
-  MFB_CHECK(sh->pred.reserve((size_t)nsteps * g.Lloc_cap * sizeof(float)));
-  MFB_CHECK(sh->gdst.reserve((size_t)2 * nsteps * g.Lloc_cap * 4));
+  MFB_CHECK(ps.rpos.reserve((size_t)2 * nsteps * g.Lloc_cap * sizeof(int)));
+  MFB_CHECK(ps.pred.reserve((size_t)nsteps * g.Lloc_cap * sizeof(float)));
+  MFB_CHECK(ps.gdst.reserve((size_t)2 * nsteps * g.Lloc_cap * 4));
   if (2ll * g.Lfull >= (1ll << 26) || g.G > 64) {
     mfb_set_error("shard_plan: batch too large for the packed exchange positions");
     return MFB_ERR_UNSUPPORTED;
@@ -695,10 +717,10 @@ extern "C" int mfb_shard_plan(mfb_shard *sh, const int64_t *d_pos_users, const i
   k_shard_offsets<<<1, 256, 0, st>>>(sh->start.as<uint32_t>(), g, sh->own_off.as<uint32_t>(), sh->rbase.as<uint32_t>());
   MFB_KERNEL_CHECK();
   sh->h_start.resize((size_t)nkeys + 1);
-  sh->h_own_off.resize((size_t)nsteps + 1);
+  ps.h_own_off.resize((size_t)nsteps + 1);
   int h_err = 0;
   MFB_CUDA(cudaMemcpyAsync(sh->h_start.data(), sh->start.ptr, (size_t)(nkeys + 1) * 4, cudaMemcpyDeviceToHost, st));
-  MFB_CUDA(cudaMemcpyAsync(sh->h_own_off.data(), sh->own_off.ptr, (size_t)(nsteps + 1) * 4, cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaMemcpyAsync(ps.h_own_off.data(), sh->own_off.ptr, (size_t)(nsteps + 1) * 4, cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaMemcpyAsync(&h_err, sh->err.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
   if (h_err) {
@@ -712,39 +734,39 @@ extern "C" int mfb_shard_plan(mfb_shard *sh, const int64_t *d_pos_users, const i
         const int k = (s * g.GP + o) * g.GP + c;
         h_counts[((int64_t)s * g.G + o) * g.G + c] = (int64_t)sh->h_start[k + 1] - (int64_t)sh->h_start[k];
       }
-  const int64_t n_own = sh->h_own_off[nsteps];
+  const int64_t n_own = ps.h_own_off[nsteps];
   const size_t own_cap = (size_t)std::max<int64_t>(n_own, 1);
-  MFB_CHECK(sh->ent.reserve(own_cap * 4));
-  MFB_CHECK(sh->k2a.reserve(own_cap * 4));
-  MFB_CHECK(sh->k2b.reserve(own_cap * 4));
-  MFB_CHECK(sh->v2a.reserve(own_cap * 4));
-  MFB_CHECK(sh->v2b.reserve(own_cap * 4));
-  MFB_CHECK(sh->segf.reserve(own_cap * 4));
-  MFB_CHECK(sh->segl.reserve(own_cap * 4));
-  MFB_CHECK(sh->info.reserve(own_cap * sizeof(PosInfo)));
-  MFB_CHECK(sh->sdst.reserve(own_cap * 4));
+  MFB_CHECK(ps.ent.reserve(own_cap * 4));
+  MFB_CHECK(ps.k2a.reserve(own_cap * 4));
+  MFB_CHECK(ps.k2b.reserve(own_cap * 4));
+  MFB_CHECK(ps.v2a.reserve(own_cap * 4));
+  MFB_CHECK(ps.v2b.reserve(own_cap * 4));
+  MFB_CHECK(ps.segf.reserve(own_cap * 4));
+  MFB_CHECK(ps.segl.reserve(own_cap * 4));
+  MFB_CHECK(ps.info.reserve(own_cap * sizeof(PosInfo)));
+  MFB_CHECK(ps.sdst.reserve(own_cap * 4));
   k_shard_layout<<<(unsigned)((n_e + 255) / 256), 256, 0, st>>>(
       sk, sv, n_e, g, sh->ids_u.as<int>(), sh->ids_i.as<int>(), sh->start.as<uint32_t>(), sh->own_off.as<uint32_t>(),
-      sh->rbase.as<uint32_t>(), sh->ent.as<uint32_t>(), sh->k2a.as<uint32_t>(), sh->v2a.as<uint32_t>(),
-      sh->rpos.as<int>(), sh->sdst.as<uint32_t>(), sh->gdst.as<uint32_t>());
+      sh->rbase.as<uint32_t>(), ps.ent.as<uint32_t>(), ps.k2a.as<uint32_t>(), ps.v2a.as<uint32_t>(),
+      ps.rpos.as<int>(), ps.sdst.as<uint32_t>(), ps.gdst.as<uint32_t>());
   MFB_KERNEL_CHECK();
-  sh->skeys2 = sh->k2a.as<uint32_t>();
-  sh->svals2 = sh->v2a.as<uint32_t>();
+  ps.skeys2 = ps.k2a.as<uint32_t>();
+  ps.svals2 = ps.v2a.as<uint32_t>();
   int sort2_kernels = 0;
   if (n_own > 0) {
-    MFB_CHECK(mfb_radix_sort_pairs(sh->k2a.as<uint32_t>(), sh->v2a.as<uint32_t>(), sh->k2b.as<uint32_t>(),
-                                   sh->v2b.as<uint32_t>(), n_own, sb + g.rb + 1, sh->hist, &sh->skeys2, &sh->svals2, st));
+    MFB_CHECK(mfb_radix_sort_pairs(ps.k2a.as<uint32_t>(), ps.v2a.as<uint32_t>(), ps.k2b.as<uint32_t>(),
+                                   ps.v2b.as<uint32_t>(), n_own, sb + g.rb + 1, sh->hist, &ps.skeys2, &ps.svals2, st));
     const unsigned grid = (unsigned)((n_own + 255) / 256);
-    k_segments<<<grid, 256, 0, st>>>(sh->skeys2, n_own, sh->segf.as<uint32_t>(), sh->segl.as<uint32_t>());
+    k_segments<<<grid, 256, 0, st>>>(ps.skeys2, n_own, ps.segf.as<uint32_t>(), ps.segl.as<uint32_t>());
     MFB_KERNEL_CHECK();
-    k_posinfo<<<grid, 256, 0, st>>>(sh->skeys2, n_own, sh->segf.as<uint32_t>(), sh->segl.as<uint32_t>(), nullptr,
-                                    sh->info.as<PosInfo>());
+    k_posinfo<<<grid, 256, 0, st>>>(ps.skeys2, n_own, ps.segf.as<uint32_t>(), ps.segl.as<uint32_t>(), nullptr,
+                                    ps.info.as<PosInfo>());
     MFB_KERNEL_CHECK();
     sort2_kernels = 3 * ((sb + g.rb + 1 + 7) / 8) + 2;
   }
   // gradient-reduction scratch for the largest step of the chunk
   int64_t max_serve = 0;
-  for (int s = 0; s < nsteps; ++s) max_serve = std::max<int64_t>(max_serve, sh->h_own_off[s + 1] - sh->h_own_off[s]);
+  for (int s = 0; s < nsteps; ++s) max_serve = std::max<int64_t>(max_serve, ps.h_own_off[s + 1] - ps.h_own_off[s]);
   const int64_t nwin = (max_serve + SH_WIN - 1) / SH_WIN;
   MFB_CHECK(sh->partial.reserve((size_t)std::max<int64_t>(2 * nwin, 1) * sh->stride * sizeof(float)));
   const size_t old_cap = sh->tickets.cap;
@@ -752,7 +774,11 @@ extern "C" int mfb_shard_plan(mfb_shard *sh, const int64_t *d_pos_users, const i
   if (sh->tickets.cap != old_cap) MFB_CUDA(cudaMemsetAsync(sh->tickets.ptr, 0, sh->tickets.cap, st));
   MFB_CHECK(mfb_ensure_scalars(sh->m, sh->m->step + nsteps + 1));
   sh->launches += 4 + 3 * ((sb + 2 * g.gb + 7) / 8) + sort2_kernels;
-  sh->planned = true;
+  MFB_CUDA(cudaEventRecord(ps.ev_planned, st));
+  ps.planned = true;
+  ps.wait_planned = true;     // the first step call makes its stream wait for the planning stream
+  ps.was_used = false;
+  sh->active = 1 - sh->active;
   return MFB_OK;
 }
 
@@ -763,11 +789,13 @@ struct StepView {
   int n_serve;
 };
 int step_view(const mfb_shard *sh, int s, StepView *v) {
-  if (!sh || !sh->planned || s < 0 || s >= sh->g.ns) {
+  if (!sh) return MFB_ERR_INVALID;
+  const PlanSet &ps = sh->sets[sh->active];
+  if (!ps.planned || s < 0 || s >= ps.g.ns) {
     mfb_set_error("shard step %d: no plan covers it (call mfb_shard_plan first)", s);
     return MFB_ERR_INVALID;
   }
-  const Geom &g = sh->g;
+  const Geom &g = ps.g;
   const long long first = (g.step0 + s) * g.batch;
   v->b = (int)std::min<long long>(g.batch, g.n_pos - first);
   v->b_lo = part_lo(g.rank, v->b, g.G);
@@ -775,8 +803,17 @@ int step_view(const mfb_shard *sh, int s, StepView *v) {
   v->m_lo = part_lo(g.rank, g.m_neg, g.G);
   v->m_loc = part_lo(g.rank + 1, g.m_neg, g.G) - v->m_lo;
   v->Lloc = v->b_loc + v->m_loc;
-  v->base = sh->h_own_off[s];
-  v->n_serve = (int)(sh->h_own_off[s + 1] - sh->h_own_off[s]);
+  v->base = ps.h_own_off[s];
+  v->n_serve = (int)(ps.h_own_off[s + 1] - ps.h_own_off[s]);
+  return MFB_OK;
+}
+// first use of a freshly planned set on the step stream: order it after the planner's last kernel
+int sync_plan(mfb_shard *sh, cudaStream_t st) {
+  PlanSet &ps = sh->sets[sh->active];
+  if (ps.wait_planned) {
+    MFB_CUDA(cudaStreamWaitEvent(st, ps.ev_planned, 0));
+    ps.wait_planned = false;
+  }
   return MFB_OK;
 }
 }  // namespace
@@ -784,9 +821,11 @@ int step_view(const mfb_shard *sh, int s, StepView *v) {
 extern "C" int mfb_shard_gather(mfb_shard *sh, int32_t s, float *d_send, mfb_stream stream) {
   StepView v;
   MFB_CHECK(step_view(sh, s, &v));
+  cudaStream_t st = (cudaStream_t)stream;
+  MFB_CHECK(sync_plan(sh, st));
+  PlanSet &ps = sh->sets[sh->active];
   if (v.n_serve == 0) return MFB_OK;
   if (!d_send) return MFB_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
   mfb_model *m = sh->m;
   const int D = m->desc.dim;
   const int target = (int)m->step;   // the rows must be current for the step BEFORE the one being computed
@@ -795,17 +834,17 @@ extern "C" int mfb_shard_gather(mfb_shard *sh, int32_t s, float *d_send, mfb_str
   {
 #define CALL(V, N)                                                                                                   \
   if (fast)                                                                                                          \
-    k_shard_catchup<V, N, true><<<grid, SH_THREADS, 0, st>>>(sh->info.as<PosInfo>(), v.base, v.n_serve, sh->g.rb,    \
+    k_shard_catchup<V, N, true><<<grid, SH_THREADS, 0, st>>>(ps.info.as<PosInfo>(), v.base, v.n_serve, ps.g.rb,    \
                                                              m->users, m->items, m->opt, D, target);                 \
   else                                                                                                               \
-    k_shard_catchup<V, N, false><<<grid, SH_THREADS, 0, st>>>(sh->info.as<PosInfo>(), v.base, v.n_serve, sh->g.rb,   \
+    k_shard_catchup<V, N, false><<<grid, SH_THREADS, 0, st>>>(ps.info.as<PosInfo>(), v.base, v.n_serve, ps.g.rb,   \
                                                               m->users, m->items, m->opt, D, target);
     MFB_DISPATCH_SHAPE(sh->shape, CALL);
 #undef CALL
     MFB_KERNEL_CHECK();
   }
 #define CALL(V, N)                                                                                                 \
-  k_shard_gather<V, N><<<grid, SH_THREADS, 0, st>>>(sh->ent.as<uint32_t>() + v.base, v.n_serve, m->users, m->items, D, \
+  k_shard_gather<V, N><<<grid, SH_THREADS, 0, st>>>(ps.ent.as<uint32_t>() + v.base, v.n_serve, m->users, m->items, D, \
                                                     sh->Dp, sh->stride, d_send);
   MFB_DISPATCH_SHAPE(sh->shape, CALL);
 #undef CALL
@@ -819,12 +858,14 @@ extern "C" int mfb_shard_forward(mfb_shard *sh, int loss, int32_t s, const float
   StepView v;
   MFB_CHECK(step_view(sh, s, &v));
   if (loss < MFB_LOSS_POINTWISE || loss > MFB_LOSS_ADAPTIVE_HINGE) return MFB_ERR_INVALID;
-  if ((loss == MFB_LOSS_HINGE || loss == MFB_LOSS_BPR) && sh->g.m_neg != v.b) {
+  if ((loss == MFB_LOSS_HINGE || loss == MFB_LOSS_BPR) && sh->sets[sh->active].g.m_neg != v.b) {
     mfb_set_error("%s loss needs as many negatives as positives (got %d and %d)", loss == MFB_LOSS_HINGE ? "hinge" : "bpr",
-                  sh->g.m_neg, v.b);
+                  sh->sets[sh->active].g.m_neg, v.b);
     return MFB_ERR_SHAPE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  MFB_CHECK(sync_plan(sh, st));
+  PlanSet &ps = sh->sets[sh->active];
   const int adaptive = loss == MFB_LOSS_ADAPTIVE_HINGE;
   if (adaptive) {
     if (!d_gmax_cell) return MFB_ERR_INVALID;
@@ -832,10 +873,10 @@ extern "C" int mfb_shard_forward(mfb_shard *sh, int loss, int32_t s, const float
   }
   if (v.Lloc == 0) return MFB_OK;
   if (!d_recv) return MFB_ERR_INVALID;
-  const Geom &g = sh->g;
-  const int *rpu = sh->rpos.as<int>() + (long long)s * g.Lloc_cap;
-  const int *rpi = sh->rpos.as<int>() + ((long long)g.ns + s) * g.Lloc_cap;
-  float *pred = sh->pred.as<float>() + (long long)s * g.Lloc_cap;
+  const Geom &g = ps.g;
+  const int *rpu = ps.rpos.as<int>() + (long long)s * g.Lloc_cap;
+  const int *rpi = ps.rpos.as<int>() + ((long long)g.ns + s) * g.Lloc_cap;
+  float *pred = ps.pred.as<float>() + (long long)s * g.Lloc_cap;
   const int D = sh->m->desc.dim;
 #define CALL(V, N)                                                                                               \
   k_shard_forward<V, N><<<grid_warps(v.Lloc, SH_WARPS), SH_THREADS, 0, st>>>(                                    \
@@ -853,14 +894,16 @@ static int shard_backward_impl(mfb_shard *sh, int loss, int32_t s, const float *
   MFB_CHECK(step_view(sh, s, &v));
   if (loss < MFB_LOSS_POINTWISE || loss > MFB_LOSS_ADAPTIVE_HINGE || !d_loss_partial) return MFB_ERR_INVALID;
   if (loss == MFB_LOSS_ADAPTIVE_HINGE && !d_gmax_cell) return MFB_ERR_INVALID;
-  const Geom &g = sh->g;
-  const int *rpu = sh->rpos.as<int>() + (long long)s * g.Lloc_cap;
-  const int *rpi = sh->rpos.as<int>() + ((long long)g.ns + s) * g.Lloc_cap;
-  const float *pred = sh->pred.as<float>() + (long long)s * g.Lloc_cap;
+  MFB_CHECK(sync_plan(sh, st));
+  PlanSet &ps = sh->sets[sh->active];
+  const Geom &g = ps.g;
+  const int *rpu = ps.rpos.as<int>() + (long long)s * g.Lloc_cap;
+  const int *rpi = ps.rpos.as<int>() + ((long long)g.ns + s) * g.Lloc_cap;
+  const float *pred = ps.pred.as<float>() + (long long)s * g.Lloc_cap;
   const int D = sh->m->desc.dim;
   const unsigned long long *cell = (const unsigned long long *)d_gmax_cell;
-  const uint32_t *gdu = direct ? sh->gdst.as<uint32_t>() + (long long)s * g.Lloc_cap : nullptr;
-  const uint32_t *gdi = direct ? sh->gdst.as<uint32_t>() + ((long long)g.ns + s) * g.Lloc_cap : nullptr;
+  const uint32_t *gdu = direct ? ps.gdst.as<uint32_t>() + (long long)s * g.Lloc_cap : nullptr;
+  const uint32_t *gdi = direct ? ps.gdst.as<uint32_t>() + ((long long)g.ns + s) * g.Lloc_cap : nullptr;
   if (v.Lloc > 0) {
     if (!d_recv || (!d_gsend && !direct)) return MFB_ERR_INVALID;
     const int grid = grid_warps(v.Lloc, SH_WARPS);
@@ -896,17 +939,19 @@ extern "C" int mfb_shard_update(mfb_shard *sh, int32_t s, const float *d_grecv, 
   StepView v;
   MFB_CHECK(step_view(sh, s, &v));
   cudaStream_t st = (cudaStream_t)stream;
+  MFB_CHECK(sync_plan(sh, st));
+  PlanSet &ps = sh->sets[sh->active];
   mfb_model *m = sh->m;
   const int t = (int)m->step + 1;
   MFB_CHECK(mfb_ensure_scalars(m, t + 1));
   if (v.n_serve > 0) {
     if (!d_grecv) return MFB_ERR_INVALID;
     ShUpdArgs a;
-    a.info = sh->info.as<PosInfo>();
-    a.svals = sh->svals2;
+    a.info = ps.info.as<PosInfo>();
+    a.svals = ps.svals2;
     a.base = v.base;
     a.n = v.n_serve;
-    a.rb = sh->g.rb;
+    a.rb = ps.g.rb;
     a.D = m->desc.dim;
     a.Dp = sh->Dp;
     a.stride = sh->stride;
@@ -929,6 +974,8 @@ extern "C" int mfb_shard_update(mfb_shard *sh, int32_t s, const float *d_grecv, 
     sh->launches += 1;
   }
   m->step = t;   // the dense optimiser stepped every row; rows not served here catch up lazily
+  MFB_CUDA(cudaEventRecord(ps.ev_used, st));   // the planner may recycle this set once the step has run
+  ps.was_used = true;
   return MFB_OK;
 }
 
@@ -1016,16 +1063,19 @@ extern "C" int mfb_ipc_close(void *d_ptr) {
 // synchronisation and no collective call.  d_loss_partial: 2 doubles per step (as mfb_shard_backward).
 extern "C" int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int32_t s_end, double *d_loss_partial,
                                    mfb_stream stream) {
-  if (!sh || !sh->planned || !sh->peers_set || !d_loss_partial || s_begin < 0 || s_end > sh->g.ns || s_begin > s_end) {
+  if (!sh) return MFB_ERR_INVALID;
+  PlanSet &ps = sh->sets[sh->active];
+  if (!ps.planned || !sh->peers_set || !d_loss_partial || s_begin < 0 || s_end > ps.g.ns || s_begin > s_end) {
     mfb_set_error("shard_run_steps: needs a plan, an exchange buffer with peers, and a step range inside the plan");
     return MFB_ERR_INVALID;
   }
-  if (sh->g.batch != sh->x_batch || sh->g.m_neg != sh->x_m_neg) {
+  if (ps.g.batch != sh->x_batch || ps.g.m_neg != sh->x_m_neg) {
     mfb_set_error("shard_run_steps: the exchange buffer was sized for batch %d / %d negatives, the plan has %d / %d",
-                  sh->x_batch, sh->x_m_neg, sh->g.batch, sh->g.m_neg);
+                  sh->x_batch, sh->x_m_neg, ps.g.batch, ps.g.m_neg);
     return MFB_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  MFB_CHECK(sync_plan(sh, st));
   mfb_model *m = sh->m;
   const int G = sh->world, D = m->desc.dim;
   const bool fast = m->desc.fast_math != 0, adaptive = loss == MFB_LOSS_ADAPTIVE_HINGE;
@@ -1046,13 +1096,13 @@ extern "C" int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int
       const int target = (int)m->step;
 #define CALL(V, N)                                                                                                   \
   if (fast)                                                                                                          \
-    k_shard_catchup<V, N, true><<<grid, SH_THREADS, 0, st>>>(sh->info.as<PosInfo>(), v.base, v.n_serve, sh->g.rb,    \
+    k_shard_catchup<V, N, true><<<grid, SH_THREADS, 0, st>>>(ps.info.as<PosInfo>(), v.base, v.n_serve, ps.g.rb,    \
                                                              m->users, m->items, m->opt, D, target);                 \
   else                                                                                                               \
-    k_shard_catchup<V, N, false><<<grid, SH_THREADS, 0, st>>>(sh->info.as<PosInfo>(), v.base, v.n_serve, sh->g.rb,   \
+    k_shard_catchup<V, N, false><<<grid, SH_THREADS, 0, st>>>(ps.info.as<PosInfo>(), v.base, v.n_serve, ps.g.rb,   \
                                                               m->users, m->items, m->opt, D, target);                \
-  k_shard_gather_direct<V, N><<<grid, SH_THREADS, 0, st>>>(sh->ent.as<uint32_t>() + v.base,                          \
-                                                           sh->sdst.as<uint32_t>() + v.base, v.n_serve, m->users,    \
+  k_shard_gather_direct<V, N><<<grid, SH_THREADS, 0, st>>>(ps.ent.as<uint32_t>() + v.base,                          \
+                                                           ps.sdst.as<uint32_t>() + v.base, v.n_serve, m->users,    \
                                                            m->items, D, sh->Dp, sh->stride, pd, x.recv_off);
       MFB_DISPATCH_SHAPE(sh->shape, CALL);
 #undef CALL

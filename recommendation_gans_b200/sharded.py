@@ -216,10 +216,21 @@ class CudaShardBackend(object):
         with torch.cuda.device(self.device):
             N.check(getattr(self._lib, name)(self._shard, *args), name)
 
+    def plan_begin(self):
+        """Planning runs on its own stream so that chunk c+1 is planned while chunk c executes; everything queued on
+        the current stream so far (the id tensors) is ordered before the first plan."""
+        if getattr(self, '_plan_stream', None) is None:
+            self._plan_stream = torch.cuda.Stream(device=self.device)
+        self._plan_stream.wait_stream(torch.cuda.current_stream(self.device))
+
     def plan(self, pos_users, pos_items, batch, n_neg, neg_users, neg_items, step0, nsteps):
         counts = np.zeros((nsteps, self.world, self.world), dtype=np.int64)
-        self._call('mfb_shard_plan', N.dptr(pos_users), N.dptr(pos_items), pos_users.numel(), int(batch), int(n_neg),
-                   N.dptr(neg_users), N.dptr(neg_items), int(step0), int(nsteps), N.hptr(counts), N.stream_ptr())
+        if getattr(self, '_plan_stream', None) is None:
+            self.plan_begin()
+        with torch.cuda.stream(self._plan_stream):
+            self._call('mfb_shard_plan', N.dptr(pos_users), N.dptr(pos_items), pos_users.numel(), int(batch),
+                       int(n_neg), N.dptr(neg_users), N.dptr(neg_items), int(step0), int(nsteps), N.hptr(counts),
+                       N.stream_ptr())
         return counts
 
     def gather(self, s, send):
@@ -346,30 +357,44 @@ class ShardedMF(object):
         cell = be.zeros(1, torch.int64)
         if self.direct and getattr(be, 'direct_geometry', None) != (int(batch), int(n_neg)):
             be.enable_direct(batch, n_neg, comm)
-        for c0 in range(0, nsteps, self.chunk_steps):
-            ns = min(self.chunk_steps, nsteps - c0)
-            counts = be.plan(pos_users, pos_items, batch, n_neg, neg_users[c0 * m:(c0 + ns) * m],
-                             neg_items[c0 * m:(c0 + ns) * m], step0 + c0, ns)
+        chunks = [(c0, min(self.chunk_steps, nsteps - c0)) for c0 in range(0, nsteps, self.chunk_steps)]
+
+        def plan(idx):
+            c0, ns = chunks[idx]
+            return be.plan(pos_users, pos_items, batch, n_neg, neg_users[c0 * m:(c0 + ns) * m],
+                           neg_items[c0 * m:(c0 + ns) * m], step0 + c0, ns)
+        if hasattr(be, 'plan_begin'):
+            be.plan_begin()
+        counts_next = plan(0)
+        partials = []
+        for idx, (c0, ns) in enumerate(chunks):
+            counts = counts_next
             send_counts = counts[:, self.rank, :] * stride     # [ns, world] floats to each computing rank
             recv_counts = counts[:, :, self.rank] * stride     # [ns, world] floats from each owner
             n_send, n_recv = send_counts.sum(1), recv_counts.sum(1)
-            send, grecv = self._buf('send', n_send.max()), self._buf('grecv', n_send.max())
-            recv, gsend = self._buf('recv', n_recv.max()), self._buf('gsend', n_recv.max())
             partial = be.zeros(2 * ns, torch.float64)
+            partials.append(partial)
             if self.direct:
                 if comm.same_process:
                     comm.barrier()     # one device: nobody spins on a peer that is still planning (device-wide syncs)
                 be.run_steps(kind, 0, ns, partial)
-                be.direct_check()
-            for s in range(ns if not self.direct else 0):
-                be.gather(s, send)
-                comm.all_to_all(recv[:n_recv[s]], recv_counts[s], send[:n_send[s]], send_counts[s])
-                be.forward(kind, s, recv, cell)
-                if kind == 'adaptive_hinge':
-                    comm.all_reduce_max(cell)
-                be.backward(kind, s, recv, cell, gsend, partial[2 * s:2 * s + 2])
-                comm.all_to_all(grecv[:n_send[s]], send_counts[s], gsend[:n_recv[s]], recv_counts[s])
-                be.update(s, grecv)
+            else:
+                send, grecv = self._buf('send', n_send.max()), self._buf('grecv', n_send.max())
+                recv, gsend = self._buf('recv', n_recv.max()), self._buf('gsend', n_recv.max())
+                for s in range(ns):
+                    be.gather(s, send)
+                    comm.all_to_all(recv[:n_recv[s]], recv_counts[s], send[:n_send[s]], send_counts[s])
+                    be.forward(kind, s, recv, cell)
+                    if kind == 'adaptive_hinge':
+                        comm.all_reduce_max(cell)
+                    be.backward(kind, s, recv, cell, gsend, partial[2 * s:2 * s + 2])
+                    comm.all_to_all(grecv[:n_send[s]], send_counts[s], gsend[:n_recv[s]], recv_counts[s])
+                    be.update(s, grecv)
+            if idx + 1 < len(chunks):
+                counts_next = plan(idx + 1)    # planned on the planning stream while this chunk executes
+        if self.direct:
+            be.direct_check()
+        for (c0, ns), partial in zip(chunks, partials):
             comm.all_reduce_sum(partial)
             p = partial.cpu().numpy().reshape(ns, 2)
             for s in range(ns):
@@ -387,8 +412,9 @@ class ShardedMF(object):
         total = (n_pos + batch - 1) // batch
         m = n_neg * batch
         out = []
-        for c0 in range(0, total, self.chunk_steps):
-            ns = min(self.chunk_steps, total - c0)
+        block = 16 * self.chunk_steps           # negatives are drawn for 16 chunks at a time
+        for c0 in range(0, total, block):
+            ns = min(block, total - c0)
             neg_u, neg_i = be.draw_negatives(state625, pop_users, pop_items, ns * m)
             out.append(self.train_steps(loss, pos_users, pos_items, batch, n_neg, neg_u, neg_i, step0=c0, nsteps=ns))
         return np.concatenate(out)

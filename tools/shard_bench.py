@@ -22,8 +22,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=192, warmup=32, loss='bpr',
-        zipf=False, chunk_steps=32, fast_math=True, pop_len=4_000_000, comm=None, phase_times=False, direct=True):
+def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=192, warmup=64, loss='bpr',
+        zipf=False, chunk_steps=32, fast_math=True, pop_len=4_000_000, comm=None, phase_times=False, direct=True,
+        per_chunk=False):
     import recommendation_gans_b200  # noqa: F401
     from recommendation_gans_b200 import sharded
     import torch.distributed as dist
@@ -65,8 +66,9 @@ def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=
     t0 = time.perf_counter()
     e0.record()
     chunk_ms, marks, losses = [], [e0], []
-    for c0 in range(0, steps, chunk_steps):          # one call per chunk so every chunk's device time is on record
-        ns = min(chunk_steps, steps - c0)
+    call_steps = chunk_steps if per_chunk else steps   # per_chunk: one call per chunk puts every chunk's device time on
+    for c0 in range(0, steps, call_steps):             # record, but planning then no longer overlaps the previous chunk
+        ns = min(call_steps, steps - c0)
         lo = (warmup + c0) * m
         losses.append(shard.train_steps(loss, pos_u, pos_i, batch, n_neg, neg_u[lo:lo + ns * m], neg_i[lo:lo + ns * m],
                                         step0=warmup + c0, nsteps=ns))
@@ -98,7 +100,7 @@ def run(users=10_000_000, items=2_000_000, dim=128, batch=65536, n_neg=1, steps=
         'exchange_bytes_per_step_per_gpu_each_way': rows_per_step / world * stride * 4 * (world - 1) / world,
         'algorithmic_bytes_per_step': (6 * 2 * (1 + n_neg) * (dim + 1) * 4 + 16) * batch,
         'gpu_launches': be.launches - l0, 'final_loss': float(losses[-1]),
-        'chunk_ms': [round(x, 2) for x in chunk_ms],
+        'chunk_ms': [round(x, 2) for x in chunk_ms] if per_chunk else None,
     }
     out['hbm_gbs_algorithmic_total'] = out['algorithmic_bytes_per_step'] / (out['ms_per_step'] * 1e-3) / 1e9
     if phase_times and not direct:
@@ -171,10 +173,11 @@ def main():
     ap.add_argument('--batch', type=int, default=65536)
     ap.add_argument('--n-neg', type=int, default=1)
     ap.add_argument('--steps', type=int, default=192)
-    ap.add_argument('--warmup', type=int, default=32)
+    ap.add_argument('--warmup', type=int, default=64)
     ap.add_argument('--chunk-steps', type=int, default=32)
     ap.add_argument('--zipf', action='store_true')
     ap.add_argument('--phases', action='store_true')
+    ap.add_argument('--per-chunk', action='store_true', help='one call per chunk: per-chunk device times (no plan overlap)')
     ap.add_argument('--collectives', action='store_true', help='use all_to_all_single/all_reduce instead of peer memory')
     args = ap.parse_args()
     import torch.distributed as dist
@@ -183,7 +186,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     out = run(args.users, args.items, args.dim, args.batch, args.n_neg, args.steps, args.warmup, zipf=args.zipf,
-              chunk_steps=args.chunk_steps, phase_times=args.phases, direct=not args.collectives)
+              chunk_steps=args.chunk_steps, phase_times=args.phases, direct=not args.collectives, per_chunk=args.per_chunk)
     if not dist.is_initialized() or dist.get_rank() == 0:
         print(json.dumps(out))
     if dist.is_initialized():
