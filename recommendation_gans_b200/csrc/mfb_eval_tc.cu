@@ -45,6 +45,7 @@ constexpr int TC_EPI_WARPS = 16;   // (TMEM lane quarter) x (user block) x (half
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_KATOM = 64;       // bf16 elements per 128-byte swizzle atom
 constexpr int MODE_DUMP = 0, MODE_MAX = 1, MODE_COLLECT = 2;
+constexpr int TC_MAX_SPLIT = 4;    // item-tile splits per user block (grid.y) when the user blocks alone cannot fill the SMs
 constexpr float MASKED_SCORE_TC = -3.402823466e38f;
 
 // ---------------------------------------------------------------------------------------------
@@ -251,7 +252,7 @@ struct TcArgs {
   int dbg;   // experiment switches: 1 = skip score processing, 2 = skip appends, 4 = skip mask build, 8 = skip bias pre-store
 };
 
-template <int MODE>
+template <int MODE, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)   // 18 warps (allocated as 20): 96 registers per thread
 k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__ CUtensorMap map_users,
           const TcArgs a) {
@@ -276,11 +277,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   float *bias_s = sc_s + TC_EPI_WARPS * TC_SCR_ROWS * TC_SROW;               // [16 warps][64]: item biases, prefetched
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Item tiles can be split over gridDim.y CTAs per user block (small user shards would otherwise leave SMs idle):
+  // CTA (x, y) takes the tiles y, y + S, y + 2S, ... of the launch's tile sequence and owns its own candidate sub-lists.
+  const int S = SPLIT ? (int)gridDim.y : 1, split = SPLIT ? (int)blockIdx.y : 0;   // SPLIT=false folds to the launch's own tile sequence
+  const int tb = a.tile_begin + split * a.tile_step, ts = a.tile_step * S, nt = (a.n_tiles - split + S - 1) / S;
   const int u0 = blockIdx.x * TC_N;
   // every CTA streams the same item tiles out of L2: start each CTA at a different tile so that concurrently
   // running CTAs do not all hit the same L2 slices at the same moment
-  const int tile_off = (int)(((long long)blockIdx.x * 37) % (a.n_tiles > 0 ? a.n_tiles : 1));
-  auto logical = [&](int i) { int li = i + tile_off; return li >= a.n_tiles ? li - a.n_tiles : li; };
+  const int tile_off = (int)(((long long)blockIdx.x * 37) % (nt > 0 ? nt : 1));
+  auto logical = [&](int i) { int li = i + tile_off; return li >= nt ? li - nt : li; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -309,12 +314,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       mbar_expect_tx(ufull, u_bytes);
       for (int ka = 0; ka < katoms; ++ka)
         tma_load_2d(sU + (size_t)ka * TC_N * 128, &map_users, ufull, ka * TC_KATOM, u0);
-      for (int i = 0; i < a.n_tiles; ++i) {
+      for (int i = 0; i < nt; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
         mbar_wait_backoff(empty + s, ph ^ 1u);
         mbar_expect_tx(full + s, v_bytes);
-        const int row0 = (a.tile_begin + logical(i) * a.tile_step) * TC_M;
+        const int row0 = (tb + logical(i) * ts) * TC_M;
         for (int ka = 0; ka < katoms; ++ka)
           tma_load_2d(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
       }
@@ -327,7 +332,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     if (lane == 0) {
       mbar_wait_backoff(ufull, 0);
       tc_fence_after();
-      for (int i = 0; i < a.n_tiles; ++i) {
+      for (int i = 0; i < nt; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
         const int b = i & 1;
@@ -378,21 +383,21 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     const uint2 *my_mask = use_mask ? a.mask_bits + ((long long)blockIdx.x * a.total_tiles * 16 + (q + 4 * e)) * 32 + lane
                                     : nullptr;
     auto load_mask = [&](int tile_idx) {
-      if (!use_mask || tile_idx >= a.n_tiles || (a.dbg & 4)) return make_uint2(0u, 0u);
-      const int tile_id = a.tile_begin + logical(tile_idx) * a.tile_step;
+      if (!use_mask || tile_idx >= nt || (a.dbg & 4)) return make_uint2(0u, 0u);
+      const int tile_id = tb + logical(tile_idx) * ts;
       return __ldg(my_mask + (long long)tile_id * 16 * 32);
     };
     uint2 mw_next = load_mask(0);
     const float nu = (MODE != MODE_DUMP && user_ok) ? a.user_norm[gu] : 0.f;
     const float thr_u = (MODE == MODE_COLLECT && user_ok) ? a.thr[gu] : INFINITY;
     int my_cnt = 0;
-    int2 *my_cand = (MODE == MODE_COLLECT) ? a.cand + ((long long)gu * 2 + ch) * a.cap2 : nullptr;
+    int2 *my_cand = (MODE == MODE_COLLECT) ? a.cand + (((long long)gu * S + split) * 2 + ch) * a.cap2 : nullptr;
 
     // item biases of a tile's 64 columns (they differ per column, not per user): fetched into this warp's slot with
     // cp.async at the top of the tile loop, written into the accumulator's next use at the bottom
     auto prefetch_bias = [&](int tile_idx) {
-      if (tile_idx < a.n_tiles && lane < 16) {
-        const int tile_id = a.tile_begin + logical(tile_idx) * a.tile_step;
+      if (tile_idx < nt && lane < 16) {
+        const int tile_id = tb + logical(tile_idx) * ts;
         const float *src = a.item_bias + (long long)tile_id * TC_M + ch * 64 + lane * 4;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_bias + lane * 4)), "l"(src) : "memory");
       }
@@ -421,16 +426,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + buf);
     };
-    for (int i = 0; i < 2 && i < a.n_tiles; ++i) {
+    for (int i = 0; i < 2 && i < nt; ++i) {
       prefetch_bias(i);
       prestore_bias(i);
       __syncwarp();
     }
-    for (int i = 0; i < a.n_tiles; ++i) {
+    for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
       const uint32_t bph = (uint32_t)(i >> 1) & 1u;
       const int li = logical(i);
-      const int tile_id = a.tile_begin + li * a.tile_step;
+      const int tile_id = tb + li * ts;
       // error radius of every score of this tile for this user: |u| * max over the tile of err_coeff * |v|
       const float rad = (MODE != MODE_DUMP) ? nu * __ldg(a.tile_nmax + tile_id) : 0.f;
       prefetch_bias(i + 2);   // consumed by the pre-store at the bottom of this iteration
@@ -458,7 +463,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
 #pragma unroll
           for (int c = 2; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[c]), __uint_as_float(r[c + 1])));
           mx -= rad;   // approx - err <= exact: a certified lower bound (train items: see k_tc_threshold_small)
-          a.gmax[(long long)(li * 4 + ch * 2 + (cc0 >> 5)) * a.n_users_pad + gu] = float_to_ordered(mx);
+          a.gmax[(long long)((li * S + split) * 4 + ch * 2 + (cc0 >> 5)) * a.n_users_pad + gu] = float_to_ordered(mx);
         } else {
           // margin = score - (threshold - radius) on the FMA pipe; its sign bit (1 = below) is funnel-shifted into
           // one of four byte accumulators, columns taken from high to low so that column c lands on bit c
@@ -509,9 +514,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
         }
       }
       // hand the accumulators back: pre-store the biases of the tile that will use them next
-      if (i + 2 < a.n_tiles) prestore_bias(b);
+      if (i + 2 < nt) prestore_bias(b);
     }
-    if (MODE == MODE_COLLECT && user_ok) a.cand_cnt[(long long)gu * 2 + ch] = my_cnt;
+    if (MODE == MODE_COLLECT && user_ok) a.cand_cnt[((long long)gu * S + split) * 2 + ch] = my_cnt;
   }
   // teardown
   tc_fence_before();
@@ -718,9 +723,10 @@ constexpr int RS_WARPS = 4;
 // smem per warp: user row [D] | scores [RS_MAXC] (upper bounds, then exact) | lower bounds [RS_MAXC] | ids [RS_MAXC]
 // (staging the candidate rows through shared memory with cp.async was measured 2x slower: the kernel is
 // latency-bound and the extra shared memory cuts the resident warps)
+template <int RS_MAXSUB>   // upper bound of nsub: 2 (no item-tile split) or 2 * TC_MAX_SPLIT
 __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     const long long *__restrict__ user_ids, int n_users, TableView users, TableView items, int D,
-    const int2 *__restrict__ cand, const int *__restrict__ cand_cnt, int cap2, const float *__restrict__ thr,
+    const int2 *__restrict__ cand, const int *__restrict__ cand_cnt, int cap2, int nsub, const float *__restrict__ thr,
     const float *__restrict__ unorm, const float *__restrict__ item_norm,
     const long long *__restrict__ indptr, const int *__restrict__ indices, int k, int *__restrict__ out_ids,
     float *__restrict__ out_scores, int *__restrict__ redo_flag, int *__restrict__ surv_cnt, int check_mask) {
@@ -733,9 +739,18 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
   int *ids = reinterpret_cast<int *>(lob + RS_MAXC);
   if (u >= n_users) return;
   const long long uid = user_ids[u];
-  const int cnt0 = cand_cnt[2 * u], cnt1 = cand_cnt[2 * u + 1];   // the user's two sub-lists (item-column halves)
-  const int cnt = cnt0 + cnt1;
-  if (cnt0 > cap2 || cnt1 > cap2 || cnt > RS_MAXC || cnt < k || !(thr[u] > -INFINITY)) {   // overflow / no bound: exact path
+  // the user's nsub sub-lists (item-column halves x item-tile splits): pre[j] = entries before sub-list j
+  int pre[RS_MAXSUB + 1];
+  bool over = false;
+  pre[0] = 0;
+#pragma unroll
+  for (int j = 0; j < RS_MAXSUB; ++j) {
+    const int cj = (j < nsub) ? cand_cnt[(long long)nsub * u + j] : 0;
+    over |= cj > cap2;
+    pre[j + 1] = pre[j] + cj;
+  }
+  const int cnt = pre[RS_MAXSUB];
+  if (over || cnt > RS_MAXC || cnt < k || !(thr[u] > -INFINITY)) {   // overflow / no bound: exact path
     if (lane == 0) {
       redo_flag[u] = 1;
       surv_cnt[u] = 0;
@@ -761,7 +776,11 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     for (int j = 0; j < KR; ++j) {
       const int c = c0 + j * 32 + lane;
       if (c < cnt) {
-        const int2 rec = (c < cnt0) ? cand[(long long)(2 * u) * cap2 + c] : cand[(long long)(2 * u + 1) * cap2 + (c - cnt0)];
+        int sub = 0;
+#pragma unroll
+        for (int j = 1; j < RS_MAXSUB; ++j) sub += (c >= pre[j]) ? 1 : 0;      // pre[] is non-decreasing
+        sub = sub < nsub ? sub : nsub - 1;
+        const int2 rec = cand[((long long)nsub * u + sub) * cap2 + (c - pre[sub])];
         const float e = item_norm[rec.x];   // err_coeff * |v|, indexed by item id
         const float sg = __int_as_float(rec.y);
         const float lo = fmaf(-e, nu, sg);
@@ -980,11 +999,17 @@ size_t tc_smem_bytes(int D) {
 }
 
 template <int MODE>
-int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, int n_users, cudaStream_t st) {
+int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, int n_users, cudaStream_t st,
+                int splits = 1) {
   const size_t smem = tc_smem_bytes(a.D);
-  MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (n_users + TC_N - 1) / TC_N;
-  k_tc_gemm<MODE><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
+  const dim3 grid((n_users + TC_N - 1) / TC_N, splits);
+  if (splits > 1) {
+    MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tc_gemm<MODE, true><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
+  } else {
+    MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tc_gemm<MODE, false><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
+  }
   MFB_KERNEL_CHECK();
   return MFB_OK;
 }
@@ -1012,7 +1037,17 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   while ((i_tiles + sample_step - 1) / sample_step > 8 * TH_VPL) ++sample_step;   // groups = 4*n_sample <= 32*TH_VPL
   const int n_sample = (i_tiles + sample_step - 1) / sample_step;
   const int groups = n_sample * 4;
-  const int cap2 = RS_MAXC / 2;
+  // small user shards (user-sharded evaluation on many GPUs): split the item tiles of a user block over up to
+  // TC_MAX_SPLIT CTAs so the grid still covers the SMs; every (user, split, column half) has its own candidate list
+  int splits = 1;
+  {
+    const int user_ctas = n_users_pad / TC_N;
+    while (splits < TC_MAX_SPLIT && user_ctas * (splits + 1) <= m->num_sms && n_sample >= 2 * (splits + 1)) ++splits;
+    if (const char *e = getenv("MFB_TC_SPLIT")) if (*e) splits = atoi(e) < 1 ? 1 : (atoi(e) > TC_MAX_SPLIT ? TC_MAX_SPLIT : atoi(e));
+  }
+  const int nsub = 2 * splits;
+  const int cap2 = RS_MAXC / nsub;
+  m->eval.nsub = nsub;
 
   EvalBuf &eb = m->eval;
   MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__nv_bfloat16)));
@@ -1021,8 +1056,8 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   MFB_CHECK(eb.vnorm.reserve(((size_t)items_pad * 3 + i_tiles) * sizeof(float) + 16));
   MFB_CHECK(eb.gmax.reserve((size_t)groups * n_users_pad * sizeof(int)));
   MFB_CHECK(eb.thr.reserve((size_t)n_users_pad * 2 * sizeof(float)));
-  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * 2 * cap2 * sizeof(int2)));
-  MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * 5 + 64));
+  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * nsub * cap2 * sizeof(int2)));
+  MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * (2 * TC_MAX_SPLIT + 3) + 64));
   MFB_CHECK(eb.redo.reserve((size_t)n_users_pad * (sizeof(long long) + (size_t)k * (sizeof(int) + sizeof(float))) + 64));
   __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
   float *unorm = eb.unorm.as<float>(), *vnorm = eb.vnorm.as<float>();
@@ -1031,7 +1066,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   float *tile_nmax = vnorm_item + items_pad;   // per tile: largest scaled norm
   float *thr = eb.thr.as<float>(), *eps = thr + n_users_pad;
   int *cand_cnt = eb.cnt.as<int>();
-  int *redo_flag = cand_cnt + 2 * (size_t)n_users_pad;
+  int *redo_flag = cand_cnt + 2 * TC_MAX_SPLIT * (size_t)n_users_pad;
   int *redo_pos = redo_flag + n_users_pad;
   int *surv_cnt = redo_pos + n_users_pad;
   int *redo_cnt = surv_cnt + n_users_pad;
@@ -1092,7 +1127,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.tile_step = sample_step;
   a.n_tiles = n_sample;
   a.gmax = eb.gmax.as<int>();
-  MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st));
+  MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st, splits));
   if (small_thr) {
     const int tb = (n_users + 127) / 128;
     int *gm = eb.gmax.as<int>();
@@ -1115,16 +1150,21 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.cand = eb.cand.as<int2>();
   a.cand_cnt = cand_cnt;
   a.cap2 = cap2;
-  MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st));
+  MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st, splits));
   // exact re-score + mask + top-k
   MFB_CUDA(cudaMemsetAsync(redo_cnt, 0, sizeof(int), st));
   const size_t rs_smem = (size_t)RS_WARPS * (D + 3 * RS_MAXC) * sizeof(float);
-  MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
-  k_tc_rescore<<<(n_users + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>((const long long *)d_user_ids, n_users, m->users, m->items, D,
-                                                        eb.cand.as<int2>(), cand_cnt, cap2, thr, unorm, vnorm_item,
-                                                        (const long long *)d_train_indptr, d_train_indices, k,
-                                                        d_out_ids, d_out_scores, redo_flag, surv_cnt,
-                                                        masked_in_gemm ? 0 : 1);
+#define MFB_RESCORE(MAXSUB)                                                                                          \
+  do {                                                                                                               \
+    MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore<MAXSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)); \
+    k_tc_rescore<MAXSUB><<<(n_users + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>(                       \
+        (const long long *)d_user_ids, n_users, m->users, m->items, D, eb.cand.as<int2>(), cand_cnt, cap2, nsub, thr, \
+        unorm, vnorm_item, (const long long *)d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, redo_flag,  \
+        surv_cnt, masked_in_gemm ? 0 : 1);                                                                            \
+  } while (0)
+  if (nsub == 2) MFB_RESCORE(2);
+  else MFB_RESCORE(2 * TC_MAX_SPLIT);
+#undef MFB_RESCORE
   MFB_KERNEL_CHECK();
   long long *redo_users = eb.redo.as<long long>();
   k_tc_compact_redo<<<(n_users + 255) / 256, 256, 0, st>>>(redo_flag, (const long long *)d_user_ids, n_users, redo_users,
@@ -1150,22 +1190,30 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
 // debug: candidate-list statistics of the last tensor-core top-k call: {users, sum, max, over_cap, re-scored}
 int mfb_tc_stats(mfb_model *m, int n_users, long long *h_out, cudaStream_t st) {
   const int n_users_pad = ((n_users + TC_N - 1) / TC_N) * TC_N;
-  std::vector<int> cnt((size_t)n_users * 2);
-  MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.ptr, (size_t)n_users * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  const int nsub = m->eval.nsub;
+  std::vector<int> cnt((size_t)n_users * nsub);
+  MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.ptr, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
   long long sum = 0, mx = 0, over = 0;
   for (int u = 0; u < n_users; ++u) {
-    const int c0 = cnt[2 * (size_t)u], c1 = cnt[2 * (size_t)u + 1];
-    sum += c0 + c1;
-    if (c0 + c1 > mx) mx = c0 + c1;
-    if (c0 > RS_MAXC / 2 || c1 > RS_MAXC / 2) ++over;
+    long long tot = 0;
+    bool ov = false;
+    for (int j = 0; j < nsub; ++j) {
+      const int c = cnt[(size_t)u * nsub + j];
+      tot += c;
+      ov |= c > RS_MAXC / nsub;
+    }
+    sum += tot;
+    if (tot > mx) mx = tot;
+    if (ov) ++over;
   }
+  cnt.resize((size_t)n_users);
   h_out[0] = n_users;
   h_out[1] = sum;
   h_out[2] = mx;
   h_out[3] = over;
   // listed items that survived the bound filter and were re-scored exactly
-  MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.as<int>() + 4 * (size_t)n_users_pad, (size_t)n_users * sizeof(int),
+  MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.as<int>() + (2 * TC_MAX_SPLIT + 2) * (size_t)n_users_pad, (size_t)n_users * sizeof(int),
                            cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
   long long surv = 0;

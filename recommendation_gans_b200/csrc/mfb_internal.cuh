@@ -122,6 +122,7 @@ struct PlanBuf {
 // Workspaces of the tensor-core evaluation path (mfb_eval_tc.cu)
 struct EvalBuf {
   DevBuf ub, vb, unorm, vnorm, gmax, thr, cand, cnt, redo, mcnt, mptr, mpairs;
+  int nsub = 2;   // candidate sub-lists per user in the last tensor-core pass (2 column halves x item-tile splits)
 };
 
 struct mfb_model {

@@ -170,8 +170,11 @@ def test_tc_raw_scores_match_bf16_matmul(U, I, D):
 
 @pytest.mark.parametrize('U,I,D,k,scale,skew', [(600, 12000, 128, 20, 0.3, False), (300, 9000, 64, 5, 0.05, False),
                                                 (1000, 20000, 128, 10, 1.0, False), (900, 16000, 128, 20, 0.01, True)])
-def test_tc_topk_equals_exact_kernel(U, I, D, k, scale, skew, monkeypatch):
+@pytest.mark.parametrize('split', [None, '1', '3'], ids=['auto_split', 'split1', 'split3'])
+def test_tc_topk_equals_exact_kernel(U, I, D, k, scale, skew, split, monkeypatch):
     """Tensor-core path returns bit-identical ids to the exact fp32 kernel (same exact re-score definition).
+    split: item tiles of a user block divided over grid.y CTAs with their own candidate sub-lists (auto = what a small
+    user shard gets; 1 = the full-size configuration).
     skew=True: heavy-tailed item norms and a shared popular direction, the shape a trained model has, with popularity
     correlated with the item id -- the item layout and per-item error radii must keep the candidate lists short."""
     from recommendation_gans_b200.engine import MFEngine
@@ -191,6 +194,8 @@ def test_tc_topk_equals_exact_kernel(U, I, D, k, scale, skew, monkeypatch):
     indptr = torch.from_numpy(train.indptr.astype(np.int64)).cuda()
     indices = torch.from_numpy(train.indices.astype(np.int32)).cuda()
     users = rs.permutation(U).astype(np.int64)
+    if split is not None:
+        monkeypatch.setenv('MFB_TC_SPLIT', split)
     monkeypatch.setenv('MFB_TC', '0')
     exact = MFEngine(make_net(tabs))
     monkeypatch.setenv('MFB_TC', '1')
