@@ -49,3 +49,21 @@ def test_no_cpu_fallback():
     net = BilinearNet(7, 5, 4)
     with pytest.raises(RuntimeError):
         net(torch.tensor([0, 1]), torch.tensor([1, 2]))
+
+
+def test_library_staleness_is_decided_by_content(tmp_path, monkeypatch):
+    """The prebuilt library travels to the GPU box in a snapshot that does not keep a meaningful mtime order; a rebuild
+    there would have every rank of a multi-GPU run rewriting the .so under the others.  Staleness therefore compares a
+    content hash of the sources with the one recorded at build time."""
+    import os
+    from recommendation_gans_b200 import build as B
+    B.build_library()
+    assert not B.is_stale()
+    for path in B.sources():                     # touching every source must not make the library stale
+        os.utime(path, None)
+    assert not B.is_stale()
+    extra = tmp_path / 'extra.cuh'
+    extra.write_text('// a change in any dependency')
+    real = B._dependencies
+    monkeypatch.setattr(B, '_dependencies', lambda: real() + [str(extra)])
+    assert B.is_stale()
