@@ -259,6 +259,11 @@ int mfb_ipc_open(const void *h_handle64, void **d_ptr);
 int mfb_ipc_close(void *d_ptr);
 int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int32_t s_end, double *d_loss_partial,
                         mfb_stream stream);
+/* One phase of step s (0 owner gather | 1 forward | 2 backward | 3 owner update) with the signal at the end of a phase
+ * and the wait at the head of the next as separate launches: for a host that drives several ranks of ONE device in
+ * lockstep on one stream (phase p for every rank before phase p+1 for any), so that no wait is ever launched before
+ * its signals.  d_loss_partial: the step's 2 doubles. */
+int mfb_shard_run_phase(mfb_shard *sh, int loss, int32_t s, int32_t phase, double *d_loss_partial, mfb_stream stream);
 int mfb_shard_direct_check(mfb_shard *sh, mfb_stream stream);
 
 /* ---- in-situ kernel timing (measurement only) ---------------------------------------------- */

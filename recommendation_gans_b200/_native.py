@@ -93,6 +93,7 @@ SIGNATURES = {
     'mfb_ipc_open': (ctypes.c_int, [c_void, ctypes.POINTER(c_void)]),
     'mfb_ipc_close': (ctypes.c_int, [c_void]),
     'mfb_shard_run_steps': (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int32, ctypes.c_int32, c_void, c_void]),
+    'mfb_shard_run_phase': (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int32, ctypes.c_int32, c_void, c_void]),
     'mfb_shard_direct_check': (ctypes.c_int, [c_void, c_void]),
     'mfb_profile_enable': (ctypes.c_int, [c_void, ctypes.c_int]),
     'mfb_profile_read': (ctypes.c_int, [c_void, c_void, c_void]),

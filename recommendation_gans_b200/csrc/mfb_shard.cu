@@ -378,13 +378,15 @@ __global__ void k_shard_signal_wait(char *const *__restrict__ peers, char *__res
                                     size_t flags_off, int kind, unsigned long long seq, size_t cells_off,
                                     const unsigned long long *__restrict__ local_cell,
                                     unsigned long long *__restrict__ out_cell, int *__restrict__ err,
-                                    long long timeout_clocks) {
+                                    long long timeout_clocks, int do_signal, int do_wait) {
   const int c = threadIdx.x;
-  if (c < G) {
+  if (c < G && do_signal) {
     char *pb = peers[c];
     if (local_cell != nullptr) reinterpret_cast<unsigned long long *>(pb + cells_off)[me] = *local_cell;
     __threadfence_system();
     st_release_sys(reinterpret_cast<unsigned long long *>(pb + flags_off) + kind * MAX_PEERS + me, seq);
+  }
+  if (c < G && do_wait) {
     const unsigned long long *f = reinterpret_cast<const unsigned long long *>(xbuf + flags_off) + kind * MAX_PEERS + c;
     const long long t0 = clock64();
     while (ld_acquire_sys(f) < seq) {
@@ -396,7 +398,7 @@ __global__ void k_shard_signal_wait(char *const *__restrict__ peers, char *__res
     }
   }
   __syncthreads();
-  if (out_cell != nullptr && threadIdx.x == 0) {
+  if (out_cell != nullptr && do_wait && threadIdx.x == 0) {
     const unsigned long long *cells = reinterpret_cast<const unsigned long long *>(xbuf + cells_off);
     unsigned long long best = 0ull;
     for (int k = 0; k < G; ++k) {
@@ -1059,23 +1061,17 @@ extern "C" int mfb_ipc_close(void *d_ptr) {
   return MFB_OK;
 }
 
-// Steps [s_begin, s_end) of the planned chunk with the direct exchange: everything is enqueued on `stream`, no host
-// synchronisation and no collective call.  d_loss_partial: 2 doubles per step (as mfb_shard_backward).
-extern "C" int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int32_t s_end, double *d_loss_partial,
-                                   mfb_stream stream) {
-  if (!sh) return MFB_ERR_INVALID;
+// One step of the direct exchange is four phases; between two phases lies one signal/wait pair:
+//   0 owner     catch-up, rows straight into the computing ranks' receive buffers        | ROWS
+//   1 compute   forward (+ local adaptive-hinge maximum)                                 | MAX (adaptive hinge only)
+//   2 compute   gradient rows straight into the owners' buffers, partial loss sums       | GRADS
+//   3 owner     ordered reduction + optimiser step
+// fused = true (one process per GPU): the signal and the wait of a pair are ONE kernel at the head of the next phase.
+// fused = false: each phase ends with its signal and the next begins with the wait -- a host that drives several
+// ranks of ONE device phase by phase on one stream (the 1-GPU tests) then never launches a wait before the matching
+// signals, so nothing ever spins.
+static int shard_phase(mfb_shard *sh, int loss, int s, int phase, double *d_loss_partial, cudaStream_t st, bool fused) {
   PlanSet &ps = sh->sets[sh->active];
-  if (!ps.planned || !sh->peers_set || !d_loss_partial || s_begin < 0 || s_end > ps.g.ns || s_begin > s_end) {
-    mfb_set_error("shard_run_steps: needs a plan, an exchange buffer with peers, and a step range inside the plan");
-    return MFB_ERR_INVALID;
-  }
-  if (ps.g.batch != sh->x_batch || ps.g.m_neg != sh->x_m_neg) {
-    mfb_set_error("shard_run_steps: the exchange buffer was sized for batch %d / %d negatives, the plan has %d / %d",
-                  sh->x_batch, sh->x_m_neg, ps.g.batch, ps.g.m_neg);
-    return MFB_ERR_INVALID;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  MFB_CHECK(sync_plan(sh, st));
   mfb_model *m = sh->m;
   const int G = sh->world, D = m->desc.dim;
   const bool fast = m->desc.fast_math != 0, adaptive = loss == MFB_LOSS_ADAPTIVE_HINGE;
@@ -1086,11 +1082,15 @@ extern "C" int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int
   unsigned long long *local_cell = sh->gcell.as<unsigned long long>(), *global_cell = local_cell + 1;
   char *const *pd = sh->peers_dev.as<char *>();
   const long long timeout = 6000000000ll;   // ~3 s of SM clocks: a dead peer ends in an error, not in a hung GPU
-  for (int s = s_begin; s < s_end; ++s) {
-    StepView v;
-    MFB_CHECK(step_view(sh, s, &v));
-    const unsigned long long seq = ++sh->seq;
-    // owner: catch-up, rows straight into the computing ranks' receive buffers, signal
+  StepView v;
+  MFB_CHECK(step_view(sh, s, &v));
+  auto flag = [&](int kind, const unsigned long long *cell_in, unsigned long long *cell_out, int do_signal, int do_wait) {
+    k_shard_signal_wait<<<1, 32, 0, st>>>(pd, xb, G, sh->rank, x.flags_off, kind, sh->seq, x.cells_off, cell_in, cell_out,
+                                          err, timeout, do_signal, do_wait);
+    sh->launches += 1;
+  };
+  if (phase == 0) {
+    ++sh->seq;
     if (v.n_serve > 0) {
       const int grid = grid_warps(v.n_serve, SH_WARPS);
       const int target = (int)m->step;
@@ -1109,28 +1109,63 @@ extern "C" int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int
       MFB_KERNEL_CHECK();
       sh->launches += 2;
     }
-    // computing rank: signal the rows this rank stored, wait for every owner's, forward
-    k_shard_signal_wait<<<1, 32, 0, st>>>(pd, xb, G, sh->rank, x.flags_off, FLAG_ROWS, seq, x.cells_off, nullptr, nullptr,
-                                          err, timeout);
+    if (!fused) flag(FLAG_ROWS, nullptr, nullptr, 1, 0);
+  } else if (phase == 1) {
+    flag(FLAG_ROWS, nullptr, nullptr, fused ? 1 : 0, 1);
     MFB_KERNEL_CHECK();
-    MFB_CHECK(mfb_shard_forward(sh, loss, s, recv, (int64_t *)local_cell, stream));
-    if (adaptive) {
-      // publish the local maximum to every peer, wait for theirs, fold
-      k_shard_signal_wait<<<1, 32, 0, st>>>(pd, xb, G, sh->rank, x.flags_off, FLAG_MAX, seq, x.cells_off, local_cell,
-                                            global_cell, err, timeout);
-      MFB_KERNEL_CHECK();
-      sh->launches += 1;
-    }
-    // gradient rows straight into the owners' buffers, signal; owner waits for all of them, then steps
-    MFB_CHECK(shard_backward_impl(sh, loss, s, recv, (const int64_t *)global_cell, nullptr, true,
-                                  d_loss_partial + 2 * (s - s_begin), st));
-    k_shard_signal_wait<<<1, 32, 0, st>>>(pd, xb, G, sh->rank, x.flags_off, FLAG_GRADS, seq, x.cells_off, nullptr,
-                                          nullptr, err, timeout);
+    MFB_CHECK(mfb_shard_forward(sh, loss, s, recv, (int64_t *)local_cell, (mfb_stream)st));
+    if (adaptive && !fused) flag(FLAG_MAX, local_cell, nullptr, 1, 0);
+  } else if (phase == 2) {
+    if (adaptive) flag(FLAG_MAX, local_cell, global_cell, fused ? 1 : 0, 1);
     MFB_KERNEL_CHECK();
-    sh->launches += 2;
-    MFB_CHECK(mfb_shard_update(sh, s, grecv, stream));
+    MFB_CHECK(shard_backward_impl(sh, loss, s, recv, (const int64_t *)global_cell, nullptr, true, d_loss_partial, st));
+    if (!fused) flag(FLAG_GRADS, nullptr, nullptr, 1, 0);
+  } else {
+    flag(FLAG_GRADS, nullptr, nullptr, fused ? 1 : 0, 1);
+    MFB_KERNEL_CHECK();
+    MFB_CHECK(mfb_shard_update(sh, s, grecv, (mfb_stream)st));
+  }
+  MFB_KERNEL_CHECK();
+  return MFB_OK;
+}
+
+static int shard_direct_ready(mfb_shard *sh, const double *d_loss_partial, int s_begin, int s_end) {
+  if (!sh) return MFB_ERR_INVALID;
+  PlanSet &ps = sh->sets[sh->active];
+  if (!ps.planned || !sh->peers_set || !d_loss_partial || s_begin < 0 || s_end > ps.g.ns || s_begin > s_end) {
+    mfb_set_error("direct exchange: needs a plan, an exchange buffer with peers, and a step range inside the plan");
+    return MFB_ERR_INVALID;
+  }
+  if (ps.g.batch != sh->x_batch || ps.g.m_neg != sh->x_m_neg) {
+    mfb_set_error("direct exchange: the buffer was sized for batch %d / %d negatives, the plan has %d / %d",
+                  sh->x_batch, sh->x_m_neg, ps.g.batch, ps.g.m_neg);
+    return MFB_ERR_INVALID;
   }
   return MFB_OK;
+}
+
+// Steps [s_begin, s_end) of the planned chunk with the direct exchange: everything is enqueued on `stream`, no host
+// synchronisation and no collective call.  d_loss_partial: 2 doubles per step (as mfb_shard_backward).
+extern "C" int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int32_t s_end, double *d_loss_partial,
+                                   mfb_stream stream) {
+  MFB_CHECK(shard_direct_ready(sh, d_loss_partial, s_begin, s_end));
+  cudaStream_t st = (cudaStream_t)stream;
+  MFB_CHECK(sync_plan(sh, st));
+  for (int s = s_begin; s < s_end; ++s)
+    for (int phase = 0; phase < 4; ++phase)
+      MFB_CHECK(shard_phase(sh, loss, s, phase, d_loss_partial + 2 * (s - s_begin), st, true));
+  return MFB_OK;
+}
+
+// One phase (0..3, see above) of step s with unfused flags, for a host that drives several ranks of one device in
+// lockstep: call phase p for every rank before phase p+1 for any.  d_loss_partial: the step's 2 doubles.
+extern "C" int mfb_shard_run_phase(mfb_shard *sh, int loss, int32_t s, int32_t phase, double *d_loss_partial,
+                                   mfb_stream stream) {
+  MFB_CHECK(shard_direct_ready(sh, d_loss_partial, s, s + 1));
+  if (phase < 0 || phase > 3) return MFB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  MFB_CHECK(sync_plan(sh, st));
+  return shard_phase(sh, loss, s, phase, d_loss_partial, st, false);
 }
 
 // Synchronises the stream and reports whether a wait on a peer timed out since the last check.

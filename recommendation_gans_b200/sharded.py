@@ -15,8 +15,9 @@ row counts are known to every rank from the plan.  The kernels live behind the C
 include/mfb200.h); torch.distributed (NCCL) moves the buffers.
 
 `ShardedMF.train_steps` is the same code for every transport: `DistComm` (torch.distributed: NCCL on GPUs, gloo
-in the CPU tests) or `LocalComm` (G virtual ranks as threads of one process sharing one GPU -- how the 1-GPU parity
-tests exercise G > 1).  The kernel backend is `CudaShardBackend`; there is no CPU product path (the CPU tests
+in the CPU tests) or `LocalComm` (G virtual ranks as threads of one process sharing one GPU and one stream -- how the
+1-GPU parity tests exercise G > 1; the direct exchange then runs phase by phase in lockstep so that no flag wait is
+ever launched before its signals).  The kernel backend is `CudaShardBackend`; there is no CPU product path (the CPU tests
 inject tests/shard_spec_backend.py, an executable numpy specification, to check the exchange logic under gloo).
 """
 import ctypes
@@ -280,6 +281,10 @@ class CudaShardBackend(object):
         self._call('mfb_shard_run_steps', N.LOSS[loss], int(s_begin), int(s_end), ctypes.c_void_p(partial.data_ptr()),
                    N.stream_ptr())
 
+    def run_phase(self, loss, s, phase, partial):
+        self._call('mfb_shard_run_phase', N.LOSS[loss], int(s), int(phase), ctypes.c_void_p(partial.data_ptr()),
+                   N.stream_ptr())
+
     def direct_check(self):
         self._call('mfb_shard_direct_check', N.stream_ptr())
 
@@ -374,9 +379,14 @@ class ShardedMF(object):
             n_send, n_recv = send_counts.sum(1), recv_counts.sum(1)
             partial = be.zeros(2 * ns, torch.float64)
             partials.append(partial)
-            if self.direct:
-                if comm.same_process:
-                    comm.barrier()     # one device: nobody spins on a peer that is still planning (device-wide syncs)
+            if self.direct and comm.same_process and comm.world > 1:
+                # virtual ranks share one device and one stream: phase p of every rank is enqueued before phase p+1 of
+                # any, so a wait kernel is never launched before the signals it waits for (nothing ever spins)
+                for s in range(ns):
+                    for phase in range(4):
+                        comm.barrier()
+                        be.run_phase(kind, s, phase, partial[2 * s:2 * s + 2])
+            elif self.direct:
                 be.run_steps(kind, 0, ns, partial)
             else:
                 send, grecv = self._buf('send', n_send.max()), self._buf('grecv', n_send.max())
@@ -437,14 +447,8 @@ def run_local_ranks(world, make_rank, work):
 
     def body(rank):
         try:
-            if torch.cuda.is_available():
-                with torch.cuda.stream(torch.cuda.Stream()):
-                    shard = make_rank(rank, group.comm(rank))
-                    results[rank] = work(shard)
-                    torch.cuda.current_stream().synchronize()
-            else:
-                shard = make_rank(rank, group.comm(rank))
-                results[rank] = work(shard)
+            shard = make_rank(rank, group.comm(rank))      # all virtual ranks enqueue on the same (current) stream
+            results[rank] = work(shard)
         except BaseException as exc:   # noqa: BLE001 -- re-raised in the caller; abort the barrier so peers stop
             errors.append(exc)
             group.barrier.abort()

@@ -125,3 +125,52 @@ def test_sharded_nccl_two_gpus(name, direct, tmp_path):
         z = np.load(tmp_path / ('r%d.npz' % r))
         res.append((z['losses'], [z['t%d' % k] for k in range(4)]))
     _check(_case(path), res, 2)
+
+
+@pytest.mark.parametrize('loss,kernel_loss,opt,n_neg', [('adaptive_hinge', 'adaptive_hinge', 'adam', 1),
+                                                        ('pointwise', 'pointwise', 'adam', 2),
+                                                        ('bpr', 'bpr_pairwise', 'adam', 1), ('hinge', 'hinge', 'sgd', 1)])
+@pytest.mark.parametrize('world,direct,fast_math', [(2, True, False), (3, False, False), (4, True, True)])
+def test_sharded_many_chunks_match_oracle(loss, kernel_loss, opt, n_neg, world, direct, fast_math):
+    """Several planned chunks (double-buffered plans, planning overlapped with execution), Zipf-skewed items (segments
+    longer than a reduction window, popular rows served to every rank) and long gaps between uses of a row (dense
+    replay) against the single-process oracle on the same inputs."""
+    from oracle import mf_oracle as O
+    torch.set_num_threads(1)
+    rs = np.random.RandomState(29)
+    U, I, D, B = 500, 300, 16, 96
+    n_steps = 60
+    n_pos = n_steps * B - (0 if loss in ('bpr', 'hinge') else 7)
+    p = 1.0 / np.arange(1, I + 1) ** 1.05
+    users = rs.randint(0, U, n_pos)
+    items = rs.choice(I, n_pos, p=p / p.sum())
+    neg = np.stack([rs.randint(0, U, n_steps * n_neg * B), rs.randint(0, I, n_steps * n_neg * B)], 1)
+    tabs = [t.numpy() for t in O.init_tables(U, I, D, torch_seed=5)]
+    lr, l2 = (1e-3, 1e-5) if opt == 'adam' else (5e-2, 1e-4)
+    oracle = O.OracleMF(*[torch.from_numpy(t) for t in tabs], optimizer=opt, lr=lr, l2=l2, batch_size=B,
+                        num_negative_samples=n_neg, loss_fn=O.LOSS_FUNCTIONS[loss])
+    ref_losses = []
+    k = n_neg * B
+    for s in range(n_steps):
+        ref_losses.append(oracle.train_step(torch.from_numpy(users[s * B:(s + 1) * B]),
+                                            torch.from_numpy(items[s * B:(s + 1) * B]),
+                                            torch.from_numpy(neg[s * k:(s + 1) * k, 0].copy()),
+                                            torch.from_numpy(neg[s * k:(s + 1) * k, 1].copy())).item())
+
+    def make(rank, comm):
+        be = sharded.CudaShardBackend(rank, world, U, I, D, local_tables=sharded.slice_tables(tabs, rank, world),
+                                      optimizer=opt, lr=lr, l2=l2, fast_math=fast_math)
+        return sharded.ShardedMF(be, comm, chunk_steps=7, direct=direct)
+
+    def work(shard):
+        losses = shard.train_steps(kernel_loss, users, items, B, n_neg, neg[:, 0].copy(), neg[:, 1].copy())
+        tables = shard.local_tables()
+        shard.close()
+        return losses, tables
+    results = sharded.run_local_ranks(world, make, work)
+    for losses, _ in results:
+        np.testing.assert_allclose(losses, ref_losses, rtol=1e-5)
+    got = sharded.assemble_tables([r[1] for r in results], world)
+    for i, (g, e) in enumerate(zip(got, oracle.numpy_tables())):
+        err = rel_err(g, e)
+        assert err < 1e-5 or (i >= 2 and np.abs(g - e).max() < 2e-2 * lr), (i, err)
