@@ -266,6 +266,13 @@ int mfb_shard_run_steps(mfb_shard *sh, int loss, int32_t s_begin, int32_t s_end,
 int mfb_shard_run_phase(mfb_shard *sh, int loss, int32_t s, int32_t phase, double *d_loss_partial, mfb_stream stream);
 int mfb_shard_direct_check(mfb_shard *sh, mfb_stream stream);
 
+/* mrr_score (evaluation.py:13-60): average ranks (scipy.stats.rankdata of -predict(user), train items forced last) of
+ * every listed user's test items, written at the items' positions in the test CSR: d_out_rank[p] for
+ * p in [test_indptr[u], test_indptr[u+1]).  Probabilities are computed exactly as mfb_predict_user does. */
+int mfb_rank_test_items(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_test_indptr,
+                        const int32_t *d_test_indices, const int64_t *d_train_indptr, const int32_t *d_train_indices,
+                        float *d_out_rank, mfb_stream stream);
+
 /* ---- in-situ kernel timing (measurement only) ---------------------------------------------- */
 /* When enabled, every kernel launched for this model is bracketed by CUDA events on the launch
  * stream.  mfb_profile_read synchronises, then reports per kernel class the summed device time

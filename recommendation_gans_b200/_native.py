@@ -65,6 +65,7 @@ SIGNATURES = {
                                 c_void]),
     'mfb_topk_hits': (ctypes.c_int, [c_void, c_void, ctypes.c_int64, ctypes.c_int32, c_void, c_void, c_void,
                                      ctypes.c_int32, c_void, c_void, c_void]),
+    'mfb_rank_test_items': (ctypes.c_int, [c_void, c_void, ctypes.c_int64, c_void, c_void, c_void, c_void, c_void, c_void]),
     'mfb_model_rng_seed': (ctypes.c_int, [c_void, c_void, c_void]),
     'mfb_model_rng_state': (ctypes.c_int, [c_void, c_void, c_void]),
     'mfb_train_epoch': (ctypes.c_int, [c_void, ctypes.c_int, c_void, c_void, ctypes.c_int64, ctypes.c_int32,

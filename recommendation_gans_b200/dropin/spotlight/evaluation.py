@@ -163,6 +163,25 @@ def map_at_k(model, test, k=5):
     return np.mean(apk_)
 
 
+def mrr_score(model, test, train=None):
+    """Mean reciprocal rank per user with test items (evaluation.py:13-60): the rank of every test item in
+    -model.predict(user) with the user's train items forced last, average ranks for ties (scipy.stats.rankdata).  One
+    kernel compares every item's probability with the user's test-item probabilities; no score vector, no sort."""
+    eng = _native_engine(model)
+    test_csr = test.tocsr()
+    user_ids = np.nonzero(np.diff(test_csr.indptr))[0].astype(np.int64)
+    if len(user_ids) == 0:
+        return np.array([])
+    t_indptr, t_indices = _csr_to_device(test_csr, eng.device)
+    r_indptr = r_indices = None
+    if train is not None:
+        r_indptr, r_indices = _csr_to_device(train, eng.device)
+    ranks = eng.rank_test_items(torch.from_numpy(user_ids).to(eng.device), t_indptr, t_indices, r_indptr,
+                                r_indices).cpu().numpy().astype(np.float64)
+    indptr = t_indptr.cpu().numpy()
+    return np.array([(1.0 / ranks[indptr[u]:indptr[u + 1]]).mean() for u in user_ids])
+
+
 def hit_ratio(model, test, k=10):
     """Fraction of users with test items whose target is among the top-k recommendations (evaluation.py:192-213; no
     train mask).  The reference evaluates `target in predictions[:k]` on numpy arrays: with one test item per user

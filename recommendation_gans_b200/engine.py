@@ -380,6 +380,15 @@ class MFEngine(object):
         self._call('mfb_debug_tc_scores', N.dptr(user_ids), n, N.dptr(out), N.stream_ptr())
         return out[:, :n]
 
+    def rank_test_items(self, user_ids, test_indptr, test_indices, train_indptr=None, train_indices=None):
+        """Average ranks (scipy rankdata of -predict(user), train items last) of the listed users' test items, aligned
+        with test_indices (evaluation.py:52-58)."""
+        user_ids = _as_i64_cuda(user_ids, self.device)
+        out = torch.zeros(test_indices.numel(), dtype=torch.float32, device=self.device)
+        self._call('mfb_rank_test_items', N.dptr(user_ids), user_ids.numel(), N.dptr(test_indptr), N.dptr(test_indices),
+                   N.dptr(train_indptr), N.dptr(train_indices), N.dptr(out), N.stream_ptr())
+        return out
+
     def topk_hits(self, topk_ids, user_ids, test_indptr, test_indices, ks):
         user_ids = _as_i64_cuda(user_ids, self.device)
         n, k = topk_ids.shape

@@ -233,3 +233,44 @@ def test_hit_ratio_matches_reference_loop():
     two = _interactions(np.repeat(users[:5], 2), rs.randint(0, I, 10), U, I)      # 2 targets, k=10: numpy raises
     with pytest.raises(ValueError):
         hit_ratio(_Model(), two, k=k)
+
+
+@pytest.mark.parametrize('with_train', [False, True], ids=['nomask', 'trainmask'])
+def test_mrr_score_matches_reference_loop(with_train):
+    """evaluation.mrr_score (evaluation.py:13-60) vs the reference's loop restated on the oracle's predictions:
+    -predict(user), train items set to FLOAT_MAX, scipy.stats.rankdata, mean reciprocal rank of the test items."""
+    import scipy.stats as st
+    from spotlight.evaluation import mrr_score
+    from oracle import mf_oracle as O
+    rs = np.random.RandomState(8)
+    U, I, D = 120, 700, 32
+    tabs = _random_tables(rs, U, I, D, 0.5)
+    tabs[1][5] = tabs[1][9]                                   # two items with identical rows and biases: an exact tie
+    tabs[3][5] = tabs[3][9]
+    net = make_net(tabs)
+
+    class _Model(object):
+        _net = net
+        _num_items = I
+    tu, ti = rs.randint(0, U, 600), rs.randint(0, I, 600)
+    tu[tu == 3] = 4                                           # a user without test items
+    ti[:40] = rs.choice([5, 9], 40)                           # the tied items are test items of several users
+    test = _interactions(tu, ti, U, I)
+    ru, ri = rs.randint(0, U, 3000), rs.randint(0, I, 3000)
+    ru[:30], ri[:30] = tu[:30], ti[:30]                       # some test items are also train items
+    train = _interactions(ru, ri, U, I) if with_train else None
+    oracle = O.OracleMF(*[torch.from_numpy(t) for t in tabs])
+    test_csr = test.tocsr()
+    train_csr = train.tocsr() if with_train else None
+    expect = []
+    for u in range(U):
+        row = test_csr[u].indices
+        if not len(row):
+            continue
+        pred = -oracle.predict(u)
+        if with_train:
+            pred[train_csr[u].indices] = np.finfo(np.float32).max
+        expect.append((1.0 / st.rankdata(pred)[row]).mean())
+    got = mrr_score(_Model(), test, train=train)
+    assert got.shape == (len(expect),)
+    np.testing.assert_allclose(got, expect, rtol=1e-4)
