@@ -48,8 +48,9 @@ typedef enum {
   MFB_LOSS_ADAPTIVE_HINGE = 3
 } mfb_loss;
 
-/* spotlight/optimizers.py:4-15 -> torch.optim.SGD (momentum 0) / torch.optim.Adam (dense) */
-typedef enum { MFB_OPT_SGD = 0, MFB_OPT_ADAM = 1 } mfb_optimizer;
+/* spotlight/optimizers.py:4-22 -> torch.optim.SGD (momentum 0) / torch.optim.Adam / torch.optim.RMSprop (momentum 0,
+ * not centered), all dense.  RMSprop: beta2 carries alpha, the *_v buffers are square_avg, the *_m buffers are unused. */
+typedef enum { MFB_OPT_SGD = 0, MFB_OPT_ADAM = 1, MFB_OPT_RMSPROP = 2 } mfb_optimizer;
 
 /* BilinearNet parameters (spotlight/factorization/representations.py:47-60) and the
  * optimiser configuration (implicit.py:182-192).  All tables row-major fp32 on the device. */

@@ -18,6 +18,8 @@ import torch
 
 REF = os.environ.get('REF_PATH', '/root/reference')
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+# GOLDEN_ONLY_STEPS=name1,name2 regenerates only those step-level files (steps_<name>.npz)
+ONLY_STEPS = set(filter(None, os.environ.get('GOLDEN_ONLY_STEPS', '').split(',')))
 
 
 def import_reference():
@@ -51,6 +53,14 @@ def main():
     ref_implicit, sampling, losses, evaluation, optimizers, Interactions, BilinearNet = import_reference()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
+    if not ONLY_STEPS:
+        make_streams_forward_losses(sampling, losses, BilinearNet)
+    make_steps(ref_implicit, optimizers, Interactions, BilinearNet)
+    if not ONLY_STEPS:
+        make_fits(ref_implicit, evaluation, optimizers, Interactions, BilinearNet)
+
+
+def make_streams_forward_losses(sampling, losses, BilinearNet):
 
     # ---------------------------------------------------------------- A. index streams
     rng = {}
@@ -101,6 +111,9 @@ def main():
     fl['pos'] = pos.detach().numpy().copy()
     np.savez_compressed(os.path.join(OUT, 'forward_losses.npz'), **fl)
 
+
+
+def make_steps(ref_implicit, optimizers, Interactions, BilinearNet):
     # ---------------------------------------------------------------- D. step-level
     U, I, D, B = 120, 90, 16, 64
     cases = [
@@ -112,8 +125,12 @@ def main():
         ('adaptive_adam', 'adaptive_hinge', 'adam', 3, 1e-5, 1e-3, 64 * 12 + 9, False),
         ('hinge_adam', 'hinge', 'adam', 1, 1e-5, 1e-3, 64 * 12, True),           # full batches only
         ('hinge_sgd', 'hinge', 'sgd', 1, 0.0, 5e-2, 64 * 8, False),
+        ('pointwise_rms', 'pointwise', 'rms', 3, 1e-5, 1e-3, 64 * 11 + 21, True),   # torch.optim.RMSprop (--optim rms)
+        ('bpr_rms_wd0', 'bpr', 'rms', 1, 0.0, 1e-3, 64 * 10 + 5, False),
     ]
     for name, loss, opt, n_neg, l2, lr, n_pos, zipf in cases:
+        if ONLY_STEPS and name not in ONLY_STEPS:
+            continue
         rs = np.random.RandomState(100 + len(name))
         users, items = synth(rs, U, I, n_pos, zipf)
         neg_pairs = np.stack(synth(rs, U, I, n_pos), 1)
@@ -150,6 +167,9 @@ def main():
         np.savez_compressed(os.path.join(OUT, 'steps_%s.npz' % name), **d)
         print(name, step_losses[0], step_losses[-1])
 
+
+
+def make_fits(ref_implicit, evaluation, optimizers, Interactions, BilinearNet):
     # ---------------------------------------------------------------- E. fit + predict + evaluate
     U, I, D, B = 150, 110, 16, 128
     for name, loss, n_neg in (('fit_pointwise', 'pointwise', 4), ('fit_bpr', 'bpr', 1)):

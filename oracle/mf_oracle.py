@@ -110,6 +110,8 @@ def make_optimizer(params, kind, lr, weight_decay, betas=(0.5, 0.999), eps=1e-8)
         return torch.optim.Adam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
     if kind == 'sgd':
         return torch.optim.SGD(params, lr=lr, weight_decay=weight_decay)
+    if kind == 'rms':                                                 # spotlight/optimizers.py:18-22
+        return torch.optim.RMSprop(params, lr=lr, weight_decay=weight_decay)
     raise ValueError(kind)
 
 
@@ -139,6 +141,19 @@ def adam_dense_step_numpy(p, m, v, g, step, lr, beta1, beta2, eps, wd):
     v[...] = v * f(beta2) + (f(1 - beta2) * g) * g
     denom = np.sqrt(v) / f(bc2_sqrt) + f(eps)
     p[...] = p + (f(-step_size) * m) / denom
+
+
+def rms_dense_step_numpy(p, v, g, lr, alpha, eps, wd):
+    """Elementwise fp32 restatement of one dense torch RMSprop step (rmsprop.py _single_tensor_rmsprop, momentum 0, not
+    centered): `grad.add(param, alpha=wd)`, `square_avg.mul_(alpha).addcmul_(grad, grad, value=1-alpha)`,
+    `avg = square_avg.sqrt().add_(eps)`, `param.addcdiv_(grad, avg, value=-lr)`.  In-place on p, v (float32)."""
+    f = np.float32
+    g = g.astype(np.float32)
+    if wd != 0:
+        g = g + f(wd) * p
+    v[...] = v * f(alpha) + (f(1 - alpha) * g) * g
+    avg = np.sqrt(v) + f(eps)
+    p[...] = p + (f(-lr) * g) / avg
 
 
 def sgd_dense_step_numpy(p, g, lr, wd):

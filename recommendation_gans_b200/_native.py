@@ -20,7 +20,7 @@ c_void = ctypes.c_void_p
 MFB_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_RANGE, ERR_SHAPE, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5, -6
 LOSS = {'pointwise': 0, 'bpr': 1, 'hinge': 2, 'adaptive_hinge': 3}
-OPT_SGD, OPT_ADAM = 0, 1
+OPT_SGD, OPT_ADAM, OPT_RMSPROP = 0, 1, 2
 MAX_TOPK = 32
 
 

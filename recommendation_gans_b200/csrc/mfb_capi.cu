@@ -78,9 +78,14 @@ extern "C" int mfb_model_create(const mfb_model_desc *d, mfb_model **out) {
     mfb_set_error("model_create: null parameter table");
     return MFB_ERR_INVALID;
   }
-  if (d->optimizer != MFB_OPT_SGD && d->optimizer != MFB_OPT_ADAM) {
-    mfb_set_error("model_create: optimizer %d unsupported (SGD without momentum, Adam)", d->optimizer);
+  if (d->optimizer != MFB_OPT_SGD && d->optimizer != MFB_OPT_ADAM && d->optimizer != MFB_OPT_RMSPROP) {
+    mfb_set_error("model_create: optimizer %d unsupported (SGD without momentum, Adam, RMSprop)", d->optimizer);
     return MFB_ERR_UNSUPPORTED;
+  }
+  if (d->optimizer == MFB_OPT_RMSPROP &&
+      (!d->d_user_emb_v || !d->d_item_emb_v || !d->d_user_bias_v || !d->d_item_bias_v)) {
+    mfb_set_error("model_create: RMSprop needs square_avg buffers (the *_v fields) for all four tables");
+    return MFB_ERR_INVALID;
   }
   if (d->optimizer == MFB_OPT_ADAM &&
       (!d->d_user_emb_m || !d->d_user_emb_v || !d->d_item_emb_m || !d->d_item_emb_v || !d->d_user_bias_m ||

@@ -177,6 +177,21 @@ __device__ __forceinline__ void sgd_elem(float &p, float g, const OptView &o) {
   p = fmaf(-o.lr, g, p);
 }
 
+// which per-row state an optimiser keeps: bit 0 = exp_avg (Adam), bit 1 = exp_avg_sq (Adam) / square_avg (RMSprop)
+__device__ __forceinline__ int opt_state_bits(int kind) {
+  return kind == MFB_OPT_ADAM ? 3 : (kind == MFB_OPT_RMSPROP ? 2 : 0);
+}
+
+// One dense torch.optim.RMSprop update of a single element (torch/optim/rmsprop.py _single_tensor_rmsprop, momentum 0,
+// not centered): grad += wd*p; square_avg = square_avg*alpha + (1-alpha)*grad*grad; avg = sqrt(square_avg) + eps;
+// p += (-lr*grad)/avg.  (o.beta2 carries alpha.)
+__device__ __forceinline__ void rms_elem(float &p, float &v, float g, const OptView &o) {
+  g = fmaf(o.wd, p, g);
+  v = __fadd_rn(__fmul_rn(v, o.beta2), __fmul_rn(__fmul_rn(o.one_minus_beta2, g), g));
+  const float avg = __fadd_rn(__fsqrt_rn(v), o.eps);
+  p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-o.lr, g), avg));
+}
+
 // Full optimiser state of one table row held by a warp.
 template <int VEC, int NIT>
 struct RowState {
@@ -186,31 +201,29 @@ struct RowState {
 
 template <int VEC, int NIT>
 __device__ __forceinline__ void row_load(RowState<VEC, NIT> &r, const TableView &T, long long row, int D, int lane,
-                                         bool adam) {
+                                         int state) {   // state bits: opt_state_bits()
   frag_load<VEC, NIT>(r.p, T.p + row * D, D, lane);
   r.bp = T.bp[row];
-  if (adam) {
+  if (state & 1) {
     frag_load<VEC, NIT>(r.m, T.m + row * D, D, lane);
-    frag_load<VEC, NIT>(r.v, T.v + row * D, D, lane);
     r.bm = T.bm[row];
+  }
+  if (state & 2) {
+    frag_load<VEC, NIT>(r.v, T.v + row * D, D, lane);
     r.bv = T.bv[row];
   }
 }
 
 template <int VEC, int NIT>
 __device__ __forceinline__ void row_store(const RowState<VEC, NIT> &r, const TableView &T, long long row, int D,
-                                          int lane, bool adam) {
+                                          int lane, int state) {
   frag_store<VEC, NIT>(r.p, T.p + row * D, D, lane);
-  if (adam) {
-    frag_store<VEC, NIT>(r.m, T.m + row * D, D, lane);
-    frag_store<VEC, NIT>(r.v, T.v + row * D, D, lane);
-  }
+  if (state & 1) frag_store<VEC, NIT>(r.m, T.m + row * D, D, lane);
+  if (state & 2) frag_store<VEC, NIT>(r.v, T.v + row * D, D, lane);
   if (lane == 0) {
     T.bp[row] = r.bp;
-    if (adam) {
-      T.bm[row] = r.bm;
-      T.bv[row] = r.bv;
-    }
+    if (state & 1) T.bm[row] = r.bm;
+    if (state & 2) T.bv[row] = r.bv;
   }
 }
 
@@ -271,6 +284,12 @@ __device__ __forceinline__ void row_replay(RowState<VEC, NIT> &r, int from, int 
       for (int k = 0; k < NIT * VEC; ++k) adam_elem<FAST>(r.p.x[k], r.m.x[k], r.v.x[k], 0.f, neg_ss, bc2, o);
       adam_elem<FAST>(r.bp, r.bm, r.bv, 0.f, neg_ss, bc2, o);
     }
+  } else if (o.kind == MFB_OPT_RMSPROP) {
+    for (int s = from + 1; s <= to; ++s) {   // (wd == 0: p stays, square_avg still decays every step)
+#pragma unroll
+      for (int k = 0; k < NIT * VEC; ++k) rms_elem(r.p.x[k], r.v.x[k], 0.f, o);
+      rms_elem(r.bp, r.bv, 0.f, o);
+    }
   } else {
     if (o.wd == 0.f) return;  // p - lr*(0 + 0*p) == p
     for (int s = from + 1; s <= to; ++s) {
@@ -311,6 +330,10 @@ __device__ __forceinline__ void apply_step(RowState<VEC, NIT> &r, const Frag<VEC
 #pragma unroll
     for (int k = 0; k < NIT * VEC; ++k) adam_elem<FAST>(r.p.x[k], r.m.x[k], r.v.x[k], g.x[k], neg_ss, bc2, opt);
     adam_elem<FAST>(r.bp, r.bm, r.bv, gb, neg_ss, bc2, opt);
+  } else if (opt.kind == MFB_OPT_RMSPROP) {
+#pragma unroll
+    for (int k = 0; k < NIT * VEC; ++k) rms_elem(r.p.x[k], r.v.x[k], g.x[k], opt);
+    rms_elem(r.bp, r.bv, gb, opt);
   } else {
 #pragma unroll
     for (int k = 0; k < NIT * VEC; ++k) sgd_elem(r.p.x[k], g.x[k], opt);

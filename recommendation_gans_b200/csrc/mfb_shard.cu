@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_catchup(const PosInfo *__r
   const TableView &T = ((raw.x >> rb) & 1u) ? items : users;
   const int last = T.last[row];
   if (last >= target) return;
-  const bool adam = opt.kind == MFB_OPT_ADAM;
+  const int adam = opt_state_bits(opt.kind);
   RowState<VEC, NIT> r;
   row_load<VEC, NIT>(r, T, row, D, lane, adam);
   row_replay<VEC, NIT, FAST>(r, last, target, opt);
@@ -468,7 +468,7 @@ template <int VEC, int NIT, bool FAST>
 __global__ void __launch_bounds__(SH_UPD_WARPS * 32) k_shard_update(const ShUpdArgs a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int D = a.D;
-  const bool adam = a.opt.kind == MFB_OPT_ADAM;
+  const int adam = opt_state_bits(a.opt.kind);   // which per-row optimiser state exists
   const int ql = (int)blockIdx.x * SH_UPD_WARPS + wid;
   if (ql >= a.n) return;
   const long long q = a.base + ql;

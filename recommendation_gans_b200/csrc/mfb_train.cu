@@ -574,7 +574,7 @@ template <int VEC, int NIT, bool FAST, int KIND>
 __global__ void __launch_bounds__(UPD_WARPS * 32, MFB_UPD_MINB) k_update(const UpdArgs a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int D = a.D;
-  const bool adam = a.opt.kind == MFB_OPT_ADAM;
+  const int adam = opt_state_bits(a.opt.kind);   // which per-row optimiser state exists
 
   pdl_launch_dependents();
   if ((int)blockIdx.x < a.cu_blocks) {
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_flush(TableView T, OptView op
   if (row >= T.rows) return;
   const int last = T.last[row];
   if (last >= t) return;
-  const bool adam = opt.kind == MFB_OPT_ADAM;
+  const int adam = opt_state_bits(opt.kind);
   RowState<VEC, NIT> r;
   row_load<VEC, NIT>(r, T, row, D, lane, adam);
   row_replay<VEC, NIT, FAST>(r, last, t, opt);

@@ -1,8 +1,8 @@
 """Optimiser factories with the reference's signatures (spotlight/optimizers.py:4-22).
 
 They return ordinary torch optimiser objects; the fused CUDA step reads their hyper-parameters
-and owns their state tensors (engine.MFEngine), it never calls `.step()` on them.  Adam and plain
-SGD are on the fused path; RMSprop is accepted here for API parity but rejected by the engine."""
+and owns their state tensors (engine.MFEngine), it never calls `.step()` on them.  Adam, RMSprop
+and plain SGD are all on the fused path (dense-optimiser semantics, see csrc/mfb_rowops.cuh)."""
 import torch.optim as optim
 
 

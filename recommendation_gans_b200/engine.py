@@ -148,6 +148,17 @@ class MFEngine(object):
         desc.lr, desc.beta1, desc.beta2 = hyper['lr'], hyper['beta1'], hyper['beta2']
         desc.eps, desc.weight_decay = hyper['eps'], hyper['weight_decay']
         self.optimizer_kind = kind
+        if kind == N.OPT_RMSPROP:
+            sq = []
+            for p in (ue, ie, ub, ib):
+                st = optimizer.state[p]
+                if 'square_avg' not in st:     # same layout torch.optim.RMSprop creates lazily
+                    st['step'] = torch.tensor(0.0, dtype=torch.float32)
+                    st['square_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                sq.append(st['square_avg'])
+                self._state_tensors.append(st['square_avg'])
+            desc.d_user_emb_v, desc.d_item_emb_v = sq[0].data_ptr(), sq[1].data_ptr()
+            desc.d_user_bias_v, desc.d_item_bias_v = sq[2].data_ptr(), sq[3].data_ptr()
         if kind == N.OPT_ADAM:
             moments = []
             for p in (ue, ie, ub, ib):
@@ -165,7 +176,7 @@ class MFEngine(object):
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
             N.check(self._lib.mfb_model_create(ctypes.byref(desc), ctypes.byref(self._handle)), 'model_create')
-        if kind == N.OPT_ADAM:
+        if kind in (N.OPT_ADAM, N.OPT_RMSPROP):
             start = int(float(optimizer.state[ue]['step']))
             if start:
                 self._call('mfb_model_set_step', start)
@@ -189,12 +200,18 @@ class MFEngine(object):
             hyper['beta1'], hyper['beta2'] = float(g['betas'][0]), float(g['betas'][1])
             hyper['eps'] = float(g['eps'])
             return N.OPT_ADAM, hyper
+        if isinstance(opt, torch.optim.RMSprop):
+            if g.get('momentum', 0) != 0 or g.get('centered', False):
+                raise NotImplementedError('mfb200: RMSprop momentum / centered are not supported')
+            hyper['beta2'] = float(g['alpha'])          # the C ABI carries alpha in beta2
+            hyper['eps'] = float(g['eps'])
+            return N.OPT_RMSPROP, hyper
         if isinstance(opt, torch.optim.SGD):
             if g.get('momentum', 0) != 0 or g.get('dampening', 0) != 0 or g.get('nesterov', False):
                 raise NotImplementedError('mfb200: SGD momentum/dampening/nesterov are not supported')
             return N.OPT_SGD, hyper
-        raise NotImplementedError('mfb200: optimiser %s is outside the fused path (Adam and plain SGD are '
-                                  'supported)' % type(opt).__name__)
+        raise NotImplementedError('mfb200: optimiser %s is outside the fused path (Adam, RMSprop and plain SGD '
+                                  'are supported)' % type(opt).__name__)
 
     def _call(self, name, *args):
         if not self._handle:
@@ -221,7 +238,7 @@ class MFEngine(object):
         return int(self._lib.mfb_model_step(self._handle))
 
     def _sync_optimizer_step(self):
-        if self._optimizer is not None and self.optimizer_kind == N.OPT_ADAM:
+        if self._optimizer is not None and self.optimizer_kind in (N.OPT_ADAM, N.OPT_RMSPROP):
             t = float(self.step)
             for p in self._params:
                 self._optimizer.state[p]['step'] = torch.tensor(t, dtype=torch.float32)

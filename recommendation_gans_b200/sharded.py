@@ -181,6 +181,8 @@ class CudaShardBackend(object):
             self.optimizer = torch.optim.Adam(net.parameters(), lr=lr, betas=betas, weight_decay=l2)
         elif optimizer == 'sgd':
             self.optimizer = torch.optim.SGD(net.parameters(), lr=lr, weight_decay=l2)
+        elif optimizer == 'rms':
+            self.optimizer = torch.optim.RMSprop(net.parameters(), lr=lr, weight_decay=l2)
         else:
             raise NotImplementedError('optimizer %r' % (optimizer,))
         self.engine = MFEngine(net, self.optimizer, fast_math=fast_math)

@@ -7,7 +7,7 @@ reference's dense torch Adam/SGD over whole tables.  Test helper, no
 """
 import numpy as np
 
-from oracle.mf_oracle import adam_dense_step_numpy, sgd_dense_step_numpy
+from oracle.mf_oracle import adam_dense_step_numpy, rms_dense_step_numpy, sgd_dense_step_numpy
 
 f32 = np.float32
 
@@ -74,6 +74,8 @@ class LazyMF:
         m, v = self.state[name]
         if self.opt == 'adam':
             adam_dense_step_numpy(p[r], m[r], v[r], g, s, self.lr, self.betas[0], self.betas[1], self.eps, self.wd)
+        elif self.opt == 'rms':                      # torch.optim.RMSprop defaults: alpha 0.99, eps 1e-8
+            rms_dense_step_numpy(p[r], v[r], g, self.lr, 0.99, 1e-8, self.wd)
         else:
             sgd_dense_step_numpy(p[r], g, self.lr, self.wd)
 
