@@ -105,6 +105,16 @@ int mfb_mt_sample_items(uint32_t *h_state, int64_t num_items, int64_t count, int
 /* raw tempered 32-bit outputs (test hook) */
 int mfb_mt_words(uint32_t *h_state, int64_t nwords, uint32_t *d_out, mfb_stream stream);
 
+/* spotlight/sampling.py:46-70 get_negative_samples (with the rank-shift resampling of :37-44): num_samples uniform
+ * (user, item) pairs; a pair that is a known interaction (key CSR: the entries whose stored value == 1, as
+ * Interactions.has_key, interactions.py:159-160) has its item re-drawn uniformly outside the user's row (row CSR: every
+ * stored entry).  Consumes numpy's legacy MT19937 stream exactly as the reference (np.random.choice x2, then one
+ * np.random.randint per re-draw in sample order); h_state is advanced in place.  CSR indices sorted within rows. */
+int mfb_negative_pairs(uint32_t *h_state, int64_t num_users, int64_t num_items, int64_t num_samples,
+                       const int64_t *d_key_indptr, const int32_t *d_key_indices, const int64_t *d_row_indptr,
+                       const int32_t *d_row_indices, int64_t *d_out_users, int64_t *d_out_items, int64_t *h_n_redrawn,
+                       mfb_stream stream);
+
 /* ---- forward / predict ---------------------------------------------------------------- */
 /* BilinearNet.forward (representations.py:62-91) on m (user,item) pairs:
  * out[j] = sigmoid(<U[u_j],V[i_j]> + bu[u_j] + bi[i_j]).  Also ImplicitFactorizationModel.predict

@@ -259,6 +259,29 @@ def fit_epochs(model, users, items, val_users, val_items, n_epochs, gen):
 
 
 # ----------------------------------------------------------------------------------------
+# offline negative pairs: spotlight/sampling.py:37-70
+# ----------------------------------------------------------------------------------------
+def get_negative_samples(users, items, num_users, num_items, num_samples, rs):
+    """sampling.py:46-70 on the train pairs (users, items), drawing from the numpy RandomState `rs` in the order the
+    reference draws from numpy's global generator: choice(num_users, n), choice(num_items, n), then for every sample
+    whose pair is a known interaction (CSR value == 1, interactions.py:159-160) one randint(0, free items, 1) mapped to
+    the raw-th item outside the user's row (sampling.py:37-44).  Returns an int64 array [n, 2]."""
+    import scipy.sparse as sp
+    csr = sp.coo_matrix((np.ones(len(users)), (users, items)), shape=(num_users, num_items)).tocsr()
+    csr.sort_indices()
+    us = rs.choice(num_users, num_samples)
+    its = rs.choice(num_items, num_samples)
+    out = np.stack([us, its], 1).astype(np.int64)
+    for k in range(num_samples):
+        u, i = us[k], its[k]
+        if csr[u, i] == 1:
+            row = csr.indices[csr.indptr[u]:csr.indptr[u + 1]]
+            raw = rs.randint(0, num_items - len(row), size=1)
+            out[k, 1] = (raw + np.searchsorted(row - np.arange(len(row)), raw, side='right'))[0]
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # evaluation: spotlight/evaluation.py:108-185
 # ----------------------------------------------------------------------------------------
 def csr_from_pairs(users, items, num_users, num_items):

@@ -272,3 +272,188 @@ extern "C" int mfb_mt_sample_items(uint32_t *h_state, int64_t num_items, int64_t
   mfb_set_error("mt_sample_items: rejection sampling did not converge");
   return MFB_ERR_INVALID;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Offline negative-pair generator: spotlight/sampling.py:46-70 (get_negative_samples) with the rank-shift
+// resampling of sampling.py:37-44 (negsamp_vectorized_bsearch_preverif), bit-exact with the reference's
+// consumption of numpy's legacy global MT19937 stream:
+//   users = np.random.choice(num_users, n); items = np.random.choice(num_items, n)      (two randint streams)
+//   for i in order: if has_key(users[i], items[i]):                                       (CSR value == 1)
+//       raw = np.random.randint(0, num_items - len(row(users[i])), 1)                     (masked rejection, 32-bit)
+//       items[i] = raw + searchsorted(row - arange(len(row)), raw, 'right')               (raw-th item outside row)
+// The membership test and the rank shift are data-parallel; only the order in which the re-draws consume the stream
+// is sequential, and that part touches two row pointers and a few stream words per re-draw.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void k_neg_flag(const long long *__restrict__ users, const long long *__restrict__ items, long long n,
+                           const long long *__restrict__ key_indptr, const int *__restrict__ key_indices,
+                           int *__restrict__ flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long u = users[i];
+  const int it = (int)items[i];
+  long long lo = key_indptr[u], end = key_indptr[u + 1], hi = end;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (key_indices[mid] < it) lo = mid + 1; else hi = mid;
+  }
+  flag[i] = (lo < end && key_indices[lo] == it) ? 1 : 0;
+}
+
+// ordered compaction of the flagged sample indices (single CTA, stream order preserved)
+__global__ void __launch_bounds__(1024) k_neg_compact(const int *__restrict__ flag, long long n,
+                                                      long long *__restrict__ list, long long *__restrict__ count) {
+  __shared__ int warp_sums[32];
+  __shared__ long long base_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  for (long long start = 0; start < n; start += 1024) {
+    const long long i = start + tid;
+    const int ok = (i < n) ? flag[i] : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int c = warp_sums[w];
+      if (w < wid) before += c;
+      total += c;
+    }
+    if (ok) list[base_s + before + in_warp] = i;
+    __syncthreads();
+    if (tid == 0) base_s += total;
+    __syncthreads();
+  }
+  if (tid == 0) *count = base_s;
+}
+
+// the sequential part: re-draw c takes stream words until (word & mask_c) <= rng_c, rng_c = free items of its user - 1
+// result[0] = words consumed (or -1: the buffer ran out), result[1] = 1 if some user has no free item
+__global__ void k_neg_redraw_serial(const long long *__restrict__ list, long long cnt,
+                                    const long long *__restrict__ users, const long long *__restrict__ row_indptr,
+                                    long long num_items, const uint32_t *__restrict__ words, long long nwords,
+                                    uint32_t *__restrict__ raw, long long *__restrict__ result) {
+  long long w = 0;
+  result[1] = 0;
+  for (long long c = 0; c < cnt; ++c) {
+    const long long u = users[list[c]];
+    const long long free_items = num_items - (row_indptr[u + 1] - row_indptr[u]);
+    if (free_items <= 0) {   // numpy: randint(0, 0) raises ValueError("high <= 0")
+      result[0] = w;
+      result[1] = 1;
+      return;
+    }
+    const uint32_t rng = (uint32_t)(free_items - 1);
+    if (rng == 0) {          // numpy returns low without touching the stream
+      raw[c] = 0u;
+      continue;
+    }
+    uint32_t mask = rng;
+    mask |= mask >> 1;
+    mask |= mask >> 2;
+    mask |= mask >> 4;
+    mask |= mask >> 8;
+    mask |= mask >> 16;
+    uint32_t v;
+    do {
+      if (w >= nwords) {
+        result[0] = -1;
+        return;
+      }
+      v = words[w++] & mask;
+    } while (v > rng);
+    raw[c] = v;
+  }
+  result[0] = w;
+}
+
+// items[list[c]] = the raw[c]-th item (0-based) outside the user's sorted row: raw + #{j : row[j] - j <= raw}
+__global__ void k_neg_rank_shift(const long long *__restrict__ list, long long cnt, const long long *__restrict__ users,
+                                 const long long *__restrict__ row_indptr, const int *__restrict__ row_indices,
+                                 const uint32_t *__restrict__ raw, long long *__restrict__ items) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cnt) return;
+  const long long i = list[c], u = users[i];
+  const long long r0 = row_indptr[u], len = row_indptr[u + 1] - r0;
+  const long long x = (long long)raw[c];
+  long long lo = 0, hi = len;                       // searchsorted(row - arange, x, side='right')
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((long long)row_indices[r0 + mid] - mid <= x) lo = mid + 1; else hi = mid;
+  }
+  items[i] = x + lo;
+}
+
+DevBuf g_nflag, g_nlist, g_nraw;
+
+}  // namespace
+
+extern "C" int mfb_negative_pairs(uint32_t *h_state, int64_t num_users, int64_t num_items, int64_t num_samples,
+                                  const int64_t *d_key_indptr, const int32_t *d_key_indices,
+                                  const int64_t *d_row_indptr, const int32_t *d_row_indices, int64_t *d_out_users,
+                                  int64_t *d_out_items, int64_t *h_n_redrawn, mfb_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h_state || num_users <= 0 || num_items <= 0 || num_samples < 0 || !d_key_indptr || !d_row_indptr ||
+      (num_samples > 0 && (!d_out_users || !d_out_items))) {
+    mfb_set_error("negative_pairs: bad arguments");
+    return MFB_ERR_INVALID;
+  }
+  if (h_n_redrawn) *h_n_redrawn = 0;
+  if (num_samples == 0) return MFB_OK;
+  MFB_CHECK(mfb_mt_sample_items(h_state, num_users, num_samples, d_out_users, stream));
+  MFB_CHECK(mfb_mt_sample_items(h_state, num_items, num_samples, d_out_items, stream));
+  MFB_CHECK(g_nflag.reserve((size_t)num_samples * sizeof(int)));
+  MFB_CHECK(g_nlist.reserve((size_t)num_samples * sizeof(long long)));
+  MFB_CHECK(g_result.reserve(2 * sizeof(long long)));
+  k_neg_flag<<<(unsigned)((num_samples + 255) / 256), 256, 0, st>>>((const long long *)d_out_users,
+                                                                    (const long long *)d_out_items, num_samples,
+                                                                    (const long long *)d_key_indptr, d_key_indices,
+                                                                    g_nflag.as<int>());
+  k_neg_compact<<<1, 1024, 0, st>>>(g_nflag.as<int>(), num_samples, g_nlist.as<long long>(), g_result.as<long long>());
+  MFB_KERNEL_CHECK();
+  mfb_count_library_launch(2);
+  long long cnt = 0;
+  MFB_CUDA(cudaMemcpyAsync(&cnt, g_result.ptr, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  if (h_n_redrawn) *h_n_redrawn = cnt;
+  if (cnt == 0) return MFB_OK;
+  MFB_CHECK(g_nraw.reserve((size_t)cnt * sizeof(uint32_t)));
+  uint32_t saved[625];
+  memcpy(saved, h_state, sizeof(saved));
+  int64_t est = 4 * cnt + 1024;
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    uint32_t tmp[625];
+    memcpy(tmp, saved, sizeof(tmp));
+    MFB_CHECK(g_words.reserve((size_t)est * sizeof(uint32_t)));
+    MFB_CHECK(mfb_mt_generate(tmp, est, g_words.as<uint32_t>(), st));
+    k_neg_redraw_serial<<<1, 1, 0, st>>>(g_nlist.as<long long>(), cnt, (const long long *)d_out_users,
+                                         (const long long *)d_row_indptr, num_items, g_words.as<uint32_t>(), est,
+                                         g_nraw.as<uint32_t>(), g_result.as<long long>());
+    MFB_KERNEL_CHECK();
+    mfb_count_library_launch(2);
+    long long res[2];
+    MFB_CUDA(cudaMemcpyAsync(res, g_result.ptr, sizeof(res), cudaMemcpyDeviceToHost, st));
+    MFB_CUDA(cudaStreamSynchronize(st));
+    if (res[1]) {
+      mfb_set_error("high <= 0");   // numpy's ValueError from randint(0, 0): a user interacted with every item
+      return MFB_ERR_RANGE;
+    }
+    if (res[0] >= 0) {
+      k_neg_rank_shift<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(
+          g_nlist.as<long long>(), cnt, (const long long *)d_out_users, (const long long *)d_row_indptr, d_row_indices,
+          g_nraw.as<uint32_t>(), (long long *)d_out_items);
+      MFB_KERNEL_CHECK();
+      mfb_count_library_launch(1);
+      memcpy(h_state, saved, sizeof(saved));
+      if (res[0] > 0) MFB_CHECK(mfb_mt_generate(h_state, res[0], nullptr, st));   // advance by the words consumed
+      MFB_CUDA(cudaStreamSynchronize(st));
+      return MFB_OK;
+    }
+    est *= 2;
+  }
+  mfb_set_error("negative_pairs: rejection sampling did not converge");
+  return MFB_ERR_INVALID;
+}

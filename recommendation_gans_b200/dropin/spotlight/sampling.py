@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-from recommendation_gans_b200.engine import sample_items_device
+from recommendation_gans_b200.engine import negative_pairs_device, sample_items_device
 
 
 def sample_items(interaction, user_ids, num_items, shape, random_state=None):
@@ -31,19 +31,29 @@ def negsamp_vectorized_bsearch_preverif(pos_inds, n_items, n_samp=32):
     return raw + np.searchsorted(shifted, raw, side='right')
 
 
+def get_negative_samples_arrays(train, num_samples, random_state=None):
+    """get_negative_samples as two int64 numpy arrays (users, items).  The whole job runs on the GPU
+    (mfb_negative_pairs): two uniform index streams, a CSR membership test per pair, and for the pairs that are known
+    interactions a re-draw inside the user's complement -- consuming numpy's legacy MT19937 stream (the global
+    generator unless `random_state` is given) exactly as the reference's Python loop does."""
+    csr = train.tocsr()
+    csr.sum_duplicates()
+    csr.sort_indices()
+    keys = csr.copy()
+    keys.data = (keys.data == 1).astype(np.float64)      # Interactions.has_key: stored value == 1 (interactions.py:159)
+    keys.eliminate_zeros()
+    rs = random_state if random_state is not None else np.random.mtrand._rand
+    users, items, _ = negative_pairs_device(keys, csr, train.num_users, train.num_items, num_samples, rs)
+    return users.cpu().numpy(), items.cpu().numpy()
+
+
 def get_negative_samples(train, num_samples):
     """Offline (user, item) negative-pair list (sampling.py:46-70): uniform pairs, re-drawn inside the
-    user's complement when the pair is a known interaction.  One-off host preprocessing; same global
-    numpy RNG consumption order as the reference."""
-    csr = train.tocsr()
+    user's complement when the pair is a known interaction.  Same pairs and same consumption of numpy's global
+    generator as the reference; returns the reference's list of tuples."""
     logging.info("Generating %d Samples" % num_samples)
     start = time.time()
-    users = np.random.choice(train.num_users, num_samples)
-    items = np.random.choice(train.num_items, num_samples)
-    pairs = []
-    for u, i in zip(users, items):
-        if train.has_key(u, i):
-            i = negsamp_vectorized_bsearch_preverif(csr[u, :].toarray().nonzero()[1], train.num_items, 1)[0]
-        pairs.append((u, i))
+    users, items = get_negative_samples_arrays(train, num_samples)
+    pairs = list(zip(users, items))
     logging.info("Took %d seconds" % (time.time() - start))
     return pairs

@@ -61,6 +61,31 @@ def sample_items_device(num_items, count, random_state, device=None):
     return out
 
 
+def negative_pairs_device(key_csr, row_csr, num_users, num_items, num_samples, random_state, device=None):
+    """spotlight/sampling.py:46-70 on the GPU, continuing `random_state`'s MT19937 stream (numpy legacy RandomState, e.g.
+    np.random.mtrand._rand for the global generator).  key_csr: entries for which has_key is true; row_csr: all stored
+    entries (scipy CSR, sorted indices).  Returns (users, items) int64 CUDA tensors and the number of re-drawn pairs."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = device or torch.device('cuda', torch.cuda.current_device())
+    out_u = torch.empty(int(num_samples), dtype=torch.int64, device=device)
+    out_i = torch.empty(int(num_samples), dtype=torch.int64, device=device)
+
+    def dev(csr):
+        return (torch.from_numpy(csr.indptr.astype(np.int64)).to(device),
+                torch.from_numpy(csr.indices.astype(np.int32)).to(device))
+    k_ptr, k_idx = dev(key_csr)
+    r_ptr, r_idx = dev(row_csr)
+    state, extra = _get_np_state(random_state)
+    redrawn = ctypes.c_int64(0)
+    with torch.cuda.device(device):
+        N.check(lib.mfb_negative_pairs(N.hptr(state), int(num_users), int(num_items), int(num_samples), N.dptr(k_ptr),
+                                       N.dptr(k_idx), N.dptr(r_ptr), N.dptr(r_idx), N.dptr(out_u), N.dptr(out_i),
+                                       ctypes.byref(redrawn), N.stream_ptr()), 'get_negative_samples')
+    _set_np_state(random_state, state, extra)
+    return out_u, out_i, int(redrawn.value)
+
+
 def choices_indices_device(pop_len, k, rng=None, device=None):
     """Index stream of random.choices(range(pop_len), k=k), continuing `rng` (default: global random)."""
     N.require_cuda()

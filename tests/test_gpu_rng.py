@@ -78,3 +78,26 @@ def test_negative_pairs_follow_global_random(golden_dir):
     ref = random.Random(int(g['py_seed']))
     ref.choices(range(10), k=nsteps * n_neg * B)
     assert random.getstate() == ref.getstate()
+
+
+def test_negative_pair_generator_bit_exact(golden_dir):
+    """spotlight.sampling.get_negative_samples on the GPU vs the pairs the reference produced (tests/golden/
+    neg_samples.npz): bit-exact pairs, numpy's global generator left where the reference leaves it; a user who
+    interacted with every item raises numpy's ValueError."""
+    import recommendation_gans_b200  # noqa: F401
+    from spotlight.interactions import Interactions
+    from spotlight.sampling import get_negative_samples, get_negative_samples_arrays
+    g = np.load(os.path.join(golden_dir, 'neg_samples.npz'))
+    for name in g['cases']:
+        name = str(name)
+        U, I, N, seed = [int(x) for x in g[name + '_meta']]
+        train = Interactions(g[name + '_users'], g[name + '_items'], num_users=U, num_items=I)
+        np.random.seed(seed)
+        pairs = get_negative_samples(train, N)
+        assert isinstance(pairs, list) and len(pairs) == N and isinstance(pairs[0], tuple)
+        assert (np.array(pairs, dtype=np.int64) == g[name + '_pairs']).all()
+        st = np.random.get_state()
+        assert (st[1] == g[name + '_state_key']).all() and st[2] == int(g[name + '_state_pos'])
+    full = Interactions(np.zeros(6, np.int32), np.arange(6, dtype=np.int32), num_users=2, num_items=6)
+    with pytest.raises(ValueError):
+        get_negative_samples_arrays(full, 50, np.random.RandomState(0))

@@ -142,3 +142,21 @@ def test_losses_with_mask_and_2d_negatives_match_reference(golden_dir):
         np.testing.assert_allclose(val.detach().numpy(), g['loss_' + tag], rtol=1e-6)
         np.testing.assert_allclose(pos.grad.numpy(), g['dpos_' + tag], rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(neg.grad.numpy(), g['dneg_' + tag], rtol=1e-6, atol=1e-9)
+
+
+def test_negative_pair_generator_matches_reference(golden_dir):
+    """oracle.get_negative_samples vs the reference's get_negative_samples (tests/golden/neg_samples.npz, frozen by
+    oracle/make_golden_negsamples.py): pairs bit-exact and numpy's generator left in the same state."""
+    g = np.load(os.path.join(golden_dir, 'neg_samples.npz'))
+    for name in g['cases']:
+        name = str(name)
+        U, I, N, seed = [int(x) for x in g[name + '_meta']]
+        rs = np.random.RandomState(seed)
+        pairs = O.get_negative_samples(g[name + '_users'], g[name + '_items'], U, I, N, rs)
+        assert (pairs == g[name + '_pairs']).all()
+        st = rs.get_state()
+        assert (st[1] == g[name + '_state_key']).all() and st[2] == int(g[name + '_state_pos'])
+        import collections
+        seen = collections.Counter(zip(g[name + '_users'].tolist(), g[name + '_items'].tolist()))
+        once = {p for p, c in seen.items() if c == 1}    # a repeated pair is stored as 2: has_key is False for it
+        assert (1, 3) not in once and not [p for p in map(tuple, pairs.tolist()) if p in once]
