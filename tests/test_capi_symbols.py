@@ -67,3 +67,26 @@ def test_library_staleness_is_decided_by_content(tmp_path, monkeypatch):
     real = B._dependencies
     monkeypatch.setattr(B, '_dependencies', lambda: real() + [str(extra)])
     assert B.is_stale()
+
+
+def test_committed_bench_lines_keep_the_contract():
+    """The bench lines committed under profiles/ (written by bench.py on a B200) carry every key the driver reads."""
+    import glob
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    paths = [p for p in glob.glob(os.path.join(root, 'profiles', 'r01_bench_*gpu.json'))] + \
+        [os.path.join(root, 'profiles', 'r01_bench_session2.json')]
+    assert len(paths) >= 3
+    for path in paths:
+        d = json.load(open(path))
+        for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                    'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches', 'roofline'):
+            assert key in d, (path, key)
+        assert d['config']['workload'] and 'model' not in d['config']
+        assert set(d['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
+        assert set(d['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
+        assert d['gpu_launches'] > 0 and d['e2e']['h2d_bytes_per_step'] > 0
+        assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+        if d['n_gpus'] == 1:
+            assert set(d['cpu_baseline']) >= {'value', 'unit', 'cores', 'kind', 'sample'}
