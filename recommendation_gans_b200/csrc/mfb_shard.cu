@@ -324,11 +324,18 @@ __global__ void __launch_bounds__(SH_THREADS) k_shard_backward(const int *__rest
       fi.x[k] = __fmul_rn(d, a);         // d/dV[i] contribution: dz * U[u]
     }
   }
-  frag_store<VEC, NIT>(fu, gu, D, lane);
-  frag_store<VEC, NIT>(fi, gi, D, lane);
+  // tail of an exchanged row: [Dp] bias gradient, [Dp+1] 1 = the row carries a gradient, 0 = all-zero row whose values
+  // were not written (the owner then skips it; a row that only receives such entries is not touched at all and
+  // catches up lazily -- identical under the dense-optimiser semantics, and half of the gradient traffic of
+  // adaptive hinge, where only one negative of the whole batch has a gradient)
+  if (!zero) {
+    frag_store<VEC, NIT>(fu, gu, D, lane);
+    frag_store<VEC, NIT>(fi, gi, D, lane);
+  }
   if (lane == 0) {
-    gu[Dp] = d;
-    gi[Dp] = d;
+    const float2 tail = make_float2(d, zero ? 0.f : 1.f);
+    *reinterpret_cast<float2 *>(gu + Dp) = tail;
+    *reinterpret_cast<float2 *>(gi + Dp) = tail;
   }
 }
 
@@ -484,33 +491,47 @@ __global__ void __launch_bounds__(SH_UPD_WARPS * 32) k_shard_update(const ShUpdA
   const long long row = raw.x & ((1u << a.rb) - 1u);
   const TableView &T = ((raw.x >> a.rb) & 1u) ? a.items : a.users;
 
+  // tails first: [Dp] bias gradient, [Dp+1] != 0 when the row's values were written (see k_shard_backward)
+  const float *src0 = a.grecv + (long long)a.svals[q] * a.stride;
+  const float2 tail0 = __ldcg(reinterpret_cast<const float2 *>(src0 + a.Dp));
+  if (whole && run_end == ql + 1 && tail0.y == 0.f) return;   // only a zero-gradient entry: the row is not touched now
+
   RowState<VEC, NIT> r;
   if (whole) row_load<VEC, NIT>(r, T, row, D, lane, adam);
 
   Frag<VEC, NIT> g;
-  float gb;
-  {
-    const float *src = a.grecv + (long long)a.svals[q] * a.stride;
-    frag_load_cg<VEC, NIT>(g, src, D, lane);
-    gb = __ldcg(src + a.Dp);
+  float gb = tail0.x;
+  bool any = tail0.y != 0.f;
+  if (any) {
+    frag_load_cg<VEC, NIT>(g, src0, D, lane);
+  } else {
+#pragma unroll
+    for (int k = 0; k < NIT * VEC; ++k) g.x[k] = 0.f;
   }
   for (int p0 = ql + 1; p0 < run_end; p0 += 2) {   // remaining rows of the run, two in flight, added in order
     const bool has2 = p0 + 1 < run_end;
     const float *s0 = a.grecv + (long long)a.svals[a.base + p0] * a.stride;
     const float *s1 = a.grecv + (long long)a.svals[a.base + (has2 ? p0 + 1 : p0)] * a.stride;
+    const float2 t0 = __ldcg(reinterpret_cast<const float2 *>(s0 + a.Dp));
+    const float2 t1 = __ldcg(reinterpret_cast<const float2 *>(s1 + a.Dp));
+    const bool u0 = t0.y != 0.f, u1 = has2 && t1.y != 0.f;
     Frag<VEC, NIT> o0, o1;
-    frag_load_cg<VEC, NIT>(o0, s0, D, lane);
-    frag_load_cg<VEC, NIT>(o1, s1, D, lane);
-    const float b0 = __ldcg(s0 + a.Dp), b1 = __ldcg(s1 + a.Dp);
+    if (u0) frag_load_cg<VEC, NIT>(o0, s0, D, lane);
+    if (u1) frag_load_cg<VEC, NIT>(o1, s1, D, lane);
+    if (u0) {
 #pragma unroll
-    for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fadd_rn(g.x[k], o0.x[k]);
-    gb = __fadd_rn(gb, b0);
-    if (has2) {
+      for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fadd_rn(g.x[k], o0.x[k]);
+      gb = __fadd_rn(gb, t0.x);
+      any = true;
+    }
+    if (u1) {
 #pragma unroll
       for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fadd_rn(g.x[k], o1.x[k]);
-      gb = __fadd_rn(gb, b1);
+      gb = __fadd_rn(gb, t1.x);
+      any = true;
     }
   }
+  if (whole && !any) return;   // every entry of the row was a zero-gradient one: nothing to apply, `last` stays
 
   if (!whole) {
     const int first_win = fl / SH_WIN, last_win = (seg_end - 1) / SH_WIN;
