@@ -77,9 +77,11 @@ __global__ void __launch_bounds__(RK_THREADS) k_rank_test_items(const long long 
     __syncthreads();
     const float p_a = lane < nt ? tp[lane] : 2.0f, p_b = lane + 32 < nt ? tp[lane + 32] : 2.0f;   // 2 > any probability
     unsigned int gt_a = 0, eq_a = 0, gt_b = 0, eq_b = 0;
-    for (int i = wid; i < I; i += RK_WARPS) {
+    long long cur = r0;                                                  // cursor into the sorted train row
+    for (int i = wid; i < I; i += RK_WARPS) {                            // ascending items: the cursor only advances
       const float p = prob(i);                                           // same value in every lane
-      if (n_train > 0 && in_sorted(train_indices, r0, r1, i)) continue;  // train items rank after every free item
+      while (cur < r1 && train_indices[cur] < i) ++cur;
+      if (cur < r1 && train_indices[cur] == i) continue;                 // train items rank after every free item
       gt_a += p > p_a;
       eq_a += p == p_a;
       gt_b += p > p_b;
