@@ -90,3 +90,31 @@ def test_committed_bench_lines_keep_the_contract():
         assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
         if d['n_gpus'] == 1:
             assert set(d['cpu_baseline']) >= {'value', 'unit', 'cores', 'kind', 'sample'}
+
+
+def test_dropin_packages_fall_through_to_the_reference_checkout():
+    """With the drop-in directory ahead of a reference checkout on sys.path, the modules the drop-in provides win and
+    the rest of the `spotlight` / `utils` packages (what mf_spotlight.py also imports) come from the checkout.  Runs
+    only where the reference is mounted (this container); nothing is read from it on the GPU box."""
+    import os
+    import subprocess
+    import sys
+    import pytest
+    ref = os.environ.get('REF_PATH', '/root/reference')
+    if not os.path.isdir(os.path.join(ref, 'spotlight')):
+        pytest.skip('reference checkout not mounted')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dropin = os.path.join(root, 'recommendation_gans_b200', 'dropin')
+    code = (
+        "import sys, types; sys.modules.setdefault('h5py', types.ModuleType('h5py'))\n"
+        "import spotlight.interactions, spotlight.losses, spotlight.evaluation, implicit, utils.storage_utils\n"
+        "import spotlight.dataset_manilupation as dm, utils.arg_extractor as ax, spotlight.dnn_models.mlp as mlp\n"
+        "print(spotlight.interactions.__file__); print(implicit.__file__); print(dm.__file__); print(ax.__file__)\n"
+        "print(mlp.__file__); print(dm.Interactions is spotlight.interactions.Interactions)\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([dropin, root, ref]))
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, cwd=str(root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].startswith(dropin) and lines[1].startswith(dropin)
+    assert lines[2].startswith(ref) and lines[3].startswith(ref) and lines[4].startswith(ref)
+    assert lines[5] == 'True'          # the reference's module sees the drop-in's Interactions
