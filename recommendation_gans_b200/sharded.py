@@ -155,6 +155,9 @@ class CudaShardBackend(object):
                  betas=(0.5, 0.999), fast_math=None, device=None, seed=0):
         from spotlight.factorization.representations import BilinearNet   # the drop-in (package __init__ put it on sys.path)
         from .engine import MFEngine
+        if min(local_rows(num_users, rank, world), local_rows(num_items, rank, world)) <= 0:
+            raise ValueError('rank %d of %d would own no rows of a %d x %d model: use at most min(users, items) ranks'
+                             % (rank, world, num_users, num_items))
         N.require_cuda()
         self.rank, self.world = int(rank), int(world)
         self.num_users, self.num_items, self.dim = int(num_users), int(num_items), int(dim)

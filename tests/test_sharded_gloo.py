@@ -90,3 +90,8 @@ def test_assemble_inverts_slice():
         assert [p[0].shape[0] for p in parts] == [sharded.local_rows(11, r, world) for r in range(world)]
         for a, b in zip(sharded.assemble_tables(parts, world), full):
             np.testing.assert_array_equal(a, b)
+
+
+def test_more_ranks_than_rows_is_rejected_before_any_cuda_work():
+    with pytest.raises(ValueError):
+        sharded.CudaShardBackend.__init__(object.__new__(sharded.CudaShardBackend), 3, 4, 3, 100, 8)
