@@ -235,9 +235,11 @@ __device__ __forceinline__ void row_replay(RowState<VEC, NIT> &r, int from, int 
       // Zero-gradient steps in fast mode: g = wd*p is folded into the moment updates
       //   m' = (1-w)*m + (w*wd)*p          v' = beta2*v + ((1-beta2)*wd^2 * p) * p
       // (8 packed FP instructions per element pair instead of 10; a few ulps from the IEEE op order, like the MUFU
-      // sqrt/rcp this mode already uses -- the 1e-5 parity tests cover it).  The loop is FP-issue bound: carrying the
-      // reciprocal across steps with Newton updates instead of MUFU.RCP was measured 30% SLOWER on B200, this folding
-      // 8% faster at cfg5 (long replays).
+      // sqrt/rcp this mode already uses -- the 1e-5 parity tests cover it); 8% faster at cfg5 (long replays).
+      // ncu on the cfg5 catch-up kernel: XU (MUFU) pipe 81% busy, FMA pipe 42%, issue 47%.  Trading the MUFU.RCP for a
+      // reciprocal carried from step to step and refined by two Newton updates (4 packed FMAs per pair) was measured
+      // twice on B200 -- with a residual check + MUFU fallback: 30% slower; branch-free from optimiser step 64 on: 12%
+      // slower (results identical to 1e-11) -- so the packed FMA forms are no cheaper than the MUFU they replace.
       const float w = o.lerp_small ? o.lerp_coeff : o.lerp_coeff + 1.0f;      // 1 - beta1
       const float c1 = 1.0f - w, cw = w * o.wd, k3 = (o.one_minus_beta2 * o.wd) * o.wd;
       const f32x2 c1_2 = pack2(c1, c1), cw_2 = pack2(cw, cw), k3_2 = pack2(k3, k3), b2_2 = pack2(o.beta2, o.beta2),
