@@ -9,7 +9,7 @@ exchange protocol is right.  Test helper, not product code."""
 import numpy as np
 import torch
 
-from oracle.mf_oracle import adam_dense_step_numpy, sgd_dense_step_numpy
+from oracle.mf_oracle import adam_dense_step_numpy, rms_dense_step_numpy, sgd_dense_step_numpy
 from recommendation_gans_b200.sharding import shard_range
 
 f32 = np.float32
@@ -162,6 +162,8 @@ class SpecShardBackend(object):
             if self.opt == 'adam':
                 adam_dense_step_numpy(self.tables[k], self.m[k], self.v[k], grads[k], self.t, self.lr,
                                       self.betas[0], self.betas[1], self.eps, self.l2)
+            elif self.opt == 'rms':                   # torch.optim.RMSprop defaults: alpha 0.99, eps 1e-8
+                rms_dense_step_numpy(self.tables[k], self.v[k], grads[k], self.lr, 0.99, 1e-8, self.l2)
             else:
                 sgd_dense_step_numpy(self.tables[k], grads[k], self.lr, self.l2)
 

@@ -58,7 +58,8 @@ def _check(name, results, world):
         assert err < 1e-5 or (i >= 2 and np.abs(t - ref).max() < 2e-2 * c['lr']), (i, err)
 
 
-@pytest.mark.parametrize('name', ['steps_bpr_adam.npz', 'steps_pointwise_adam.npz', 'steps_hinge_sgd.npz'])
+@pytest.mark.parametrize('name', ['steps_bpr_adam.npz', 'steps_pointwise_adam.npz', 'steps_hinge_sgd.npz',
+                                  'steps_pointwise_rms.npz'])
 def test_two_gloo_ranks_match_reference(name, tmp_path):
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
