@@ -130,8 +130,9 @@ int mfb_loss_forward_backward(int loss, const float *d_pos, int64_t n_pos, const
                               float *d_loss, float *d_dpos, float *d_dneg, mfb_stream stream);
 
 /* Function-level forms of the same losses that the model driver never produces: `d_mask` (NULL or n_pos floats;
- * loss*mask summed and divided by mask.sum(), losses.py:51-55,91-95,124-128) and adaptive hinge on 2-D negatives
- * [neg_rows, neg_cols == n_pos] row-major (per-positive maximum over dim 0, first maximal row, losses.py:170).
+ * loss*mask summed and divided by mask.sum(), losses.py:51-55,91-95,124-128) and 2-D negatives
+ * [neg_rows, neg_cols == n_pos] row-major: adaptive hinge takes the per-positive maximum over dim 0 (first maximal row,
+ * losses.py:170); hinge and bpr broadcast the positives over the rows (mean over neg_rows*n_pos entries).
  * neg_rows == 0: 1-D negatives of length neg_cols. */
 int mfb_loss_forward_backward_ex(int loss, const float *d_pos, int64_t n_pos, const float *d_neg, int64_t neg_rows,
                                  int64_t neg_cols, const float *d_mask, float *d_loss, float *d_dpos, float *d_dneg,

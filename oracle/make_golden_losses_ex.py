@@ -29,7 +29,9 @@ def main():
     mask[7] = 1.0
     d.update(pos=pos0, neg1=neg1, neg2=neg2, mask=mask)
     cases = [('pointwise', 'neg1', False), ('pointwise', 'neg1', True), ('bpr', 'neg1', True), ('hinge', 'neg1', True),
-             ('adaptive_hinge', 'neg1', True), ('adaptive_hinge', 'neg2', False), ('adaptive_hinge', 'neg2', True)]
+             ('adaptive_hinge', 'neg1', True), ('adaptive_hinge', 'neg2', False), ('adaptive_hinge', 'neg2', True),
+             # pairwise losses broadcast over the rows of [n, b] negatives (mean over n*b; with a mask: / mask.sum())
+             ('bpr', 'neg2', False), ('bpr', 'neg2', True), ('hinge', 'neg2', False), ('hinge', 'neg2', True)]
     for name, negkey, use_mask in cases:
         pos = torch.from_numpy(pos0.copy()).requires_grad_(True)
         neg = torch.from_numpy(d[negkey].copy()).requires_grad_(True)

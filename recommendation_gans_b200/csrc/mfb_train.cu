@@ -316,8 +316,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_loss(int kind, const float *__
 
 // ---------------------------------------------------------------------------------------
 // k_loss_ex: the function-level forms the model driver never produces (spotlight/losses.py): a `mask` over the b
-// pairs (loss*mask summed, divided by mask.sum(), losses.py:51-55,91-95,124-128) and adaptive hinge on 2-D negatives
-// [n_rows, b] (per-positive maximum over dim 0, first maximal row, losses.py:170).  neg is row-major [n_rows, b];
+// pairs (loss*mask summed, divided by mask.sum(), losses.py:51-55,91-95,124-128) and 2-D negatives [n_rows, b]: adaptive
+// hinge takes the per-positive maximum over dim 0 (first maximal row, losses.py:170), hinge / bpr broadcast.  neg is row-major [n_rows, b];
 // n_rows == 0 means 1-D negatives of length m (adaptive hinge: the global maximum, as k_loss).  One CTA.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LOSS_THREADS) k_loss_ex(int kind, const float *__restrict__ pos, int b,
@@ -385,6 +385,41 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_loss_ex(int kind, const float 
   } else if (adaptive && grad) {
     for (long long j = tid; j < (long long)n_rows * b; j += LOSS_THREADS) dneg[j] = 0.0f;
     __syncthreads();
+  }
+  if (!adaptive && n_rows > 0) {
+    // hinge / bpr broadcast over the rows of [n_rows, b] negatives: loss[r, j] against pos[j]; the reference takes
+    // loss.mean() over n_rows*b entries, or with a mask (loss*mask[b]).sum() / mask.sum() (the mask's own sum)
+    const double denom = mask ? wsum : (double)n_rows * (double)b;
+    const float Wn = (float)denom;
+    double s2 = 0.0;
+    for (int j = tid; j < b; j += LOSS_THREADS) {
+      const float xp = pos[j], w = mask ? mask[j] : 1.0f;
+      const float scale = __fdiv_rn(w, Wn);
+      float dp_acc = 0.f;
+      for (int r = 0; r < n_rows; ++r) {
+        const float xn = neg[(long long)r * b + j];
+        float dp, dn;
+        if (kind == MFB_LOSS_BPR) {
+          const float sg = sigmoidf_acc(xp - xn);
+          s2 += (double)((1.0f - sg) * w);
+          const float g = ((-scale) * (1.0f - sg)) * sg;
+          dp = g;
+          dn = -g;
+        } else {
+          const float d = (xn - xp) + 1.0f;
+          s2 += (double)(fmaxf(d, 0.0f) * w);
+          const float a = (d >= 0.0f) ? scale : 0.0f;
+          dp = -a;
+          dn = a;
+        }
+        dp_acc += dp;
+        if (grad) dneg[(long long)r * b + j] = dn;
+      }
+      if (grad) dpos[j] = dp_acc;
+    }
+    s2 = block_sum(s2, sh);
+    if (tid == 0) *loss_out = (float)(s2 / denom);
+    return;
   }
   double s = 0.0, gsum = 0.0;
   for (int j = tid; j < b; j += LOSS_THREADS) {
@@ -850,8 +885,8 @@ extern "C" int mfb_loss_forward_backward_ex(int loss, const float *d_pos, int64_
   if (!d_pos || !d_loss || n_pos <= 0 || neg_rows < 0 || neg_cols < 0 || (neg_cols > 0 && !d_neg)) return MFB_ERR_INVALID;
   if (loss < MFB_LOSS_POINTWISE || loss > MFB_LOSS_ADAPTIVE_HINGE) return MFB_ERR_INVALID;
   if (neg_cols == 0 && loss != MFB_LOSS_POINTWISE) return MFB_ERR_SHAPE;
-  if (neg_rows > 0 && loss != MFB_LOSS_ADAPTIVE_HINGE) {
-    mfb_set_error("2-D negatives are supported by adaptive_hinge_loss only");
+  if (neg_rows > 0 && loss == MFB_LOSS_POINTWISE) {
+    mfb_set_error("2-D negatives: pointwise_loss flattens its inputs, pass them 1-D");
     return MFB_ERR_UNSUPPORTED;
   }
   const bool pairwise = loss == MFB_LOSS_HINGE || loss == MFB_LOSS_BPR || neg_rows > 0;

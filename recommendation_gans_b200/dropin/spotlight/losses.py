@@ -12,7 +12,8 @@ w.r.t. its prediction tensors exactly like the reference's torch expressions:
 All of them operate on *probabilities* because this fork's BilinearNet.forward ends in a sigmoid
 (SURVEY F1).  Predictions are 1-D tensors, as produced by ImplicitFactorizationModel; with 1-D
 negatives `adaptive_hinge_loss` reduces to a hinge against the single largest negative of the batch
-(SURVEY F2/3.3); with [n, b] negatives it is the upstream per-positive maximum (losses.py:170).  `mask` ([b]) is
+(SURVEY F2/3.3); with [n, b] negatives it is the upstream per-positive maximum (losses.py:170), and hinge / bpr
+broadcast the positives over the n rows like the reference's tensor expressions.  `mask` ([b]) is
 supported as in the reference (loss*mask summed, divided by mask.sum()).  The explicit-feedback losses
 (losses.py:175-250) are outside the accelerated path.
 """
@@ -44,9 +45,9 @@ def _prepare(name, positive_predictions, negative_predictions, mask):
     neg = negative_predictions
     if not pos.is_cuda or (neg is not None and not neg.is_cuda):
         raise RuntimeError('%s: predictions must be CUDA tensors (no CPU path exists)' % name)
-    if pos.dim() != 1 or (neg is not None and neg.dim() > (2 if name == 'adaptive_hinge_loss' else 1)):
+    if pos.dim() != 1 or (neg is not None and neg.dim() > (1 if name == 'pointwise_loss' else 2)):
         raise NotImplementedError('%s: 1-D prediction tensors are supported (as produced by '
-                                  'ImplicitFactorizationModel), plus [n, b] negatives for adaptive_hinge_loss' % name)
+                                  'ImplicitFactorizationModel), plus [n, b] negatives for the pairwise losses' % name)
     if neg is not None and neg.dim() == 0:
         neg = neg.reshape(1)
     return pos, neg

@@ -132,8 +132,10 @@ def test_losses_with_mask_and_2d_negatives_match_reference(golden_dir):
         np.testing.assert_allclose(val.item(), ref.item(), rtol=2e-6)
         np.testing.assert_allclose(pg.grad.cpu().numpy(), pc.grad.numpy(), rtol=2e-6, atol=1e-9)
         np.testing.assert_allclose(ng.grad.cpu().numpy(), nc.grad.numpy(), rtol=2e-6, atol=1e-9)
-    with pytest.raises(NotImplementedError):                   # 2-D negatives elsewhere are outside the path
-        L.hinge_loss(torch.rand(4).cuda(), torch.rand(2, 4).cuda())
+    with pytest.raises(NotImplementedError):                   # pointwise flattens: 2-D negatives are outside the path
+        L.pointwise_loss(torch.rand(4).cuda(), torch.rand(2, 4).cuda())
+    with pytest.raises(RuntimeError):                          # column count must match the positives
+        L.hinge_loss(torch.rand(4).cuda(), torch.rand(2, 5).cuda())
 
 
 def test_forward_matches_reference(golden_dir):
