@@ -9,18 +9,23 @@ interactions + their sampled negative pairs): negative draw (device MT19937, ran
 semantics), forward, loss, backward, dense-semantics Adam -- everything
 ImplicitFactorizationModel.run_train_iteration does (implicit.py:347-364).
 
-  value     device-timed throughput, ids already resident in HBM (CUDA events around K steps)
+  value     device-timed throughput, ids already resident in HBM (CUDA events around K steps);
+            the timed region is repeated and the MEDIAN is reported (min/max under `timing`)
   e2e       same K steps through the host-buffer entry point (pinned HOST ids -> H2D -> steps ->
-            D2H of the per-step losses), wall clock
-  roofline  HBM roofline of the dominant kernel (k_update) and of the whole step
+            D2H of the per-step losses), wall clock, median
+  roofline  HBM roofline of the dominant kernel (k_update); roofline_step: of the whole step
+  eval      cfg4: full-catalog top-k (k=20, train mask), users sharded over the ranks; `e2e` is
+            spotlight.evaluation.precision_recall_score on HOST Interactions (CSR upload, top-k,
+            hits, D2H inside the clock); `cpu_baseline` is the reference's per-user loop
+            (evaluation.py:155-180) on a user sample
+  zipf      the same train/eval measurements with Zipf(1.05) item ids
   cpu_baseline / --impl reference: the oracle port of the reference's torch-CPU step, timed on the
             host cores (the reference itself is pure Python on torch and is not shipped to the GPU box)
 N > 1: training does not shard without changing the math ("replicas only"), so every rank
-trains an independent replica; evaluation shards users across ranks.
+trains an independent replica; evaluation shards users; `sharded_train` row-shards the cfg5 tables.
 """
 import argparse
 import json
-import math
 import os
 import random
 import sys
@@ -44,10 +49,17 @@ WORKLOADS = {
     'cfg1': dict(name='ML-100K-shape implicit MF (943x1682, dim 32), loss=bpr->adaptive_hinge, batch 256, n_neg 1',
                  U=943, I=1682, D=32, B=256, n_neg=1, loss='bpr', lr=1e-3, l2=1e-5, n_train=81000),
 }
+L2_POLICY = 'inputs larger than L2 (tables + Adam state 256 MB, rows gathered at random)'
 
 
 def loss_kind(name):
     return {'pointwise': 'pointwise', 'hinge': 'hinge'}.get(name, 'adaptive_hinge')   # implicit.py:194-199
+
+
+def config_of(w, zipf):
+    """The `config` object: identical in the native and the reference arm."""
+    return {'workload': w['name'], 'items': 'zipf(1.05)' if zipf else 'uniform',
+            'negative_population': w['n_train'], 'l2_policy': L2_POLICY}
 
 
 def algorithmic_bytes_per_interaction(D, n_neg, adam=True):
@@ -119,16 +131,24 @@ def synth_ids(rs, n, hi, zipf):
     return rs.randint(0, hi, n).astype(np.int64)
 
 
+def stats(xs):
+    xs = sorted(float(x) for x in xs)
+    return dict(median=float(np.median(xs)), min=xs[0], max=xs[-1], n=len(xs))
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference step (torch CPU ops, all host threads)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps(w, steps, warmup, seed=0, max_seconds=150.0, pop=1000000):
+def cpu_reference_steps(w, steps, warmup, seed=0, max_seconds=150.0):
+    """run_train_iteration (implicit.py:347-364) as the reference executes it on the CPU: python random.choices over
+    the list of (user, item) tuples (len(neg_examples) == len(train), data_provider.py:81), zip, np.array,
+    from_numpy, two forwards, loss, backward, dense torch.optim.Adam."""
     import torch
     from oracle import mf_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     rs = np.random.RandomState(seed)
     tabs = O.init_tables(w['U'], w['I'], w['D'], torch_seed=0)
-    B, n_neg = w['B'], w['n_neg']
+    B, n_neg, pop = w['B'], w['n_neg'], w['n_train']
     model = O.OracleMF(*tabs, loss=w['loss'], optimizer='adam', lr=w['lr'], l2=w['l2'], batch_size=B,
                        num_negative_samples=n_neg)
     neg_list = list(zip(rs.randint(0, w['U'], pop).tolist(), rs.randint(0, w['I'], pop).tolist()))
@@ -137,8 +157,7 @@ def cpu_reference_steps(w, steps, warmup, seed=0, max_seconds=150.0, pop=1000000
     items = torch.from_numpy(synth_ids(rs, (warmup + steps) * B, w['I'], w['zipf']))
 
     def one(s):
-        # implicit.py:352-354: python random.choices over the tuple list, zip, np.array, from_numpy
-        nu, ni = zip(*rng.choices(neg_list, k=n_neg * B))
+        nu, ni = zip(*rng.choices(neg_list, k=n_neg * B))          # implicit.py:352-354
         nu, ni = torch.from_numpy(np.array(nu)).long(), torch.from_numpy(np.array(ni)).long()
         return model.train_step(users[s * B:(s + 1) * B], items[s * B:(s + 1) * B], nu, ni)
 
@@ -153,81 +172,87 @@ def cpu_reference_steps(w, steps, warmup, seed=0, max_seconds=150.0, pop=1000000
             break
     dt = time.perf_counter() - t0
     return dict(value=done * B / dt, steps=done, seconds=dt, cores=torch.get_num_threads(),
-                sample='%d full minibatch steps (B=%d) of the same workload, negative population %d pairs'
-                       % (done, B, pop))
+                sample='%d full minibatch steps (B=%d) of the same workload after %d warm-up steps, negative '
+                       'population %d pairs' % (done, B, warmup, pop))
+
+
+def cpu_reference_eval(tables, test_csr, train_csr, n_users=200):
+    """precision_recall_score's per-user loop (evaluation.py:155-180: predict -> mask -> argsort -> set
+    intersections) on the first n_users rows, through the oracle's literal restatement (ranking='reference')."""
+    import torch
+    from oracle import mf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = O.OracleMF(*[torch.from_numpy(np.ascontiguousarray(t)) for t in tables])
+    sub_test, sub_train = test_csr[:n_users], train_csr[:n_users]
+    evaluated = int((np.diff(sub_test.indptr) > 0).sum())
+    O.precision_recall_score(model, sub_test[:8], sub_train[:8], k=np.array([5, 10, 20]), ranking='reference')
+    t0 = time.perf_counter()
+    O.precision_recall_score(model, sub_test, sub_train, k=np.array([5, 10, 20]), ranking='reference')
+    dt = time.perf_counter() - t0
+    return dict(value=evaluated / dt, unit='users/s', cores=torch.get_num_threads(), kind='port',
+                sample='%d users with test items (first %d rows), full catalog, train mask, k=[5,10,20]'
+                       % (evaluated, n_users))
 
 
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
-def native_bench(args, w, rank, world):
+class _EvalModel(object):
+    """What spotlight.evaluation needs from a fitted ImplicitFactorizationModel."""
+
+    def __init__(self, net, eng, num_items):
+        self._net, self._engine_, self._num_items = net, eng, num_items
+
+
+def train_measure(args, w, zipf, rank, dev, dist, lib):
+    """K timed steps (device clock, median over repeats), the same steps end to end from pinned host ids, and the
+    per-kernel device times of a profiled pass.  Returns (measurements, net, engine)."""
     import torch
-    import recommendation_gans_b200  # noqa: F401
-    from recommendation_gans_b200 import _native as N
     from recommendation_gans_b200.engine import MFEngine
     from spotlight.factorization.representations import BilinearNet
     import spotlight.optimizers as optimizers
-
-    local_rank = int(os.environ.get('LOCAL_RANK', rank))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO'):
-            os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line
-        dist.init_process_group('nccl', device_id=dev)
-
     K, W = args.steps, args.warmup
     B, n_neg, D = w['B'], w['n_neg'], w['D']
     kind = loss_kind(w['loss'])
+    R = max(args.repeats, 1)
     rs = np.random.RandomState(rank)
     torch.manual_seed(rank)
     net = BilinearNet(w['U'], w['I'], D).cuda()
     opt = optimizers.adam_optimizer(net.parameters(), lr=w['lr'], weight_decay=w['l2'])
     eng = MFEngine(net, opt, fast_math=bool(args.fast_math))
-    lib = N.load_library()
-
-    users_h = synth_ids(rs, (W + K) * B, w['U'], False)
-    items_h = synth_ids(rs, (W + K) * B, w['I'], w['zipf'])
+    n_steps_total = W + K * R
+    users_h = synth_ids(rs, n_steps_total * B, w['U'], False)
+    items_h = synth_ids(rs, n_steps_total * B, w['I'], zipf)
     pop_u = torch.from_numpy(synth_ids(rs, w['n_train'], w['U'], False)).to(dev)
     pop_i = torch.from_numpy(synth_ids(rs, w['n_train'], w['I'], False)).to(dev)
     users_d, items_d = torch.from_numpy(users_h).to(dev), torch.from_numpy(items_h).to(dev)
     rng = random.Random(rank)
-
     eng.rng_seed(rng)
 
     def run(lo, hi):
         # negatives are drawn on the device from the model's MT19937 stream, chunk by chunk (part of the step)
         return eng.train_epoch(kind, users_d[lo * B:hi * B], items_d[lo * B:hi * B], B, n_neg, pop_u, pop_i)
 
-    # ---- warm-up (>= 3 steps), then EXACTLY K timed steps on the device clock; the timed region is
-    # repeated `--repeats` times (fresh K steps each time, training simply continues) and the best is reported
-    run(0, W)
+    run(0, W)                                   # warm-up (>= 3 steps)
     eng.rng_sync(rng)
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(dev.index)
     clocks.start()
-    best_ms, launches, final_loss = None, 0, float('nan')
-    for rep in range(max(args.repeats, 1)):
+    times, launches, final_loss = [], 0, float('nan')
+    for rep in range(R):                        # fresh K steps each time: training simply continues
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
         launches0 = eng.launches + lib.mfb_library_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        losses = run(W, W + K)
+        losses = run(W + rep * K, W + (rep + 1) * K)
         e1.record()
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
-        rep_ms = e0.elapsed_time(e1)
-        if best_ms is None or rep_ms < best_ms:
-            best_ms = rep_ms
-            launches = eng.launches + lib.mfb_library_launches() - launches0
+        times.append(e0.elapsed_time(e1))
+        launches = eng.launches + lib.mfb_library_launches() - launches0
         final_loss = float(losses[-1].item())
-    ms = best_ms
     eng.rng_sync(rng)
     clk = clocks.summary()
 
@@ -238,14 +263,13 @@ def native_bench(args, w, rank, world):
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    e2e_s = None
-    for rep in range(max(args.repeats, 1)):
+    e2e = []
+    for rep in range(R):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         host_losses = eng.train_epoch_host(kind, pu.numpy(), pi.numpy(), B, n_neg, pop_u, pop_i, rng=rng)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e_s = dt if e2e_s is None else min(e2e_s, dt)
+        e2e.append(time.perf_counter() - t0)
         assert np.isfinite(host_losses).all()
 
     # ---- per-kernel device time (separate profiled pass; events bracket every launch)
@@ -254,69 +278,201 @@ def native_bench(args, w, rank, world):
     eng.train_epoch_host(kind, pu.numpy()[:P * B], pi.numpy()[:P * B], B, n_neg, pop_u, pop_i, rng=rng)
     prof = eng.profile_read()
     eng.profile(False)
+    return dict(ms=stats(times), e2e_s=stats(e2e), launches=launches, final_loss=final_loss, clocks=clk, prof=prof,
+                prof_steps=P), net, eng
 
-    # ---- evaluation: full-catalog top-k with train mask, users sharded across ranks
-    ev = eval_bench(eng, w, rank, world, dev, rs)
+
+def eval_measure(args, eng, net, w, zipf, rank, world, dev, dist):
+    """cfg4: precision/recall@k over the users with test items (train mask on), users sharded over the ranks."""
+    import torch
+    import scipy.sparse as sp
+    from recommendation_gans_b200.sharding import shard_range
+    from spotlight.interactions import Interactions
+    from spotlight import evaluation as E
+    U, I = w['U'], w['I']
+    rs = np.random.RandomState(1234)                     # same interactions on every rank
+    n_tr, n_te = 117 * U, 14 * U                          # ML-20M: ~117 train / ~14 test interactions per user
+    train = Interactions(rs.randint(0, U, n_tr).astype(np.int32), synth_ids(rs, n_tr, I, zipf).astype(np.int32),
+                         num_users=U, num_items=I)
+    test = Interactions(rs.randint(0, U, n_te).astype(np.int32), synth_ids(rs, n_te, I, zipf).astype(np.int32),
+                        num_users=U, num_items=I)
+    train_csr, test_csr = train.csr_matrix, test.csr_matrix      # built once by Interactions (interactions.py:115)
+    for c in (train_csr, test_csr):
+        c.sum_duplicates()
+        c.sort_indices()
+    all_users = np.nonzero(np.diff(test_csr.indptr))[0].astype(np.int64)
+    lo, hi = shard_range(len(all_users), rank, world)
+    indptr = torch.from_numpy(train_csr.indptr.astype(np.int64)).to(dev)
+    indices = torch.from_numpy(train_csr.indices.astype(np.int32)).to(dev)
+    users = torch.from_numpy(all_users[lo:hi]).to(dev)
+    eng.topk(users, 20, indptr, indices)                 # warm-up pass (also brings the clocks back up)
+    times = []
+    for rep in range(max(args.repeats, 1)):
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.topk(users, 20, indptr, indices)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) / 1e3)
+    redo = eng.topk_last_redo
+    # end to end through the reference-facing call on HOST Interactions: CSR upload, top-k, hit counts, D2H
+    model = _EvalModel(net, eng, I)
+    fn = E.precision_recall_score_sharded if world > 1 else E.precision_recall_score
+    ks = np.array([5, 10, 20])
+    e2e, pr = [], None
+    devnull = open(os.devnull, 'w')
+    for rep in range(1 + max(args.repeats // 2, 3)):
+        for c in (train_csr, test_csr):                  # drop the device copies: the upload is part of the call
+            if hasattr(c, '_mfb_device'):
+                del c._mfb_device
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        so, sys.stdout = sys.stdout, devnull             # the reference prints "Cold start users"
+        try:
+            pr = fn(model, test, train=train, k=ks)
+        finally:
+            sys.stdout = so
+        torch.cuda.synchronize()
+        if rep:                                          # first call warms the allocator
+            e2e.append(time.perf_counter() - t0)
+    kern = ('k_tc_gemm (TMA + tcgen05 bf16, TMEM accumulators) + exact fp32 re-score; %d users redone by k_topk_exact'
+            % redo if os.environ.get('MFB_TC', '1') != '0' else 'k_topk_exact (fp32 CUDA cores)')
+    h2d = (train_csr.indptr.size + test_csr.indptr.size) * 8 + (train_csr.nnz + test_csr.nnz) * 4 + (hi - lo) * 8
+    out = dict(seconds=stats(times), users=hi - lo, users_total=len(all_users), kernel=kern, e2e_s=stats(e2e),
+               precision_recall=[float(pr[0]), float(pr[1])], h2d_bytes=int(h2d), d2h_bytes=int((hi - lo) * 4 * 4))
+    return out, (train_csr, test_csr)
+
+
+def reduce_max(dist, dev, values):
+    import torch
+    if not dist:
+        return [float(v) for v in values]
+    t = torch.tensor(list(values), device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def reduce_sum(dist, dev, values):
+    import torch
+    if not dist:
+        return [float(v) for v in values]
+    t = torch.tensor(list(values), device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t.tolist()]
+
+
+def native_bench(args, w, rank, world):
+    import torch
+    import recommendation_gans_b200  # noqa: F401
+    from recommendation_gans_b200 import _native as N
+
+    local_rank = int(os.environ.get('LOCAL_RANK', rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    lib = N.load_library()
+    K, W = args.steps, args.warmup
+    B, n_neg, D = w['B'], w['n_neg'], w['D']
+    peaks = measured_peaks()
+    alg_b = algorithmic_bytes_per_interaction(D, n_neg)
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('k_update_dram_bytes_per_launch')
+
+    def one_distribution(zipf, with_cpu):
+        tm, net, eng = train_measure(args, w, zipf, rank, dev, dist, lib)
+        ev, csrs = eval_measure(args, eng, net, w, zipf, rank, world, dev, dist)
+        t_train, t_train_min, t_train_max, t_e2e, t_eval, t_eval_e2e = reduce_max(
+            dist, dev, [tm['ms']['median'] / 1e3, tm['ms']['min'] / 1e3, tm['ms']['max'] / 1e3, tm['e2e_s']['median'],
+                        ev['seconds']['median'], ev['e2e_s']['median']])
+        n_eval, launches = [int(x) for x in reduce_sum(dist, dev, [ev['users'], tm['launches']])]
+        prof, P = tm['prof'], tm['prof_steps']
+        upd_ms, upd_n = prof.get('update', (0.0, 1))
+        upd_us = upd_ms * 1e3 / max(upd_n, 1)
+        upd_bytes = (alg_b - 16) * B                  # every row's p,m,v read + p,m,v write happens in k_update
+        step_bytes = alg_b * B
+        flops = 2.0 * n_eval * w['I'] * D
+        res = {
+            'value': world * K * B / t_train, 'ms_per_step': t_train * 1e3 / K,
+            'timing': {'statistic': 'median of %d timed regions of K steps each (max over ranks)' % tm['ms']['n'],
+                       'ms_per_step_min': t_train_min * 1e3 / K, 'ms_per_step_max': t_train_max * 1e3 / K},
+            'clocks': tm['clocks'], 'final_loss': tm['final_loss'],
+            'e2e': {'value': world * K * B / t_e2e, 'unit': 'interactions/s', 'h2d_bytes_per_step': 16 * B,
+                    'd2h_bytes_per_step': 4},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'hbm', 'kernel': 'k_update',
+                         'achieved': upd_bytes / (upd_us * 1e-6) / 1e9 if upd_us else None,
+                         'peak': peaks['hbm_gbs'], 'peak_source': peaks['source'], 'unit': 'GB/s',
+                         'frac': (upd_bytes / (upd_us * 1e-6) / 1e9 / peaks['hbm_gbs']) if upd_us else None,
+                         'traffic': traffic, 'us_per_launch': upd_us, 'algorithmic_bytes_per_launch': upd_bytes},
+            'roofline_step': {'bound': 'hbm', 'achieved': step_bytes / (t_train / K) / 1e9, 'peak': peaks['hbm_gbs'],
+                              'unit': 'GB/s', 'frac': step_bytes / (t_train / K) / 1e9 / peaks['hbm_gbs'],
+                              'algorithmic_bytes_per_step': step_bytes},
+            'kernel_us_per_step': {k: v[0] * 1e3 / P for k, v in prof.items()},
+            'eval': {'metric': 'top-k eval users/s (k=20, train mask, full catalog)', 'value': n_eval / t_eval,
+                     'unit': 'users/s', 'users': n_eval, 'seconds': t_eval,
+                     'timing': {'statistic': 'median of %d passes' % ev['seconds']['n'],
+                                'seconds_min': ev['seconds']['min'], 'seconds_max': ev['seconds']['max']},
+                     'kernel': ev['kernel'],
+                     'e2e': {'value': ev['users_total'] / t_eval_e2e, 'unit': 'users/s', 'seconds': t_eval_e2e,
+                             'call': 'spotlight.evaluation.precision_recall_score%s(model, test, train, k=[5,10,20]) '
+                                     'from host Interactions' % ('_sharded' if world > 1 else ''),
+                             'h2d_bytes_per_step': ev['h2d_bytes'], 'd2h_bytes_per_step': ev['d2h_bytes'],
+                             'precision_recall': ev['precision_recall']},
+                     'roofline': {'bound': 'tensor', 'achieved': flops / t_eval / 1e12,
+                                  'peak': peaks['bf16_tflops'] * world, 'unit': 'TFLOP/s',
+                                  'frac': flops / t_eval / 1e12 / (peaks['bf16_tflops'] * world)}},
+        }
+        if with_cpu and rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from tests.gpu_helpers import tables_of
+            eng.flush()
+            res['eval']['cpu_baseline'] = cpu_reference_eval(tables_of(net), csrs[1], csrs[0], n_users=args.cpu_eval_users)
+        eng.close()
+        del eng, net
+        torch.cuda.empty_cache()
+        return res
+
+    main = one_distribution(w['zipf'], True)
+    twin = None if args.no_twin else one_distribution(not w['zipf'], False)
 
     # ---- cfg5: scaled catalog, tables row-sharded over the ranks (all-to-all of rows over NVLink); strong scaling
     sh = None
     if not args.no_sharded:
         from tools.shard_bench import run as shard_run
-        sh = shard_run(steps=args.sharded_steps, warmup=64, zipf=w['zipf'], fast_math=bool(args.fast_math))
-
-    # ---- reduce over ranks: max time, summed work
-    t_train, t_e2e, t_eval, n_eval = ms / 1e3, e2e_s, ev['seconds'], ev['users']
-    if dist:
-        t = torch.tensor([t_train, t_e2e, t_eval], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_train, t_e2e, t_eval = [float(x) for x in t.tolist()]
-        c = torch.tensor([n_eval, launches], device=dev, dtype=torch.float64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        n_eval, launches = int(c[0].item()), int(c[1].item())
+        sh = shard_run(steps=args.sharded_steps, warmup=args.sharded_warmup, zipf=w['zipf'],
+                       fast_math=bool(args.fast_math))
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return None
 
-    peaks = measured_peaks()
-    alg_b = algorithmic_bytes_per_interaction(D, n_neg)
-    step_bytes = alg_b * B
-    value = world * K * B / t_train
-    upd_ms, upd_n = prof.get('update', (0.0, 1))
-    upd_us = upd_ms * 1e3 / max(upd_n, 1)
-    upd_bytes = (alg_b - 16) * B                      # every row's p,m,v read + p,m,v write happens in k_update
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('k_update_dram_bytes_per_launch')
     out = {
-        'metric': 'train interactions/s (ML-20M-shape BPR MF)', 'value': value, 'unit': 'interactions/s',
-        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': t_train * 1e3 / K, 'higher_is_better': True,
+        'metric': 'train interactions/s (ML-20M-shape BPR MF)', 'value': main['value'], 'unit': 'interactions/s',
+        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': main['ms_per_step'], 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': w['name'], 'items': 'zipf(1.05)' if w['zipf'] else 'uniform',
-                   'parallelism': 'replicas x%d (training does not shard; eval shards users)' % world,
-                   'optimizer_math': 'fast (MUFU sqrt/rcp, ftz)' if args.fast_math else 'ieee',
-                   'l2_policy': 'inputs larger than L2 (tables + Adam state 256 MB, rows gathered at random)',
-                   'negative_population': w['n_train'], 'final_loss': final_loss,
-                   'repeats': 'best of %d timed regions of K steps each' % max(args.repeats, 1)},
-        'clocks': clk,
-        'e2e': {'value': world * K * B / t_e2e, 'unit': 'interactions/s', 'h2d_bytes_per_step': 16 * B,
-                'd2h_bytes_per_step': 4},
-        'gpu_launches': launches,
-        'roofline': {'bound': 'hbm', 'kernel': 'k_update', 'achieved': upd_bytes / (upd_us * 1e-6) / 1e9 if upd_us else None,
-                     'peak': peaks['hbm_gbs'], 'peak_source': peaks['source'], 'unit': 'GB/s',
-                     'frac': (upd_bytes / (upd_us * 1e-6) / 1e9 / peaks['hbm_gbs']) if upd_us else None,
-                     'traffic': traffic, 'us_per_launch': upd_us, 'algorithmic_bytes_per_launch': upd_bytes},
-        'roofline_step': {'bound': 'hbm', 'achieved': step_bytes / (t_train / K) / 1e9, 'peak': peaks['hbm_gbs'],
-                          'unit': 'GB/s', 'frac': step_bytes / (t_train / K) / 1e9 / peaks['hbm_gbs'],
-                          'algorithmic_bytes_per_step': step_bytes},
-        'kernel_us_per_step': {k: v[0] * 1e3 / P for k, v in prof.items()},
-        'eval': {'metric': 'top-k eval users/s (k=20, train mask, full catalog)', 'value': n_eval / t_eval,
-                 'unit': 'users/s', 'users': n_eval, 'seconds': t_eval, 'kernel': ev['kernel'],
-                 'roofline': {'bound': 'tensor', 'achieved': 2.0 * n_eval * w['I'] * D / t_eval / 1e12,
-                              'peak': peaks['bf16_tflops'] * world, 'unit': 'TFLOP/s',
-                              'frac': 2.0 * n_eval * w['I'] * D / t_eval / 1e12 / (peaks['bf16_tflops'] * world)}},
+        'config': config_of(w, w['zipf']),
+        'run': {'parallelism': 'replicas x%d (training does not shard; eval shards users)' % world,
+                'optimizer_math': 'fast (MUFU sqrt/rcp, ftz)' if args.fast_math else 'ieee',
+                'final_loss': main['final_loss']},
     }
+    for key in ('timing', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'roofline_step', 'kernel_us_per_step', 'eval'):
+        out[key] = main[key]
+    if twin is not None:
+        name = 'uniform' if w['zipf'] else 'zipf'
+        out[name] = {k: twin[k] for k in ('value', 'ms_per_step', 'timing', 'e2e', 'roofline', 'roofline_step',
+                                          'kernel_us_per_step', 'eval')}
+        out[name]['items'] = 'uniform' if w['zipf'] else 'zipf(1.05)'
     if sh is not None:
         sh['roofline'] = {'bound': 'hbm', 'achieved': sh['hbm_gbs_algorithmic_total'], 'peak': peaks['hbm_gbs'] * world,
                           'unit': 'GB/s', 'frac': sh['hbm_gbs_algorithmic_total'] / (peaks['hbm_gbs'] * world),
@@ -324,7 +480,7 @@ def native_bench(args, w, rank, world):
                                   'dense-optimiser replay arithmetic (MUFU), see DESIGN.md'}
         out['sharded_train'] = sh
     if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_steps(w, steps=args.cpu_steps, warmup=1)
+        cb = cpu_reference_steps(w, steps=args.cpu_steps, warmup=max(min(W, 5), 1))
         out['cpu_baseline'] = {'value': cb['value'], 'unit': 'interactions/s', 'cores': cb['cores'], 'kind': 'port',
                                'sample': cb['sample']}
     if dist:
@@ -332,53 +488,25 @@ def native_bench(args, w, rank, world):
     return out
 
 
-def eval_bench(eng, w, rank, world, dev, rs):
-    """cfg4: precision/recall top-k pass over the rank's shard of users (train mask on)."""
-    import torch
-    U, I = w['U'], w['I']
-    from recommendation_gans_b200.sharding import shard_range
-    lo, hi = shard_range(U, rank, world)
-    n_tr = 117 * (hi - lo)                          # ML-20M: ~117 train interactions per user
-    tu = np.sort(rs.randint(lo, hi, n_tr))
-    ti = rs.randint(0, I, n_tr)
-    import scipy.sparse as sp
-    csr = sp.coo_matrix((np.ones(n_tr), (tu, ti)), shape=(U, I)).tocsr()
-    csr.sum_duplicates()
-    csr.sort_indices()
-    indptr = torch.from_numpy(csr.indptr.astype(np.int64)).to(dev)
-    indices = torch.from_numpy(csr.indices.astype(np.int32)).to(dev)
-    users = torch.arange(lo, hi, device=dev, dtype=torch.int64)
-    eng.topk(users, 20, indptr, indices)           # warm-up pass (also brings the clocks back up)
-    best = None
-    for rep in range(3):
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        eng.topk(users, 20, indptr, indices)
-        e1.record()
-        torch.cuda.synchronize()
-        t = e0.elapsed_time(e1) / 1e3
-        best = t if best is None else min(best, t)
-    redo = eng.topk_last_redo
-    kern = ('k_tc_gemm (TMA + tcgen05 bf16, TMEM accumulators) + exact fp32 re-score; %d users redone by k_topk_exact' % redo
-            if os.environ.get('MFB_TC', '1') != '0' else 'k_topk_exact (fp32 CUDA cores)')
-    return dict(seconds=best, users=hi - lo, kernel=kern)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=1978)      # one ML-20M epoch: ceil(16.2M / 8192)
+    ap.add_argument('--steps', type=int, default=494)       # a quarter of an ML-20M epoch (ceil(16.2M / 8192) = 1978)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
     ap.add_argument('--items', default='uniform', choices=['uniform', 'zipf'])
     ap.add_argument('--fast-math', type=int, default=1)
     ap.add_argument('--cpu-steps', type=int, default=120)
-    ap.add_argument('--repeats', type=int, default=3, help='timed region repeated; best reported')
+    ap.add_argument('--cpu-eval-users', type=int, default=300)
+    ap.add_argument('--repeats', type=int, default=11, help='timed regions per measurement; the median is reported')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-twin', action='store_true', help='skip the second item-id distribution')
     ap.add_argument('--no-sharded', action='store_true', help='skip the cfg5 row-sharded training object')
-    ap.add_argument('--sharded-steps', type=int, default=96)
+    ap.add_argument('--sharded-steps', type=int, default=128)
+    ap.add_argument('--sharded-warmup', type=int, default=512,
+                    help='optimiser steps before the cfg5 timed region (the lazy replay length grows until every '
+                         'row has been touched once: steady state needs a few hundred steps)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = dict(WORKLOADS[args.workload])
@@ -389,12 +517,12 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        cb = cpu_reference_steps(w, steps=args.steps, warmup=min(args.warmup, 3))
+        cb = cpu_reference_steps(w, steps=args.steps, warmup=args.warmup)
         line = {'impl': 'reference', 'metric': 'train interactions/s (ML-20M-shape BPR MF)', 'value': cb['value'],
-                'unit': 'interactions/s', 'n_gpus': args.gpus, 'steps': cb['steps'], 'warmup': min(args.warmup, 3),
+                'unit': 'interactions/s', 'n_gpus': args.gpus, 'steps': cb['steps'], 'warmup': args.warmup,
                 'ms_per_step': cb['seconds'] * 1e3 / max(cb['steps'], 1), 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': w['name'], 'items': 'zipf(1.05)' if w['zipf'] else 'uniform'},
+                'config': config_of(w, w['zipf']),
                 'cpu_baseline': {'value': cb['value'], 'unit': 'interactions/s', 'cores': cb['cores'], 'kind': 'port',
                                  'sample': cb['sample']},
                 'e2e': {'value': cb['value'], 'unit': 'interactions/s', 'h2d_bytes_per_step': 0,

@@ -338,3 +338,42 @@ def precision_recall_score(model, test_csr, train_csr=None, k=10, ranking='stabl
     precision = np.array(precision).squeeze()
     recall = np.array(recall).squeeze()
     return float(np.mean(precision)), float(np.mean(recall)), cold, per_user_topk
+
+
+def apk(actual, predicted, k=10):
+    """evaluation.py:278-310: average precision at k; a target array without any non-zero id scores 0.0."""
+    predicted = predicted[:k] if len(predicted) > k else predicted
+    score, num_hits = 0.0, 0.0
+    actual_set = set(int(a) for a in actual)
+    seen = set()
+    for i, p in enumerate(predicted):
+        p = int(p)
+        if p in actual_set and p not in seen:
+            num_hits += 1.0
+            score += num_hits / (i + 1.0)
+        seen.add(p)
+    if not np.asarray(actual).any():
+        return 0.0
+    return score / min(len(actual), k)
+
+
+def map_at_k(model, test_csr, k=5, ranking='stable_logit'):
+    """evaluation.py:334-353: mean over users with test items of apk(targets, argsort(-predict(user)), k); no train
+    mask.  ranking='reference' sorts the sigmoid outputs like the reference, 'stable_logit' is the tie-defined order."""
+    vals = []
+    for user_id in range(test_csr.shape[0]):
+        row = test_csr[user_id]
+        if not len(row.indices):
+            continue
+        if ranking == 'reference':
+            order = (-model.predict(user_id)).argsort()
+        else:
+            order = topk_stable(model.logits(user_id), None, k)
+        vals.append(apk(row.indices, order, k=k))
+    return float(np.mean(np.array(vals).squeeze()))
+
+
+def rmse_score(model, user_ids, item_ids):
+    """evaluation.py:187-190: sum over the batch of (1 - prediction)^2 (model.test logs sqrt(sum / n) as "BCE")."""
+    pred = model.predict(np.asarray(user_ids), np.asarray(item_ids))
+    return float(np.sum((1 - pred) ** 2))

@@ -114,7 +114,13 @@ class ImplicitFactorizationModel(object):
 
     def _initialize(self, interactions):
         (self._num_users, self._num_items) = (interactions.num_users, interactions.num_items)
-        if self._representation is not None:
+        if self._net is not None:
+            # A later fit() call: keep training the network the previous call left (best_model, implicit.py:338) with
+            # a fresh optimiser and engine bound to ITS parameters.  (The reference skips _initialize here and keeps
+            # stepping an optimiser that still points at the pre-deepcopy parameters, so its second fit() trains
+            # nothing; resuming from the kept weights is what its docstring promises.)
+            self._net = self._bind(self._net)
+        elif self._representation is not None:
             self._net = self._bind(self._representation)
         else:
             self._net = self._bind(BilinearNet(self._num_users, self._num_items, self._embedding_dim,

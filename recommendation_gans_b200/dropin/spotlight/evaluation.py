@@ -21,13 +21,55 @@ def _native_engine(model):
     return eng if eng is not None else net._engine()
 
 
+def _host_csr(interactions):
+    """The CSR form of an Interactions object (or a scipy matrix).  Interactions builds it once at construction
+    (interactions.py:115, `csr_matrix`); that cached matrix is used when it still describes the id arrays."""
+    cached = getattr(interactions, 'csr_matrix', None)
+    if cached is not None and hasattr(interactions, 'user_ids') and cached.shape == (interactions.num_users,
+                                                                                    interactions.num_items):
+        return cached
+    return interactions.tocsr()
+
+
 def _csr_to_device(csr, device):
+    """(indptr int64, indices int32) of a CSR matrix on `device`; the copy is kept on the matrix object so the
+    several metric passes of model.test() (implicit.py:428-460) upload a set of interactions once."""
     csr = csr.tocsr()
-    csr.sum_duplicates()
-    csr.sort_indices()
-    indptr = torch.from_numpy(csr.indptr.astype(np.int64)).to(device)
-    indices = torch.from_numpy(csr.indices.astype(np.int32)).to(device)
+    cache = getattr(csr, '_mfb_device', None)
+    if cache is not None and cache[0] == str(device) and cache[1] == csr.nnz:
+        return cache[2], cache[3]
+    if not csr.has_canonical_format:
+        csr.sum_duplicates()
+    if not csr.has_sorted_indices:
+        csr.sort_indices()
+    indptr = torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(device)
+    indices = torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(device)
+    try:
+        csr._mfb_device = (str(device), csr.nnz, indptr, indices)
+    except AttributeError:
+        pass
     return indptr, indices
+
+
+def _check_against_model(eng, test_csr, train_csr=None):
+    """What model.predict's _check_input (implicit.py:215-236) enforces inside the reference's per-user loop: ids beyond
+    the model's tables raise ValueError instead of reading out of bounds."""
+    if test_csr.shape[0] > eng.num_users and np.diff(test_csr.indptr)[eng.num_users:].any():
+        raise ValueError('Maximum user id greater than number of users in model.')
+    for name, csr in (('test', test_csr), ('train', train_csr)):
+        if csr is None:
+            continue
+        if csr.nnz and int(csr.indices.max()) >= eng.num_items:
+            raise ValueError('Maximum item id greater than number of items in model.')
+    if train_csr is not None and train_csr.shape[0] < min(test_csr.shape[0], eng.num_users):
+        # the reference indexes train[user_id] for every evaluated user (evaluation.py:162)
+        raise IndexError('row index (%d) out of range' % train_csr.shape[0])
+
+
+def _eval_users(eng, test_csr):
+    """Users with at least one test interaction (evaluation.py:157), as ids into the model's tables."""
+    row_len = np.diff(test_csr.indptr)
+    return np.nonzero(row_len[:eng.num_users])[0].astype(np.int64)
 
 
 def _get_precision_recall(predictions, targets, k):
@@ -37,25 +79,48 @@ def _get_precision_recall(predictions, targets, k):
     return float(num_hit) / k, float(num_hit) / len(targets)
 
 
+def _hits_at(eng, topk, d_users, t_indptr, t_indices, cutoffs):
+    """hits[u, j] = |top-cutoffs[j] of user u  intersected with its test items| and the users' target counts.  A cut-off
+    beyond the catalogue size sees the whole catalogue (the reference slices predictions[:k] of a num_items-long
+    ranking, evaluation.py:110); the kernel takes up to 4 ascending cut-offs per call."""
+    width = topk.shape[1]
+    clamped = np.minimum(np.asarray(cutoffs, dtype=np.int64), width)
+    uniq = np.unique(clamped)
+    hits = np.zeros((topk.shape[0], len(uniq)), dtype=np.int64)
+    ntargets = None
+    for c0 in range(0, len(uniq), 4):
+        chunk = uniq[c0:c0 + 4]
+        h, nt = eng.topk_hits(topk, d_users, t_indptr, t_indices, chunk)
+        hits[:, c0:c0 + len(chunk)] = h.cpu().numpy()
+        ntargets = nt.cpu().numpy()
+    col = {int(kk): j for j, kk in enumerate(uniq)}
+    return hits[:, [col[int(c)] for c in clamped]], ntargets
+
+
 def topk_for_users(model, user_ids, k, train=None):
     """Top-k item ids (best first) for each listed user; train items rank last when `train` is given."""
     eng = _native_engine(model)
     indptr = indices = None
     if train is not None:
-        indptr, indices = _csr_to_device(train.tocsr(), eng.device)
+        train_csr = _host_csr(train)
+        user_arr = np.asarray(user_ids, dtype=np.int64).reshape(-1)
+        if len(user_arr) and (int(user_arr.max()) >= min(eng.num_users, train_csr.shape[0]) or int(user_arr.min()) < 0):
+            raise ValueError('Maximum user id greater than number of users in model.')
+        if train_csr.nnz and int(train_csr.indices.max()) >= eng.num_items:
+            raise ValueError('Maximum item id greater than number of items in model.')
+        indptr, indices = _csr_to_device(train_csr, eng.device)
     return eng.topk(np.asarray(user_ids, dtype=np.int64), int(k), indptr, indices)
 
 
 def precision_recall_score(model, test, train=None, k=10):
     eng = _native_engine(model)
-    test_csr = test.tocsr()
-    train_csr = train.tocsr() if train is not None else None
+    test_csr = _host_csr(test)
+    train_csr = _host_csr(train) if train is not None else None
+    _check_against_model(eng, test_csr, train_csr)
     ks = np.array([k]) if np.isscalar(k) else np.asarray(k)
-    order = np.argsort(ks, kind='stable')
     ks_sorted = np.unique(ks)
     kmax = int(ks_sorted[-1])
-    row_len = np.diff(test_csr.indptr)
-    user_ids = np.nonzero(row_len)[0].astype(np.int64)       # users with >= 1 test item (evaluation.py:157)
+    user_ids = _eval_users(eng, test_csr)                    # users with >= 1 test item (evaluation.py:157)
     cold_start_users = 0
     if train_csr is not None:
         cold_start_users = int((np.diff(train_csr.indptr)[user_ids] == 0).sum())
@@ -67,19 +132,10 @@ def precision_recall_score(model, test, train=None, k=10):
     if train_csr is not None:
         m_indptr, m_indices = _csr_to_device(train_csr, eng.device)
     d_users = torch.from_numpy(user_ids).to(eng.device)
-    topk = eng.topk(d_users, kmax, m_indptr, m_indices)
-    hits = np.zeros((len(user_ids), len(ks_sorted)), dtype=np.int64)
-    ntargets = None
-    for c0 in range(0, len(ks_sorted), 4):                    # the hit kernel takes <= 4 cut-offs per call
-        chunk = ks_sorted[c0:c0 + 4]
-        h, nt = eng.topk_hits(topk, d_users, t_indptr, t_indices, chunk)
-        hits[:, c0:c0 + len(chunk)] = h.cpu().numpy()
-        ntargets = nt.cpu().numpy()
-    col = {int(kk): j for j, kk in enumerate(ks_sorted)}
-    cols = [col[int(kk)] for kk in ks]
-    precision = hits[:, cols].astype(np.float64) / ks.astype(np.float64)[None, :]
-    recall = hits[:, cols].astype(np.float64) / ntargets.astype(np.float64)[:, None]
-    del order
+    topk = eng.topk(d_users, min(kmax, eng.num_items), m_indptr, m_indices)
+    hits, ntargets = _hits_at(eng, topk, d_users, t_indptr, t_indices, ks)
+    precision = hits.astype(np.float64) / ks.astype(np.float64)[None, :]
+    recall = hits.astype(np.float64) / ntargets.astype(np.float64)[:, None]
     print("Cold start users: ", cold_start_users)
     return np.mean(precision.squeeze()), np.mean(recall.squeeze())
 
@@ -91,11 +147,12 @@ def precision_recall_score_sharded(model, test, train=None, k=10):
     import torch.distributed as dist
     from recommendation_gans_b200.sharding import allreduce_precision_recall, shard_range
     eng = _native_engine(model)
-    test_csr = test.tocsr()
-    train_csr = train.tocsr() if train is not None else None
+    test_csr = _host_csr(test)
+    train_csr = _host_csr(train) if train is not None else None
+    _check_against_model(eng, test_csr, train_csr)
     ks = np.array([k]) if np.isscalar(k) else np.asarray(k)
     ks_sorted = np.unique(ks)
-    all_users = np.nonzero(np.diff(test_csr.indptr))[0].astype(np.int64)
+    all_users = _eval_users(eng, test_csr)
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = shard_range(len(all_users), rank, world)
@@ -104,19 +161,13 @@ def precision_recall_score_sharded(model, test, train=None, k=10):
     m_indptr = m_indices = None
     if train_csr is not None:
         m_indptr, m_indices = _csr_to_device(train_csr, eng.device)
-    hits = np.zeros((len(user_ids), len(ks_sorted)), dtype=np.int64)
+    hits = np.zeros((len(user_ids), len(ks)), dtype=np.int64)
     ntargets = np.zeros(len(user_ids), dtype=np.int64)
     if len(user_ids):
         d_users = torch.from_numpy(user_ids).to(eng.device)
-        topk = eng.topk(d_users, int(ks_sorted[-1]), m_indptr, m_indices)
-        for c0 in range(0, len(ks_sorted), 4):
-            chunk = ks_sorted[c0:c0 + 4]
-            h, nt = eng.topk_hits(topk, d_users, t_indptr, t_indices, chunk)
-            hits[:, c0:c0 + len(chunk)] = h.cpu().numpy()
-            ntargets = nt.cpu().numpy()
-    col = {int(kk): j for j, kk in enumerate(ks_sorted)}
-    cols = [col[int(kk)] for kk in ks]
-    prec, rec, _ = allreduce_precision_recall(hits[:, cols], ntargets, ks, dist=dist if world > 1 else None,
+        topk = eng.topk(d_users, min(int(ks_sorted[-1]), eng.num_items), m_indptr, m_indices)
+        hits, ntargets = _hits_at(eng, topk, d_users, t_indptr, t_indices, ks)
+    prec, rec, _ = allreduce_precision_recall(hits, ntargets, ks, dist=dist if world > 1 else None,
                                               device=eng.device if (world > 1 and dist.get_backend() == 'nccl') else None)
     return float(np.mean(prec)), float(np.mean(rec))
 
@@ -145,8 +196,9 @@ def map_at_k(model, test, k=5):
     apk normalised by min(len(targets), k); a user whose only target is item 0 scores 0.0, as in the
     reference's `if not actual.any()` check (evaluation.py:308-309)."""
     eng = _native_engine(model)
-    test_csr = test.tocsr()
-    user_ids = np.nonzero(np.diff(test_csr.indptr))[0].astype(np.int64)
+    test_csr = _host_csr(test)
+    _check_against_model(eng, test_csr)
+    user_ids = _eval_users(eng, test_csr)
     if len(user_ids) == 0:
         return np.mean(np.array([]))
     t_indptr, t_indices = _csr_to_device(test_csr, eng.device)
@@ -168,14 +220,17 @@ def mrr_score(model, test, train=None):
     -model.predict(user) with the user's train items forced last, average ranks for ties (scipy.stats.rankdata).  One
     kernel compares every item's probability with the user's test-item probabilities; no score vector, no sort."""
     eng = _native_engine(model)
-    test_csr = test.tocsr()
-    user_ids = np.nonzero(np.diff(test_csr.indptr))[0].astype(np.int64)
+    test_csr = _host_csr(test)
+    _check_against_model(eng, test_csr)
+    user_ids = _eval_users(eng, test_csr)
     if len(user_ids) == 0:
         return np.array([])
     t_indptr, t_indices = _csr_to_device(test_csr, eng.device)
     r_indptr = r_indices = None
     if train is not None:
-        r_indptr, r_indices = _csr_to_device(train, eng.device)
+        train_csr = _host_csr(train)
+        _check_against_model(eng, test_csr, train_csr)
+        r_indptr, r_indices = _csr_to_device(train_csr, eng.device)
     ranks = eng.rank_test_items(torch.from_numpy(user_ids).to(eng.device), t_indptr, t_indices, r_indptr,
                                 r_indices).cpu().numpy().astype(np.float64)
     indptr = t_indptr.cpu().numpy()
@@ -188,8 +243,9 @@ def hit_ratio(model, test, k=10):
     (leave-one-out, its intended use) that is membership; with exactly k targets numpy compares position by position;
     any other count makes numpy raise ValueError -- reproduced here."""
     eng = _native_engine(model)
-    test_csr = test.tocsr()
-    user_ids = np.nonzero(np.diff(test_csr.indptr))[0].astype(np.int64)
+    test_csr = _host_csr(test)
+    _check_against_model(eng, test_csr)
+    user_ids = _eval_users(eng, test_csr)
     if len(user_ids) == 0:
         raise ZeroDivisionError('division by zero')            # num_hits / num_users with no test users
     kk = min(int(k), eng.num_items)

@@ -274,3 +274,28 @@ def test_mrr_score_matches_reference_loop(with_train):
     got = mrr_score(_Model(), test, train=train)
     assert got.shape == (len(expect),)
     np.testing.assert_allclose(got, expect, rtol=1e-4)
+
+
+@pytest.mark.parametrize('name', ['fit_pointwise', 'fit_bpr'])
+def test_map_at_k_and_bce_match_reference(golden_dir, name, tmp_path, monkeypatch):
+    """map_at_k (evaluation.py:334-353) and the "BCE" figure of model.test (rmse_score, evaluation.py:187-190,
+    implicit.py:428-437) on the reference's fitted tables vs values frozen from the reference's own functions
+    (tests/golden/metrics.npz, oracle/make_golden_metrics.py)."""
+    monkeypatch.chdir(tmp_path)
+    from implicit import ImplicitFactorizationModel
+    from spotlight.evaluation import map_at_k
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    gm = np.load(os.path.join(golden_dir, 'metrics.npz'))
+    U, I, D, B, n_neg, n_epochs = [int(x) for x in g['meta']]
+    b = int(g['split'][1])
+    test = _interactions(g['users'][b:], g['items'][b:], U, I)
+    net = make_net([g['final%d' % i] for i in range(4)])
+    model = ImplicitFactorizationModel(embedding_dim=D, representation=net, batch_size=B, use_cuda=True,
+                                       experiment_name='gpu_metrics_' + name)
+    model.set_users(U, I)
+    for k in (1, 5, 10):
+        # the only freedom is the order inside groups of tied sigmoid outputs (SURVEY F9)
+        assert map_at_k(model, test, k=k) == pytest.approx(float(gm['%s_map_k%d' % (name, k)]), abs=2e-3)
+    res = model.test(test, None, k=5, rmse_flag=True, precision_recall=False, map_recall=True)
+    assert res['bce'] == pytest.approx(float(gm['%s_bce' % name]), rel=1e-5)
+    assert res['map'] == pytest.approx(float(gm['%s_map_k5' % name]), abs=2e-3)

@@ -160,3 +160,23 @@ def test_negative_pair_generator_matches_reference(golden_dir):
         seen = collections.Counter(zip(g[name + '_users'].tolist(), g[name + '_items'].tolist()))
         once = {p for p, c in seen.items() if c == 1}    # a repeated pair is stored as 2: has_key is False for it
         assert (1, 3) not in once and not [p for p in map(tuple, pairs.tolist()) if p in once]
+
+
+@pytest.mark.parametrize('name', ['fit_pointwise', 'fit_bpr'])
+def test_map_at_k_and_rmse_match_reference(golden_dir, name):
+    """oracle map_at_k / rmse_score vs values frozen from the reference's own functions (oracle/make_golden_metrics.py,
+    evaluation.py:187-190,278-353) on the fitted tables of the fit goldens."""
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    gm = np.load(os.path.join(golden_dir, 'metrics.npz'))
+    U, I, D, B, n_neg, n_epochs = [int(x) for x in g['meta']]
+    b = int(g['split'][1])
+    users, items = g['users'], g['items']
+    model = O.OracleMF(*[_t(g['final%d' % i]) for i in range(4)])
+    test_csr = O.csr_from_pairs(users[b:], items[b:], U, I)
+    for k in (1, 5, 10):
+        assert O.map_at_k(model, test_csr, k=k, ranking='reference') == pytest.approx(float(gm['%s_map_k%d' % (name, k)]),
+                                                                                       abs=1e-12)
+        # the tie-defined ranking (what the CUDA path implements) differs only through tie order
+        assert O.map_at_k(model, test_csr, k=k) == pytest.approx(float(gm['%s_map_k%d' % (name, k)]), abs=2e-3)
+    parts = [O.rmse_score(model, users[b:][s:s + B], items[b:][s:s + B]) for s in range(0, len(users) - b, B)]
+    np.testing.assert_allclose(parts, gm['%s_rmse_parts' % name], rtol=1e-6)
