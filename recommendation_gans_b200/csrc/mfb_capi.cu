@@ -106,8 +106,10 @@ extern "C" int mfb_model_create(const mfb_model_desc *d, mfb_model **out) {
   if (const char *e = getenv("MFB_EAGER_MAX")) m->tune_eager_max = atoi(e);
   if (const char *e = getenv("MFB_CHUNK_BITS")) m->tune_chunk_bits = atoi(e) < 0 ? 0 : (atoi(e) > 12 ? 12 : atoi(e));
   if (const char *e = getenv("MFB_TC")) m->tune_tc = atoi(e);
+  if (const char *e = getenv("MFB_TC_CLUSTER")) m->tune_tc_cluster = atoi(e);
   if (const char *e = getenv("MFB_TC_SAMPLE_STEP")) m->tune_tc_sample_step = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("MFB_CU_BLOCKS")) m->tune_cu_blocks_per_sm = atoi(e) < 1 ? 1 : atoi(e);
+  if (const char *e = getenv("MFB_CHUNK_RAMP")) m->tune_chunk_ramp = atoi(e) < 0 ? 0 : atoi(e);
   auto bind = [&](TableView &T, int rows, float *p, float *pm, float *pv, float *b, float *bm, float *bv) {
     T.p = p; T.m = pm; T.v = pv; T.bp = b; T.bm = bm; T.bv = bv; T.rows = rows; T.last = nullptr;
   };
@@ -175,6 +177,8 @@ extern "C" int mfb_model_destroy(mfb_model *m) {
     for (DevBuf *b : ebufs) b->release();
   }
   if (m->st_plan) cudaStreamDestroy(m->st_plan);
+  if (m->st_rng) cudaStreamDestroy(m->st_rng);
+  for (cudaEvent_t e : m->ev_rng) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_plan) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_done) if (e) cudaEventDestroy(e);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
@@ -254,6 +258,7 @@ extern "C" int mfb_model_rng_seed(mfb_model *m, const uint32_t *h_state, mfb_str
   MFB_CHECK(m->rng_state.reserve(625 * sizeof(uint32_t)));
   // earlier draws may still be queued on the planner stream
   if (m->st_plan) MFB_CUDA(cudaStreamSynchronize(m->st_plan));
+  if (m->st_rng) MFB_CUDA(cudaStreamSynchronize(m->st_rng));
   MFB_CUDA(cudaMemcpyAsync(m->rng_state.ptr, h_state, 625 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   MFB_CUDA(cudaStreamSynchronize(st));
   m->rng_seeded = true;
@@ -268,6 +273,7 @@ extern "C" int mfb_model_rng_state(mfb_model *m, uint32_t *h_state, mfb_stream s
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (m->st_plan) MFB_CUDA(cudaStreamSynchronize(m->st_plan));
+  if (m->st_rng) MFB_CUDA(cudaStreamSynchronize(m->st_rng));
   MFB_CUDA(cudaMemcpyAsync(h_state, m->rng_state.ptr, 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
   return MFB_OK;

@@ -100,10 +100,34 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// same load, delivered to the same shared-memory offset (and signalling the same mbarrier offset) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// commit that arrives on the barrier at this offset in every CTA of cta_mask (stage release towards all producers)
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
                : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -252,7 +276,11 @@ struct TcArgs {
   int dbg;   // experiment switches: 1 = skip score processing, 2 = skip appends, 4 = skip mask build, 8 = skip bias pre-store
 };
 
-template <int MODE, bool SPLIT>
+// CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster (neighbouring user blocks) walk the item
+// tiles in lockstep: each loads HALF of every tile and multicasts it into both CTAs' stage buffers, so the L2 -> SM
+// operand traffic -- what bounds the bare TMA + MMA pipeline at K = 128 -- is halved.  A stage is released towards both
+// producers (multicast commit; the empty barriers count CL arrivals).  map_items' box holds TC_M / CL rows.
+template <int MODE, bool SPLIT, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)   // 18 warps (allocated as 20): 96 registers per thread
 k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__ CUtensorMap map_users,
           const TcArgs a) {
@@ -284,13 +312,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   const int u0 = blockIdx.x * TC_N;
   // every CTA streams the same item tiles out of L2: start each CTA at a different tile so that concurrently
   // running CTAs do not all hit the same L2 slices at the same moment
-  const int tile_off = (int)(((long long)blockIdx.x * 37) % (nt > 0 ? nt : 1));
+  // (the CTAs of a cluster share their tile sequence)
+  const int tile_off = (int)(((long long)(blockIdx.x / CL) * 37) % (nt > 0 ? nt : 1));
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
   auto logical = [&](int i) { int li = i + tile_off; return li >= nt ? li - nt : li; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, 1);
+      mbar_init(empty + s, CL);   // one release per CTA whose producer writes into this stage
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull + b, 1);
@@ -304,7 +334,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast at them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -320,8 +351,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
         mbar_wait_backoff(empty + s, ph ^ 1u);
         mbar_expect_tx(full + s, v_bytes);
         const int row0 = (tb + logical(i) * ts) * TC_M;
-        for (int ka = 0; ka < katoms; ++ka)
-          tma_load_2d(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
+        if (CL > 1) {
+          constexpr int HALF = TC_M / CL;       // my share of the tile's rows, delivered to every CTA of the cluster
+          for (int ka = 0; ka < katoms; ++ka)
+            tma_load_2d_mc(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128 + (size_t)crank * HALF * 128, &map_items,
+                           full + s, ka * TC_KATOM, row0 + crank * HALF, (uint16_t)((1u << CL) - 1u));
+        } else {
+          for (int ka = 0; ka < katoms; ++ka)
+            tma_load_2d(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -362,7 +400,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
               tc_mma_bf16(d_tmem, udesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc, 1u);
           }
         }
-        tc_commit(empty + s);    // smem stage reusable once these MMAs retire
+        if (CL > 1) tc_commit_mc(empty + s, (uint16_t)((1u << CL) - 1u));   // release towards every producer of the cluster
+        else tc_commit(empty + s);    // smem stage reusable once these MMAs retire
         tc_commit(tfull + b);    // accumulators ready for the epilogue
       }
     }
@@ -518,9 +557,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     }
     if (MODE == MODE_COLLECT && user_ok) a.cand_cnt[((long long)gu * S + split) * 2 + ch] = my_cnt;
   }
-  // teardown
+  // teardown (a CTA of a cluster must not leave while its peer may still multicast into it or arrive on its barriers)
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
@@ -998,20 +1038,46 @@ size_t tc_smem_bytes(int D) {
          (size_t)TC_EPI_WARPS * 64 * 4;
 }
 
-template <int MODE>
-int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, int n_users, cudaStream_t st,
-                int splits = 1) {
-  const size_t smem = tc_smem_bytes(a.D);
-  const dim3 grid((n_users + TC_N - 1) / TC_N, splits);
-  if (splits > 1) {
-    MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tc_gemm<MODE, true><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
+template <int MODE, bool SPLIT, int CL>
+int launch_gemm_cl(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, dim3 grid, size_t smem,
+                   cudaStream_t st) {
+  MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, SPLIT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CL == 1) {
+    k_tc_gemm<MODE, SPLIT, CL><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
   } else {
-    MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tc_gemm<MODE, false><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MFB_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<MODE, SPLIT, CL>, mi, mu, a));
   }
   MFB_KERNEL_CHECK();
   return MFB_OK;
+}
+
+// cluster = CTAs per cluster (1 or 2); with 2 the grid's x extent is rounded up to even (a.n_users_pad covers the
+// phantom block) and `mi` must have been encoded with a box of TC_M / 2 rows
+template <int MODE>
+int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, int n_users, cudaStream_t st,
+                int splits = 1, int cluster = 1) {
+  const size_t smem = tc_smem_bytes(a.D);
+  int gx = (n_users + TC_N - 1) / TC_N;
+  if (cluster > 1) gx = ((gx + cluster - 1) / cluster) * cluster;
+  const dim3 grid(gx, splits);
+  if (cluster > 1) {
+    if (splits > 1) return launch_gemm_cl<MODE, true, 2>(mi, mu, a, grid, smem, st);
+    return launch_gemm_cl<MODE, false, 2>(mi, mu, a, grid, smem, st);
+  }
+  if (splits > 1) return launch_gemm_cl<MODE, true, 1>(mi, mu, a, grid, smem, st);
+  return launch_gemm_cl<MODE, false, 1>(mi, mu, a, grid, smem, st);
 }
 
 }  // namespace
@@ -1030,7 +1096,9 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
                 int *h_n_redo) {
   const int n_users = (int)n_users64;
   const int D = m->desc.dim, I = m->items.rows;
-  const int n_users_pad = ((n_users + TC_N - 1) / TC_N) * TC_N;
+  const int cluster = m->tune_tc_cluster >= 2 ? 2 : 1;     // CTAs per cluster sharing each item tile (TMA multicast)
+  const int n_users_pad = ((n_users + TC_N * cluster - 1) / (TC_N * cluster)) * (TC_N * cluster);
+  m->eval.n_users_pad = n_users_pad;
   const int i_tiles = (I + TC_M - 1) / TC_M;
   const int items_pad = i_tiles * TC_M;
   int sample_step = m->tune_tc_sample_step > 0 ? m->tune_tc_sample_step : 4;
@@ -1084,7 +1152,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   MFB_KERNEL_CHECK();
 
   CUtensorMap map_items, map_users;
-  MFB_CHECK(make_tmap(&map_items, vb, items_pad, D, TC_M));
+  MFB_CHECK(make_tmap(&map_items, vb, items_pad, D, TC_M / cluster));   // a CTA loads its share of a tile's rows
   MFB_CHECK(make_tmap(&map_users, ub, n_users_pad, D, TC_N));
 
   TcArgs a;
@@ -1127,7 +1195,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.tile_step = sample_step;
   a.n_tiles = n_sample;
   a.gmax = eb.gmax.as<int>();
-  MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st, splits));
+  MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st, splits, cluster));
   if (small_thr) {
     const int tb = (n_users + 127) / 128;
     int *gm = eb.gmax.as<int>();
@@ -1150,7 +1218,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.cand = eb.cand.as<int2>();
   a.cand_cnt = cand_cnt;
   a.cap2 = cap2;
-  MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st, splits));
+  MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st, splits, cluster));
   // exact re-score + mask + top-k
   MFB_CUDA(cudaMemsetAsync(redo_cnt, 0, sizeof(int), st));
   const size_t rs_smem = (size_t)RS_WARPS * (D + 3 * RS_MAXC) * sizeof(float);
@@ -1189,7 +1257,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
 
 // debug: candidate-list statistics of the last tensor-core top-k call: {users, sum, max, over_cap, re-scored}
 int mfb_tc_stats(mfb_model *m, int n_users, long long *h_out, cudaStream_t st) {
-  const int n_users_pad = ((n_users + TC_N - 1) / TC_N) * TC_N;
+  const int n_users_pad = m->eval.n_users_pad;
   const int nsub = m->eval.nsub;
   std::vector<int> cnt((size_t)n_users * nsub);
   MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.ptr, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, st));

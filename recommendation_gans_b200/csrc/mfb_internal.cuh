@@ -123,6 +123,7 @@ struct PlanBuf {
 struct EvalBuf {
   DevBuf ub, vb, unorm, vnorm, gmax, thr, cand, cnt, redo, mcnt, mptr, mpairs;
   int nsub = 2;   // candidate sub-lists per user in the last tensor-core pass (2 column halves x item-tile splits)
+  int n_users_pad = 0;   // padded user count of the last tensor-core pass (layout of the per-user scratch arrays)
 };
 
 struct mfb_model {
@@ -130,16 +131,19 @@ struct mfb_model {
   Profiler prof;
   EvalBuf eval;
   int tune_tc = 1, tune_tc_sample_step = 4;   // MFB_TC=0 forces the exact-fp32 evaluation kernel
+  int tune_tc_cluster = 1;                    // CTAs per cluster sharing item tiles by TMA multicast (MFB_TC_CLUSTER=1: off)
   int last_topk_redo = 0;                     // users re-done by the exact kernel in the last mfb_topk call
   PlanBuf plan[2];
   cudaStream_t st_plan = nullptr;   // planner stream
-  cudaEvent_t ev_plan[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaStream_t st_rng = nullptr;    // MT19937 word generation (sequential, one CTA) runs ahead of the planner here
+  cudaEvent_t ev_plan[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_rng[2] = {nullptr, nullptr};
   cudaEvent_t ev_join = nullptr;
   int num_sms = 148;
   DevBuf rng_state;            // device-resident MT19937 state (624 words + position) of the negative sampler
   bool rng_seeded = false;
   // tuning knobs (environment overrides read at model creation: MFB_EAGER_MAX, MFB_CHUNK_BITS, MFB_CU_BLOCKS)
   int tune_eager_max = 64, tune_chunk_bits = 6, tune_cu_blocks_per_sm = 2;
+  int tune_chunk_ramp = 0;     // steps in the first planner chunk of a call (MFB_CHUNK_RAMP; 0 = no ramp)
   TableView users, items;
   OptView opt;
   int64_t step = 0;            // optimiser steps applied so far

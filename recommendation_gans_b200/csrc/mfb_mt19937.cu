@@ -4,13 +4,15 @@
 //   spotlight/sampling.py:33 random_state.randint(0, num_items, shape, dtype=int64)
 // The generator state travels as (624 words, position) exactly as random.getstate()[1], so the
 // host RNG objects stay in sync with what the reference would have consumed.
+#include <mutex>
+
 #include "mfb_internal.cuh"
 
 namespace {
 
 constexpr int MT_N = 624;
 constexpr int MT_M = 397;
-constexpr int MT_THREADS = 256;
+constexpr int MT_THREADS = 640;   // one thread per state word (624) in the generator kernel
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   y ^= y >> 11;
@@ -25,13 +27,16 @@ __device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t nxt, uint32_t 
   return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
 }
 
-// One CTA walks the stream sequentially; the 624-word regeneration is done in three
-// data-parallel phases (new[k] needs old[k], old[k+1] and old/new[(k+397)%624]).
+// One CTA walks the stream sequentially, one thread per state word.  new[k] needs old[k], old[k+1] and
+// new-or-old[(k+397) % 624]; the "new" operands are themselves mixes of old words (at most two levels deep, plus
+// new[0] for k = 623), so every word of the next state is computed from the OLD state alone: one data-parallel phase
+// and one barrier per 624-word regeneration instead of three dependent phases.
 // state_io: 624 words + position (625 uint32).  out may be nullptr (advance only).
 __global__ void __launch_bounds__(MT_THREADS) k_mt_generate(uint32_t *state_io, unsigned long long nwords,
                                                             uint32_t *out) {
   __shared__ uint32_t buf[2][MT_N];
   const int tid = threadIdx.x;
+  constexpr int G = MT_N - MT_M;   // 227
   int cur = 0;
   for (int i = tid; i < MT_N; i += MT_THREADS) buf[0][i] = state_io[i];
   int pos = (int)state_io[MT_N];
@@ -41,25 +46,21 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_generate(uint32_t *state_io, 
     if (pos >= MT_N) {
       const uint32_t *o = buf[cur];
       uint32_t *n = buf[cur ^ 1];
-      // phase A: k in [0,227): far = old[k+397]
-      if (tid < MT_N - MT_M) n[tid] = mt_mix(o[tid], o[tid + 1], o[tid + MT_M]);
-      __syncthreads();
-      // phase B: k in [227,454): far = new[k-227]
-      {
-        int k = tid + (MT_N - MT_M);
-        if (k < 2 * (MT_N - MT_M)) n[k] = mt_mix(o[k], o[k + 1], n[k - (MT_N - MT_M)]);
-      }
-      __syncthreads();
-      // phase C: k in [454,624): far = new[k-227]; k=623 wraps to new[0]
-      {
-        int k = tid + 2 * (MT_N - MT_M);
-        if (k < MT_N) {
-          uint32_t nxt = (k == MT_N - 1) ? n[0] : o[k + 1];
-          n[k] = mt_mix(o[k], nxt, n[k - (MT_N - MT_M)]);
+      for (int k = tid; k < MT_N; k += MT_THREADS) {
+        uint32_t far;
+        if (k < G) {
+          far = o[k + MT_M];
+        } else if (k < 2 * G) {
+          far = mt_mix(o[k - G], o[k - G + 1], o[k - G + MT_M]);                 // new[k-227]
+        } else {
+          const uint32_t inner = mt_mix(o[k - 2 * G], o[k - 2 * G + 1], o[k - 2 * G + MT_M]);   // new[k-454]
+          far = mt_mix(o[k - G], o[k - G + 1], inner);                             // new[k-227]
         }
+        const uint32_t nxt = (k == MT_N - 1) ? mt_mix(o[0], o[1], o[MT_M]) : o[k + 1];   // k = 623 wraps to new[0]
+        n[k] = mt_mix(o[k], nxt, far);
       }
-      __syncthreads();
-      cur ^= 1;
+      __syncthreads();   // the only barrier per regeneration: buffers alternate, so the words read above are not
+      cur ^= 1;          // overwritten before the NEXT barrier
       pos = 0;
     }
     unsigned long long left = nwords - emitted;
@@ -69,8 +70,8 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_generate(uint32_t *state_io, 
     }
     emitted += take;
     pos += take;
-    __syncthreads();
   }
+  __syncthreads();
   for (int i = tid; i < MT_N; i += MT_THREADS) state_io[i] = buf[cur][i];
   if (tid == 0) state_io[MT_N] = (uint32_t)pos;
 }
@@ -140,6 +141,22 @@ __global__ void __launch_bounds__(1024) k_masked_compact(const uint32_t *__restr
 
 DevBuf g_state, g_words, g_result;  // library-global scratch for the model-less RNG entry points
 
+// The model-less entry points share the scratch above: one caller at a time (ranks running as threads of one process
+// call these concurrently, and ctypes releases the GIL), and the scratch follows the calling thread's device.
+std::recursive_mutex g_rng_mutex;
+int g_rng_device = -1;
+void release_rng_scratch();
+struct RngScratchGuard {
+  std::lock_guard<std::recursive_mutex> lock;
+  RngScratchGuard() : lock(g_rng_mutex) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != g_rng_device) {
+      if (g_rng_device >= 0) release_rng_scratch();
+      g_rng_device = dev;
+    }
+  }
+};
+
 int upload_state(const uint32_t *h_state, cudaStream_t st) {
   MFB_CHECK(g_state.reserve(625 * sizeof(uint32_t)));
   if (h_state[624] > 624) {
@@ -188,6 +205,7 @@ int mfb_mt_generate(uint32_t *h_state, int64_t nwords, uint32_t *d_words, cudaSt
 }
 
 extern "C" int mfb_mt_words(uint32_t *h_state, int64_t nwords, uint32_t *d_out, mfb_stream stream) {
+  RngScratchGuard guard;
   if (!h_state || (nwords > 0 && !d_out)) return MFB_ERR_INVALID;
   return mfb_mt_generate(h_state, nwords, d_out, (cudaStream_t)stream);
 }
@@ -214,6 +232,7 @@ static int choices_impl(uint32_t *h_state, const int64_t *d_pop_users, const int
 extern "C" int mfb_mt_choices_pairs(uint32_t *h_state, const int64_t *d_pop_users, const int64_t *d_pop_items,
                                     int64_t pop_len, int64_t k, int64_t *d_out_users, int64_t *d_out_items,
                                     mfb_stream stream) {
+  RngScratchGuard guard;
   if (!d_pop_users || !d_pop_items || !d_out_users || !d_out_items) return MFB_ERR_INVALID;
   return choices_impl(h_state, d_pop_users, d_pop_items, pop_len, k, d_out_users, d_out_items, nullptr,
                       (cudaStream_t)stream);
@@ -221,12 +240,14 @@ extern "C" int mfb_mt_choices_pairs(uint32_t *h_state, const int64_t *d_pop_user
 
 extern "C" int mfb_mt_choices_indices(uint32_t *h_state, int64_t pop_len, int64_t k, int64_t *d_out,
                                       mfb_stream stream) {
+  RngScratchGuard guard;
   if (!d_out) return MFB_ERR_INVALID;
   return choices_impl(h_state, nullptr, nullptr, pop_len, k, nullptr, nullptr, d_out, (cudaStream_t)stream);
 }
 
 extern "C" int mfb_mt_sample_items(uint32_t *h_state, int64_t num_items, int64_t count, int64_t *d_out,
                                    mfb_stream stream) {
+  RngScratchGuard guard;
   cudaStream_t st = (cudaStream_t)stream;
   if (!h_state || num_items <= 0 || count < 0 || (count > 0 && !d_out) || num_items > 0xFFFFFFFFll) {
     mfb_set_error("mt_sample_items: bad arguments (num_items=%lld, count=%lld)", (long long)num_items,
@@ -388,6 +409,9 @@ __global__ void k_neg_rank_shift(const long long *__restrict__ list, long long c
 }
 
 DevBuf g_nflag, g_nlist, g_nraw;
+void release_rng_scratch() {
+  for (DevBuf *b : {&g_state, &g_words, &g_result, &g_nflag, &g_nlist, &g_nraw}) b->release();
+}
 
 }  // namespace
 
@@ -395,6 +419,7 @@ extern "C" int mfb_negative_pairs(uint32_t *h_state, int64_t num_users, int64_t 
                                   const int64_t *d_key_indptr, const int32_t *d_key_indices,
                                   const int64_t *d_row_indptr, const int32_t *d_row_indices, int64_t *d_out_users,
                                   int64_t *d_out_items, int64_t *h_n_redrawn, mfb_stream stream) {
+  RngScratchGuard guard;
   cudaStream_t st = (cudaStream_t)stream;
   if (!h_state || num_users <= 0 || num_items <= 0 || num_samples < 0 || !d_key_indptr || !d_row_indptr ||
       (num_samples > 0 && (!d_out_users || !d_out_items))) {

@@ -92,6 +92,13 @@ __global__ void k_pack(const long long *__restrict__ pos_u, const long long *__r
 
 // When neg_begin >= 0 (adaptive hinge), the maximum over slots j >= neg_begin is reduced per block
 // and folded into *gmax with one (usually skipped) 64-bit atomicMax per block.
+// A warp owns FWD_SPW consecutive slots and issues the row loads of all of them before the first use: the kernel is
+// bound by dependent-load latency (ids -> rows), so loads in flight per warp are what counts.
+#ifndef MFB_FWD_SPW
+#define MFB_FWD_SPW 2
+#endif
+constexpr int FWD_SPW = MFB_FWD_SPW;
+
 template <int VEC, int NIT>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_forward(const int *__restrict__ slot_u,
                                                            const int *__restrict__ slot_i, int L, TableView users,
@@ -100,31 +107,47 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_forward(const int *__restrict
                                                            int neg_begin, unsigned long long *__restrict__ gmax) {
   __shared__ unsigned long long wmax[WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int j = blockIdx.x * WARPS_PER_BLOCK + wid;
+  const int j0 = (blockIdx.x * WARPS_PER_BLOCK + wid) * FWD_SPW;
   unsigned long long mine = 0ull;
   pdl_launch_dependents();
-  long long u = 0, i = 0;
-  if (j < L) {
-    u = slot_u[j];       // planner output: independent of the previous kernel
-    i = slot_i[j];
+  long long u[FWD_SPW], i[FWD_SPW];
+#pragma unroll
+  for (int s = 0; s < FWD_SPW; ++s) {
+    const bool ok = j0 + s < L;
+    u[s] = ok ? slot_u[j0 + s] : 0;       // planner output: independent of the previous kernel
+    i[s] = ok ? slot_i[j0 + s] : 0;
   }
   pdl_wait();            // tables are written by the previous step's update
-  if (j < L) {
-    Frag<VEC, NIT> fu, fi;
-    frag_load<VEC, NIT>(fu, users.p + u * D, D, lane);
-    frag_load<VEC, NIT>(fi, items.p + i * D, D, lane);
-    float acc = 0.f;
+  if (j0 < L) {
+    Frag<VEC, NIT> fu[FWD_SPW], fi[FWD_SPW];
+    float bu[FWD_SPW], bi[FWD_SPW];
 #pragma unroll
-    for (int k = 0; k < NIT * VEC; ++k) acc = fmaf(fu.x[k], fi.x[k], acc);
-    acc = warp_sum(acc);
-    if (snap_u != nullptr) {
-      frag_store<VEC, NIT>(fu, snap_u + (long long)j * D, D, lane);
-      frag_store<VEC, NIT>(fi, snap_i + (long long)j * D, D, lane);
+    for (int s = 0; s < FWD_SPW; ++s) {   // (slots past L re-read row 0: harmless, never stored)
+      frag_load<VEC, NIT>(fu[s], users.p + u[s] * D, D, lane);
+      frag_load<VEC, NIT>(fi[s], items.p + i[s] * D, D, lane);
+      bu[s] = users.bp[u[s]];
+      bi[s] = items.bp[i[s]];
     }
-    const float z = (acc + users.bp[u]) + items.bp[i];
-    const float y = sigmoidf_acc(z);
-    if (lane == 0) pred[j] = y;
-    if (neg_begin >= 0 && j >= neg_begin) mine = pack_max(y, j - neg_begin);
+#pragma unroll
+    for (int s = 0; s < FWD_SPW; ++s) {
+      const int j = j0 + s;
+      if (j >= L) break;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < NIT * VEC; ++k) acc = fmaf(fu[s].x[k], fi[s].x[k], acc);
+      acc = warp_sum(acc);
+      if (snap_u != nullptr) {
+        frag_store<VEC, NIT>(fu[s], snap_u + (long long)j * D, D, lane);
+        frag_store<VEC, NIT>(fi[s], snap_i + (long long)j * D, D, lane);
+      }
+      const float z = (acc + bu[s]) + bi[s];
+      const float y = sigmoidf_acc(z);
+      if (lane == 0) pred[j] = y;
+      if (neg_begin >= 0 && j >= neg_begin) {
+        const unsigned long long cand = pack_max(y, j - neg_begin);
+        mine = cand > mine ? cand : mine;
+      }
+    }
   }
   if (neg_begin >= 0) {  // uniform across the grid
     if (lane == 0) wmax[wid] = mine;
@@ -580,6 +603,9 @@ constexpr int UPD_WIN = 32;
 #ifndef MFB_UPD_INFLIGHT
 #define MFB_UPD_INFLIGHT 2   // measured: 2 slots in flight (48 regs, 16 B spill) beats 4 (96 B spill) by 8%
 #endif
+#ifndef MFB_UPD_INTERLEAVE
+#define MFB_UPD_INTERLEAVE 1
+#endif
 constexpr int UPD_WARPS = MFB_UPD_WARPS;   // warps per k_update block
 
 struct UpdArgs {
@@ -633,8 +659,21 @@ __global__ void __launch_bounds__(UPD_WARPS * 32, MFB_UPD_MINB) k_update(const U
   }
 
   // ---- update role -----------------------------------------------------------------------
-  const int ql = ((int)blockIdx.x - a.cu_blocks) * UPD_WARPS + wid;  // position within the step
-  if (ql >= a.n) return;
+  // Position within the step.  The sorted positions of a step are [user rows | item rows] (n/2 each).  User rows carry
+  // long eager replays (MUFU-bound), item rows are touched almost every step (load/store-bound): even blocks walk the
+  // user half, odd blocks the item half, so both kinds are resident on every SM at the same time instead of one
+  // after the other.
+  int ql;
+  if (MFB_UPD_INTERLEAVE) {
+    const int ub = (int)blockIdx.x - a.cu_blocks;
+    const int half = a.n >> 1;
+    const int in_half = (ub >> 1) * UPD_WARPS + wid;
+    if (in_half >= half) return;
+    ql = (ub & 1) * half + in_half;
+  } else {
+    ql = ((int)blockIdx.x - a.cu_blocks) * UPD_WARPS + wid;
+    if (ql >= a.n) return;
+  }
   const long long q = a.base + ql;
   // independent loads first: this kernel is bound by dependent-load latency, not bandwidth
   const uint4 raw = *reinterpret_cast<const uint4 *>(a.info + q);
@@ -730,13 +769,25 @@ __global__ void __launch_bounds__(UPD_WARPS * 32, MFB_UPD_MINB) k_update(const U
     const float *hp = a.partial + (long long)(nwin + first_win) * a.pstride;
     frag_load_cg<VEC, NIT>(g, hp, D, lane);
     gb = __ldcg(hp + D);
-    for (int w = first_win + 1; w <= last_win; ++w) {
-      const float *wp = a.partial + (long long)w * a.pstride;
-      Frag<VEC, NIT> o;
-      frag_load_cg<VEC, NIT>(o, wp, D, lane);
+    for (int w0 = first_win + 1; w0 <= last_win; w0 += 4) {   // four partial rows in flight, added in position order
+      Frag<VEC, NIT> o[4];
+      float ob[4];
 #pragma unroll
-      for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fadd_rn(g.x[k], o.x[k]);
-      gb = __fadd_rn(gb, __ldcg(wp + D));
+      for (int u = 0; u < 4; ++u) {
+        if (w0 + u <= last_win) {
+          const float *wp = a.partial + (long long)(w0 + u) * a.pstride;
+          frag_load_cg<VEC, NIT>(o[u], wp, D, lane);
+          ob[u] = __ldcg(wp + D);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (w0 + u <= last_win) {
+#pragma unroll
+          for (int k = 0; k < NIT * VEC; ++k) g.x[k] = __fadd_rn(g.x[k], o[u].x[k]);
+          gb = __fadd_rn(gb, ob[u]);
+        }
+      }
     }
     row_load<VEC, NIT>(r, T, row, D, lane, adam);
   }
@@ -927,7 +978,7 @@ extern "C" int mfb_predict_pairs(mfb_model *m, const int64_t *d_users, const int
   for (int64_t off = 0; off < count; off += (1 << 24)) {
     int L = (int)((count - off < (1 << 24)) ? (count - off) : (1 << 24));
 #define CALL(V, N)                                                                                               \
-  k_forward<V, N><<<grid_for_warps(L), BLOCK_THREADS, 0, st>>>(slot_u + off, slot_i + off, L, m->users, m->items, D, \
+  k_forward<V, N><<<grid_for_warps((L + FWD_SPW - 1) / FWD_SPW), BLOCK_THREADS, 0, st>>>(slot_u + off, slot_i + off, L, m->users, m->items, D, \
                                                                 nullptr, nullptr, d_out + off, -1, nullptr)
     MFB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
@@ -974,10 +1025,16 @@ struct StepGeom {
 
 static int ensure_streams(mfb_model *m) {
   if (m->st_plan) return MFB_OK;
-  MFB_CUDA(cudaStreamCreateWithFlags(&m->st_plan, cudaStreamNonBlocking));
+  // The planner's and the generator's kernels are small and run while the step kernels fill every SM: highest stream
+  // priority lets their blocks take the next free slots instead of queueing behind a whole k_update grid.
+  int prio_lo = 0, prio_hi = 0;
+  MFB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  MFB_CUDA(cudaStreamCreateWithPriority(&m->st_plan, cudaStreamNonBlocking, prio_hi));
+  MFB_CUDA(cudaStreamCreateWithPriority(&m->st_rng, cudaStreamNonBlocking, prio_hi));
   auto mk = [](cudaEvent_t *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
   for (auto &e : m->ev_plan) MFB_CUDA(mk(&e));
   for (auto &e : m->ev_done) MFB_CUDA(mk(&e));
+  for (auto &e : m->ev_rng) MFB_CUDA(mk(&e));
   MFB_CUDA(mk(&m->ev_join));
   int dev = 0;
   MFB_CUDA(cudaGetDevice(&dev));
@@ -985,20 +1042,35 @@ static int ensure_streams(mfb_model *m) {
   return MFB_OK;
 }
 
-static void chunk_extent(const StepGeom &g, int64_t s0, int *ns, int *b_last, int64_t *nkeys) {
-  *ns = (int)((g.nsteps - s0 < g.chunk) ? (g.nsteps - s0) : g.chunk);
+static void chunk_extent(const StepGeom &g, int64_t s0, int cap, int *ns, int *b_last, int64_t *nkeys) {
+  *ns = (int)((g.nsteps - s0 < cap) ? (g.nsteps - s0) : cap);
   const int64_t last_first = (s0 + *ns - 1) * (int64_t)g.batch;
   *b_last = (int)((g.n_pos - last_first < g.batch) ? (g.n_pos - last_first) : g.batch);
   // all steps are full except possibly the last of the epoch (which is last in its chunk)
   *nkeys = 2 * ((int64_t)(*ns - 1) * g.Lfull + (*b_last + g.m_neg));
 }
 
-static int plan_chunk(mfb_model *m, PlanBuf &pb, const StepGeom &g, const int64_t *d_pos_users,
-                      const int64_t *d_pos_items, const int64_t *d_neg_users, const int64_t *d_neg_items, int64_t s0,
-                      int *flag, cudaStream_t sp) {
+// MT19937 words of a chunk's negative draws, on the RNG stream: the generator is one sequential stream (one CTA), so it
+// runs ahead of the planner on its own stream instead of sitting on the planner's critical path.
+static int draw_chunk_words(mfb_model *m, PlanBuf &pb, const StepGeom &g, int64_t s0, int cap, cudaStream_t sr) {
+  if (!(g.pop_len > 0 && g.m_neg > 0)) return MFB_OK;
   int ns, b_last;
   int64_t nkeys;
-  chunk_extent(g, s0, &ns, &b_last, &nkeys);
+  chunk_extent(g, s0, cap, &ns, &b_last, &nkeys);
+  const int64_t k = (int64_t)ns * g.m_neg;
+  MFB_CHECK(pb.words.reserve((size_t)(2 * (int64_t)g.chunk * g.m_neg) * sizeof(uint32_t)));
+  int tk = m->prof.begin(PK_SAMPLE, sr, 0);
+  MFB_CHECK(mfb_mt_generate_async(m->rng_state.as<uint32_t>(), 2 * k, pb.words.as<uint32_t>(), sr));
+  m->prof.end(tk, sr);
+  return MFB_OK;
+}
+
+static int plan_chunk(mfb_model *m, PlanBuf &pb, const StepGeom &g, const int64_t *d_pos_users,
+                      const int64_t *d_pos_items, const int64_t *d_neg_users, const int64_t *d_neg_items, int64_t s0,
+                      int cap, int *flag, cudaStream_t sp) {
+  int ns, b_last;
+  int64_t nkeys;
+  chunk_extent(g, s0, cap, &ns, &b_last, &nkeys);
   const size_t slots = (size_t)g.chunk * g.Lfull;
   MFB_CHECK(pb.slots.reserve(slots * 2 * sizeof(int)));
   MFB_CHECK(pb.pred.reserve(slots * sizeof(float)));
@@ -1022,12 +1094,11 @@ static int plan_chunk(mfb_model *m, PlanBuf &pb, const StepGeom &g, const int64_
   long long neg_step0 = 0;
   if (g.pop_len > 0 && g.m_neg > 0) {
     // random.choices(neg_examples, k = n_neg*batch) for each step of the chunk, in step order
+    // (the words were drawn by draw_chunk_words on the RNG stream; the caller made this stream wait for them)
     const int64_t k = (int64_t)ns * g.m_neg;
-    MFB_CHECK(pb.words.reserve((size_t)(2 * k) * sizeof(uint32_t)));
-    MFB_CHECK(pb.neg_u.reserve((size_t)k * sizeof(int64_t)));
-    MFB_CHECK(pb.neg_i.reserve((size_t)k * sizeof(int64_t)));
+    MFB_CHECK(pb.neg_u.reserve((size_t)((int64_t)g.chunk * g.m_neg) * sizeof(int64_t)));
+    MFB_CHECK(pb.neg_i.reserve((size_t)((int64_t)g.chunk * g.m_neg) * sizeof(int64_t)));
     tk = m->prof.begin(PK_SAMPLE, sp, 0);
-    MFB_CHECK(mfb_mt_generate_async(m->rng_state.as<uint32_t>(), 2 * k, pb.words.as<uint32_t>(), sp));
     MFB_CHECK(mfb_choices_async(pb.words.as<uint32_t>(), k, g.pop_len, g.pop_users, g.pop_items,
                                 pb.neg_u.as<int64_t>(), pb.neg_i.as<int64_t>(), sp));
     m->prof.end(tk, sp);
@@ -1095,7 +1166,8 @@ static void launch_update_kind(const UpdArgs &a, int loss, int grid, cudaStream_
 
 static int launch_update(mfb_model *m, const Shape &sh, const StepGeom &g, const UpdArgs &a, int cls,
                          cudaStream_t st) {
-  const int grid = a.cu_blocks + (a.n + UPD_WARPS - 1) / UPD_WARPS;
+  const int grid = a.cu_blocks + (MFB_UPD_INTERLEAVE ? 2 * ((a.n / 2 + UPD_WARPS - 1) / UPD_WARPS)
+                                                     : (a.n + UPD_WARPS - 1) / UPD_WARPS);
   if (grid == 0) return MFB_OK;
   int tk = m->prof.begin(cls, st);
 #define CALL(V, N)                                        \
@@ -1110,11 +1182,11 @@ static int launch_update(mfb_model *m, const Shape &sh, const StepGeom &g, const
   return MFB_OK;
 }
 
-static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom &g, int64_t s0,
+static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom &g, int64_t s0, int cap,
                       float *d_step_losses, cudaStream_t st) {
   int ns, b_last;
   int64_t nkeys;
-  chunk_extent(g, s0, &ns, &b_last, &nkeys);
+  chunk_extent(g, s0, cap, &ns, &b_last, &nkeys);
   const int D = g.D, Lfull = g.Lfull, m_neg = g.m_neg;
   const size_t slots = (size_t)g.chunk * Lfull;
   const int *slot_u = pb.slots.as<int>();
@@ -1163,7 +1235,7 @@ static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom
     const int neg_begin = g.adaptive ? b : -1;
     tk = m->prof.begin(PK_FORWARD, st);
 #define CALL(V, N)                                                                                             \
-  launch_pdl(k_forward<V, N>, grid_for_warps(L), BLOCK_THREADS, st, su, si, L, m->users, m->items, D, snap_u, snap_i, \
+  launch_pdl(k_forward<V, N>, grid_for_warps((L + FWD_SPW - 1) / FWD_SPW), BLOCK_THREADS, st, su, si, L, m->users, m->items, D, snap_u, snap_i, \
              pred, neg_begin, gmax + s)
     MFB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
@@ -1264,25 +1336,53 @@ static int run_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const i
     MFB_CHECK(m->ws_tickets.reserve((size_t)2 * g.Lfull * sizeof(int)));
     if (m->ws_tickets.cap != before) MFB_CUDA(cudaMemsetAsync(m->ws_tickets.ptr, 0, m->ws_tickets.cap, st));
   }
-  // the planner stream starts after everything already queued on the caller's stream (the ids may have
-  // been produced there) ...
-  cudaStream_t sp = m->st_plan;
+  // Chunk schedule: the first chunk's plan sits on the critical path (nothing to overlap it with), so chunks start
+  // small and grow -- every later plan then hides behind the execution of the chunk before it (a plan costs a fixed
+  // ~30 launches + ~14 us per step, a step executes in ~40 us: sizes may roughly triple from chunk to chunk).
+  std::vector<std::pair<int64_t, int>> sched;
+  {
+    int cap = m->tune_chunk_ramp > 0 ? m->tune_chunk_ramp : g.chunk;
+    if (cap > g.chunk) cap = g.chunk;
+    int rep = 0;
+    for (int64_t s0 = 0; s0 < g.nsteps;) {
+      const int ns = (int)((g.nsteps - s0 < cap) ? (g.nsteps - s0) : cap);
+      sched.push_back({s0, cap});
+      s0 += ns;
+      if (++rep >= 2 && cap < g.chunk) {   // two chunks of the first size, then doubling
+        cap = cap * 2 > g.chunk ? g.chunk : cap * 2;
+      }
+    }
+  }
+  // the planner and RNG streams start after everything already queued on the caller's stream (the ids may have
+  // been produced there, the generator state is uploaded there) ...
+  cudaStream_t sp = m->st_plan, sr = m->st_rng;
   MFB_CUDA(cudaEventRecord(m->ev_join, st));
   MFB_CUDA(cudaStreamWaitEvent(sp, m->ev_join, 0));
-  const int64_t nchunks = (g.nsteps + g.chunk - 1) / g.chunk;
-  MFB_CHECK(plan_chunk(m, m->plan[0], g, d_pos_users, d_pos_items, d_neg_users, d_neg_items, 0, flag, sp));
-  MFB_CUDA(cudaEventRecord(m->ev_plan[0], sp));
-  for (int64_t c = 0; c < nchunks; ++c) {
-    const int cur = (int)(c & 1), nxt = cur ^ 1;
-    if (c + 1 < nchunks) {
-      // ... and re-uses a plan buffer only after the chunk that trained from it has finished
-      if (c >= 1) MFB_CUDA(cudaStreamWaitEvent(sp, m->ev_done[nxt], 0));
-      MFB_CHECK(plan_chunk(m, m->plan[nxt], g, d_pos_users, d_pos_items, d_neg_users, d_neg_items,
-                           (c + 1) * g.chunk, flag, sp));
-      MFB_CUDA(cudaEventRecord(m->ev_plan[nxt], sp));
+  MFB_CUDA(cudaStreamWaitEvent(sr, m->ev_join, 0));
+  const bool draws = g.pop_len > 0 && g.m_neg > 0;
+  const int64_t nchunks = (int64_t)sched.size();
+  auto plan = [&](int64_t c) -> int {
+    PlanBuf &pb = m->plan[c & 1];
+    if (draws) {
+      // plan buffer c&1 was last read by the planner of chunk c-2 (ev_plan) -- its words may be overwritten now
+      if (c >= 2) MFB_CUDA(cudaStreamWaitEvent(sr, m->ev_plan[c & 1], 0));
+      MFB_CHECK(draw_chunk_words(m, pb, g, sched[c].first, sched[c].second, sr));
+      MFB_CUDA(cudaEventRecord(m->ev_rng[c & 1], sr));
     }
+    // ... re-uses a plan buffer only after the chunk that trained from it has finished
+    if (c >= 2) MFB_CUDA(cudaStreamWaitEvent(sp, m->ev_done[c & 1], 0));
+    if (draws) MFB_CUDA(cudaStreamWaitEvent(sp, m->ev_rng[c & 1], 0));
+    MFB_CHECK(plan_chunk(m, pb, g, d_pos_users, d_pos_items, d_neg_users, d_neg_items, sched[c].first, sched[c].second,
+                         flag, sp));
+    MFB_CUDA(cudaEventRecord(m->ev_plan[c & 1], sp));
+    return MFB_OK;
+  };
+  MFB_CHECK(plan(0));
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int cur = (int)(c & 1);
+    if (c + 1 < nchunks) MFB_CHECK(plan(c + 1));
     MFB_CUDA(cudaStreamWaitEvent(st, m->ev_plan[cur], 0));
-    MFB_CHECK(exec_chunk(m, m->plan[cur], sh, g, c * g.chunk, d_step_losses, st));
+    MFB_CHECK(exec_chunk(m, m->plan[cur], sh, g, sched[c].first, sched[c].second, d_step_losses, st));
     MFB_CUDA(cudaEventRecord(m->ev_done[cur], st));
   }
   // ids were clamped on the device; report a bad id once, after the queue drains

@@ -28,12 +28,16 @@ def _record(rep):
             f.write(json.dumps(rep) + '\n')
 
 
-def _assert_tables(rep):
+def _assert_tables(rep, factor=None):
     """All four tables within 1e-5 relative (max-norm) of the fp32 reference run -- no lr-unit exception for the bias
-    tables here -- or, where duplicate-heavy batches put the reference's own fp32 rounding above that bar, no farther
-    from the exact (float64) arithmetic than 1.5x the fp32 reference itself is (config_parity.table_report)."""
+    tables here.  Where duplicate-heavy batches put the reference's OWN fp32 rounding above that bar (`env` > 1e-5:
+    its deviation from a float64 run of the same algorithm, config_parity.table_report), the CUDA result must be no
+    farther from the exact arithmetic than `factor` x the fp32 reference is: 2x with IEEE sqrt/div, 4x with the
+    MUFU approximations of the fast mode (each approximate op carries ~2 ulp instead of 0.5)."""
+    if factor is None:
+        factor = 4.0 if rep['fast_math'] else 2.0
     for i, t in enumerate(rep['tables']):
-        assert t['rel'] < 1e-5 or (t['env'] > 1e-5 and t['rel64'] <= 1.5 * t['env']), (i, t)
+        assert t['rel'] < 1e-5 or (t['env'] > 1e-5 and t['rel64'] <= factor * t['env']), (i, t)
 
 
 @pytest.mark.parametrize('fast_math', [False, True], ids=['ieee', 'fast'])
