@@ -185,14 +185,25 @@ int mfb_train_epoch_host(mfb_model *m, int loss, const int64_t *h_pos_users, con
                          float *h_step_losses, mfb_stream stream);
 
 /* ---- full-catalog evaluation ------------------------------------------------------------ */
-/* Scores every listed user against all items and keeps the top-k (k <= MFB_MAX_TOPK) item ids,
+/* Scores every listed user against all items and keeps the top-k item ids (any 1 <= k <= num_items),
  * best first, ties -> lower item id, ranking on the pre-sigmoid score; items in the user's
  * train row (CSR, sorted indices; may be NULL) rank last (evaluation.py:160-169).
- * Replaces the per-user predict + argsort loop of precision_recall_score. */
+ * Replaces the per-user predict + argsort loop of precision_recall_score, which accepts any k
+ * (evaluation.py:144-150).  k <= MFB_MAX_TOPK with embedding_dim 64 or 128 takes the tensor-core path
+ * (bit-identical ids); larger k the exact fp32 kernel, in passes of 256 ranks. */
 #define MFB_MAX_TOPK 32
 int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
              const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
              mfb_stream stream);
+/* The same ranking over rows of a dense score matrix [n_rows, n_items] that some other model produced -- the
+ * `representation=` escape hatch of ImplicitFactorizationModel (implicit.py:169-180: MLP, NeuMF, ...), whose scores
+ * come from a torch module instead of the bilinear kernel.  Descending score, ties -> lower item id, train items of
+ * the row's user (d_user_ids[row]; NULL: user = row) last.  d_out_scores (may be NULL) receives the given scores
+ * (-FLT_MAX for train items, as evaluation.py:163 sets them).  d_cut_scratch: n_rows * 8 bytes of device scratch,
+ * required only when k > 256. */
+int mfb_topk_scores(const float *d_scores, int64_t n_rows, int64_t n_items, const int64_t *d_user_ids,
+                    const int64_t *d_train_indptr, const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids,
+                    float *d_out_scores, void *d_cut_scratch, mfb_stream stream);
 /* Users that the last mfb_topk call had to redo with the exact-fp32 kernel (tensor-core path bookkeeping). */
 int mfb_topk_last_redo(const mfb_model *m);
 /* Test hook: raw tensor-core scores (bf16 inputs, fp32 accumulate, + item bias), item-major

@@ -173,7 +173,8 @@ extern "C" int mfb_model_destroy(mfb_model *m) {
   m->rng_state.release();
   {
     DevBuf *ebufs[] = {&m->eval.ub, &m->eval.vb, &m->eval.unorm, &m->eval.vnorm, &m->eval.gmax, &m->eval.thr,
-                       &m->eval.cand, &m->eval.cnt, &m->eval.redo, &m->eval.mcnt, &m->eval.mptr, &m->eval.mpairs};
+                       &m->eval.cand, &m->eval.cnt, &m->eval.redo, &m->eval.mcnt, &m->eval.mptr, &m->eval.mpairs,
+                       &m->eval.cut};
     for (DevBuf *b : ebufs) b->release();
   }
   if (m->st_plan) cudaStreamDestroy(m->st_plan);

@@ -18,34 +18,71 @@ constexpr int EV_USERS = 16;    // users per CTA (2 groups of 8, one group per h
 constexpr int EV_UPT = 8;       // users per thread
 constexpr float MASKED_SCORE = -3.402823466e38f;  // ranks after every real score, before empty slots
 
-// Warp-resident sorted top-k list: lane r holds the r-th best (value, id).
+// Warp-resident sorted top-k list of up to 32 * KL entries: rank r lives in register r / 32 of lane r % 32.
+// Candidates arrive in ascending item id, so a new entry goes after every entry with val >= nv (ties -> lower id first).
+template <int KL>
 struct TopK {
-  float val;
-  int id;
+  float val[KL];
+  int id[KL];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < KL; ++j) {
+      val[j] = -INFINITY;
+      id[j] = 0x7fffffff;
+    }
+  }
+  // value at rank r (warp-uniform r)
+  __device__ __forceinline__ float value_at(int r) const {
+    float v = val[0];
+#pragma unroll
+    for (int j = 1; j < KL; ++j) v = (r >> 5) == j ? val[j] : v;
+    return __shfl_sync(0xffffffffu, v, r & 31);
+  }
+  __device__ __forceinline__ void insert(float nv, int nid, int lane) {
+    int pos = 0;
+#pragma unroll
+    for (int j = 0; j < KL; ++j) pos += __popc(__ballot_sync(0xffffffffu, val[j] >= nv));
+#pragma unroll
+    for (int j = KL - 1; j >= 0; --j) {     // high registers first: register j-1 still holds its old entries
+      float up_v = __shfl_up_sync(0xffffffffu, val[j], 1);
+      int up_i = __shfl_up_sync(0xffffffffu, id[j], 1);
+      if (j > 0) {
+        const float pv = __shfl_sync(0xffffffffu, val[j - 1], 31);
+        const int pi = __shfl_sync(0xffffffffu, id[j - 1], 31);
+        if (lane == 0) {
+          up_v = pv;
+          up_i = pi;
+        }
+      }
+      const int r = j * 32 + lane;
+      if (r > pos) {
+        val[j] = up_v;
+        id[j] = up_i;
+      } else if (r == pos) {
+        val[j] = nv;
+        id[j] = nid;
+      }
+    }
+  }
 };
 
-__device__ __forceinline__ void topk_insert(TopK &mine, float nv, int nid, int lane, int k) {
-  // candidates arrive in ascending item id, so a new entry goes after every entry with val >= nv
-  unsigned ge = __ballot_sync(0xffffffffu, mine.val >= nv);
-  int pos = __popc(ge);
-  float up_v = __shfl_up_sync(0xffffffffu, mine.val, 1);
-  int up_i = __shfl_up_sync(0xffffffffu, mine.id, 1);
-  if (lane > pos) {
-    mine.val = up_v;
-    mine.id = up_i;
-  } else if (lane == pos) {
-    mine.val = nv;
-    mine.id = nid;
-  }
-  (void)k;
+// A candidate is admissible when it ranks strictly after the cut-off (cut_val, cut_id) of the previous pass
+// (k > 32 * KL is served in passes of 32 * KL ranks); cut_id < 0: no cut-off.
+__device__ __forceinline__ bool after_cut(float sc, int it, float cut_val, int cut_id) {
+  return cut_id < 0 || sc < cut_val || (sc == cut_val && it > cut_id);
 }
 
 // grid: ceil(n_users / EV_USERS).  dynamic smem: Vs[EV_ITEMS][D+1] | Us[EV_USERS][D] | S[EV_USERS][EV_ITEMS]
+template <int KL>
 __global__ void __launch_bounds__(EV_THREADS) k_topk_exact(const long long *__restrict__ user_ids, int n_users,
                                                            TableView users, TableView items, int D,
                                                            const long long *__restrict__ indptr,
-                                                           const int *__restrict__ indices, int k,
-                                                           int *__restrict__ out_ids, float *__restrict__ out_scores) {
+                                                           const int *__restrict__ indices, int k, int out_stride,
+                                                           int *__restrict__ out_ids, float *__restrict__ out_scores,
+                                                           const float *__restrict__ cut_val_in,
+                                                           const int *__restrict__ cut_id_in,
+                                                           float *__restrict__ cut_val_out,
+                                                           int *__restrict__ cut_id_out) {
   extern __shared__ float smem[];
   const int ldv = D + 1;
   float *Vs = smem;
@@ -72,12 +109,20 @@ __global__ void __launch_bounds__(EV_THREADS) k_topk_exact(const long long *__re
   }
 
   // each warp owns two users of the tile for masking / top-k
-  TopK top[2];
+  TopK<KL> top[2];
   long long cur[2], end[2];
+  float cutv[2];
+  int cuti[2];
 #pragma unroll
   for (int w = 0; w < 2; ++w) {
-    top[w].val = -INFINITY;
-    top[w].id = 0x7fffffff;
+    top[w].init();
+    const int ui = u0 + wid * 2 + w;
+    cutv[w] = 0.f;
+    cuti[w] = -1;
+    if (cut_id_in != nullptr && ui < n_users) {
+      cutv[w] = cut_val_in[ui];
+      cuti[w] = cut_id_in[ui];
+    }
     long long uid = s_uid[wid * 2 + w];
     cur[w] = end[w] = 0;
     if (uid >= 0 && indptr != nullptr) {
@@ -149,15 +194,15 @@ __global__ void __launch_bounds__(EV_THREADS) k_topk_exact(const long long *__re
         const int il = c * 32 + lane;
         const int it = i0 + il;
         float sc = srow[il];
-        float thr = __shfl_sync(0xffffffffu, top[w].val, k - 1);
-        unsigned cand = __ballot_sync(0xffffffffu, (it < I) && (sc > thr));
+        float thr = top[w].value_at(k - 1);
+        unsigned cand = __ballot_sync(0xffffffffu, (it < I) && (sc > thr) && after_cut(sc, it, cutv[w], cuti[w]));
         while (cand) {
           int src = __ffs(cand) - 1;
           cand &= cand - 1;
           float nv = __shfl_sync(0xffffffffu, sc, src);
           int nid = i0 + c * 32 + src;
-          thr = __shfl_sync(0xffffffffu, top[w].val, k - 1);
-          if (nv > thr) topk_insert(top[w], nv, nid, lane, k);
+          thr = top[w].value_at(k - 1);
+          if (nv > thr) top[w].insert(nv, nid, lane);
         }
       }
     }
@@ -165,11 +210,89 @@ __global__ void __launch_bounds__(EV_THREADS) k_topk_exact(const long long *__re
 #pragma unroll
   for (int w = 0; w < 2; ++w) {
     const int ui = u0 + wid * 2 + w;
-    if (ui < n_users && lane < k) {
-      out_ids[(long long)ui * k + lane] = top[w].id;
-      if (out_scores) {
-        float z = top[w].val;
-        out_scores[(long long)ui * k + lane] = (z == MASKED_SCORE) ? 0.f : 1.0f / (1.0f + expf(-z));
+    if (ui >= n_users) continue;
+#pragma unroll
+    for (int j = 0; j < KL; ++j) {
+      const int r = j * 32 + lane;
+      if (r < k) {
+        out_ids[(long long)ui * out_stride + r] = top[w].id[j];
+        if (out_scores) {
+          float z = top[w].val[j];
+          out_scores[(long long)ui * out_stride + r] = (z == MASKED_SCORE) ? 0.f : 1.0f / (1.0f + expf(-z));
+        }
+        if (cut_id_out != nullptr && r == k - 1) {    // where the next pass resumes
+          cut_val_out[ui] = top[w].val[j];
+          cut_id_out[ui] = top[w].id[j];
+        }
+      }
+    }
+  }
+}
+
+// Top-k of the rows of a dense score matrix [n_rows, n_items] (scores produced by any model, e.g. an MLP / NeuMF
+// `representation=`): descending score, ties -> lower item id, the row user's train items last.  One warp per row.
+template <int KL>
+__global__ void __launch_bounds__(EV_THREADS) k_topk_dense(const float *__restrict__ scores, int n_rows, int n_items,
+                                                           const long long *__restrict__ user_ids,
+                                                           const long long *__restrict__ indptr,
+                                                           const int *__restrict__ indices, int k, int out_stride,
+                                                           int *__restrict__ out_ids, float *__restrict__ out_scores,
+                                                           const float *__restrict__ cut_val_in,
+                                                           const int *__restrict__ cut_id_in,
+                                                           float *__restrict__ cut_val_out,
+                                                           int *__restrict__ cut_id_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (EV_THREADS / 32) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  TopK<KL> top;
+  top.init();
+  float cutv = 0.f;
+  int cuti = -1;
+  if (cut_id_in != nullptr) {
+    cutv = cut_val_in[row];
+    cuti = cut_id_in[row];
+  }
+  long long cur = 0, end = 0;
+  if (indptr != nullptr) {
+    const long long uid = user_ids ? user_ids[row] : row;
+    cur = indptr[uid];
+    end = indptr[uid + 1];
+  }
+  const float *srow = scores + (long long)row * n_items;
+  for (int i0 = 0; i0 < n_items; i0 += 32) {
+    const int it = i0 + lane;
+    float sc = (it < n_items) ? srow[it] : -INFINITY;
+    // train items inside [i0, i0+32): the CSR row is sorted, the cursor only moves forward
+    unsigned masked = 0u;
+    while (cur < end) {
+      const long long p = cur + lane;
+      const int idx = (p < end) ? indices[p] : 0x7fffffff;
+      const bool in = idx < i0 + 32;
+      masked |= __reduce_or_sync(0xffffffffu, (in && idx >= i0) ? (1u << (idx - i0)) : 0u);
+      const unsigned nin = __popc(__ballot_sync(0xffffffffu, in));
+      cur += nin;
+      if (nin < 32) break;
+    }
+    if ((masked >> lane) & 1u) sc = MASKED_SCORE;
+    float thr = top.value_at(k - 1);
+    unsigned cand = __ballot_sync(0xffffffffu, (it < n_items) && (sc > thr) && after_cut(sc, it, cutv, cuti));
+    while (cand) {
+      const int src = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const float nv = __shfl_sync(0xffffffffu, sc, src);
+      thr = top.value_at(k - 1);
+      if (nv > thr) top.insert(nv, i0 + src, lane);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KL; ++j) {
+    const int r = j * 32 + lane;
+    if (r < k) {
+      out_ids[(long long)row * out_stride + r] = top.id[j];
+      if (out_scores) out_scores[(long long)row * out_stride + r] = top.val[j];
+      if (cut_id_out != nullptr && r == k - 1) {
+        cut_val_out[row] = top.val[j];
+        cut_id_out[row] = top.id[j];
       }
     }
   }
@@ -200,6 +323,17 @@ __global__ void k_topk_hits(const int *__restrict__ topk, const long long *__res
 
 }  // namespace
 
+constexpr int EV_PASS_RANKS = 256;   // ranks per pass of the warp-resident list (8 registers x 32 lanes)
+
+// launch one pass of KERNEL<KL> with KL chosen from the pass width
+#define MFB_TOPK_DISPATCH(KERNEL, kpass, GRID, SMEM, ...)                                   \
+  do {                                                                                      \
+    if ((kpass) <= 32) KERNEL<1><<<GRID, EV_THREADS, SMEM, st>>>(__VA_ARGS__);              \
+    else if ((kpass) <= 64) KERNEL<2><<<GRID, EV_THREADS, SMEM, st>>>(__VA_ARGS__);         \
+    else if ((kpass) <= 128) KERNEL<4><<<GRID, EV_THREADS, SMEM, st>>>(__VA_ARGS__);        \
+    else KERNEL<8><<<GRID, EV_THREADS, SMEM, st>>>(__VA_ARGS__);                            \
+  } while (0)
+
 static int topk_exact_impl(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
                            const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
                            cudaStream_t st) {
@@ -209,14 +343,29 @@ static int topk_exact_impl(mfb_model *m, const int64_t *d_user_ids, int64_t n_us
     mfb_set_error("topk: embedding_dim %d needs %zu B of shared memory", D, smem);
     return MFB_ERR_UNSUPPORTED;
   }
-  MFB_CUDA(cudaFuncSetAttribute(k_topk_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((n_users + EV_USERS - 1) / EV_USERS);
-  int tk = m->prof.begin(PK_TOPK, st);
-  k_topk_exact<<<grid, EV_THREADS, smem, st>>>((const long long *)d_user_ids, (int)n_users, m->users, m->items, D,
-                                               (const long long *)d_train_indptr, d_train_indices, k, d_out_ids,
-                                               d_out_scores);
-  m->prof.end(tk, st);
-  MFB_KERNEL_CHECK();
+  // k beyond one pass of the warp-resident list: further passes resume after the last (score, id) of the previous one
+  float *cut_val = nullptr;
+  int *cut_id = nullptr;
+  if (k > EV_PASS_RANKS) {
+    MFB_CHECK(m->eval.cut.reserve((size_t)n_users * (sizeof(float) + sizeof(int))));
+    cut_val = m->eval.cut.as<float>();
+    cut_id = reinterpret_cast<int *>(cut_val + n_users);
+  }
+  for (int done = 0; done < k; done += EV_PASS_RANKS) {
+    const int kpass = (k - done < EV_PASS_RANKS) ? (k - done) : EV_PASS_RANKS;
+    int tk = m->prof.begin(PK_TOPK, st);
+    MFB_TOPK_DISPATCH(k_topk_exact, kpass, grid, smem, (const long long *)d_user_ids, (int)n_users, m->users, m->items, D,
+                      (const long long *)d_train_indptr, d_train_indices, kpass, (int)k, d_out_ids + done,
+                      d_out_scores ? d_out_scores + done : nullptr, done ? cut_val : nullptr, done ? cut_id : nullptr,
+                      cut_val, cut_id);
+    m->prof.end(tk, st);
+    MFB_KERNEL_CHECK();
+  }
   return MFB_OK;
 }
 
@@ -225,8 +374,8 @@ extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users
                         mfb_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!m || !d_user_ids || !d_out_ids || n_users < 0) return MFB_ERR_INVALID;
-  if (k <= 0 || k > MFB_MAX_TOPK || k > m->items.rows) {
-    mfb_set_error("topk: k=%d outside 1..min(%d, num_items)", k, MFB_MAX_TOPK);
+  if (k <= 0 || k > m->items.rows) {
+    mfb_set_error("topk: k=%d outside 1..num_items (%d)", k, m->items.rows);
     return MFB_ERR_UNSUPPORTED;
   }
   if ((d_train_indptr == nullptr) != (d_train_indices == nullptr)) return MFB_ERR_INVALID;
@@ -234,11 +383,44 @@ extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users
   MFB_CHECK(mfb_flush(m, stream));
   m->last_topk_redo = 0;
   // large problems go through the tensor-core path (bf16 candidates + exact fp32 re-score: same ids as the
-  // exact kernel); small ones are not worth the extra passes
+  // exact kernel); small ones -- and k beyond MFB_MAX_TOPK -- take the exact kernel
   if (mfb_tc_supported(m, k) && n_users >= 64 && n_users < (1ll << 30))
     return mfb_topk_tc(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st,
                        topk_exact_impl, &m->last_topk_redo);
   return topk_exact_impl(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st);
+}
+
+// Top-k of dense score rows (scores from any model): see k_topk_dense.  d_user_ids maps a row to the user whose train
+// row masks it (null: row r is user r); d_cut_scratch: n_rows * 8 bytes of device scratch, needed only when k > 256.
+extern "C" int mfb_topk_scores(const float *d_scores, int64_t n_rows, int64_t n_items, const int64_t *d_user_ids,
+                               const int64_t *d_train_indptr, const int32_t *d_train_indices, int32_t k,
+                               int32_t *d_out_ids, float *d_out_scores, void *d_cut_scratch, mfb_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_scores || !d_out_ids || n_rows < 0 || n_items <= 0 || n_items >= (1ll << 31) || n_rows >= (1ll << 31))
+    return MFB_ERR_INVALID;
+  if (k <= 0 || k > n_items) {
+    mfb_set_error("topk_scores: k=%d outside 1..num_items (%lld)", k, (long long)n_items);
+    return MFB_ERR_UNSUPPORTED;
+  }
+  if ((d_train_indptr == nullptr) != (d_train_indices == nullptr)) return MFB_ERR_INVALID;
+  if (k > EV_PASS_RANKS && d_cut_scratch == nullptr) {
+    mfb_set_error("topk_scores: k=%d > %d needs the cut-off scratch", k, EV_PASS_RANKS);
+    return MFB_ERR_INVALID;
+  }
+  if (n_rows == 0) return MFB_OK;
+  float *cut_val = reinterpret_cast<float *>(d_cut_scratch);
+  int *cut_id = cut_val ? reinterpret_cast<int *>(cut_val + n_rows) : nullptr;
+  const int grid = (int)((n_rows + EV_THREADS / 32 - 1) / (EV_THREADS / 32));
+  for (int done = 0; done < k; done += EV_PASS_RANKS) {
+    const int kpass = (k - done < EV_PASS_RANKS) ? (k - done) : EV_PASS_RANKS;
+    mfb_count_library_launch(1);
+    MFB_TOPK_DISPATCH(k_topk_dense, kpass, grid, 0, d_scores, (int)n_rows, (int)n_items, (const long long *)d_user_ids,
+                      (const long long *)d_train_indptr, d_train_indices, kpass, (int)k, d_out_ids + done,
+                      d_out_scores ? d_out_scores + done : nullptr, done ? cut_val : nullptr, done ? cut_id : nullptr,
+                      cut_val, cut_id);
+    MFB_KERNEL_CHECK();
+  }
+  return MFB_OK;
 }
 
 // Number of users the last mfb_topk call re-did with the exact kernel (tensor-core path only).

@@ -121,7 +121,7 @@ struct PlanBuf {
 
 // Workspaces of the tensor-core evaluation path (mfb_eval_tc.cu)
 struct EvalBuf {
-  DevBuf ub, vb, unorm, vnorm, gmax, thr, cand, cnt, redo, mcnt, mptr, mpairs;
+  DevBuf ub, vb, unorm, vnorm, gmax, thr, cand, cnt, redo, mcnt, mptr, mpairs, cut;
   int nsub = 2;   // candidate sub-lists per user in the last tensor-core pass (2 column halves x item-tile splits)
   int n_users_pad = 0;   // padded user count of the last tensor-core pass (layout of the per-user scratch arrays)
 };

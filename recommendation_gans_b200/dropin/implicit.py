@@ -75,6 +75,7 @@ class ImplicitFactorizationModel(object):
         self._loss_func = None
         self._loss_kind = None
         self._engine_ = None
+        self._generic = False
         self._neg_pop = None
         self.best_model = None
         self.best_validation = None
@@ -98,11 +99,12 @@ class ImplicitFactorizationModel(object):
 
     # -------------------------------------------------------------------------------------------
     def _bind(self, net):
-        if not isinstance(net, BilinearNet):
-            raise NotImplementedError('mfb200 accelerates the BilinearNet representation only; got %s'
-                                      % type(net).__name__)
-        if self._sparse or any(getattr(l, 'sparse', False) for l in
-                               (net.user_embeddings, net.item_embeddings, net.user_biases, net.item_biases)):
+        """BilinearNet runs on the fused CUDA step; any other torch module (`representation=` MLP, NeuMF, ...,
+        implicit.py:169-180) trains on the generic torch-autograd step -- with the negative pairs still drawn on the
+        device from Python's `random` stream and the evaluation still ranked by the CUDA top-k kernel."""
+        self._generic = not isinstance(net, BilinearNet)
+        if not self._generic and (self._sparse or any(getattr(l, 'sparse', False) for l in
+                                  (net.user_embeddings, net.item_embeddings, net.user_biases, net.item_biases))):
             raise NotImplementedError('mfb200: sparse=True embeddings are not supported '
                                       '(the reference script always uses sparse=False)')
         return net.cuda()
@@ -139,8 +141,11 @@ class ImplicitFactorizationModel(object):
             self._loss_kind, self._loss_func = 'hinge', _losses.hinge_loss
         else:
             self._loss_kind, self._loss_func = 'adaptive_hinge', _losses.adaptive_hinge_loss
-        self._engine_ = MFEngine(self._net, self._optimizer)
-        self._net._attach_engine(self._engine_)
+        if self._generic:
+            self._engine_ = None
+        else:
+            self._engine_ = MFEngine(self._net, self._optimizer)
+            self._net._attach_engine(self._engine_)
         self.configuration = {
             'num_users': self._num_users, 'num_items': self._num_items, 'weight_decay': self._l2,
             'lr': self._learning_rate, 'embedding_dim': self._embedding_dim,
@@ -167,7 +172,7 @@ class ImplicitFactorizationModel(object):
             pairs = np.asarray(self.neg_examples, dtype=np.int64).reshape(-1, 2)
             if pairs[:, 0].max() >= self._num_users or pairs[:, 1].max() >= self._num_items or pairs.min() < 0:
                 raise IndexError('index out of range in self')       # what nn.Embedding raises in the reference
-            dev = self._engine_.device
+            dev = next(self._net.parameters()).device
             self._neg_pop = (torch.from_numpy(np.ascontiguousarray(pairs[:, 0])).to(dev),
                              torch.from_numpy(np.ascontiguousarray(pairs[:, 1])).to(dev), self.neg_examples)
         return self._neg_pop
@@ -178,9 +183,11 @@ class ImplicitFactorizationModel(object):
         item_ids = train_set.item_ids
         users, items = shuffle(user_ids, item_ids, random_state=self._random_state)   # once per fit
 
-        if not self._initialized or self._engine_ is None:
+        if not self._initialized or (self._engine_ is None and not self._generic) or self._optimizer is None:
             self._initialize(train_set)
         self._check_input(user_ids, item_ids)
+        if self._generic:
+            return self._fit_generic(users, items, valid_set, verbose)
         dev = self._engine_.device
         users_d = torch.from_numpy(np.ascontiguousarray(users)).to(dev).long()
         items_d = torch.from_numpy(np.ascontiguousarray(items)).to(dev).long()
@@ -232,8 +239,96 @@ class ImplicitFactorizationModel(object):
         self.save_readable_model(self.experiment_saved_models, self.best_model.state_dict())
         logging.info("Model chosen from epoch %d", self.best_epoch)
 
+    # -------------------------------------------------------------------------------------------
+    # generic representation (MLP, NeuMF, any torch module): implicit.py:279-343 with torch autograd
+    def _generic_step(self, batch_user, batch_item, neg_user, neg_item, train):
+        """run_train_iteration / run_val_iteration (implicit.py:347-379) on a torch module.  Module outputs of shape
+        [n, 1] (MLP, NeuMF) are flattened: every loss of losses.py treats [n, 1] and [n] alike."""
+        pos = self._net(batch_user, batch_item).reshape(-1)
+        if train:
+            self._optimizer.zero_grad()
+        if neg_user is not None:
+            neg = self._net(neg_user, neg_item).reshape(-1)
+            loss = self._loss_func(pos, neg)
+        else:
+            loss = self._loss_func(pos)
+        if train:
+            loss.backward()
+            self._optimizer.step()
+        return loss.detach()
+
+    def _fit_generic(self, users, items, valid_set, verbose):
+        from recommendation_gans_b200.engine import draw_negative_pairs_device
+        dev = next(self._net.parameters()).device
+        users_d = torch.from_numpy(np.ascontiguousarray(users)).to(dev).long()
+        items_d = torch.from_numpy(np.ascontiguousarray(items)).to(dev).long()
+        val_users_d = torch.from_numpy(np.ascontiguousarray(valid_set.user_ids)).to(dev).long()
+        val_items_d = torch.from_numpy(np.ascontiguousarray(valid_set.item_ids)).to(dev).long()
+        B = self._batch_size
+        pop = self._negative_population()
+        k = self._num_negative_samples * B if pop is not None else 0
+        total_losses = {"train_loss": [], "validation_loss": [], "curr_epoch": []}
+
+        def run(ids_u, ids_i, train):
+            # all negative pairs of the pass in one device draw: the same stream positions as one
+            # random.choices(neg_examples, k) per minibatch (implicit.py:352,370)
+            nsteps = (len(ids_u) + B - 1) // B
+            neg_u = neg_i = None
+            if pop is not None:
+                neg_u, neg_i = draw_negative_pairs_device(pop[0], pop[1], nsteps * k, rng=random)
+            losses = []
+            for s in range(nsteps):
+                nu = neg_u[s * k:(s + 1) * k] if pop is not None else None
+                ni = neg_i[s * k:(s + 1) * k] if pop is not None else None
+                losses.append(self._generic_step(ids_u[s * B:(s + 1) * B], ids_i[s * B:(s + 1) * B], nu, ni, train))
+            return [float(x) for x in torch.stack(losses).cpu().numpy()]     # one device->host read per pass
+
+        for epoch_num in range(self._n_iter):
+            self._net.train()
+            train_steps = run(users_d, items_d, True)
+            train_epoch_loss = sum(train_steps) / len(train_steps)
+            if np.isnan(train_epoch_loss) or train_epoch_loss == 0.0:
+                raise ValueError('Degenerate epoch loss: {}'.format(train_epoch_loss))
+            self._net.eval()
+            with torch.no_grad():
+                val_steps = run(val_users_d, val_items_d, False)
+            valid_epoch_loss = sum(val_steps) / len(val_steps)
+            if self.best_validation is None or valid_epoch_loss < self.best_validation:
+                self.best_model = copy.deepcopy(self._net)
+                self.best_validation = valid_epoch_loss
+                self.best_epoch = epoch_num
+            if verbose:
+                logging.info('Epoch {}: training_loss {:10.5f}'.format(epoch_num, train_epoch_loss))
+                logging.info('Epoch {}: validation_loss {:10.5f}'.format(epoch_num, valid_epoch_loss))
+            total_losses["train_loss"].append(np.mean(train_steps))
+            total_losses["validation_loss"].append(np.mean(val_steps))
+            total_losses['curr_epoch'].append(epoch_num)
+            save_statistics(experiment_log_dir=self.experiment_logs, filename='summary.csv',
+                            stats_dict=total_losses, current_epoch=epoch_num,
+                            continue_from_mode=(self.starting_epoch != 0 or epoch_num > 0))
+        self._net = self.best_model
+        self._optimizer = None                              # bound to the pre-copy parameters: rebuilt by the next fit
+        self.save_readable_model(self.experiment_saved_models, self.best_model.state_dict())
+        logging.info("Model chosen from epoch %d", self.best_epoch)
+
     # single-step API (implicit.py:347-379): same kernels, one minibatch
     def _one_batch(self, batch_user, batch_item, train):
+        if self._generic:
+            from recommendation_gans_b200.engine import draw_negative_pairs_device
+            if self._optimizer is None:
+                raise RuntimeError('model is not initialised for training (call fit or _initialize first)')
+            dev = next(self._net.parameters()).device
+            pop = self._negative_population()
+            nu = ni = None
+            if pop is not None:
+                nu, ni = draw_negative_pairs_device(pop[0], pop[1], self._num_negative_samples * self._batch_size,
+                                                    rng=random)
+            bu = torch.as_tensor(batch_user, device=dev).long()
+            bi = torch.as_tensor(batch_item, device=dev).long()
+            if train:
+                return self._generic_step(bu, bi, nu, ni, True)
+            with torch.no_grad():
+                return self._generic_step(bu, bi, nu, ni, False)
         if self._engine_ is None:
             raise RuntimeError('model is not initialised for training (call fit or _initialize first)')
         if len(batch_user) > self._batch_size:
@@ -250,7 +345,10 @@ class ImplicitFactorizationModel(object):
         return fn(self._loss_kind, batch_user, batch_item, self._batch_size, n_neg, neg_u, neg_i)[0]
 
     def run_train_iteration(self, batch_user, batch_item):
-        return self._one_batch(batch_user, batch_item, True)
+        loss = self._one_batch(batch_user, batch_item, True)
+        if self._engine_ is not None:
+            self._engine_.flush()       # the reference leaves net.*.weight current after every iteration
+        return loss
 
     def run_val_iteration(self, batch_user, batch_item):
         return self._one_batch(batch_user, batch_item, False)
@@ -259,6 +357,11 @@ class ImplicitFactorizationModel(object):
     def predict(self, user_ids, item_ids=None):
         self._check_input(user_ids, item_ids, allow_items_none=True)
         self._net.train(False)
+        if self._generic:
+            users, items = _predict_process_ids(user_ids, item_ids, self._num_items, True)
+            with torch.no_grad():
+                out = self._net(users, items)
+            return out.cpu().detach().numpy().flatten()
         eng = self._engine_ if self._engine_ is not None else self._net._engine()
         if np.isscalar(user_ids) and item_ids is None:
             out = eng.predict_user(int(user_ids))

@@ -13,10 +13,53 @@ import torch
 FLOAT_MAX = np.finfo(np.float32).max
 
 
+class _ModuleRanker(object):
+    """Ranking backend for a model whose scores come from an arbitrary torch module (`representation=` MLP / NeuMF,
+    implicit.py:169-180): the module scores blocks of users against the whole catalogue and the CUDA ranking kernel
+    (mfb_topk_scores) keeps the top-k with the train mask -- the score matrix lives only one block at a time."""
+
+    def __init__(self, model):
+        self.net = model._net
+        self.device = next(self.net.parameters()).device
+        self.num_users, self.num_items = int(model._num_users), int(model._num_items)
+
+    def topk(self, user_ids, k, train_indptr=None, train_indices=None, with_scores=False):
+        from recommendation_gans_b200.engine import topk_scores_device
+        user_ids = torch.as_tensor(user_ids, dtype=torch.int64, device=self.device).reshape(-1)
+        n, I = user_ids.numel(), self.num_items
+        ids = torch.empty((n, int(k)), dtype=torch.int32, device=self.device)
+        scores = torch.empty((n, int(k)), dtype=torch.float32, device=self.device) if with_scores else None
+        block = max(1, min(4096, (1 << 24) // I))
+        items = torch.arange(I, device=self.device, dtype=torch.int64)
+        was_training = self.net.training
+        self.net.train(False)
+        with torch.no_grad():
+            for lo in range(0, n, block):
+                u = user_ids[lo:lo + block]
+                s = self.net(u.repeat_interleave(I), items.repeat(u.numel())).reshape(u.numel(), I)
+                out = topk_scores_device(s, k, u, train_indptr, train_indices, with_scores=with_scores)
+                if with_scores:
+                    ids[lo:lo + block], scores[lo:lo + block] = out
+                else:
+                    ids[lo:lo + block] = out
+        self.net.train(was_training)
+        return (ids, scores) if with_scores else ids
+
+    def topk_hits(self, topk_ids, user_ids, test_indptr, test_indices, ks):
+        from recommendation_gans_b200.engine import topk_hits_device
+        return topk_hits_device(topk_ids, user_ids, test_indptr, test_indices, ks)
+
+    def rank_test_items(self, *args, **kwargs):
+        raise NotImplementedError('mrr_score: average ranks are implemented for the BilinearNet representation only')
+
+
 def _native_engine(model):
+    """The ranking backend of a fitted model: the fused engine for BilinearNet, the module ranker for anything else."""
     net = getattr(model, '_net', None)
-    if net is None or not hasattr(net, '_engine'):
-        raise NotImplementedError('evaluation: only models backed by the CUDA BilinearNet are supported')
+    if net is None:
+        raise ValueError('evaluation: the model has no network (call fit or set_users first)')
+    if not hasattr(net, '_engine'):
+        return _ModuleRanker(model)
     eng = getattr(model, '_engine_', None)
     return eng if eng is not None else net._engine()
 

@@ -11,6 +11,31 @@ import torch.nn as nn
 from spotlight.layers import ScaledEmbedding, ZeroEmbedding
 
 
+class _BilinearFunction(torch.autograd.Function):
+    """sigmoid(<U[u],V[i]> + bu[u] + bi[i]) with the fused CUDA forward and a backward that produces the same dense
+    table gradients as autograd through the reference's nn.Embedding expressions (embedding_dense_backward).  Used
+    when a caller differentiates through `forward` itself -- a hand-written loop `loss(net(u, i), net(u', i'))
+    .backward(); optimizer.step()` -- instead of ImplicitFactorizationModel's fused step.  The backward is plain
+    torch: this is the compatibility path, not the hot path."""
+
+    @staticmethod
+    def forward(ctx, net, users, items, ue, ie, ub, ib):
+        out = net._engine().predict_pairs(users, items)
+        ctx.save_for_backward(users, items, ue, ie, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        users, items, ue, ie, out = ctx.saved_tensors
+        dz = (grad_out * out * (1.0 - out)).unsqueeze(1)
+        u_rows, i_rows = ue.detach()[users], ie.detach()[items]
+        g_ue = torch.zeros_like(ue).index_add_(0, users, dz * i_rows)
+        g_ie = torch.zeros_like(ie).index_add_(0, items, dz * u_rows)
+        g_ub = torch.zeros(ue.shape[0], 1, dtype=ue.dtype, device=ue.device).index_add_(0, users, dz)
+        g_ib = torch.zeros(ie.shape[0], 1, dtype=ie.dtype, device=ie.device).index_add_(0, items, dz)
+        return None, None, None, g_ue, g_ie, g_ub, g_ib
+
+
 class BilinearNet(nn.Module):
 
     def __init__(self, num_users, num_items, embedding_dim=32,
@@ -49,4 +74,9 @@ class BilinearNet(nn.Module):
         if users.numel() == 1 and items.numel() == 1:
             # the reference squeezes the [1, D] embeddings to 1-D and then fails in .sum(1)
             raise IndexError('Dimension out of range (expected to be in range of [-1, 0], but got 1)')
+        params = (self.user_embeddings.weight, self.item_embeddings.weight, self.user_biases.weight,
+                  self.item_biases.weight)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            dev = params[0].device
+            return _BilinearFunction.apply(self, users.to(dev).long(), items.to(dev).long(), *params)
         return self._engine().predict_pairs(users, items)

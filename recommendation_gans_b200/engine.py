@@ -99,6 +99,61 @@ def choices_indices_device(pop_len, k, rng=None, device=None):
     return out
 
 
+def draw_negative_pairs_device(pop_users, pop_items, k, rng=None):
+    """random.choices(neg_examples, k=k) (implicit.py:352) on the device, continuing `rng` (default: global random);
+    pop_users / pop_items: the pair list as two int64 CUDA tensors.  Model-less: also serves `representation=` modules
+    that train on the torch-autograd step."""
+    N.require_cuda()
+    lib = N.load_library()
+    rng = rng or _py_random
+    out_u = torch.empty(int(k), dtype=torch.int64, device=pop_users.device)
+    out_i = torch.empty(int(k), dtype=torch.int64, device=pop_users.device)
+    if k == 0:
+        return out_u, out_i
+    state, extra = _get_py_state(rng)
+    with torch.cuda.device(pop_users.device):
+        N.check(lib.mfb_mt_choices_pairs(N.hptr(state), N.dptr(pop_users), N.dptr(pop_items), pop_users.numel(), int(k),
+                                         N.dptr(out_u), N.dptr(out_i), N.stream_ptr()), 'draw_negative_pairs')
+    _set_py_state(rng, state, extra)
+    return out_u, out_i
+
+
+def topk_scores_device(scores, k, user_ids=None, train_indptr=None, train_indices=None, with_scores=False):
+    """Top-k item ids of every row of a dense CUDA score matrix [n_rows, n_items] (descending score, ties -> lower id,
+    train items of the row's user last) -- mfb_topk_scores; the ranking kernel for models whose scores come from a
+    torch module."""
+    N.require_cuda()
+    lib = N.load_library()
+    scores = scores.detach().to(torch.float32).contiguous()
+    n_rows, n_items = scores.shape
+    ids = torch.empty((n_rows, int(k)), dtype=torch.int32, device=scores.device)
+    out = torch.empty((n_rows, int(k)), dtype=torch.float32, device=scores.device) if with_scores else None
+    scratch = torch.empty(2 * n_rows, dtype=torch.float32, device=scores.device) if k > 256 else None
+    if user_ids is not None:
+        user_ids = _as_i64_cuda(user_ids, scores.device)
+    with torch.cuda.device(scores.device):
+        N.check(lib.mfb_topk_scores(N.dptr(scores), n_rows, n_items, N.dptr(user_ids), N.dptr(train_indptr),
+                                    N.dptr(train_indices), int(k), N.dptr(ids), N.dptr(out), N.dptr(scratch),
+                                    N.stream_ptr()), 'topk_scores')
+    return (ids, out) if with_scores else ids
+
+
+def topk_hits_device(topk_ids, user_ids, test_indptr, test_indices, ks):
+    """_get_precision_recall (evaluation.py:108-113) for every row of topk_ids: (hits [n, len(ks)], ntargets [n])."""
+    N.require_cuda()
+    lib = N.load_library()
+    user_ids = _as_i64_cuda(user_ids, topk_ids.device)
+    n, k = topk_ids.shape
+    ks_arr = np.ascontiguousarray(ks, dtype=np.int32)
+    hits = torch.empty((n, len(ks_arr)), dtype=torch.int32, device=topk_ids.device)
+    ntargets = torch.empty(n, dtype=torch.int32, device=topk_ids.device)
+    with torch.cuda.device(topk_ids.device):
+        N.check(lib.mfb_topk_hits(N.dptr(topk_ids), N.dptr(user_ids), n, int(k), N.dptr(test_indptr),
+                                  N.dptr(test_indices), N.hptr(ks_arr), len(ks_arr), N.dptr(hits), N.dptr(ntargets),
+                                  N.stream_ptr()), 'topk_hits')
+    return hits, ntargets
+
+
 def mt_words_device(state625, nwords, device=None):
     N.require_cuda()
     lib = N.load_library()
@@ -271,18 +326,7 @@ class MFEngine(object):
     # -- negatives ----------------------------------------------------------------------------
     def draw_negative_pairs(self, pop_users, pop_items, k, rng=None):
         """random.choices(neg_examples, k=k) (implicit.py:352) continuing `rng` (default: global random)."""
-        rng = rng or _py_random
-        out_u = torch.empty(int(k), dtype=torch.int64, device=self.device)
-        out_i = torch.empty(int(k), dtype=torch.int64, device=self.device)
-        if k == 0:
-            return out_u, out_i
-        state, extra = _get_py_state(rng)
-        with torch.cuda.device(self.device):
-            N.check(self._lib.mfb_mt_choices_pairs(N.hptr(state), N.dptr(pop_users), N.dptr(pop_items),
-                                                   pop_users.numel(), int(k), N.dptr(out_u), N.dptr(out_i),
-                                                   N.stream_ptr()), 'draw_negative_pairs')
-        _set_py_state(rng, state, extra)
-        return out_u, out_i
+        return draw_negative_pairs_device(pop_users, pop_items, k, rng)
 
     # -- training / validation ------------------------------------------------------------------
     def _steps(self, fn, loss, pos_users, pos_items, batch, n_neg, neg_users, neg_items):
@@ -432,13 +476,4 @@ class MFEngine(object):
         return out
 
     def topk_hits(self, topk_ids, user_ids, test_indptr, test_indices, ks):
-        user_ids = _as_i64_cuda(user_ids, self.device)
-        n, k = topk_ids.shape
-        ks_arr = np.ascontiguousarray(ks, dtype=np.int32)
-        hits = torch.empty((n, len(ks_arr)), dtype=torch.int32, device=self.device)
-        ntargets = torch.empty(n, dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
-            N.check(self._lib.mfb_topk_hits(N.dptr(topk_ids), N.dptr(user_ids), n, int(k), N.dptr(test_indptr),
-                                            N.dptr(test_indices), N.hptr(ks_arr), len(ks_arr), N.dptr(hits),
-                                            N.dptr(ntargets), N.stream_ptr()), 'topk_hits')
-        return hits, ntargets
+        return topk_hits_device(topk_ids, user_ids, test_indptr, test_indices, ks)

@@ -142,7 +142,7 @@ def test_forward_matches_reference(golden_dir):
     from tests.gpu_helpers import make_net
     g = np.load(os.path.join(golden_dir, 'forward_losses.npz'))
     net = make_net([g['tables%d' % i] for i in range(4)])
-    pred = net(torch.from_numpy(g['users']).cuda(), torch.from_numpy(g['items']).cuda()).cpu().numpy()
+    pred = net(torch.from_numpy(g["users"]).cuda(), torch.from_numpy(g["items"]).cuda()).detach().cpu().numpy()
     np.testing.assert_allclose(pred, g['pred'], rtol=1e-5, atol=1e-7)
     with pytest.raises(IndexError):                            # the reference breaks on a single pair
         net(torch.tensor([1]).cuda(), torch.tensor([2]).cuda())
