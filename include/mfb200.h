@@ -195,6 +195,14 @@ int mfb_train_epoch_host(mfb_model *m, int loss, const int64_t *h_pos_users, con
 int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
              const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
              mfb_stream stream);
+/* mfb_topk for a caller that ranks the SAME (user list, train CSR) repeatedly -- model.test() runs three ranking passes
+ * over one test set (implicit.py:428-460), a validation loop one per epoch.  plan_key != 0 names that pair (the caller
+ * guarantees: equal key => equal d_user_ids contents, equal CSR contents); the model-independent preprocessing of the
+ * train mask (its per-tile bit images for the tensor-core epilogue) is then built once and reused while the key
+ * matches.  plan_key == 0 is mfb_topk.  Results never depend on the key. */
+int mfb_topk_keyed(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
+                   const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
+                   uint64_t plan_key, mfb_stream stream);
 /* The same ranking over rows of a dense score matrix [n_rows, n_items] that some other model produced -- the
  * `representation=` escape hatch of ImplicitFactorizationModel (implicit.py:169-180: MLP, NeuMF, ...), whose scores
  * come from a torch module instead of the bilinear kernel.  Descending score, ties -> lower item id, train items of

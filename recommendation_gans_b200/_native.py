@@ -65,6 +65,8 @@ SIGNATURES = {
                                             ctypes.c_int32, c_void, c_void, c_void, ctypes.c_int64, c_void, c_void]),
     'mfb_topk': (ctypes.c_int, [c_void, c_void, ctypes.c_int64, c_void, c_void, ctypes.c_int32, c_void, c_void,
                                 c_void]),
+    'mfb_topk_keyed': (ctypes.c_int, [c_void, c_void, ctypes.c_int64, c_void, c_void, ctypes.c_int32, c_void, c_void,
+                                      ctypes.c_uint64, c_void]),
     'mfb_topk_scores': (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int64, c_void, c_void, c_void, ctypes.c_int32, c_void,
                                        c_void, c_void, c_void]),
     'mfb_topk_hits': (ctypes.c_int, [c_void, c_void, ctypes.c_int64, ctypes.c_int32, c_void, c_void, c_void,

@@ -369,9 +369,9 @@ static int topk_exact_impl(mfb_model *m, const int64_t *d_user_ids, int64_t n_us
   return MFB_OK;
 }
 
-extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
-                        const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
-                        mfb_stream stream) {
+static int topk_impl(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
+                     const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
+                     mfb_stream stream, uint64_t plan_key) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!m || !d_user_ids || !d_out_ids || n_users < 0) return MFB_ERR_INVALID;
   if (k <= 0 || k > m->items.rows) {
@@ -386,8 +386,21 @@ extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users
   // exact kernel); small ones -- and k beyond MFB_MAX_TOPK -- take the exact kernel
   if (mfb_tc_supported(m, k) && n_users >= 64 && n_users < (1ll << 30))
     return mfb_topk_tc(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st,
-                       topk_exact_impl, &m->last_topk_redo);
+                       topk_exact_impl, &m->last_topk_redo, plan_key);
   return topk_exact_impl(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st);
+}
+
+extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
+                        const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
+                        mfb_stream stream) {
+  return topk_impl(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, stream, 0);
+}
+
+extern "C" int mfb_topk_keyed(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
+                              const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
+                              uint64_t plan_key, mfb_stream stream) {
+  return topk_impl(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, stream,
+                   plan_key);
 }
 
 // Top-k of dense score rows (scores from any model): see k_topk_dense.  d_user_ids maps a row to the user whose train

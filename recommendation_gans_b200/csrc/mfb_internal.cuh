@@ -124,6 +124,11 @@ struct EvalBuf {
   DevBuf ub, vb, unorm, vnorm, gmax, thr, cand, cnt, redo, mcnt, mptr, mpairs, cut;
   int nsub = 2;   // candidate sub-lists per user in the last tensor-core pass (2 column halves x item-tile splits)
   int n_users_pad = 0;   // padded user count of the last tensor-core pass (layout of the per-user scratch arrays)
+  // train-mask bitmap currently held in mpairs / mptr: caller-chosen key of the (user list, train CSR) it was built
+  // from (0 = none) and the geometry it was built for
+  uint64_t mask_key = 0;
+  int mask_users = 0, mask_tiles = 0, mask_step = 0, mask_pad = 0;
+  const void *mask_bits_ptr = nullptr, *mask_dirty_ptr = nullptr;
 };
 
 struct mfb_model {
@@ -166,7 +171,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const 
                 const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores, cudaStream_t st,
                 int (*exact_topk)(mfb_model *, const int64_t *, int64_t, const int64_t *, const int32_t *, int32_t,
                                   int32_t *, float *, cudaStream_t),
-                int *h_n_redo);
+                int *h_n_redo, uint64_t plan_key);
 int mfb_tc_stats(mfb_model *m, int n_users, long long *h_out, cudaStream_t st);
 int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, float *d_out, cudaStream_t st);
 

@@ -7,10 +7,13 @@ predict -> mask -> argsort -> set-intersection loop with two CUDA kernels: fused
 Ranking is on the pre-sigmoid score with ties -> lower item id (the reference's own tie order is
 whatever numpy's unstable argsort produces).
 """
+import itertools
+
 import numpy as np
 import torch
 
 FLOAT_MAX = np.finfo(np.float32).max
+_TOKENS = itertools.count(1)      # names of uploaded CSR contents (plan keys of mfb_topk_keyed)
 
 
 class _ModuleRanker(object):
@@ -23,7 +26,7 @@ class _ModuleRanker(object):
         self.device = next(self.net.parameters()).device
         self.num_users, self.num_items = int(model._num_users), int(model._num_items)
 
-    def topk(self, user_ids, k, train_indptr=None, train_indices=None, with_scores=False):
+    def topk(self, user_ids, k, train_indptr=None, train_indices=None, with_scores=False, plan_key=0):
         from recommendation_gans_b200.engine import topk_scores_device
         user_ids = torch.as_tensor(user_ids, dtype=torch.int64, device=self.device).reshape(-1)
         n, I = user_ids.numel(), self.num_items
@@ -88,10 +91,19 @@ def _csr_to_device(csr, device):
     indptr = torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(device)
     indices = torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(device)
     try:
-        csr._mfb_device = (str(device), csr.nnz, indptr, indices)
+        csr._mfb_device = (str(device), csr.nnz, indptr, indices, next(_TOKENS))
     except AttributeError:
         pass
     return indptr, indices
+
+
+def _plan_key(test_csr, train_csr):
+    """Key of the (evaluated users, train mask) pair for mfb_topk_keyed: both are functions of the uploaded CSR
+    contents, which `_csr_to_device` names with a token; 0 (no reuse) when either is not cached."""
+    a, b = getattr(test_csr, '_mfb_device', None), getattr(train_csr, '_mfb_device', None)
+    if a is None or b is None or len(a) < 5 or len(b) < 5:
+        return 0
+    return ((b[4] & 0xFFFFFFFF) << 32) | (a[4] & 0xFFFFFFFF)
 
 
 def _check_against_model(eng, test_csr, train_csr=None):
@@ -175,7 +187,8 @@ def precision_recall_score(model, test, train=None, k=10):
     if train_csr is not None:
         m_indptr, m_indices = _csr_to_device(train_csr, eng.device)
     d_users = torch.from_numpy(user_ids).to(eng.device)
-    topk = eng.topk(d_users, min(kmax, eng.num_items), m_indptr, m_indices)
+    topk = eng.topk(d_users, min(kmax, eng.num_items), m_indptr, m_indices,
+                    plan_key=_plan_key(test_csr, train_csr) if train_csr is not None else 0)
     hits, ntargets = _hits_at(eng, topk, d_users, t_indptr, t_indices, ks)
     precision = hits.astype(np.float64) / ks.astype(np.float64)[None, :]
     recall = hits.astype(np.float64) / ntargets.astype(np.float64)[:, None]
@@ -208,7 +221,9 @@ def precision_recall_score_sharded(model, test, train=None, k=10):
     ntargets = np.zeros(len(user_ids), dtype=np.int64)
     if len(user_ids):
         d_users = torch.from_numpy(user_ids).to(eng.device)
-        topk = eng.topk(d_users, min(int(ks_sorted[-1]), eng.num_items), m_indptr, m_indices)
+        key = _plan_key(test_csr, train_csr) if train_csr is not None else 0
+        topk = eng.topk(d_users, min(int(ks_sorted[-1]), eng.num_items), m_indptr, m_indices,
+                        plan_key=(key ^ ((rank + 1) << 20) ^ (world << 28)) if key else 0)
         hits, ntargets = _hits_at(eng, topk, d_users, t_indptr, t_indices, ks)
     prec, rec, _ = allreduce_precision_recall(hits, ntargets, ks, dist=dist if world > 1 else None,
                                               device=eng.device if (world > 1 and dist.get_backend() == 'nccl') else None)

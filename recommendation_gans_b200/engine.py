@@ -438,13 +438,15 @@ class MFEngine(object):
         self._call('mfb_predict_user', int(user), N.dptr(out), N.stream_ptr())
         return out
 
-    def topk(self, user_ids, k, train_indptr=None, train_indices=None, with_scores=False):
+    def topk(self, user_ids, k, train_indptr=None, train_indices=None, with_scores=False, plan_key=0):
+        """plan_key != 0: the caller promises that this key always comes with the same user list and train CSR; the
+        model-independent train-mask preprocessing is then reused between calls (mfb_topk_keyed)."""
         user_ids = _as_i64_cuda(user_ids, self.device)
         n = user_ids.numel()
         ids = torch.empty((n, k), dtype=torch.int32, device=self.device)
         scores = torch.empty((n, k), dtype=torch.float32, device=self.device) if with_scores else None
-        self._call('mfb_topk', N.dptr(user_ids), n, N.dptr(train_indptr), N.dptr(train_indices), int(k),
-                   N.dptr(ids), N.dptr(scores), N.stream_ptr())
+        self._call('mfb_topk_keyed', N.dptr(user_ids), n, N.dptr(train_indptr), N.dptr(train_indices), int(k),
+                   N.dptr(ids), N.dptr(scores), ctypes.c_uint64(int(plan_key) & 0xFFFFFFFFFFFFFFFF), N.stream_ptr())
         return (ids, scores) if with_scores else ids
 
     @property

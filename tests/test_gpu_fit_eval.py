@@ -299,3 +299,32 @@ def test_map_at_k_and_bce_match_reference(golden_dir, name, tmp_path, monkeypatc
     res = model.test(test, None, k=5, rmse_flag=True, precision_recall=False, map_recall=True)
     assert res['bce'] == pytest.approx(float(gm['%s_bce' % name]), rel=1e-5)
     assert res['map'] == pytest.approx(float(gm['%s_map_k5' % name]), abs=2e-3)
+
+
+def test_keyed_topk_reuses_the_mask_images_without_changing_results():
+    """mfb_topk_keyed: the second call with the same key skips the train-mask preprocessing; ids and scores equal the
+    unkeyed call; a new key (other users, other CSR) rebuilds."""
+    from recommendation_gans_b200.engine import MFEngine
+    rs = np.random.RandomState(21)
+    U, I, D, k = 700, 3000, 128, 20
+    tabs = _random_tables(rs, U, I, D, 0.3)
+    eng = MFEngine(make_net(tabs))
+
+    def csr(seed):
+        r = np.random.RandomState(seed)
+        c = O.csr_from_pairs(r.randint(0, U, 30 * U), r.randint(0, I, 30 * U), U, I)
+        c.sum_duplicates()
+        c.sort_indices()
+        return (torch.from_numpy(c.indptr.astype(np.int64)).cuda(), torch.from_numpy(c.indices.astype(np.int32)).cuda())
+    a, b = csr(1), csr(2)
+    users_a, users_b = rs.permutation(U).astype(np.int64), np.arange(0, U, 2, dtype=np.int64)
+    ref_a = eng.topk(users_a, k, *a, with_scores=True)
+    ref_b = eng.topk(users_b, k, *b, with_scores=True)
+    for rep in range(2):
+        got = eng.topk(users_a, k, *a, with_scores=True, plan_key=11)
+        assert (got[0] == ref_a[0]).all() and (got[1] == ref_a[1]).all()
+    got = eng.topk(users_b, k, *b, with_scores=True, plan_key=12)
+    assert (got[0] == ref_b[0]).all() and (got[1] == ref_b[1]).all()
+    got = eng.topk(users_a, k, *a, with_scores=True, plan_key=11)          # back to the first pair: rebuilt for key 11
+    assert (got[0] == ref_a[0]).all() and (got[1] == ref_a[1]).all()
+    assert eng.topk_last_redo < U // 20
