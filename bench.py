@@ -345,7 +345,7 @@ def eval_measure(args, eng, net, w, zipf, rank, world, dev, dist):
         torch.cuda.synchronize()
         if rep:                                          # first call warms the allocator
             e2e.append(time.perf_counter() - t0)
-    kern = ('k_tc_gemm (TMA + tcgen05 bf16, TMEM accumulators) + exact fp32 re-score; %d users redone by k_topk_exact'
+    kern = ('k_tc_gemm (TMA + tcgen05 kind::f16 with fp16 operands, fp32 TMEM accumulators) + exact fp32 re-score; %d users redone by k_topk_exact'
             % redo if os.environ.get('MFB_TC', '1') != '0' else 'k_topk_exact (fp32 CUDA cores)')
     h2d = (train_csr.indptr.size + test_csr.indptr.size) * 8 + (train_csr.nnz + test_csr.nnz) * 4 + (hi - lo) * 8
     out = dict(seconds=stats(times), first_call=first_call, unkeyed=unkeyed, users=hi - lo, users_total=len(all_users),

@@ -214,7 +214,7 @@ int mfb_topk_scores(const float *d_scores, int64_t n_rows, int64_t n_items, cons
                     float *d_out_scores, void *d_cut_scratch, mfb_stream stream);
 /* Users that the last mfb_topk call had to redo with the exact-fp32 kernel (tensor-core path bookkeeping). */
 int mfb_topk_last_redo(const mfb_model *m);
-/* Test hook: raw tensor-core scores (bf16 inputs, fp32 accumulate, + item bias), item-major
+/* Test hook: raw tensor-core scores (fp16 inputs, fp32 accumulate, + item bias), item-major
  * [num_items][ceil(n_users/256)*256]; embedding_dim 64 or 128 only. */
 /* Debug: candidate-list statistics of the last tensor-core mfb_topk call, h_out[5]:
  * {users, listed items total, max per user, users over capacity, items re-scored exactly}. */

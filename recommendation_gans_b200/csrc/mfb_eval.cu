@@ -382,7 +382,7 @@ static int topk_impl(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, c
   if (n_users == 0) return MFB_OK;
   MFB_CHECK(mfb_flush(m, stream));
   m->last_topk_redo = 0;
-  // large problems go through the tensor-core path (bf16 candidates + exact fp32 re-score: same ids as the
+  // large problems go through the tensor-core path (fp16 candidates + exact fp32 re-score: same ids as the
   // exact kernel); small ones -- and k beyond MFB_MAX_TOPK -- take the exact kernel
   if (mfb_tc_supported(m, k) && n_users >= 64 && n_users < (1ll << 30))
     return mfb_topk_tc(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st,
@@ -444,7 +444,7 @@ extern "C" int mfb_debug_tc_stats(mfb_model *m, int64_t n_users, int64_t *h_out,
   return mfb_tc_stats(m, (int)n_users, (long long *)h_out, (cudaStream_t)stream);
 }
 
-// Test hook: raw tensor-core (bf16 x bf16 -> fp32, + item bias) scores of the listed users, item-major
+// Test hook: raw tensor-core (fp16 x fp16 -> fp32, + item bias) scores of the listed users, item-major
 // [num_items][ceil(n_users/256)*256].
 extern "C" int mfb_debug_tc_scores(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, float *d_out,
                                    mfb_stream stream) {

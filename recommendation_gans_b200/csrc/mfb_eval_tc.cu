@@ -4,7 +4,7 @@
 // user = users x items x D flops) for the top-k metrics.  The user x item score matrix is never
 // written to HBM:
 //
-//   1. k_tc_convert      bf16 copies of the user/item embedding rows (+ L2 norms for the error bound)
+//   1. k_tc_convert      fp16 copies of the user/item embedding rows (+ L2 norms for the error bound)
 //   2. k_tc_gemm<MAX>    scores of a SAMPLE of item tiles; epilogue keeps, per user, the maximum of each
 //                        32-item group  ->  k_tc_threshold: a per-user lower bound of the k-th best score
 //   3. k_tc_gemm<COLLECT> all item tiles; epilogue appends every (user, item) whose approximate score
@@ -14,14 +14,14 @@
 //                        overflowed or cannot be certified are flagged and redone by k_topk_exact.
 //
 // GEMM mapping: A = item tile (M = 128 rows -> TMEM lanes), B = 256 users (N -> TMEM columns), K = D,
-// bf16 inputs, fp32 accumulation in TMEM.  One thread owns one ITEM, so a warp-wide ballot tests one
+// fp16 inputs, fp32 accumulation in TMEM.  One thread owns one ITEM, so a warp-wide ballot tests one
 // user's score against 32 items in a single instruction; the item bias is pre-stored into the
 // accumulator in fp32 (tcgen05.st) and the MMA accumulates on top of it.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2-9 =
 // epilogue (two per TMEM lane quarter, each owning 128 of the 256 user columns).  Pipelines: smem full/empty (TMA <-> MMA, 4 stages), TMEM
 // full/empty (MMA <-> epilogue, 2 accumulators of 256 columns).
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -43,7 +43,7 @@ constexpr int TC_SCR_ROWS = MFB_TC_SCR_ROWS;   // scratch rows per epilogue warp
                                                // (32 = a private row per lane, no rounds)
 constexpr int TC_EPI_WARPS = 16;   // (TMEM lane quarter) x (user block) x (half of the tile's item columns)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr int TC_KATOM = 64;       // bf16 elements per 128-byte swizzle atom
+constexpr int TC_KATOM = 64;       // 16-bit elements per 128-byte swizzle atom
 constexpr int MODE_DUMP = 0, MODE_MAX = 1, MODE_COLLECT = 2;
 constexpr int TC_MAX_SPLIT = 4;    // item-tile splits per user block (grid.y) when the user blocks alone cannot fill the SMs
 constexpr float MASKED_SCORE_TC = -3.402823466e38f;
@@ -130,7 +130,7 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
                "h"(cta_mask)
                : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -198,15 +198,16 @@ __device__ __forceinline__ int tc_pos_of(int item, int T, uint32_t magic) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 1. fp32 -> bf16 row conversion (+ row norms).  rows_out >= rows: padding rows are zero.
+// 1. fp32 -> fp16 row conversion (+ row norms).  rows_out >= rows: padding rows are zero.
 //    `ids` (may be null) selects which source rows to convert (the evaluated users, in list order).
 //    perm_T > 0: destination row r is a tile position, the source row is tc_item_of(r); the item biases are
 //    copied into position order too.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_tc_convert(const float *__restrict__ src, const long long *__restrict__ ids, int rows, int rows_out,
-                             int D, __nv_bfloat16 *__restrict__ dst, float *__restrict__ norm, float norm_scale,
-                             int perm_T, const float *__restrict__ bias_src, float *__restrict__ bias_dst,
-                             float *__restrict__ norm_by_src) {
+                             int D, __half *__restrict__ dst, float *__restrict__ norm, float norm_scale,
+                             float norm_offset, int perm_T, const float *__restrict__ bias_src,
+                             float *__restrict__ bias_dst, float *__restrict__ norm_by_src,
+                             int *__restrict__ overflow) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows_out) return;
@@ -220,15 +221,20 @@ __global__ void k_tc_convert(const float *__restrict__ src, const long long *__r
   } else {
     srow = (r < rows) ? (ids ? ids[r] : r) : -1;
   }
+  bool big = false;
   for (int d = lane; d < D; d += 32) {
     float x = (srow >= 0) ? src[srow * D + d] : 0.f;
-    dst[(long long)r * D + d] = __float2bfloat16_rn(x);
+    dst[(long long)r * D + d] = __float2half_rn(x);
+    big |= !(fabsf(x) <= 60000.0f);    // beyond the fp16 range (or NaN): the error model below does not hold
     ss = fmaf(x, x, ss);
   }
+  if (big) atomicExch(overflow, 1);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if (lane == 0 && norm) norm[r] = norm_scale * sqrtf(ss);
-  if (lane == 0 && norm_by_src && srow >= 0) norm_by_src[srow] = norm_scale * sqrtf(ss);
+  // the stored value is an UPPER bound of scale * |row| + offset: sqrtf and the fp32 sum of squares are rounded
+  const float nrm = norm_scale * (sqrtf(ss) * 1.0001f) + norm_offset;
+  if (lane == 0 && norm) norm[r] = nrm;
+  if (lane == 0 && norm_by_src && srow >= 0) norm_by_src[srow] = nrm;
 }
 
 // per item tile: the largest (pre-scaled) row norm, one warp per tile
@@ -256,14 +262,14 @@ struct TcArgs {
   int total_tiles;              // T of the item layout (all tiles of the catalog)
   const float *item_bias;       // [items_pad]  item biases in position order; padding positions hold MASKED_SCORE_TC
   const float *tile_nmax;       // [total_tiles] max over the tile's items of err_coeff * |v|, where
-                                //              |bf16 score - fp32 score| <= err_coeff * |u| * |v|
+                                //              |fp16-GEMM score - fp32 score| <= err_coeff * |u| * |v|
   const float *user_norm;       // [n_users_pad] L2 norm of each evaluated user's row
   // MODE_MAX: gmax[(i*4 + column group) * n_users_pad + user]  (ordered-int encoded)
   int *gmax;
   int n_users_pad;
   // MODE_COLLECT
   const float *thr;             // [n_users_pad] collection threshold per user
-  int2 *cand;                   // [n_users_pad][2][cap2]: (item id, bf16-GEMM score incl. item bias, as float bits);
+  int2 *cand;                   // [n_users_pad][2][cap2]: (item id, fp16-GEMM score incl. item bias, as float bits);
                                 // the two sub-lists of a user belong to the two epilogue warps that share its columns
   int *cand_cnt;                // [n_users_pad][2]
   int cap2;
@@ -364,9 +370,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = F16 (bits 7-9, 10-12 = 0),
     // both K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28.  M = 128 users, N = 128 items.
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     if (lane == 0) {
       mbar_wait_backoff(ufull, 0);
       tc_fence_after();
@@ -379,14 +385,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
         mbar_wait_backoff(full + s, ph);     // item tile landed
         tc_fence_after();
         if (a.dbg & 32) {   // timing experiment only (results are garbage): one M=128 x N=256 MMA shape per K step
-          const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+          const uint32_t idesc2 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256);
           for (int ka = 0; ka < katoms; ++ka) {
             const uint64_t udesc = umma_desc_sw128(smem_u32(sU + (size_t)ka * TC_N * 128));
             const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (size_t)ka * TC_M * 128));
 #pragma unroll
             for (int k = 0; k < TC_KATOM / 16; ++k)
-              tc_mma_bf16(d_tmem, vdesc + (uint64_t)(2 * k), udesc + (uint64_t)(2 * k), idesc2, 1u);
+              tc_mma_f16(d_tmem, vdesc + (uint64_t)(2 * k), udesc + (uint64_t)(2 * k), idesc2, 1u);
           }
         } else
 #pragma unroll
@@ -396,8 +402,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
             const uint64_t udesc = umma_desc_sw128(smem_u32(sU + (size_t)ka * TC_N * 128 + (size_t)ub * 128 * 128));
             const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128));
 #pragma unroll
-            for (int k = 0; k < TC_KATOM / 16; ++k)   // 16 bf16 = 32 bytes per MMA along K: +2 in the (>>4) address field
-              tc_mma_bf16(d_tmem, udesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc, 1u);
+            for (int k = 0; k < TC_KATOM / 16; ++k)   // 16 halves = 32 bytes per MMA along K: +2 in the (>>4) address field
+              tc_mma_f16(d_tmem, udesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc, 1u);
           }
         }
         if (CL > 1) tc_commit_mc(empty + s, (uint16_t)((1u << CL) - 1u));   // release towards every producer of the cluster
@@ -570,7 +576,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // threshold from the sampled group maxima: the m-th largest group maximum is a lower bound of the m-th best
 // item score; m = k + (user's train items) so that at least k of the counted items are unmasked.
-// thr_collect = bound - 2*eps_u (eps_u bounds |bf16 score - fp32 score|), certified later by k_tc_rescore.
+// thr_collect = bound - 2*eps_u (eps_u bounds |fp16-GEMM score - fp32 score|), certified later by k_tc_rescore.
 // ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // train mask for the COLLECT epilogue: a dense bitmap, built on the device per mfb_topk call.
@@ -1018,10 +1024,10 @@ int make_tmap(CUtensorMap *map, void *base, int rows, int D, int box_rows) {
     encode = (PFN_tmapEncodeTiled)fn;
   }
   cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(__nv_bfloat16)};
+  cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(__half)};
   cuuint32_t box[2] = {(cuuint32_t)TC_KATOM, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr,
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1118,8 +1124,8 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   m->eval.nsub = nsub;
 
   EvalBuf &eb = m->eval;
-  MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__nv_bfloat16)));
-  MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__nv_bfloat16)));
+  MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__half)));
+  MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__half)));
   MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
   MFB_CHECK(eb.vnorm.reserve(((size_t)items_pad * 3 + i_tiles) * sizeof(float) + 16));
   MFB_CHECK(eb.gmax.reserve((size_t)groups * n_users_pad * sizeof(int)));
@@ -1127,7 +1133,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * nsub * cap2 * sizeof(int2)));
   MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * (2 * TC_MAX_SPLIT + 3) + 64));
   MFB_CHECK(eb.redo.reserve((size_t)n_users_pad * (sizeof(long long) + (size_t)k * (sizeof(int) + sizeof(float))) + 64));
-  __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
+  __half *ub = eb.ub.as<__half>(), *vb = eb.vb.as<__half>();
   float *unorm = eb.unorm.as<float>(), *vnorm = eb.vnorm.as<float>();
   float *vbias = vnorm + items_pad;   // item biases in position order
   float *vnorm_item = vbias + items_pad;   // scaled norms again, indexed by item id (for k_tc_rescore)
@@ -1140,14 +1146,25 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   int *redo_cnt = surv_cnt + n_users_pad;
 
   int tk = m->prof.begin(PK_TOPK, st, 8);
+  // Error model of the fp16 GEMM score against the exact fp32 score.  fp16 round-to-nearest: |x - fp16(x)| <= h|x| + s
+  // with h = 2^-11 (11 significant bits) and s = 2^-25 (half a subnormal ulp; covers |x| < 6.1e-5), for |x| <= 65504.
+  // Products of two fp16 numbers are exact in fp32, so
+  //   |sum_d u_d v_d - sum_d fp16(u_d) fp16(v_d)| <= (2h + h^2) sum|u_d v_d| + s(1+h)(|u|_1 + |v|_1) + D s^2
+  //                                               <= (2h + h^2) |u||v| + s(1+h) sqrt(D) (|u| + |v|) + D s^2
+  // (Cauchy-Schwarz); fp32 accumulation in the tensor core and in the exact kernel adds < 2 * D * 2^-23 relative.
+  //   c = 2^-10 * 1.075  (7% slack over 2h + h^2 + accumulation)      a = 2^-25 * sqrt(D) * 1.01
+  // Stored per item: E_i = c|v_i| + a; per user: N_u = |u| + a/c.  Then E_i * N_u >= c|u||v_i| + a(|u| + |v_i|) + a^2/c,
+  // which bounds the expression above (a^2/c > D s^2).  Rows with an element beyond the fp16 range raise `overflow`
+  // and the whole call is served by the exact kernel.
+  const float err_coeff = 1.0498e-3f;
+  const float err_add = 2.98023224e-8f * sqrtf((float)D) * 1.01f;
+  int *overflow = redo_cnt + 1;
+  MFB_CUDA(cudaMemsetAsync(redo_cnt, 0, 2 * sizeof(int), st));
   k_tc_convert<<<(n_users_pad + 7) / 8, 256, 0, st>>>(m->users.p, (const long long *)d_user_ids, n_users, n_users_pad, D,
-                                                     ub, unorm, 1.0f, 0, nullptr, nullptr, nullptr);
-  // bf16 round-to-nearest: each operand within 2^-9 relative (8 significant bits), so each product within
-  // 2^-8 + 2^-18; sum over the row bounded by Cauchy-Schwarz; fp32 accumulation of 128 terms adds < 1e-5 relative.
-  // 0.0042 = 2^-8 * 1.075 leaves 7% slack.  The item norms are stored pre-multiplied by it.
-  const float err_coeff = 0.0042f;
-  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, vnorm, err_coeff, i_tiles,
-                                                    m->items.bp, vbias, vnorm_item);
+                                                     ub, unorm, 1.0f, err_add / err_coeff, 0, nullptr, nullptr, nullptr,
+                                                     overflow);
+  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, vnorm, err_coeff, err_add,
+                                                    i_tiles, m->items.bp, vbias, vnorm_item, overflow);
   k_tc_tile_maxnorm<<<(i_tiles + 7) / 8, 256, 0, st>>>(vnorm, i_tiles, tile_nmax);
   MFB_KERNEL_CHECK();
 
@@ -1235,7 +1252,6 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.cap2 = cap2;
   MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st, splits, cluster));
   // exact re-score + mask + top-k
-  MFB_CUDA(cudaMemsetAsync(redo_cnt, 0, sizeof(int), st));
   const size_t rs_smem = (size_t)RS_WARPS * (D + 3 * RS_MAXC) * sizeof(float);
 #define MFB_RESCORE(MAXSUB)                                                                                          \
   do {                                                                                                               \
@@ -1254,9 +1270,14 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
                                                            redo_pos, redo_cnt);
   MFB_KERNEL_CHECK();
   m->prof.end(tk, st);
-  int n_redo = 0;
-  MFB_CUDA(cudaMemcpyAsync(&n_redo, redo_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int counters[2] = {0, 0};
+  MFB_CUDA(cudaMemcpyAsync(counters, redo_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
+  if (counters[1]) {   // an embedding value beyond the fp16 range: the candidate certificates do not hold
+    if (h_n_redo) *h_n_redo = n_users;
+    return exact_topk(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st);
+  }
+  const int n_redo = counters[0];
   if (h_n_redo) *h_n_redo = n_redo;
   if (n_redo > 0) {
     int *tmp_ids = reinterpret_cast<int *>(redo_users + n_users_pad);
@@ -1312,15 +1333,18 @@ int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, flo
   const int i_tiles = (I + TC_M - 1) / TC_M;
   const int items_pad = i_tiles * TC_M;
   EvalBuf &eb = m->eval;
-  MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__nv_bfloat16)));
-  MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__nv_bfloat16)));
+  MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__half)));
+  MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__half)));
   MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
   MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * 3 * sizeof(float) + 16));
-  __nv_bfloat16 *ub = eb.ub.as<__nv_bfloat16>(), *vb = eb.vb.as<__nv_bfloat16>();
+  MFB_CHECK(eb.cnt.reserve(64));
+  __half *ub = eb.ub.as<__half>(), *vb = eb.vb.as<__half>();
   k_tc_convert<<<(n_users_pad + 7) / 8, 256, 0, st>>>(m->users.p, (const long long *)d_user_ids, n_users, n_users_pad, D,
-                                                     ub, eb.unorm.as<float>(), 1.0f, 0, nullptr, nullptr, nullptr);
+                                                     ub, eb.unorm.as<float>(), 1.0f, 0.f, 0, nullptr, nullptr, nullptr,
+                                                     eb.cnt.as<int>());
   k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, eb.vnorm.as<float>(), 1.0f,
-                                                    i_tiles, m->items.bp, eb.vnorm.as<float>() + items_pad, nullptr);
+                                                    0.f, i_tiles, m->items.bp, eb.vnorm.as<float>() + items_pad, nullptr,
+                                                    eb.cnt.as<int>());
   MFB_KERNEL_CHECK();
   CUtensorMap map_items, map_users;
   MFB_CHECK(make_tmap(&map_items, vb, items_pad, D, TC_M));

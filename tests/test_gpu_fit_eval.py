@@ -154,16 +154,16 @@ def _random_tables(rs, U, I, D, scale=0.3):
 
 
 @pytest.mark.parametrize('U,I,D', [(300, 1500, 128), (70, 1100, 64), (513, 2049, 128)])
-def test_tc_raw_scores_match_bf16_matmul(U, I, D):
-    """The tcgen05 GEMM (descriptors, swizzle, TMEM layout, bias pre-store) against torch on bf16-rounded inputs."""
+def test_tc_raw_scores_match_fp16_matmul(U, I, D):
+    """The tcgen05 GEMM (descriptors, swizzle, TMEM layout, bias pre-store) against torch on fp16-rounded inputs."""
     from recommendation_gans_b200.engine import MFEngine
     rs = np.random.RandomState(U)
     tabs = _random_tables(rs, U, I, D)
     eng = MFEngine(make_net(tabs))
     users = np.arange(U, dtype=np.int64)[::-1].copy()
     got = eng.debug_tc_scores(users).cpu().numpy()                       # [I, U]
-    ub = torch.from_numpy(tabs[0][users]).cuda().bfloat16().float()
-    vb = torch.from_numpy(tabs[1]).cuda().bfloat16().float()
+    ub = torch.from_numpy(tabs[0][users]).cuda().half().float()
+    vb = torch.from_numpy(tabs[1]).cuda().half().float()
     ref = (vb.double() @ ub.double().T).float().cpu().numpy() + tabs[3]   # + item bias (fp32)
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
 
@@ -327,4 +327,40 @@ def test_keyed_topk_reuses_the_mask_images_without_changing_results():
     assert (got[0] == ref_b[0]).all() and (got[1] == ref_b[1]).all()
     got = eng.topk(users_a, k, *a, with_scores=True, plan_key=11)          # back to the first pair: rebuilt for key 11
     assert (got[0] == ref_a[0]).all() and (got[1] == ref_a[1]).all()
-    assert eng.topk_last_redo < U // 20
+
+
+def test_tc_topk_certificates_hold_for_sparse_and_huge_rows():
+    """Adversarial inputs for the fp16 error model: one-hot-like rows (no averaging over the row: the rounding error of a
+    single product is the whole error), values in the fp16 subnormal range, and values beyond the fp16 range (the call
+    must fall back to the exact kernel).  Ids and scores must equal the exact kernel's in every case."""
+    from recommendation_gans_b200.engine import MFEngine
+    rs = np.random.RandomState(31)
+    U, I, D, k = 300, 4000, 128, 20
+    cases = {}
+    ue, ie = np.zeros((U, D), np.float32), np.zeros((I, D), np.float32)
+    ue[np.arange(U), rs.randint(0, 4, U)] = rs.uniform(0.5, 2.0, U).astype(np.float32)
+    ie[np.arange(I), rs.randint(0, 4, I)] = (1.0 + rs.randint(0, 2000, I) * 2.0 ** -11).astype(np.float32)   # dense near-ties
+    cases['one_hot'] = (ue, ie)
+    cases['subnormal'] = (rs.normal(0, 2e-5, (U, D)).astype(np.float32), rs.normal(0, 2e-5, (I, D)).astype(np.float32))
+    big_u = rs.normal(0, 0.3, (U, D)).astype(np.float32)
+    big_u[5, 7] = 1.0e5
+    cases['beyond_fp16'] = (big_u, rs.normal(0, 0.3, (I, D)).astype(np.float32))
+    import os
+    for name, (a, b) in cases.items():
+        tabs = (a, b, np.zeros((U, 1), np.float32), rs.normal(0, 1e-6, (I, 1)).astype(np.float32))
+        old = os.environ.get('MFB_TC')
+        os.environ['MFB_TC'] = '0'
+        exact = MFEngine(make_net(tabs))
+        os.environ['MFB_TC'] = '1'
+        tc = MFEngine(make_net(tabs))
+        if old is None:
+            os.environ.pop('MFB_TC')
+        else:
+            os.environ['MFB_TC'] = old
+        users = np.arange(U, dtype=np.int64)
+        ids_e, sc_e = exact.topk(users, k, with_scores=True)
+        ids_t, sc_t = tc.topk(users, k, with_scores=True)
+        assert (ids_e == ids_t).all(), name
+        assert (sc_e == sc_t).all(), name
+        if name == 'beyond_fp16':
+            assert tc.topk_last_redo == U
