@@ -114,7 +114,14 @@ def _check_against_model(eng, test_csr, train_csr=None):
     for name, csr in (('test', test_csr), ('train', train_csr)):
         if csr is None:
             continue
-        if csr.nnz and int(csr.indices.max()) >= eng.num_items:
+        top = getattr(csr, '_mfb_max_item', None)          # one pass over the indices per matrix object
+        if top is None or top[0] != csr.nnz:
+            top = (csr.nnz, int(csr.indices.max()) if csr.nnz else -1)
+            try:
+                csr._mfb_max_item = top
+            except AttributeError:
+                pass
+        if top[1] >= eng.num_items:
             raise ValueError('Maximum item id greater than number of items in model.')
     if train_csr is not None and train_csr.shape[0] < min(test_csr.shape[0], eng.num_users):
         # the reference indexes train[user_id] for every evaluated user (evaluation.py:162)
