@@ -189,7 +189,7 @@ int mfb_train_epoch_host(mfb_model *m, int loss, const int64_t *h_pos_users, con
  * best first, ties -> lower item id, ranking on the pre-sigmoid score; items in the user's
  * train row (CSR, sorted indices; may be NULL) rank last (evaluation.py:160-169).
  * Replaces the per-user predict + argsort loop of precision_recall_score, which accepts any k
- * (evaluation.py:144-150).  k <= MFB_MAX_TOPK with embedding_dim 64 or 128 takes the tensor-core path
+ * (evaluation.py:144-150).  k <= MFB_MAX_TOPK with embedding_dim <= 128 takes the tensor-core path
  * (bit-identical ids); larger k the exact fp32 kernel, in passes of 256 ranks. */
 #define MFB_MAX_TOPK 32
 int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
@@ -215,7 +215,7 @@ int mfb_topk_scores(const float *d_scores, int64_t n_rows, int64_t n_items, cons
 /* Users that the last mfb_topk call had to redo with the exact-fp32 kernel (tensor-core path bookkeeping). */
 int mfb_topk_last_redo(const mfb_model *m);
 /* Test hook: raw tensor-core scores (fp16 inputs, fp32 accumulate, + item bias), item-major
- * [num_items][ceil(n_users/256)*256]; embedding_dim 64 or 128 only. */
+ * [num_items][ceil(n_users/256)*256]; embedding_dim <= 128. */
 /* Debug: candidate-list statistics of the last tensor-core mfb_topk call, h_out[5]:
  * {users, listed items total, max per user, users over capacity, items re-scored exactly}. */
 int mfb_debug_tc_stats(mfb_model *m, int64_t n_users, int64_t *h_out, mfb_stream stream);

@@ -449,7 +449,7 @@ extern "C" int mfb_debug_tc_stats(mfb_model *m, int64_t n_users, int64_t *h_out,
 extern "C" int mfb_debug_tc_scores(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, float *d_out,
                                    mfb_stream stream) {
   if (!m || !d_user_ids || !d_out || n_users <= 0) return MFB_ERR_INVALID;
-  if (!(m->desc.dim == 64 || m->desc.dim == 128)) return MFB_ERR_UNSUPPORTED;
+  if (m->desc.dim < 1 || m->desc.dim > 128) return MFB_ERR_UNSUPPORTED;
   MFB_CHECK(mfb_flush(m, stream));
   return mfb_tc_dump_scores(m, d_user_ids, (int)n_users, d_out, (cudaStream_t)stream);
 }

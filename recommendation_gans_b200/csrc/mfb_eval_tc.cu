@@ -178,6 +178,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// 256-bit read-only global load (32-byte aligned address)
+__device__ __forceinline__ void ld_global_nc_v8(const float *p, float (&r)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
+
 // order-preserving float -> int32 map (for integer redux max)
 __device__ __forceinline__ int float_to_ordered(float f) {
   int i = __float_as_int(f);
@@ -204,7 +211,7 @@ __device__ __forceinline__ int tc_pos_of(int item, int T, uint32_t magic) {
 //    copied into position order too.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_tc_convert(const float *__restrict__ src, const long long *__restrict__ ids, int rows, int rows_out,
-                             int D, __half *__restrict__ dst, float *__restrict__ norm, float norm_scale,
+                             int D, int Dp, __half *__restrict__ dst, float *__restrict__ norm, float norm_scale,
                              float norm_offset, int perm_T, const float *__restrict__ bias_src,
                              float *__restrict__ bias_dst, float *__restrict__ norm_by_src,
                              int *__restrict__ overflow) {
@@ -222,9 +229,9 @@ __global__ void k_tc_convert(const float *__restrict__ src, const long long *__r
     srow = (r < rows) ? (ids ? ids[r] : r) : -1;
   }
   bool big = false;
-  for (int d = lane; d < D; d += 32) {
-    float x = (srow >= 0) ? src[srow * D + d] : 0.f;
-    dst[(long long)r * D + d] = __float2half_rn(x);
+  for (int d = lane; d < Dp; d += 32) {     // Dp = D rounded up to the GEMM's K granularity: zero columns change no score
+    float x = (srow >= 0 && d < D) ? src[srow * D + d] : 0.f;
+    dst[(long long)r * Dp + d] = __float2half_rn(x);
     big |= !(fabsf(x) <= 60000.0f);    // beyond the fp16 range (or NaN): the error model below does not hold
     ss = fmaf(x, x, ss);
   }
@@ -663,6 +670,7 @@ __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restric
   // set (k_tc_mask_bitmap); null = no train mask.
   const int u = blockIdx.x * 128 + threadIdx.x;
   if (u >= n_users) return;
+  const unsigned act = __activemask();   // lanes of this warp that own a user (uniform control flow from here on)
   uint32_t dirty[8];
   if (dirty_g != nullptr) {
     const uint4 d0 = *reinterpret_cast<const uint4 *>(dirty_g + (long long)u * 8);
@@ -694,6 +702,8 @@ __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restric
       nxt[t] = (g + NB + t < groups) ? col[(long long)(g + NB + t) * n_users_pad] : INT_MIN;
 #pragma unroll
     for (int t = 0; t < NB; ++t) {
+      // most values are below the K-th largest seen so far: skip the K-deep network unless some lane of the warp needs it
+      if (!__any_sync(act, v[t] > top[K - 1])) continue;
 #pragma unroll
       for (int j = 0; j < K; ++j) {
         const int hi = max(top[j], v[t]);
@@ -803,7 +813,12 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     }
     return;
   }
-  for (int d = lane * 4; d < D; d += 128) *reinterpret_cast<float4 *>(urow + d) = *reinterpret_cast<const float4 *>(users.p + uid * D + d);
+  const bool vec = (D & 31) == 0;      // whole 32-float chunks: vector loads; otherwise (e.g. the CLI's default D = 50) scalar
+  if (vec) {
+    for (int d = lane * 4; d < D; d += 128) *reinterpret_cast<float4 *>(urow + d) = *reinterpret_cast<const float4 *>(users.p + uid * D + d);
+  } else {
+    for (int d = lane; d < D; d += 32) urow[d] = users.p[uid * D + d];
+  }
   const float ub = users.bp[uid];
   long long tlo = 0, thi = 0;
   if (indptr && check_mask) {    // (the GEMM epilogue already dropped train items when it applied the mask itself)
@@ -887,18 +902,29 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     const float *v = items.p + (long long)my_item * D;
     const float ib = items.bp[my_item];
     // exact score: sequential fp32 FMA over d = 0..D-1 (bit-identical to k_topk_exact); 8 row loads in flight
+    // Every lane walks its own row, so one warp-wide load instruction touches 32 different cache lines: the kernel is
+    // bound by the L1 tag rate (ncu: l1tex 82 % of peak), not by bytes.  256-bit loads (sm_100: LDG.256, one whole
+    // 32-byte sector per lane) halve the number of look-ups per row.
     float acc = 0.f;
+    if (!vec) {
+      for (int d = 0; d < D; ++d) acc = fmaf(urow[d], __ldg(v + d), acc);
+    } else
     for (int d0 = 0; d0 < D; d0 += 32) {
-      float4 x[8];
+      float x[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float4 *>(v + d0 + 4 * j);
+      for (int j = 0; j < 4; ++j) ld_global_nc_v8(v + d0 + 8 * j, x[j]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 y = *reinterpret_cast<const float4 *>(urow + d0 + 4 * j);
-        acc = fmaf(y.x, x[j].x, acc);
-        acc = fmaf(y.y, x[j].y, acc);
-        acc = fmaf(y.z, x[j].z, acc);
-        acc = fmaf(y.w, x[j].w, acc);
+      for (int j = 0; j < 4; ++j) {
+        const float4 y0 = *reinterpret_cast<const float4 *>(urow + d0 + 8 * j);
+        const float4 y1 = *reinterpret_cast<const float4 *>(urow + d0 + 8 * j + 4);
+        acc = fmaf(y0.x, x[j][0], acc);
+        acc = fmaf(y0.y, x[j][1], acc);
+        acc = fmaf(y0.z, x[j][2], acc);
+        acc = fmaf(y0.w, x[j][3], acc);
+        acc = fmaf(y1.x, x[j][4], acc);
+        acc = fmaf(y1.y, x[j][5], acc);
+        acc = fmaf(y1.z, x[j][6], acc);
+        acc = fmaf(y1.w, x[j][7], acc);
       }
     }
     float z = (acc + ub) + ib;
@@ -1088,10 +1114,13 @@ int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, i
 
 }  // namespace
 
+// embedding_dim up to 128 (any value: the fp16 operand copies are zero-padded to K = 64 or 128)
 bool mfb_tc_supported(const mfb_model *m, int k) {
   const int D = m->desc.dim;
-  return (D == 64 || D == 128) && k <= MFB_MAX_TOPK && m->items.rows >= 8 * TC_M && m->tune_tc != 0;
+  return D >= 1 && D <= 128 && k <= MFB_MAX_TOPK && m->items.rows >= 8 * TC_M && m->tune_tc != 0 &&
+         ((uintptr_t)m->items.p & 31) == 0 && ((uintptr_t)m->users.p & 15) == 0;
 }
+static inline int tc_padded_dim(int D) { return D <= 64 ? 64 : 128; }
 
 // Top-k for the listed users through the tensor-core path.  d_out_* as in mfb_topk.
 // exact_topk: callback into the exact kernel for the (few) users that could not be certified.
@@ -1124,8 +1153,9 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   m->eval.nsub = nsub;
 
   EvalBuf &eb = m->eval;
-  MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__half)));
-  MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__half)));
+  const int Dp = tc_padded_dim(D);
+  MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * Dp * sizeof(__half)));
+  MFB_CHECK(eb.vb.reserve((size_t)items_pad * Dp * sizeof(__half)));
   MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
   MFB_CHECK(eb.vnorm.reserve(((size_t)items_pad * 3 + i_tiles) * sizeof(float) + 16));
   MFB_CHECK(eb.gmax.reserve((size_t)groups * n_users_pad * sizeof(int)));
@@ -1161,22 +1191,22 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   int *overflow = redo_cnt + 1;
   MFB_CUDA(cudaMemsetAsync(redo_cnt, 0, 2 * sizeof(int), st));
   k_tc_convert<<<(n_users_pad + 7) / 8, 256, 0, st>>>(m->users.p, (const long long *)d_user_ids, n_users, n_users_pad, D,
-                                                     ub, unorm, 1.0f, err_add / err_coeff, 0, nullptr, nullptr, nullptr,
+                                                     Dp, ub, unorm, 1.0f, err_add / err_coeff, 0, nullptr, nullptr, nullptr,
                                                      overflow);
-  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, vnorm, err_coeff, err_add,
+  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, Dp, vb, vnorm, err_coeff, err_add,
                                                     i_tiles, m->items.bp, vbias, vnorm_item, overflow);
   k_tc_tile_maxnorm<<<(i_tiles + 7) / 8, 256, 0, st>>>(vnorm, i_tiles, tile_nmax);
   MFB_KERNEL_CHECK();
 
   CUtensorMap map_items, map_users;
-  MFB_CHECK(make_tmap(&map_items, vb, items_pad, D, TC_M / cluster));   // a CTA loads its share of a tile's rows
-  MFB_CHECK(make_tmap(&map_users, ub, n_users_pad, D, TC_N));
+  MFB_CHECK(make_tmap(&map_items, vb, items_pad, Dp, TC_M / cluster));   // a CTA loads its share of a tile's rows
+  MFB_CHECK(make_tmap(&map_users, ub, n_users_pad, Dp, TC_N));
 
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.num_items = I;
   a.n_users = n_users;
-  a.D = D;
+  a.D = Dp;
   a.total_tiles = i_tiles;
   a.item_bias = vbias;
   a.tile_nmax = tile_nmax;
@@ -1333,27 +1363,28 @@ int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, flo
   const int i_tiles = (I + TC_M - 1) / TC_M;
   const int items_pad = i_tiles * TC_M;
   EvalBuf &eb = m->eval;
-  MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * D * sizeof(__half)));
-  MFB_CHECK(eb.vb.reserve((size_t)items_pad * D * sizeof(__half)));
+  const int Dp = tc_padded_dim(D);
+  MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * Dp * sizeof(__half)));
+  MFB_CHECK(eb.vb.reserve((size_t)items_pad * Dp * sizeof(__half)));
   MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
   MFB_CHECK(eb.vnorm.reserve((size_t)items_pad * 3 * sizeof(float) + 16));
   MFB_CHECK(eb.cnt.reserve(64));
   __half *ub = eb.ub.as<__half>(), *vb = eb.vb.as<__half>();
   k_tc_convert<<<(n_users_pad + 7) / 8, 256, 0, st>>>(m->users.p, (const long long *)d_user_ids, n_users, n_users_pad, D,
-                                                     ub, eb.unorm.as<float>(), 1.0f, 0.f, 0, nullptr, nullptr, nullptr,
+                                                     Dp, ub, eb.unorm.as<float>(), 1.0f, 0.f, 0, nullptr, nullptr, nullptr,
                                                      eb.cnt.as<int>());
-  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, vb, eb.vnorm.as<float>(), 1.0f,
+  k_tc_convert<<<(items_pad + 7) / 8, 256, 0, st>>>(m->items.p, nullptr, I, items_pad, D, Dp, vb, eb.vnorm.as<float>(), 1.0f,
                                                     0.f, i_tiles, m->items.bp, eb.vnorm.as<float>() + items_pad, nullptr,
                                                     eb.cnt.as<int>());
   MFB_KERNEL_CHECK();
   CUtensorMap map_items, map_users;
-  MFB_CHECK(make_tmap(&map_items, vb, items_pad, D, TC_M));
-  MFB_CHECK(make_tmap(&map_users, ub, n_users_pad, D, TC_N));
+  MFB_CHECK(make_tmap(&map_items, vb, items_pad, Dp, TC_M));
+  MFB_CHECK(make_tmap(&map_users, ub, n_users_pad, Dp, TC_N));
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.num_items = I;
   a.n_users = n_users;
-  a.D = D;
+  a.D = Dp;
   a.total_tiles = i_tiles;
   a.item_bias = eb.vnorm.as<float>() + items_pad;
   a.n_users_pad = n_users_pad;

@@ -153,7 +153,7 @@ def _random_tables(rs, U, I, D, scale=0.3):
             rs.normal(0, 0.1, (U, 1)).astype(np.float32), rs.normal(0, 0.1, (I, 1)).astype(np.float32))
 
 
-@pytest.mark.parametrize('U,I,D', [(300, 1500, 128), (70, 1100, 64), (513, 2049, 128)])
+@pytest.mark.parametrize('U,I,D', [(300, 1500, 128), (70, 1100, 64), (513, 2049, 128), (90, 1300, 32), (257, 1100, 50)])
 def test_tc_raw_scores_match_fp16_matmul(U, I, D):
     """The tcgen05 GEMM (descriptors, swizzle, TMEM layout, bias pre-store) against torch on fp16-rounded inputs."""
     from recommendation_gans_b200.engine import MFEngine
@@ -169,7 +169,9 @@ def test_tc_raw_scores_match_fp16_matmul(U, I, D):
 
 
 @pytest.mark.parametrize('U,I,D,k,scale,skew', [(600, 12000, 128, 20, 0.3, False), (300, 9000, 64, 5, 0.05, False),
-                                                (1000, 20000, 128, 10, 1.0, False), (900, 16000, 128, 20, 0.01, True)])
+                                                (1000, 20000, 128, 10, 1.0, False), (900, 16000, 128, 20, 0.01, True),
+                                                (500, 9000, 32, 10, 0.2, False), (400, 8000, 50, 20, 0.1, True),
+                                                (300, 7000, 100, 5, 0.3, False)])
 @pytest.mark.parametrize('split', [None, '1', '3'], ids=['auto_split', 'split1', 'split3'])
 def test_tc_topk_equals_exact_kernel(U, I, D, k, scale, skew, split, monkeypatch):
     """Tensor-core path returns bit-identical ids to the exact fp32 kernel (same exact re-score definition).
