@@ -100,14 +100,25 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// same load, delivered to the same shared-memory offset (and signalling the same mbarrier offset) of every CTA in cta_mask
-__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
-                                               uint16_t cta_mask) {
+// ---- CTA pair (cta_group::2): the two CTAs of a cluster issue ONE MMA stream (from the leader, rank 0) over both SMs'
+// tensor cores; each CTA keeps its own A rows (users) and HALF of every B tile (items), so an SM reads 6 KB instead of
+// 8 KB of shared memory per 128x128x16 of work and receives half of the TMA traffic.
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// TMA load into this CTA's shared memory whose transaction bytes are counted on an mbarrier of the pair's leader
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
-      "[%2], %5;" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -123,12 +134,23 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// commit that arrives on the barrier at this offset in every CTA of cta_mask (stage release towards all producers)
-__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+// pair commit: arrives on the barrier at this offset in every CTA of cta_mask once the pair's MMAs so far have retired
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    smem_u32(bar)),
                "h"(cta_mask)
                : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -289,10 +311,14 @@ struct TcArgs {
   int dbg;   // experiment switches: 1 = skip score processing, 2 = skip appends, 4 = skip mask build, 8 = skip bias pre-store
 };
 
-// CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster (neighbouring user blocks) walk the item
-// tiles in lockstep: each loads HALF of every tile and multicasts it into both CTAs' stage buffers, so the L2 -> SM
-// operand traffic -- what bounds the bare TMA + MMA pipeline at K = 128 -- is halved.  A stage is released towards both
-// producers (multicast commit; the empty barriers count CL arrivals).  map_items' box holds TC_M / CL rows.
+// CL = CTAs per cluster (1 or 2).  CL = 2 is a cta_group::2 CTA PAIR (neighbouring user blocks): each CTA keeps its own
+// 256 users and its own accumulators, loads HALF of every item tile (rows [rank*64, rank*64+64)) into its own ring --
+// map_items' box holds TC_M / CL rows -- and the leader (rank 0) issues M = 256 MMAs that run on both SMs' tensor cores,
+// each reading its own users and both halves of the tile.  Why: a 128x128x16 MMA reads 4 KB of A and 4 KB of B from
+// shared memory in 64 cycles = 128 B/clk, the whole shared-memory bandwidth of an SM, before the TMA writes and the
+// epilogue's own traffic; the pair reads 6 KB per SM and halves the TMA writes.  Barriers: the leader's `full` counts the
+// bytes of both halves; `empty` / `tfull` are released in both CTAs by multicast commits; the leader's `tempty` counts
+// the epilogue warps of both CTAs.
 template <int MODE, bool SPLIT, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)   // 18 warps (allocated as 20): 96 registers per thread
 k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__ CUtensorMap map_users,
@@ -304,7 +330,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int katoms = a.D / TC_KATOM;
   const uint32_t u_bytes = (uint32_t)TC_N * 128u * katoms;       // users, resident: [katom][256 rows][128 B]
-  const uint32_t v_bytes = (uint32_t)TC_M * 128u * katoms;       // one item stage:  [katom][128 rows][128 B]
+  const uint32_t v_bytes = (uint32_t)TC_M * 128u * katoms;       // one item stage:  [katom][128 rows][128 B] (pair: a CTA
+                                                                 // fills half of its slot; v_bytes = bytes of both halves)
   uint8_t *sU = smem;
   uint8_t *sV = sU + u_bytes;
   uint8_t *tail = sV + (size_t)TC_STAGES * v_bytes;
@@ -333,21 +360,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, CL);   // one release per CTA whose producer writes into this stage
+      mbar_init(empty + s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull + b, 1);
-      mbar_init(tempty + b, TC_EPI_WARPS);   // one arrival per epilogue warp
+      mbar_init(tempty + b, TC_EPI_WARPS * CL);   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_init(ufull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns = 2 buffers x 2 user blocks x 128 item columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CL > 1) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
-  if (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast at them
+  if (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -355,21 +387,31 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_expect_tx(ufull, u_bytes);
-      for (int ka = 0; ka < katoms; ++ka)
-        tma_load_2d(sU + (size_t)ka * TC_N * 128, &map_users, ufull, ka * TC_KATOM, u0);
+      if (CL > 1) {
+        // pair: both CTAs load their own users; the bytes of both are counted on the leader's barrier
+        const uint32_t lead_ufull = mapa_u32(smem_u32(ufull), 0);
+        if (crank == 0) mbar_expect_tx(ufull, 2 * u_bytes);
+        for (int ka = 0; ka < katoms; ++ka)
+          tma_load_2d_pair(sU + (size_t)ka * TC_N * 128, &map_users, lead_ufull, ka * TC_KATOM, u0);
+      } else {
+        mbar_expect_tx(ufull, u_bytes);
+        for (int ka = 0; ka < katoms; ++ka)
+          tma_load_2d(sU + (size_t)ka * TC_N * 128, &map_users, ufull, ka * TC_KATOM, u0);
+      }
       for (int i = 0; i < nt; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
         mbar_wait_backoff(empty + s, ph ^ 1u);
-        mbar_expect_tx(full + s, v_bytes);
         const int row0 = (tb + logical(i) * ts) * TC_M;
         if (CL > 1) {
-          constexpr int HALF = TC_M / CL;       // my share of the tile's rows, delivered to every CTA of the cluster
+          constexpr int HALF = TC_M / CL;       // my half of the tile's rows, into MY ring slot (K atoms [ka][64 rows][128 B])
+          const uint32_t lead_full = mapa_u32(smem_u32(full + s), 0);
+          if (crank == 0) mbar_expect_tx(full + s, v_bytes);   // v_bytes = both halves
           for (int ka = 0; ka < katoms; ++ka)
-            tma_load_2d_mc(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128 + (size_t)crank * HALF * 128, &map_items,
-                           full + s, ka * TC_KATOM, row0 + crank * HALF, (uint16_t)((1u << CL) - 1u));
+            tma_load_2d_pair(sV + (size_t)s * v_bytes + (size_t)ka * HALF * 128, &map_items, lead_full, ka * TC_KATOM,
+                             row0 + crank * HALF);
         } else {
+          mbar_expect_tx(full + s, v_bytes);
           for (int ka = 0; ka < katoms; ++ka)
             tma_load_2d(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
         }
@@ -379,8 +421,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     // ===== MMA issuer =====
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = F16 (bits 7-9, 10-12 = 0),
     // both K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28.  M = 128 users, N = 128 items.
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    if (lane == 0) {
+    // pair: M = 256 (128 users of each CTA), issued by the leader only
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_M >> 3) << 17) | ((uint32_t)((CL > 1 ? 256 : 128) >> 4) << 24);
+    if (lane == 0 && crank == 0) {
       mbar_wait_backoff(ufull, 0);
       tc_fence_after();
       for (int i = 0; i < nt; ++i) {
@@ -388,34 +431,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
         const int b = i & 1;
         const uint32_t bph = (uint32_t)(i >> 1) & 1u;
-        mbar_wait_backoff(tempty + b, bph);  // accumulators drained AND the item biases pre-stored by the epilogue
-        mbar_wait_backoff(full + s, ph);     // item tile landed
+        mbar_wait_backoff(tempty + b, bph);  // accumulators drained AND the item biases pre-stored by the epilogue(s)
+        mbar_wait_backoff(full + s, ph);     // item tile landed (both halves of a pair)
         tc_fence_after();
-        if (a.dbg & 32) {   // timing experiment only (results are garbage): one M=128 x N=256 MMA shape per K step
-          const uint32_t idesc2 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256);
-          for (int ka = 0; ka < katoms; ++ka) {
-            const uint64_t udesc = umma_desc_sw128(smem_u32(sU + (size_t)ka * TC_N * 128));
-            const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (size_t)ka * TC_M * 128));
-#pragma unroll
-            for (int k = 0; k < TC_KATOM / 16; ++k)
-              tc_mma_f16(d_tmem, vdesc + (uint64_t)(2 * k), udesc + (uint64_t)(2 * k), idesc2, 1u);
-          }
-        } else
 #pragma unroll
         for (int ub = 0; ub < 2; ++ub) {     // the two 128-user blocks share the item tile
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256 + ub * 128);
           for (int ka = 0; ka < katoms; ++ka) {
             const uint64_t udesc = umma_desc_sw128(smem_u32(sU + (size_t)ka * TC_N * 128 + (size_t)ub * 128 * 128));
-            const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128));
+            const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (size_t)s * v_bytes + (size_t)ka * (TC_M / CL) * 128));
 #pragma unroll
-            for (int k = 0; k < TC_KATOM / 16; ++k)   // 16 halves = 32 bytes per MMA along K: +2 in the (>>4) address field
-              tc_mma_f16(d_tmem, udesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc, 1u);
+            for (int k = 0; k < TC_KATOM / 16; ++k) {  // 16 halves = 32 bytes per MMA along K: +2 in the (>>4) address field
+              if (CL > 1) tc_mma_f16_pair(d_tmem, udesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc, 1u);
+              else tc_mma_f16(d_tmem, udesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc, 1u);
+            }
           }
         }
-        if (CL > 1) tc_commit_mc(empty + s, (uint16_t)((1u << CL) - 1u));   // release towards every producer of the cluster
-        else tc_commit(empty + s);    // smem stage reusable once these MMAs retire
-        tc_commit(tfull + b);    // accumulators ready for the epilogue
+        if (CL > 1) {
+          tc_commit_pair(empty + s, (uint16_t)3u);    // ring slot reusable in BOTH CTAs once these MMAs retire
+          tc_commit_pair(tfull + b, (uint16_t)3u);    // accumulators ready for both epilogues
+        } else {
+          tc_commit(empty + s);    // smem stage reusable once these MMAs retire
+          tc_commit(tfull + b);    // accumulators ready for the epilogue
+        }
       }
     }
   } else {
@@ -476,7 +514,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + buf);
+      if (lane == 0) {
+        if (CL > 1) mbar_arrive_remote(mapa_u32(smem_u32(tempty + buf), 0));   // the pair's leader owns the MMA stream
+        else mbar_arrive(tempty + buf);
+      }
     };
     for (int i = 0; i < 2 && i < nt; ++i) {
       prefetch_bias(i);
@@ -576,7 +617,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    if (CL > 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
   }
 }
 
