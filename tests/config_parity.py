@@ -61,6 +61,10 @@ def oracle_run(cfg, zipf, dtype=torch.float32):
     init = [t.numpy().copy() for t in O.init_tables(c['U'], c['I'], c['D'], torch_seed=0)]
     model = O.OracleMF(*[torch.from_numpy(t).to(dtype) for t in init], loss=c['loss'], optimizer='adam', lr=LR, l2=L2,
                        batch_size=c['B'], num_negative_samples=c['n_neg'])
+    if dtype == torch.float64:
+        # the yardstick run only has to be (much) more accurate than fp32: torch's fused CPU Adam applies the same
+        # update rule 2.4x faster (its own rounding sits at 1e-16); the fp32 run keeps the reference's default path
+        model.opt = torch.optim.Adam(model.tables, lr=LR, betas=(0.5, 0.999), eps=1e-8, weight_decay=L2, fused=True)
     B, k = c['B'], c['n_neg'] * c['B']
     tu, ti = torch.from_numpy(users), torch.from_numpy(items)
     nu, ni = torch.from_numpy(neg_u), torch.from_numpy(neg_i)
