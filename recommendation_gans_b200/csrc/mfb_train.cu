@@ -522,8 +522,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_loss_steps(int kind, const flo
 // adaptive-hinge maximum; same formulas as loss_block (torch backward of spotlight/losses.py).
 // Hinge-type terms on probabilities are always active: neg - pos + 1 >= 0 for values in [0, 1].
 template <int KIND>
-__device__ __forceinline__ float slot_dz(int j, int b, int m, const float *__restrict__ pred, float gmax,
-                                         int jstar) {
+__device__ __forceinline__ float slot_dz(int j, int b, int m, const float *pred, float gmax, int jstar) {
   const float x = pred[j];
   float d;
   if (KIND == MFB_LOSS_POINTWISE) {
@@ -648,54 +647,28 @@ struct UpdArgs {
   int cu_target;              // optimiser step the listed rows are brought to
 };
 
+// One row of the lazy list: replay its zero-gradient steps up to cu_target.
+template <int VEC, int NIT, bool FAST>
+__device__ __forceinline__ void catchup_row(const UpdArgs &a, uint32_t rk, int lane) {
+  const int D = a.D;
+  const int adam = opt_state_bits(a.opt.kind);
+  const long long row = rk & ((1u << a.rb) - 1u);
+  const TableView &T = ((rk >> a.rb) & 1u) ? a.items : a.users;
+  const int last = T.last[row];
+  if (last >= a.cu_target) return;
+  RowState<VEC, NIT> r;
+  row_load<VEC, NIT>(r, T, row, D, lane, adam);
+  row_replay<VEC, NIT, FAST>(r, last, a.cu_target, a.opt);
+  row_store<VEC, NIT>(r, T, row, D, lane, adam);
+  if (lane == 0) T.last[row] = a.cu_target;
+}
+
+// The update role for sorted position ql of the step (one warp): `raw` = its PosInfo record, j0 = its slot.
 template <int VEC, int NIT, bool FAST, int KIND>
-__global__ void __launch_bounds__(UPD_WARPS * 32, MFB_UPD_MINB) k_update(const UpdArgs a) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+__device__ __forceinline__ void update_position(const UpdArgs &a, int ql, const uint4 raw, int j0, int lane) {
   const int D = a.D;
   const int adam = opt_state_bits(a.opt.kind);   // which per-row optimiser state exists
-
-  pdl_launch_dependents();
-  if ((int)blockIdx.x < a.cu_blocks) {
-    // ---- lazy catch-up role ------------------------------------------------------------
-    const int cnt = *a.lazy_cnt;
-    pdl_wait();
-    const int stride = a.cu_blocks * UPD_WARPS;
-    for (int i = blockIdx.x * UPD_WARPS + wid; i < cnt; i += stride) {
-      const uint32_t rk = a.lazy_rows[i];
-      const long long row = rk & ((1u << a.rb) - 1u);
-      const TableView &T = ((rk >> a.rb) & 1u) ? a.items : a.users;
-      const int last = T.last[row];
-      if (last >= a.cu_target) continue;
-      RowState<VEC, NIT> r;
-      row_load<VEC, NIT>(r, T, row, D, lane, adam);
-      row_replay<VEC, NIT, FAST>(r, last, a.cu_target, a.opt);
-      row_store<VEC, NIT>(r, T, row, D, lane, adam);
-      if (lane == 0) T.last[row] = a.cu_target;
-    }
-    return;
-  }
-
-  // ---- update role -----------------------------------------------------------------------
-  // Position within the step.  The sorted positions of a step are [user rows | item rows] (n/2 each).  User rows carry
-  // long eager replays (MUFU-bound), item rows are touched almost every step (load/store-bound): even blocks walk the
-  // user half, odd blocks the item half, so both kinds are resident on every SM at the same time instead of one
-  // after the other.
-  int ql;
-  if (MFB_UPD_INTERLEAVE) {
-    const int ub = (int)blockIdx.x - a.cu_blocks;
-    const int half = a.n >> 1;
-    const int in_half = (ub >> 1) * UPD_WARPS + wid;
-    if (in_half >= half) return;
-    ql = (ub & 1) * half + in_half;
-  } else {
-    ql = ((int)blockIdx.x - a.cu_blocks) * UPD_WARPS + wid;
-    if (ql >= a.n) return;
-  }
   const long long q = a.base + ql;
-  // independent loads first: this kernel is bound by dependent-load latency, not bandwidth
-  const uint4 raw = *reinterpret_cast<const uint4 *>(a.info + q);
-  const int j0 = (int)a.svals[q];
-  pdl_wait();   // predictions, snapshots and the adaptive-hinge maximum come from this step's forward kernel
   const uint32_t key = raw.x;
   const long long first = raw.y;
   const bool head = first == q;
@@ -821,6 +794,44 @@ __global__ void __launch_bounds__(UPD_WARPS * 32, MFB_UPD_MINB) k_update(const U
   }
   row_store<VEC, NIT>(r, T, row, D, lane, adam);
   if (lane == 0) T.last[row] = upto;
+}
+
+template <int VEC, int NIT, bool FAST, int KIND>
+__global__ void __launch_bounds__(UPD_WARPS * 32, MFB_UPD_MINB) k_update(const UpdArgs a) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  pdl_launch_dependents();
+  if ((int)blockIdx.x < a.cu_blocks) {
+    // ---- lazy catch-up role ------------------------------------------------------------
+    const int cnt = *a.lazy_cnt;
+    pdl_wait();
+    const int stride = a.cu_blocks * UPD_WARPS;
+    for (int i = blockIdx.x * UPD_WARPS + wid; i < cnt; i += stride) catchup_row<VEC, NIT, FAST>(a, a.lazy_rows[i], lane);
+    return;
+  }
+
+  // ---- update role -----------------------------------------------------------------------
+  // Position within the step.  The sorted positions of a step are [user rows | item rows] (n/2 each).  User rows carry
+  // long eager replays (MUFU-bound), item rows are touched almost every step (load/store-bound): even blocks walk the
+  // user half, odd blocks the item half, so both kinds are resident on every SM at the same time instead of one
+  // after the other.
+  int ql;
+  if (MFB_UPD_INTERLEAVE) {
+    const int ub = (int)blockIdx.x - a.cu_blocks;
+    const int half = a.n >> 1;
+    const int in_half = (ub >> 1) * UPD_WARPS + wid;
+    if (in_half >= half) return;
+    ql = (ub & 1) * half + in_half;
+  } else {
+    ql = ((int)blockIdx.x - a.cu_blocks) * UPD_WARPS + wid;
+    if (ql >= a.n) return;
+  }
+  const long long q = a.base + ql;
+  // independent loads first: this kernel is bound by dependent-load latency, not bandwidth
+  const uint4 raw = *reinterpret_cast<const uint4 *>(a.info + q);
+  const int j0 = (int)a.svals[q];
+  pdl_wait();   // predictions, snapshots and the adaptive-hinge maximum come from this step's forward kernel
+  update_position<VEC, NIT, FAST, KIND>(a, ql, raw, j0, lane);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1243,8 +1254,8 @@ static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom
     a.lazy_rows = pb.lazy_rows.as<uint32_t>();
     a.lazy_cnt = pb.lazy_cnt.as<int>();
     a.cu_target = (int)m->step;
-    MFB_CHECK(launch_update(m, sh, g, a, PK_CATCHUP, st));
   }
+  if (g.train) MFB_CHECK(launch_update(m, sh, g, a, PK_CATCHUP, st));
   for (int s = 0; s < ns; ++s) {
     const int b = (s == ns - 1) ? b_last : g.batch;
     const int L = b + m_neg;
