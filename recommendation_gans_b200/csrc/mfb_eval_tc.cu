@@ -13,13 +13,13 @@
 //                        k_topk_exact), train mask, top-k (ties -> lower item id); users whose list
 //                        overflowed or cannot be certified are flagged and redone by k_topk_exact.
 //
-// GEMM mapping: A = item tile (M = 128 rows -> TMEM lanes), B = 256 users (N -> TMEM columns), K = D,
-// fp16 inputs, fp32 accumulation in TMEM.  One thread owns one ITEM, so a warp-wide ballot tests one
-// user's score against 32 items in a single instruction; the item bias is pre-stored into the
-// accumulator in fp32 (tcgen05.st) and the MMA accumulates on top of it.
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2-9 =
-// epilogue (two per TMEM lane quarter, each owning 128 of the 256 user columns).  Pipelines: smem full/empty (TMA <-> MMA, 4 stages), TMEM
-// full/empty (MMA <-> epilogue, 2 accumulators of 256 columns).
+// GEMM mapping: A = 256 users of the CTA (two M = 128 blocks = the 128 TMEM lanes, twice; resident in shared memory),
+// B = a tile of 128 items (N -> 128 TMEM columns per block), K = D, fp16 inputs, fp32 accumulation in TMEM.  An epilogue
+// thread owns one USER (one TMEM lane); the item bias is pre-stored into the accumulator in fp32 (tcgen05.st) and the MMA
+// accumulates on top of it.
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner (one thread each, chosen with
+// elect.sync), warps 2-17 = epilogue: (TMEM lane quarter) x (user block) x (tile parity).  Pipelines: smem full/empty
+// (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, 2 accumulator buffers of 2 x 128 columns).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -34,7 +34,7 @@ constexpr int TC_N = 256;          // users per CTA (two MMA M-blocks of 128 = t
 #ifndef MFB_TC_STAGES
 #define MFB_TC_STAGES 2
 #endif
-constexpr int TC_STAGES = MFB_TC_STAGES;
+constexpr int TC_STAGES = MFB_TC_STAGES;   // item tiles in flight in shared memory (32 KB each at K = 128)
 constexpr int TC_SROW = 36;        // row stride (floats) of an epilogue warp's score scratch: conflict-free 16-byte stores
 #ifndef MFB_TC_SCR_ROWS
 #define MFB_TC_SCR_ROWS 32
@@ -63,6 +63,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#ifdef MFB_TC_EPI_SLEEP
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(MFB_TC_EPI_SLEEP);
+  }
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -74,6 +90,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+#endif
 }
 // same, for the single-thread producer / MMA roles: back off between polls so the spinning thread does not
 // take issue slots from the epilogue warps that share its scheduler
@@ -90,7 +107,9 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) break;
+#ifndef MFB_TC_MMA_SPIN
     __nanosleep(64);
+#endif
   }
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
@@ -100,57 +119,20 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// ---- CTA pair (cta_group::2): the two CTAs of a cluster issue ONE MMA stream (from the leader, rank 0) over both SMs'
-// tensor cores; each CTA keeps its own A rows (users) and HALF of every B tile (items), so an SM reads 6 KB instead of
-// 8 KB of shared memory per 128x128x16 of work and receives half of the TMA traffic.
-// address of the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-// TMA load into this CTA's shared memory whose transaction bytes are counted on an mbarrier of the pair's leader
-__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+// One thread of the (converged) warp.  With elect.sync the compiler knows that a single thread runs the region and emits
+// bare UTCHMMA / UTMALDG instructions; under a plain `lane == 0` test it wraps every one of them in an ELECT / BRA.U.ANY
+// loop over the active threads, and the issuing thread -- not the tensor pipe -- sets the pace (measured: ~105 instead of
+// 64-71 cycles per 128x128x16 MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-// pair commit: arrives on the barrier at this offset in every CTA of cta_mask once the pair's MMAs so far have retired
-__device__ __forceinline__ void tc_commit_pair(uint64_t *bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(cta_mask)
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -163,7 +145,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-
 #define TC_LD32(r, taddr)                                                                                            \
   asm volatile(                                                                                                      \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                      \
@@ -308,18 +289,18 @@ struct TcArgs {
   // mask_bits[((cta * total_tiles + tile) * 16 + (q + 4*(ub + 2*ch))) * 32 + lane] = the 64 item-column bits of that
   // thread's user in that tile (x: columns 0..31 of the warp's half, y: 32..63); built by k_tc_mask_bitmap
   const uint2 *mask_bits;
+  long long *timing;   // MFB_TC_TIMING builds: per-role cycle counters of two CTAs
   int dbg;   // experiment switches: 1 = skip score processing, 2 = skip appends, 4 = skip mask build, 8 = skip bias pre-store
 };
 
-// CL = CTAs per cluster (1 or 2).  CL = 2 is a cta_group::2 CTA PAIR (neighbouring user blocks): each CTA keeps its own
-// 256 users and its own accumulators, loads HALF of every item tile (rows [rank*64, rank*64+64)) into its own ring --
-// map_items' box holds TC_M / CL rows -- and the leader (rank 0) issues M = 256 MMAs that run on both SMs' tensor cores,
-// each reading its own users and both halves of the tile.  Why: a 128x128x16 MMA reads 4 KB of A and 4 KB of B from
-// shared memory in 64 cycles = 128 B/clk, the whole shared-memory bandwidth of an SM, before the TMA writes and the
-// epilogue's own traffic; the pair reads 6 KB per SM and halves the TMA writes.  Barriers: the leader's `full` counts the
-// bytes of both halves; `empty` / `tfull` are released in both CTAs by multicast commits; the leader's `tempty` counts
-// the epilogue warps of both CTAs.
-template <int MODE, bool SPLIT, int CL>
+// Pipelines: a ring of TC_STAGES item tiles in shared memory (TMA -> MMA) and FOUR accumulator slots of 128 columns in
+// tensor memory (MMA -> epilogue): slot = (tile parity p) * 2 + (user block ub).  The 16 epilogue warps are split the
+// same way: warp (lane quarter q, ub, p) drains all 128 item columns of block ub in the tiles i = p, p + 2, ... -- always
+// slot (p, ub) -- so a warp's per-tile bookkeeping (tile index arithmetic, mask and bias fetches, barrier hand-shakes,
+// ~115 instructions) is paid once per 128 columns, a slot is handed to its four warps as soon as its own 8 MMAs have
+// retired, and its next use waits for those four warps only.  (The epilogue is bound by its instruction issue rate:
+// ~110 instructions per 32 scores per warp in COLLECT mode; the MMA stream needs ~1024 of the ~2000 cycles of a tile.)
+template <int MODE, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)   // 18 warps (allocated as 20): 96 registers per thread
 k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__ CUtensorMap map_users,
           const TcArgs a) {
@@ -330,19 +311,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int katoms = a.D / TC_KATOM;
   const uint32_t u_bytes = (uint32_t)TC_N * 128u * katoms;       // users, resident: [katom][256 rows][128 B]
-  const uint32_t v_bytes = (uint32_t)TC_M * 128u * katoms;       // one item stage:  [katom][128 rows][128 B] (pair: a CTA
-                                                                 // fills half of its slot; v_bytes = bytes of both halves)
+  const uint32_t v_bytes = (uint32_t)TC_M * 128u * katoms;       // one item stage:  [katom][128 rows][128 B]
   uint8_t *sU = smem;
   uint8_t *sV = sU + u_bytes;
   uint8_t *tail = sV + (size_t)TC_STAGES * v_bytes;
   uint64_t *full = reinterpret_cast<uint64_t *>(tail);           // [TC_STAGES]
   uint64_t *empty = full + TC_STAGES;                            // [TC_STAGES]
-  uint64_t *tfull = empty + TC_STAGES;                           // [2]
-  uint64_t *tempty = tfull + 2;                                  // [2]
-  uint64_t *ufull = tempty + 2;                                  // [1]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 112);
+  uint64_t *tfull = empty + TC_STAGES;                           // [4]: accumulator slot = buffer * 2 + user block
+  uint64_t *tempty = tfull + 4;                                  // [4]
+  uint64_t *ufull = tempty + 4;                                  // [1]
+  static_assert((2 * TC_STAGES + 9) * 8 <= 120, "barriers overlap the TMEM slot word");
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 120);
   float *sc_s = reinterpret_cast<float *>(tail + 128);                       // [16 warps][TC_SCR_ROWS][TC_SROW]
-  float *bias_s = sc_s + TC_EPI_WARPS * TC_SCR_ROWS * TC_SROW;               // [16 warps][64]: item biases, prefetched
+  float *bias_s = sc_s + TC_EPI_WARPS * TC_SCR_ROWS * TC_SROW;               // [16 warps][128]: item biases, prefetched
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Item tiles can be split over gridDim.y CTAs per user block (small user shards would otherwise leave SMs idle):
@@ -352,9 +333,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   const int u0 = blockIdx.x * TC_N;
   // every CTA streams the same item tiles out of L2: start each CTA at a different tile so that concurrently
   // running CTAs do not all hit the same L2 slices at the same moment
-  // (the CTAs of a cluster share their tile sequence)
-  const int tile_off = (int)(((long long)(blockIdx.x / CL) * 37) % (nt > 0 ? nt : 1));
-  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int tile_off = (int)(((long long)blockIdx.x * 37) % (nt > 0 ? nt : 1));
   auto logical = [&](int i) { int li = i + tile_off; return li >= nt ? li - nt : li; };
 
   if (threadIdx.x == 0) {
@@ -362,143 +341,159 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(tfull + b, 1);
-      mbar_init(tempty + b, TC_EPI_WARPS * CL);   // one arrival per epilogue warp (of both CTAs of a pair)
+      mbar_init(tempty + b, TC_EPI_WARPS / 4);   // one arrival per epilogue warp of the slot (4 lane quarters)
     }
     mbar_init(ufull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns = 2 buffers x 2 user blocks x 128 item columns
-    if (CL > 1) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
-  if (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      if (CL > 1) {
-        // pair: both CTAs load their own users; the bytes of both are counted on the leader's barrier
-        const uint32_t lead_ufull = mapa_u32(smem_u32(ufull), 0);
-        if (crank == 0) mbar_expect_tx(ufull, 2 * u_bytes);
-        for (int ka = 0; ka < katoms; ++ka)
-          tma_load_2d_pair(sU + (size_t)ka * TC_N * 128, &map_users, lead_ufull, ka * TC_KATOM, u0);
-      } else {
-        mbar_expect_tx(ufull, u_bytes);
-        for (int ka = 0; ka < katoms; ++ka)
-          tma_load_2d(sU + (size_t)ka * TC_N * 128, &map_users, ufull, ka * TC_KATOM, u0);
-      }
+    if (elect_one()) {
+      mbar_expect_tx(ufull, u_bytes);
+      for (int ka = 0; ka < katoms; ++ka)
+        tma_load_2d(sU + (size_t)ka * TC_N * 128, &map_users, ufull, ka * TC_KATOM, u0);
+#ifdef MFB_TC_TIMING
+      long long tw_empty = 0;
+#endif
       for (int i = 0; i < nt; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+#ifdef MFB_TC_TIMING
+        const long long c0 = clock64();
+#endif
         mbar_wait_backoff(empty + s, ph ^ 1u);
+#ifdef MFB_TC_TIMING
+        tw_empty += clock64() - c0;
+        if ((a.dbg & 32) && i >= TC_STAGES) { mbar_arrive(full + s); continue; }   // ablation: no TMA traffic after the first fills
+#endif
         const int row0 = (tb + logical(i) * ts) * TC_M;
-        if (CL > 1) {
-          constexpr int HALF = TC_M / CL;       // my half of the tile's rows, into MY ring slot (K atoms [ka][64 rows][128 B])
-          const uint32_t lead_full = mapa_u32(smem_u32(full + s), 0);
-          if (crank == 0) mbar_expect_tx(full + s, v_bytes);   // v_bytes = both halves
-          for (int ka = 0; ka < katoms; ++ka)
-            tma_load_2d_pair(sV + (size_t)s * v_bytes + (size_t)ka * HALF * 128, &map_items, lead_full, ka * TC_KATOM,
-                             row0 + crank * HALF);
-        } else {
-          mbar_expect_tx(full + s, v_bytes);
-          for (int ka = 0; ka < katoms; ++ka)
-            tma_load_2d(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
-        }
+        mbar_expect_tx(full + s, v_bytes);
+        for (int ka = 0; ka < katoms; ++ka)
+          tma_load_2d(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
       }
+#ifdef MFB_TC_TIMING
+      if (a.timing && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && blockIdx.y == 0)
+        a.timing[(blockIdx.x ? 24 : 0) + 0] = tw_empty;
+#endif
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = F16 (bits 7-9, 10-12 = 0),
     // both K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28.  M = 128 users, N = 128 items.
-    // pair: M = 256 (128 users of each CTA), issued by the leader only
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_M >> 3) << 17) | ((uint32_t)((CL > 1 ? 256 : 128) >> 4) << 24);
-    if (lane == 0 && crank == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (elect_one()) {
       mbar_wait_backoff(ufull, 0);
       tc_fence_after();
-      for (int i = 0; i < nt; ++i) {
+#ifdef MFB_TC_TIMING
+      long long tw_tempty = 0, tw_full = 0, t_issue = 0;
+      const long long t_start = clock64();
+      unsigned long long g_start;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
+#endif
+      // one (item tile, user block) unit at a time: its accumulator slot is handed over as soon as ITS 8 MMAs retire, and
+      // the next use of a slot waits only for the four warps that drain that slot
+      for (int j = 0; j < 2 * nt; ++j) {
+        const int i = j >> 1, ub = j & 1;
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-        const int b = i & 1;
+        const int slot = (i & 1) * 2 + ub;
         const uint32_t bph = (uint32_t)(i >> 1) & 1u;
-        mbar_wait_backoff(tempty + b, bph);  // accumulators drained AND the item biases pre-stored by the epilogue(s)
-        mbar_wait_backoff(full + s, ph);     // item tile landed (both halves of a pair)
+#ifdef MFB_TC_TIMING
+        const long long c0 = clock64();
+#endif
+        mbar_wait_backoff(tempty + slot, bph);  // slot drained AND the item biases pre-stored by the epilogue
+#ifdef MFB_TC_TIMING
+        const long long c1 = clock64();
+#endif
+        if (ub == 0) mbar_wait_backoff(full + s, ph);     // item tile landed
+#ifdef MFB_TC_TIMING
+        const long long c2 = clock64();
+        tw_tempty += c1 - c0;
+        tw_full += c2 - c1;
+#endif
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 128);
+#ifdef MFB_TC_TIMING
+        const int ka_n = (a.dbg & 64) ? (katoms + 1) / 2 : katoms;   // ablation: half of the MMAs
+#else
+        const int ka_n = katoms;
+#endif
+        for (int ka = 0; ka < ka_n; ++ka) {
+          const uint64_t udesc = umma_desc_sw128(smem_u32(sU + (size_t)ka * TC_N * 128 + (size_t)ub * 128 * 128));
+          const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128));
 #pragma unroll
-        for (int ub = 0; ub < 2; ++ub) {     // the two 128-user blocks share the item tile
-          const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256 + ub * 128);
-          for (int ka = 0; ka < katoms; ++ka) {
-            const uint64_t udesc = umma_desc_sw128(smem_u32(sU + (size_t)ka * TC_N * 128 + (size_t)ub * 128 * 128));
-            const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (size_t)s * v_bytes + (size_t)ka * (TC_M / CL) * 128));
-#pragma unroll
-            for (int k = 0; k < TC_KATOM / 16; ++k) {  // 16 halves = 32 bytes per MMA along K: +2 in the (>>4) address field
-              if (CL > 1) tc_mma_f16_pair(d_tmem, udesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc, 1u);
-              else tc_mma_f16(d_tmem, udesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc, 1u);
-            }
-          }
+          for (int k = 0; k < TC_KATOM / 16; ++k)   // 16 halves = 32 bytes per MMA along K: +2 in the (>>4) address field
+            tc_mma_f16(d_tmem, udesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc, 1u);
         }
-        if (CL > 1) {
-          tc_commit_pair(empty + s, (uint16_t)3u);    // ring slot reusable in BOTH CTAs once these MMAs retire
-          tc_commit_pair(tfull + b, (uint16_t)3u);    // accumulators ready for both epilogues
-        } else {
-          tc_commit(empty + s);    // smem stage reusable once these MMAs retire
-          tc_commit(tfull + b);    // accumulators ready for the epilogue
-        }
+        if (ub == 1) tc_commit(empty + s);    // smem stage reusable once both blocks' MMAs retire
+        tc_commit(tfull + slot);              // this block's accumulators ready for the epilogue
+#ifdef MFB_TC_TIMING
+        t_issue += clock64() - c2;
+#endif
       }
+#ifdef MFB_TC_TIMING
+      if (a.timing && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && blockIdx.y == 0) {
+        long long *t = a.timing + (blockIdx.x ? 24 : 0);
+        unsigned long long g_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+        t[1] = tw_tempty; t[2] = tw_full; t[3] = t_issue; t[4] = clock64() - t_start; t[5] = nt; t[16] = (long long)(g_end - g_start);
+      }
+#endif
     }
   } else {
-    // ===== epilogue warps: TMEM lane quarter q = warp % 4 (32 users), user block ub, item-column half ch =====
+    // ===== epilogue warps: TMEM lane quarter q = warp % 4 (32 users), user block ub, tile parity par =====
     const int q = warp & 3;
     const int e = (warp - 2) >> 2;                         // 0..3
-    const int ub = e & 1, ch = e >> 1;
+    const int ub = e & 1, par = e >> 1;
     const int ucol = ub * 128 + q * 32 + lane;             // this thread's user, as a column of the CTA
     const int gu = u0 + ucol;
     const bool user_ok = gu < a.n_users;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
-    const uint32_t col_base = (uint32_t)(ub * 128 + ch * 64);     // + buffer * 256
+    const uint32_t col_base = (uint32_t)(par * 256 + ub * 128);   // buffer par, block ub
     const bool use_mask = (MODE == MODE_COLLECT) && a.mask_bits != nullptr;
     float *scratch = sc_s + (warp - 2) * TC_SCR_ROWS * TC_SROW;
-    float *my_bias = bias_s + (warp - 2) * 64;
-    // this thread's mask words, one 8-byte load per tile, fetched one tile ahead of its use
-    const uint2 *my_mask = use_mask ? a.mask_bits + ((long long)blockIdx.x * a.total_tiles * 16 + (q + 4 * e)) * 32 + lane
+    float *my_bias = bias_s + (warp - 2) * TC_M;
+    // this thread's mask words of a tile: two 8-byte loads (item-column halves), fetched one tile ahead of their use
+    const uint2 *my_mask = use_mask ? a.mask_bits + ((long long)blockIdx.x * a.total_tiles * 16 + (q + 4 * ub)) * 32 + lane
                                     : nullptr;
-    auto load_mask = [&](int tile_idx) {
+    auto load_mask = [&](int tile_idx, int half) {
       if (!use_mask || tile_idx >= nt || (a.dbg & 4)) return make_uint2(0u, 0u);
       const int tile_id = tb + logical(tile_idx) * ts;
-      return __ldg(my_mask + (long long)tile_id * 16 * 32);
+      return __ldg(my_mask + ((long long)tile_id * 16 + 8 * half) * 32);
     };
-    uint2 mw_next = load_mask(0);
+    uint2 mw_next0 = load_mask(par, 0), mw_next1 = load_mask(par, 1);
     const float nu = (MODE != MODE_DUMP && user_ok) ? a.user_norm[gu] : 0.f;
     const float thr_u = (MODE == MODE_COLLECT && user_ok) ? a.thr[gu] : INFINITY;
     int my_cnt = 0;
-    int2 *my_cand = (MODE == MODE_COLLECT) ? a.cand + (((long long)gu * S + split) * 2 + ch) * a.cap2 : nullptr;
+    int2 *my_cand = (MODE == MODE_COLLECT) ? a.cand + (((long long)gu * S + split) * 2 + par) * a.cap2 : nullptr;
 
-    // item biases of a tile's 64 columns (they differ per column, not per user): fetched into this warp's slot with
+    // item biases of a tile's 128 columns (they differ per column, not per user): fetched into this warp's slot with
     // cp.async at the top of the tile loop, written into the accumulator's next use at the bottom
     auto prefetch_bias = [&](int tile_idx) {
-      if (tile_idx < nt && lane < 16) {
+      if (tile_idx < nt) {
         const int tile_id = tb + logical(tile_idx) * ts;
-        const float *src = a.item_bias + (long long)tile_id * TC_M + ch * 64 + lane * 4;
+        const float *src = a.item_bias + (long long)tile_id * TC_M + lane * 4;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_bias + lane * 4)), "l"(src) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto prestore_bias = [&](int buf) {
+    auto prestore_bias = [&]() {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
       if (!(a.dbg & 16)) {
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_M; c0 += 32) {
           uint32_t r[32];
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
@@ -508,41 +503,56 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
             r[c4 * 4 + 2] = __float_as_uint(bv.z);
             r[c4 * 4 + 3] = __float_as_uint(bv.w);
           }
-          TC_ST32(r, tmem_base + lane_addr + (uint32_t)(buf * 256) + col_base + (uint32_t)c0);
+          TC_ST32(r, tmem_base + lane_addr + col_base + (uint32_t)c0);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if (CL > 1) mbar_arrive_remote(mapa_u32(smem_u32(tempty + buf), 0));   // the pair's leader owns the MMA stream
-        else mbar_arrive(tempty + buf);
-      }
+      if (lane == 0) mbar_arrive(tempty + par * 2 + ub);
     };
-    for (int i = 0; i < 2 && i < nt; ++i) {
-      prefetch_bias(i);
-      prestore_bias(i);
+    if (par < nt) {
+      prefetch_bias(par);
+      prestore_bias();
       __syncwarp();
     }
-    for (int i = 0; i < nt; ++i) {
-      const int b = i & 1;
+#ifdef MFB_TC_TIMING
+    long long tw_tfull = 0, t_ldw = 0, t_proc = 0, t_pre = 0;
+    const long long te_start = clock64();
+#endif
+    for (int i = par; i < nt; i += 2) {
       const uint32_t bph = (uint32_t)(i >> 1) & 1u;
       const int li = logical(i);
       const int tile_id = tb + li * ts;
       // error radius of every score of this tile for this user: |u| * max over the tile of err_coeff * |v|
       const float rad = (MODE != MODE_DUMP) ? nu * __ldg(a.tile_nmax + tile_id) : 0.f;
       prefetch_bias(i + 2);   // consumed by the pre-store at the bottom of this iteration
-      const uint2 mw = mw_next;
-      mw_next = load_mask(i + 1);
-      mbar_wait(tfull + b, bph);
+      const uint2 mw0 = mw_next0, mw1 = mw_next1;
+      mw_next0 = load_mask(i + 2, 0);
+      mw_next1 = load_mask(i + 2, 1);
+#ifdef MFB_TC_TIMING
+      const long long e0 = clock64();
+#endif
+      mbar_wait(tfull + par * 2 + ub, bph);
       tc_fence_after();
+#ifdef MFB_TC_TIMING
+      const long long e1 = clock64();
+      tw_tfull += e1 - e0;
+#endif
 #pragma unroll 1
-      for (int cc0 = 0; cc0 < ((a.dbg & 1) ? 0 : 64); cc0 += 32) {
+      for (int cc0 = 0; cc0 < ((a.dbg & 1) ? 0 : TC_M); cc0 += 32) {
         uint32_t r[32];
-        TC_LD32(r, tmem_base + lane_addr + (uint32_t)(b * 256) + col_base + (uint32_t)cc0);
-        const uint32_t mword = cc0 ? mw.y : mw.x;   // bit c: item column cc0+c is a train item of my user
+#ifdef MFB_TC_TIMING
+        const long long l0 = clock64();
+#endif
+        TC_LD32(r, tmem_base + lane_addr + col_base + (uint32_t)cc0);
+        // bit c: item column cc0+c is a train item of my user
+        const uint32_t mword = (cc0 & 64) ? ((cc0 & 32) ? mw1.y : mw1.x) : ((cc0 & 32) ? mw0.y : mw0.x);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int slot0 = ch * 64 + cc0;                         // tile slot of r[0]
+#ifdef MFB_TC_TIMING
+        t_ldw += clock64() - l0;
+#endif
+        const int slot0 = cc0;                                   // tile slot of r[0]
         if (MODE == MODE_DUMP) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
@@ -556,7 +566,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
 #pragma unroll
           for (int c = 2; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[c]), __uint_as_float(r[c + 1])));
           mx -= rad;   // approx - err <= exact: a certified lower bound (train items: see k_tc_threshold_small)
-          a.gmax[(long long)((li * S + split) * 4 + ch * 2 + (cc0 >> 5)) * a.n_users_pad + gu] = float_to_ordered(mx);
+          a.gmax[(long long)((li * S + split) * 4 + (cc0 >> 5)) * a.n_users_pad + gu] = float_to_ordered(mx);
         } else {
           // margin = score - (threshold - radius) on the FMA pipe; its sign bit (1 = below) is funnel-shifted into
           // one of four byte accumulators, columns taken from high to low so that column c lands on bit c
@@ -606,19 +616,30 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
           }
         }
       }
+#ifdef MFB_TC_TIMING
+      const long long e2 = clock64();
+      t_proc += e2 - e1;
+#endif
       // hand the accumulators back: pre-store the biases of the tile that will use them next
-      if (i + 2 < nt) prestore_bias(b);
+      if (i + 2 < nt) prestore_bias();
+#ifdef MFB_TC_TIMING
+      t_pre += clock64() - e2;
+#endif
     }
-    if (MODE == MODE_COLLECT && user_ok) a.cand_cnt[((long long)gu * S + split) * 2 + ch] = my_cnt;
+#ifdef MFB_TC_TIMING
+    if (a.timing && (warp == 2 || warp == 17) && lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && blockIdx.y == 0) {
+      long long *t = a.timing + (blockIdx.x ? 24 : 0) + (warp == 2 ? 6 : 11);
+      t[0] = tw_tfull; t[1] = t_ldw; t[2] = t_proc; t[3] = t_pre; t[4] = clock64() - te_start;
+    }
+#endif
+    if (MODE == MODE_COLLECT && user_ok) a.cand_cnt[((long long)gu * S + split) * 2 + par] = my_cnt;
   }
-  // teardown (a CTA of a cluster must not leave while its peer may still multicast into it or arrive on its barriers)
+  // teardown
   tc_fence_before();
-  if (CL > 1) cluster_sync_all();
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (CL > 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
   }
 }
 
@@ -1109,49 +1130,24 @@ size_t tc_smem_bytes(int D) {
   const int katoms = D / TC_KATOM;
   return 1024 + (size_t)TC_N * 128 * katoms + (size_t)TC_STAGES * TC_M * 128 * katoms + 128 +
          (size_t)TC_EPI_WARPS * TC_SCR_ROWS * TC_SROW * 4 +
-         (size_t)TC_EPI_WARPS * 64 * 4;
+         (size_t)TC_EPI_WARPS * TC_M * 4;
 }
 
-template <int MODE, bool SPLIT, int CL>
-int launch_gemm_cl(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, dim3 grid, size_t smem,
-                   cudaStream_t st) {
-  MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, SPLIT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (CL == 1) {
-    k_tc_gemm<MODE, SPLIT, CL><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    MFB_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<MODE, SPLIT, CL>, mi, mu, a));
-  }
+template <int MODE, bool SPLIT>
+int launch_gemm_s(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, dim3 grid, size_t smem, cudaStream_t st) {
+  MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tc_gemm<MODE, SPLIT><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
   MFB_KERNEL_CHECK();
   return MFB_OK;
 }
 
-// cluster = CTAs per cluster (1 or 2); with 2 the grid's x extent is rounded up to even (a.n_users_pad covers the
-// phantom block) and `mi` must have been encoded with a box of TC_M / 2 rows
 template <int MODE>
 int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, int n_users, cudaStream_t st,
-                int splits = 1, int cluster = 1) {
+                int splits = 1) {
   const size_t smem = tc_smem_bytes(a.D);
-  int gx = (n_users + TC_N - 1) / TC_N;
-  if (cluster > 1) gx = ((gx + cluster - 1) / cluster) * cluster;
-  const dim3 grid(gx, splits);
-  if (cluster > 1) {
-    if (splits > 1) return launch_gemm_cl<MODE, true, 2>(mi, mu, a, grid, smem, st);
-    return launch_gemm_cl<MODE, false, 2>(mi, mu, a, grid, smem, st);
-  }
-  if (splits > 1) return launch_gemm_cl<MODE, true, 1>(mi, mu, a, grid, smem, st);
-  return launch_gemm_cl<MODE, false, 1>(mi, mu, a, grid, smem, st);
+  const dim3 grid((n_users + TC_N - 1) / TC_N, splits);
+  if (splits > 1) return launch_gemm_s<MODE, true>(mi, mu, a, grid, smem, st);
+  return launch_gemm_s<MODE, false>(mi, mu, a, grid, smem, st);
 }
 
 }  // namespace
@@ -1173,8 +1169,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
                 int *h_n_redo, uint64_t plan_key) {
   const int n_users = (int)n_users64;
   const int D = m->desc.dim, I = m->items.rows;
-  const int cluster = m->tune_tc_cluster >= 2 ? 2 : 1;     // CTAs per cluster sharing each item tile (TMA multicast)
-  const int n_users_pad = ((n_users + TC_N * cluster - 1) / (TC_N * cluster)) * (TC_N * cluster);
+  const int n_users_pad = ((n_users + TC_N - 1) / TC_N) * TC_N;
   m->eval.n_users_pad = n_users_pad;
   const int i_tiles = (I + TC_M - 1) / TC_M;
   const int items_pad = i_tiles * TC_M;
@@ -1241,7 +1236,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   MFB_KERNEL_CHECK();
 
   CUtensorMap map_items, map_users;
-  MFB_CHECK(make_tmap(&map_items, vb, items_pad, Dp, TC_M / cluster));   // a CTA loads its share of a tile's rows
+  MFB_CHECK(make_tmap(&map_items, vb, items_pad, Dp, TC_M));
   MFB_CHECK(make_tmap(&map_users, ub, n_users_pad, Dp, TC_N));
 
   TcArgs a;
@@ -1255,6 +1250,25 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.user_norm = unorm;
   a.n_users_pad = n_users_pad;
   if (const char *e = getenv("MFB_TC_DBG")) a.dbg = atoi(e);
+#ifdef MFB_TC_TIMING
+  static long long *d_timing = nullptr;
+  if (!d_timing) MFB_CUDA(cudaMalloc(&d_timing, 48 * sizeof(long long)));
+  a.timing = d_timing;
+  auto dump_timing = [&](const char *what) {
+    long long h[48];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_timing, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int c = 0; c < 2; ++c) {
+      const long long *t = h + 24 * c;
+      const double nt = t[5] > 0 ? (double)t[5] : 1.0;
+      fprintf(stderr, "[tc timing %s cta %d] tiles %lld | per tile: producer wait-empty %.0f | mma: wait-tempty %.0f wait-full %.0f issue %.0f total %.0f"
+              " (%.3f GHz)"
+              " | epi warp2: wait-tfull %.0f ld-wait %.0f proc(incl ld) %.0f prestore %.0f total %.0f | epi warp17: wait-tfull %.0f ld-wait %.0f proc %.0f prestore %.0f total %.0f\n",
+              what, c, t[5], t[0] / nt, t[1] / nt, t[2] / nt, t[3] / nt, t[4] / nt, t[16] > 0 ? (double)t[4] / (double)t[16] : 0.0, t[6] / nt, t[7] / nt, t[8] / nt, t[9] / nt, t[10] / nt,
+              t[11] / nt, t[12] / nt, t[13] / nt, t[14] / nt, t[15] / nt);
+    }
+  };
+#endif
   // train mask for the COLLECT epilogue (dense bitmap) + per-user dirty sampled groups for the threshold kernel
   const int ncta = n_users_pad / TC_N;
   const uint32_t magic = ((uint64_t)items_pad * (uint64_t)i_tiles < (1ull << 32) && i_tiles > 1)
@@ -1299,7 +1313,10 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.tile_step = sample_step;
   a.n_tiles = n_sample;
   a.gmax = eb.gmax.as<int>();
-  MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st, splits, cluster));
+  MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st, splits));
+#ifdef MFB_TC_TIMING
+  dump_timing("MAX");
+#endif
   if (small_thr) {
     const int tb = (n_users + 127) / 128;
     int *gm = eb.gmax.as<int>();
@@ -1322,7 +1339,10 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.cand = eb.cand.as<int2>();
   a.cand_cnt = cand_cnt;
   a.cap2 = cap2;
-  MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st, splits, cluster));
+  MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st, splits));
+#ifdef MFB_TC_TIMING
+  dump_timing("COLLECT");
+#endif
   // exact re-score + mask + top-k
   const size_t rs_smem = (size_t)RS_WARPS * (D + 3 * RS_MAXC) * sizeof(float);
 #define MFB_RESCORE(MAXSUB)                                                                                          \

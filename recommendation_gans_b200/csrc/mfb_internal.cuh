@@ -136,7 +136,6 @@ struct mfb_model {
   Profiler prof;
   EvalBuf eval;
   int tune_tc = 1, tune_tc_sample_step = 4;   // MFB_TC=0 forces the exact-fp32 evaluation kernel
-  int tune_tc_cluster = 1;                    // CTAs per cluster sharing item tiles by TMA multicast (MFB_TC_CLUSTER=1: off)
   int last_topk_redo = 0;                     // users re-done by the exact kernel in the last mfb_topk call
   PlanBuf plan[2];
   cudaStream_t st_plan = nullptr;   // planner stream

@@ -198,8 +198,6 @@ def test_tc_topk_equals_exact_kernel(U, I, D, k, scale, skew, split, monkeypatch
     users = rs.permutation(U).astype(np.int64)
     if split is not None:
         monkeypatch.setenv('MFB_TC_SPLIT', split)
-    if split == '3' or (split is None and D == 64):
-        monkeypatch.setenv('MFB_TC_CLUSTER', '2')                  # the cta_group::2 CTA-pair variant of the GEMM
     monkeypatch.setenv('MFB_TC', '0')
     exact = MFEngine(make_net(tabs))
     monkeypatch.setenv('MFB_TC', '1')
