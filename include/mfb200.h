@@ -104,6 +104,15 @@ int mfb_mt_choices_indices(uint32_t *h_state, int64_t pop_len, int64_t k, int64_
 int mfb_mt_sample_items(uint32_t *h_state, int64_t num_items, int64_t count, int64_t *d_out, mfb_stream stream);
 /* raw tempered 32-bit outputs (test hook) */
 int mfb_mt_words(uint32_t *h_state, int64_t nwords, uint32_t *d_out, mfb_stream stream);
+/* The same words generated by many CTAs: the stream is cut into shares of whole steps (words_per_step words each
+ * step) whose starting states come from a GF(2) jump-ahead of the one sequential stream random.choices draws from
+ * (implicit.py:352,370); mfb_train_epoch uses this path when a step consumes 16384 words or more.  Short streams fall
+ * back to the one-CTA generator.  Same words, same state handed back as mfb_mt_words. */
+int mfb_mt_words_parallel(uint32_t *h_state, int64_t nwords, int64_t words_per_step, uint32_t *d_out,
+                          mfb_stream stream);
+/* host only: the jump polynomial x^jump mod phi (phi = characteristic polynomial of MT19937's one-word transition) as
+ * 312 little-endian 64-bit words; word n + jump of the stream is the XOR of the words n + i over its set bits i. */
+int mfb_mt_jump_poly(int64_t jump, uint64_t *h_out);
 
 /* spotlight/sampling.py:46-70 get_negative_samples (with the rank-shift resampling of :37-44): num_samples uniform
  * (user, item) pairs; a pair that is a known interaction (key CSR: the entries whose stored value == 1, as

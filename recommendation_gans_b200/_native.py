@@ -48,6 +48,8 @@ SIGNATURES = {
     'mfb_mt_choices_indices': (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int64, c_void, c_void]),
     'mfb_mt_sample_items': (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int64, c_void, c_void]),
     'mfb_mt_words': (ctypes.c_int, [c_void, ctypes.c_int64, c_void, c_void]),
+    'mfb_mt_words_parallel': (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int64, c_void, c_void]),
+    'mfb_mt_jump_poly': (ctypes.c_int, [ctypes.c_int64, c_void]),
     'mfb_negative_pairs': (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void, c_void, c_void,
                                           c_void, c_void, c_void, c_void, c_void]),
     'mfb_predict_pairs': (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int64, c_void, c_void]),

@@ -170,6 +170,7 @@ extern "C" int mfb_model_destroy(mfb_model *m) {
     for (DevBuf *b : pbufs) b->release();
   }
   m->rng_state.release();
+  m->rng_jump.release();
   {
     DevBuf *ebufs[] = {&m->eval.ub, &m->eval.vb, &m->eval.unorm, &m->eval.vnorm, &m->eval.gmax, &m->eval.thr,
                        &m->eval.cand, &m->eval.cnt, &m->eval.redo, &m->eval.mcnt, &m->eval.mptr, &m->eval.mpairs,

@@ -72,17 +72,18 @@ __device__ __forceinline__ bool after_cut(float sc, int it, float cut_val, int c
   return cut_id < 0 || sc < cut_val || (sc == cut_val && it > cut_id);
 }
 
-// grid: ceil(n_users / EV_USERS).  dynamic smem: Vs[EV_ITEMS][D+1] | Us[EV_USERS][D] | S[EV_USERS][EV_ITEMS]
+// One tile of EV_USERS listed users [u0, u0 + EV_USERS) against the whole catalog.
+// dynamic smem: Vs[EV_ITEMS][D+1] | Us[EV_USERS][D] | S[EV_USERS][EV_ITEMS]
+// out_pos (may be null): row of the output arrays that listed user ui writes (the tensor-core path's re-done users go
+// straight to their rows of the caller's result).
 template <int KL>
-__global__ void __launch_bounds__(EV_THREADS) k_topk_exact(const long long *__restrict__ user_ids, int n_users,
-                                                           TableView users, TableView items, int D,
-                                                           const long long *__restrict__ indptr,
-                                                           const int *__restrict__ indices, int k, int out_stride,
-                                                           int *__restrict__ out_ids, float *__restrict__ out_scores,
-                                                           const float *__restrict__ cut_val_in,
-                                                           const int *__restrict__ cut_id_in,
-                                                           float *__restrict__ cut_val_out,
-                                                           int *__restrict__ cut_id_out) {
+__device__ __forceinline__ void topk_exact_tile(const long long *__restrict__ user_ids, int n_users, int u0,
+                                                const TableView &users, const TableView &items, int D,
+                                                const long long *__restrict__ indptr, const int *__restrict__ indices,
+                                                int k, int out_stride, int *__restrict__ out_ids,
+                                                float *__restrict__ out_scores, const float *__restrict__ cut_val_in,
+                                                const int *__restrict__ cut_id_in, float *__restrict__ cut_val_out,
+                                                int *__restrict__ cut_id_out, const int *__restrict__ out_pos) {
   extern __shared__ float smem[];
   const int ldv = D + 1;
   float *Vs = smem;
@@ -91,7 +92,6 @@ __global__ void __launch_bounds__(EV_THREADS) k_topk_exact(const long long *__re
   __shared__ long long s_uid[EV_USERS];
   __shared__ float s_ub[EV_USERS];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int u0 = blockIdx.x * EV_USERS;
   const int I = items.rows;
 
   if (tid < EV_USERS) {
@@ -211,14 +211,15 @@ __global__ void __launch_bounds__(EV_THREADS) k_topk_exact(const long long *__re
   for (int w = 0; w < 2; ++w) {
     const int ui = u0 + wid * 2 + w;
     if (ui >= n_users) continue;
+    const long long orow = out_pos ? out_pos[ui] : ui;
 #pragma unroll
     for (int j = 0; j < KL; ++j) {
       const int r = j * 32 + lane;
       if (r < k) {
-        out_ids[(long long)ui * out_stride + r] = top[w].id[j];
+        out_ids[orow * out_stride + r] = top[w].id[j];
         if (out_scores) {
           float z = top[w].val[j];
-          out_scores[(long long)ui * out_stride + r] = (z == MASKED_SCORE) ? 0.f : 1.0f / (1.0f + expf(-z));
+          out_scores[orow * out_stride + r] = (z == MASKED_SCORE) ? 0.f : 1.0f / (1.0f + expf(-z));
         }
         if (cut_id_out != nullptr && r == k - 1) {    // where the next pass resumes
           cut_val_out[ui] = top[w].val[j];
@@ -226,6 +227,28 @@ __global__ void __launch_bounds__(EV_THREADS) k_topk_exact(const long long *__re
         }
       }
     }
+  }
+}
+
+// grid: ceil(n_users / EV_USERS) blocks, or fewer: a block walks the user tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// n_dev (may be null): device-resident count that caps n_users -- the tensor-core path enqueues the re-do of its
+// uncertified users without knowing on the host how many there are (usually none: every block leaves at once).
+template <int KL>
+__global__ void __launch_bounds__(EV_THREADS) k_topk_exact(const long long *__restrict__ user_ids, int n_users,
+                                                           TableView users, TableView items, int D,
+                                                           const long long *__restrict__ indptr,
+                                                           const int *__restrict__ indices, int k, int out_stride,
+                                                           int *__restrict__ out_ids, float *__restrict__ out_scores,
+                                                           const float *__restrict__ cut_val_in,
+                                                           const int *__restrict__ cut_id_in,
+                                                           float *__restrict__ cut_val_out,
+                                                           int *__restrict__ cut_id_out, const int *__restrict__ n_dev,
+                                                           const int *__restrict__ out_pos) {
+  if (n_dev != nullptr) n_users = min(n_users, *n_dev);
+  for (int u0 = blockIdx.x * EV_USERS; u0 < n_users; u0 += gridDim.x * EV_USERS) {
+    __syncthreads();   // the previous tile's shared-memory state is no longer read
+    topk_exact_tile<KL>(user_ids, n_users, u0, users, items, D, indptr, indices, k, out_stride, out_ids, out_scores,
+                        cut_val_in, cut_id_in, cut_val_out, cut_id_out, out_pos);
   }
 }
 
@@ -334,20 +357,26 @@ constexpr int EV_PASS_RANKS = 256;   // ranks per pass of the warp-resident list
     else KERNEL<8><<<GRID, EV_THREADS, SMEM, st>>>(__VA_ARGS__);                            \
   } while (0)
 
+// d_n_dev / d_out_pos: see k_topk_exact (both null for an ordinary call)
 static int topk_exact_impl(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
                            const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores,
-                           cudaStream_t st) {
+                           cudaStream_t st, const int *d_n_dev, const int *d_out_pos) {
   const int D = m->desc.dim;
   size_t smem = ((size_t)EV_ITEMS * (D + 1) + (size_t)EV_USERS * D + (size_t)EV_USERS * EV_ITEMS) * sizeof(float);
   if (smem > 220 * 1024) {
     mfb_set_error("topk: embedding_dim %d needs %zu B of shared memory", D, smem);
     return MFB_ERR_UNSUPPORTED;
   }
-  MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set = 0;   // (one device per process: the attributes are set when the size first grows)
+  if (smem > smem_set) {
+    MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MFB_CUDA(cudaFuncSetAttribute(k_topk_exact<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   int grid = (int)((n_users + EV_USERS - 1) / EV_USERS);
+  if (d_n_dev != nullptr && grid > 2 * m->num_sms) grid = 2 * m->num_sms;   // count unknown here: the blocks stride
   // k beyond one pass of the warp-resident list: further passes resume after the last (score, id) of the previous one
   float *cut_val = nullptr;
   int *cut_id = nullptr;
@@ -362,7 +391,7 @@ static int topk_exact_impl(mfb_model *m, const int64_t *d_user_ids, int64_t n_us
     MFB_TOPK_DISPATCH(k_topk_exact, kpass, grid, smem, (const long long *)d_user_ids, (int)n_users, m->users, m->items, D,
                       (const long long *)d_train_indptr, d_train_indices, kpass, (int)k, d_out_ids + done,
                       d_out_scores ? d_out_scores + done : nullptr, done ? cut_val : nullptr, done ? cut_id : nullptr,
-                      cut_val, cut_id);
+                      cut_val, cut_id, d_n_dev, d_out_pos);
     m->prof.end(tk, st);
     MFB_KERNEL_CHECK();
   }
@@ -387,7 +416,8 @@ static int topk_impl(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, c
   if (mfb_tc_supported(m, k) && n_users >= 64 && n_users < (1ll << 30))
     return mfb_topk_tc(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st,
                        topk_exact_impl, &m->last_topk_redo, plan_key);
-  return topk_exact_impl(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st);
+  return topk_exact_impl(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st, nullptr,
+                         nullptr);
 }
 
 extern "C" int mfb_topk(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
@@ -437,7 +467,18 @@ extern "C" int mfb_topk_scores(const float *d_scores, int64_t n_rows, int64_t n_
 }
 
 // Number of users the last mfb_topk call re-did with the exact kernel (tensor-core path only).
-extern "C" int mfb_topk_last_redo(const mfb_model *m) { return m ? m->last_topk_redo : -1; }
+extern "C" int mfb_topk_last_redo(const mfb_model *mc) {
+  mfb_model *m = const_cast<mfb_model *>(mc);
+  if (!m) return -1;
+  if (m->last_topk_redo < 0 && m->eval.redo_cnt_dev != nullptr) {   // the tensor-core pass left the count on the device
+    int n = 0;
+    if (cudaStreamSynchronize(m->eval.redo_stream) != cudaSuccess ||
+        cudaMemcpy(&n, m->eval.redo_cnt_dev, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return -1;
+    m->last_topk_redo = n;
+  }
+  return m->last_topk_redo;
+}
 
 extern "C" int mfb_debug_tc_stats(mfb_model *m, int64_t n_users, int64_t *h_out, mfb_stream stream) {
   if (!m || !h_out || n_users <= 0) return MFB_ERR_INVALID;

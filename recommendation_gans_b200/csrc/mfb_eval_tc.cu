@@ -1070,26 +1070,17 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
 }
 
 // compact the flagged users into a list for the exact kernel
+// (redo_cnt[1] = the fp16-range overflow flag of k_tc_convert: the certificates do not hold, every user is re-done)
 __global__ void k_tc_compact_redo(const int *__restrict__ redo_flag, const long long *__restrict__ user_ids,
                                   int n_users, long long *__restrict__ redo_users, int *__restrict__ redo_pos,
                                   int *__restrict__ redo_cnt) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= n_users) return;
-  if (redo_flag[u]) {
+  if (redo_flag[u] || redo_cnt[1] != 0) {
     const int at = atomicAdd(redo_cnt, 1);
     redo_users[at] = user_ids[u];
     redo_pos[at] = u;
   }
-}
-
-__global__ void k_tc_scatter_redo(const int *__restrict__ redo_pos, int n_redo, int k, const int *__restrict__ src_ids,
-                                  const float *__restrict__ src_scores, int *__restrict__ out_ids,
-                                  float *__restrict__ out_scores) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_redo * k) return;
-  const int r = i / k, j = i - r * k;
-  out_ids[(long long)redo_pos[r] * k + j] = src_ids[i];
-  if (out_scores) out_scores[(long long)redo_pos[r] * k + j] = src_scores[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1135,7 +1126,11 @@ size_t tc_smem_bytes(int D) {
 
 template <int MODE, bool SPLIT>
 int launch_gemm_s(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, dim3 grid, size_t smem, cudaStream_t st) {
-  MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set = 0;   // (one device per process: the attribute is set when the size first grows)
+  if (smem > smem_set) {
+    MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   k_tc_gemm<MODE, SPLIT><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
   MFB_KERNEL_CHECK();
   return MFB_OK;
@@ -1165,7 +1160,7 @@ static inline int tc_padded_dim(int D) { return D <= 64 ? 64 : 128; }
 int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, const int64_t *d_train_indptr,
                 const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores, cudaStream_t st,
                 int (*exact_topk)(mfb_model *, const int64_t *, int64_t, const int64_t *, const int32_t *, int32_t,
-                                  int32_t *, float *, cudaStream_t),
+                                  int32_t *, float *, cudaStream_t, const int *, const int *),
                 int *h_n_redo, uint64_t plan_key) {
   const int n_users = (int)n_users64;
   const int D = m->desc.dim, I = m->items.rows;
@@ -1347,7 +1342,11 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   const size_t rs_smem = (size_t)RS_WARPS * (D + 3 * RS_MAXC) * sizeof(float);
 #define MFB_RESCORE(MAXSUB)                                                                                          \
   do {                                                                                                               \
-    MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore<MAXSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)); \
+    static size_t rs_set = 0;                                                                                        \
+    if (rs_smem > rs_set) {                                                                                          \
+      MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore<MAXSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)); \
+      rs_set = rs_smem;                                                                                              \
+    }                                                                                                                \
     k_tc_rescore<MAXSUB><<<(n_users + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>(                       \
         (const long long *)d_user_ids, n_users, m->users, m->items, D, eb.cand.as<int2>(), cand_cnt, cap2, nsub, thr, \
         unorm, vnorm_item, (const long long *)d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, redo_flag,  \
@@ -1362,24 +1361,14 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
                                                            redo_pos, redo_cnt);
   MFB_KERNEL_CHECK();
   m->prof.end(tk, st);
-  int counters[2] = {0, 0};
-  MFB_CUDA(cudaMemcpyAsync(counters, redo_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  MFB_CUDA(cudaStreamSynchronize(st));
-  if (counters[1]) {   // an embedding value beyond the fp16 range: the candidate certificates do not hold
-    if (h_n_redo) *h_n_redo = n_users;
-    return exact_topk(m, d_user_ids, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, st);
-  }
-  const int n_redo = counters[0];
-  if (h_n_redo) *h_n_redo = n_redo;
-  if (n_redo > 0) {
-    int *tmp_ids = reinterpret_cast<int *>(redo_users + n_users_pad);
-    float *tmp_scores = reinterpret_cast<float *>(tmp_ids + (size_t)n_users_pad * k);
-    MFB_CHECK(exact_topk(m, (const int64_t *)redo_users, n_redo, d_train_indptr, d_train_indices, k, tmp_ids,
-                         d_out_scores ? tmp_scores : nullptr, st));
-    k_tc_scatter_redo<<<(n_redo * k + 255) / 256, 256, 0, st>>>(redo_pos, n_redo, k, tmp_ids, tmp_scores, d_out_ids,
-                                                                d_out_scores);
-    MFB_KERNEL_CHECK();
-  }
+  // The flagged users are re-done by the exact kernel straight into their rows of the result.  Their number stays on
+  // the device (the launch covers the worst case with a grid of striding blocks that leave at once when there is
+  // nothing to do), so the whole pass is enqueued without a host synchronisation; mfb_topk_last_redo reads it on demand.
+  MFB_CHECK(exact_topk(m, (const int64_t *)redo_users, n_users, d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores,
+                       st, redo_cnt, redo_pos));
+  eb.redo_cnt_dev = redo_cnt;
+  eb.redo_stream = st;
+  if (h_n_redo) *h_n_redo = -1;   // pending
   return MFB_OK;
 }
 

@@ -129,6 +129,9 @@ struct EvalBuf {
   uint64_t mask_key = 0;
   int mask_users = 0, mask_tiles = 0, mask_step = 0, mask_pad = 0;
   const void *mask_bits_ptr = nullptr, *mask_dirty_ptr = nullptr;
+  // users re-done by the exact kernel in the last tensor-core pass: counted on the device, read on demand
+  const int *redo_cnt_dev = nullptr;
+  cudaStream_t redo_stream = nullptr;
 };
 
 struct mfb_model {
@@ -136,7 +139,7 @@ struct mfb_model {
   Profiler prof;
   EvalBuf eval;
   int tune_tc = 1, tune_tc_sample_step = 4;   // MFB_TC=0 forces the exact-fp32 evaluation kernel
-  int last_topk_redo = 0;                     // users re-done by the exact kernel in the last mfb_topk call
+  int last_topk_redo = 0;                     // users re-done by the exact kernel in the last mfb_topk call (-1: still on the device)
   PlanBuf plan[2];
   cudaStream_t st_plan = nullptr;   // planner stream
   cudaStream_t st_rng = nullptr;    // MT19937 word generation (sequential, one CTA) runs ahead of the planner here
@@ -144,6 +147,7 @@ struct mfb_model {
   cudaEvent_t ev_join = nullptr;
   int num_sms = 148;
   DevBuf rng_state;            // device-resident MT19937 state (624 words + position) of the negative sampler
+  DevBuf rng_jump;             // jump-ahead scratch of the multi-CTA generator (raw words + share states)
   bool rng_seeded = false;
   // tuning knobs (environment overrides read at model creation: MFB_EAGER_MAX, MFB_CHUNK_BITS, MFB_CU_BLOCKS)
   int tune_eager_max = 64, tune_chunk_bits = 6, tune_cu_blocks_per_sm = 2;
@@ -169,7 +173,7 @@ bool mfb_tc_supported(const mfb_model *m, int k);
 int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users, const int64_t *d_train_indptr,
                 const int32_t *d_train_indices, int32_t k, int32_t *d_out_ids, float *d_out_scores, cudaStream_t st,
                 int (*exact_topk)(mfb_model *, const int64_t *, int64_t, const int64_t *, const int32_t *, int32_t,
-                                  int32_t *, float *, cudaStream_t),
+                                  int32_t *, float *, cudaStream_t, const int *, const int *),
                 int *h_n_redo, uint64_t plan_key);
 int mfb_tc_stats(mfb_model *m, int n_users, long long *h_out, cudaStream_t st);
 int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, float *d_out, cudaStream_t st);
@@ -177,6 +181,9 @@ int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, flo
 // ---- MT19937 (mfb_mt19937.cu)
 int mfb_mt_generate(uint32_t *h_state, int64_t nwords, uint32_t *d_words, cudaStream_t st);
 int mfb_mt_generate_async(uint32_t *d_state, int64_t nwords, uint32_t *d_words, cudaStream_t st);
+// the same stream cut into shares that many CTAs generate at once (mfb_mt_jump.cu); falls back to the call above
+int mfb_mt_generate_parallel(uint32_t *d_state, int64_t nwords, uint32_t *d_words, int64_t words_per_step,
+                             DevBuf *scratch, cudaStream_t st);
 int mfb_choices_async(const uint32_t *d_words, int64_t k, int64_t pop_len, const int64_t *d_pop_users,
                       const int64_t *d_pop_items, int64_t *d_out_users, int64_t *d_out_items, cudaStream_t st);
 

@@ -7,73 +7,13 @@
 #include <mutex>
 
 #include "mfb_internal.cuh"
+#include "mfb_mt.cuh"
 
 namespace {
 
-constexpr int MT_N = 624;
-constexpr int MT_M = 397;
-constexpr int MT_THREADS = 640;   // one thread per state word (624) in the generator kernel
-
-__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
-  y ^= y >> 11;
-  y ^= (y << 7) & 0x9D2C5680u;
-  y ^= (y << 15) & 0xEFC60000u;
-  y ^= y >> 18;
-  return y;
-}
-
-__device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t nxt, uint32_t far) {
-  uint32_t y = (cur & 0x80000000u) | (nxt & 0x7FFFFFFFu);
-  return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
-}
-
-// One CTA walks the stream sequentially, one thread per state word.  new[k] needs old[k], old[k+1] and
-// new-or-old[(k+397) % 624]; the "new" operands are themselves mixes of old words (at most two levels deep, plus
-// new[0] for k = 623), so every word of the next state is computed from the OLD state alone: one data-parallel phase
-// and one barrier per 624-word regeneration instead of three dependent phases.
-// state_io: 624 words + position (625 uint32).  out may be nullptr (advance only).
 __global__ void __launch_bounds__(MT_THREADS) k_mt_generate(uint32_t *state_io, unsigned long long nwords,
                                                             uint32_t *out) {
-  __shared__ uint32_t buf[2][MT_N];
-  const int tid = threadIdx.x;
-  constexpr int G = MT_N - MT_M;   // 227
-  int cur = 0;
-  for (int i = tid; i < MT_N; i += MT_THREADS) buf[0][i] = state_io[i];
-  int pos = (int)state_io[MT_N];
-  __syncthreads();
-  unsigned long long emitted = 0;
-  while (emitted < nwords) {
-    if (pos >= MT_N) {
-      const uint32_t *o = buf[cur];
-      uint32_t *n = buf[cur ^ 1];
-      for (int k = tid; k < MT_N; k += MT_THREADS) {
-        uint32_t far;
-        if (k < G) {
-          far = o[k + MT_M];
-        } else if (k < 2 * G) {
-          far = mt_mix(o[k - G], o[k - G + 1], o[k - G + MT_M]);                 // new[k-227]
-        } else {
-          const uint32_t inner = mt_mix(o[k - 2 * G], o[k - 2 * G + 1], o[k - 2 * G + MT_M]);   // new[k-454]
-          far = mt_mix(o[k - G], o[k - G + 1], inner);                             // new[k-227]
-        }
-        const uint32_t nxt = (k == MT_N - 1) ? mt_mix(o[0], o[1], o[MT_M]) : o[k + 1];   // k = 623 wraps to new[0]
-        n[k] = mt_mix(o[k], nxt, far);
-      }
-      __syncthreads();   // the only barrier per regeneration: buffers alternate, so the words read above are not
-      cur ^= 1;          // overwritten before the NEXT barrier
-      pos = 0;
-    }
-    unsigned long long left = nwords - emitted;
-    int take = (left < (unsigned long long)(MT_N - pos)) ? (int)left : (MT_N - pos);
-    if (out != nullptr) {
-      for (int i = tid; i < take; i += MT_THREADS) out[emitted + i] = mt_temper(buf[cur][pos + i]);
-    }
-    emitted += take;
-    pos += take;
-  }
-  __syncthreads();
-  for (int i = tid; i < MT_N; i += MT_THREADS) state_io[i] = buf[cur][i];
-  if (tid == 0) state_io[MT_N] = (uint32_t)pos;
+  mt_generate_body(state_io, state_io, nwords, out, false);
 }
 
 // random.random(): a = w0 >> 5, b = w1 >> 6, x = (a*2^26 + b) / 2^53; index = floor(x * n).
@@ -139,7 +79,7 @@ __global__ void __launch_bounds__(1024) k_masked_compact(const uint32_t *__restr
   if (tid == 0) result[1] = base_s;
 }
 
-DevBuf g_state, g_words, g_result;  // library-global scratch for the model-less RNG entry points
+DevBuf g_state, g_words, g_result, g_jump;  // library-global scratch for the model-less RNG entry points
 
 // The model-less entry points share the scratch above: one caller at a time (ranks running as threads of one process
 // call these concurrently, and ctypes releases the GIL), and the scratch follows the calling thread's device.
@@ -194,7 +134,12 @@ int mfb_choices_async(const uint32_t *d_words, int64_t k, int64_t pop_len, const
 int mfb_mt_generate(uint32_t *h_state, int64_t nwords, uint32_t *d_words, cudaStream_t st) {
   if (nwords < 0) return MFB_ERR_INVALID;
   MFB_CHECK(upload_state(h_state, st));
-  if (nwords > 0) {
+  if (nwords >= 8 * 65536 && d_words != nullptr) {
+    // long draws (the row-sharded path draws the negatives of hundreds of steps at once): up to 64 shares by jump-ahead
+    int64_t share = (nwords + 63) / 64;
+    share = share < 65536 ? 65536 : ((share + 65535) / 65536) * 65536;   // few distinct sizes -> few polynomial sets
+    MFB_CHECK(mfb_mt_generate_parallel(g_state.as<uint32_t>(), nwords, d_words, share, &g_jump, st));
+  } else if (nwords > 0) {
     mfb_count_library_launch(1);
     k_mt_generate<<<1, MT_THREADS, 0, st>>>(g_state.as<uint32_t>(), (unsigned long long)nwords, d_words);
     MFB_KERNEL_CHECK();
@@ -410,7 +355,7 @@ __global__ void k_neg_rank_shift(const long long *__restrict__ list, long long c
 
 DevBuf g_nflag, g_nlist, g_nraw;
 void release_rng_scratch() {
-  for (DevBuf *b : {&g_state, &g_words, &g_result, &g_nflag, &g_nlist, &g_nraw}) b->release();
+  for (DevBuf *b : {&g_state, &g_words, &g_result, &g_jump, &g_nflag, &g_nlist, &g_nraw}) b->release();
 }
 
 }  // namespace

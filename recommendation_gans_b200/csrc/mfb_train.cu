@@ -1080,8 +1080,9 @@ static void chunk_extent(const StepGeom &g, int64_t s0, int cap, int *ns, int *b
   *nkeys = 2 * ((int64_t)(*ns - 1) * g.Lfull + (*b_last + g.m_neg));
 }
 
-// MT19937 words of a chunk's negative draws, on the RNG stream: the generator is one sequential stream (one CTA), so it
-// runs ahead of the planner on its own stream instead of sitting on the planner's critical path.
+// MT19937 words of a chunk's negative draws, on the RNG stream, ahead of the planner.  The generator is one sequential
+// stream; with 16 384 or more words per step it is cut into shares by jump-ahead and generated by many CTAs
+// (mfb_mt_jump.cu), otherwise by one CTA.
 static int draw_chunk_words(mfb_model *m, PlanBuf &pb, const StepGeom &g, int64_t s0, int cap, cudaStream_t sr) {
   if (!(g.pop_len > 0 && g.m_neg > 0)) return MFB_OK;
   int ns, b_last;
@@ -1090,7 +1091,8 @@ static int draw_chunk_words(mfb_model *m, PlanBuf &pb, const StepGeom &g, int64_
   const int64_t k = (int64_t)ns * g.m_neg;
   MFB_CHECK(pb.words.reserve((size_t)(2 * (int64_t)g.chunk * g.m_neg) * sizeof(uint32_t)));
   int tk = m->prof.begin(PK_SAMPLE, sr, 0);
-  MFB_CHECK(mfb_mt_generate_async(m->rng_state.as<uint32_t>(), 2 * k, pb.words.as<uint32_t>(), sr));
+  MFB_CHECK(mfb_mt_generate_parallel(m->rng_state.as<uint32_t>(), 2 * k, pb.words.as<uint32_t>(), 2 * (int64_t)g.m_neg,
+                                     &m->rng_jump, sr));
   m->prof.end(tk, sr);
   return MFB_OK;
 }

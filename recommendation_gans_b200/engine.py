@@ -163,6 +163,17 @@ def mt_words_device(state625, nwords, device=None):
     return out
 
 
+def mt_words_device_parallel(state625, nwords, words_per_step, device=None):
+    """mt_words_device through the multi-CTA generator (GF(2) jump-ahead, csrc/mfb_mt_jump.cu): same words, same state."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = device or torch.device('cuda', torch.cuda.current_device())
+    out = torch.empty(int(nwords), dtype=torch.int32, device=device)
+    N.check(lib.mfb_mt_words_parallel(N.hptr(state625), int(nwords), int(words_per_step), N.dptr(out), N.stream_ptr()),
+            'mt_words_parallel')
+    return out
+
+
 def loss_forward_backward(kind, pos, neg, need_grad, mask=None):
     """spotlight/losses.py on probability tensors -> (loss, dpos, dneg).  pos is 1-D [b]; neg is 1-D, or [n, b] for
     adaptive_hinge (per-positive maximum over dim 0); mask is None or [b] (loss*mask summed over mask.sum())."""

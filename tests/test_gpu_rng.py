@@ -20,7 +20,8 @@ def _eng():
 
 def test_raw_words_and_state():
     E = _eng()
-    for seed, pos0, n in ((0, 624, 5000), (3, 624, 1), (9, 100, 624 * 7 + 5), (4, 0, 624)):
+    # (the last case is long enough for the model-less entry points to take the multi-CTA generator)
+    for seed, pos0, n in ((0, 624, 5000), (3, 624, 1), (9, 100, 624 * 7 + 5), (4, 0, 624), (6, 77, 9 * 65536 + 123)):
         gen = R.MT19937.from_numpy_seed(seed)
         if pos0 != 624:
             gen.words(624 + pos0)          # move into the middle of a block
@@ -30,6 +31,32 @@ def test_raw_words_and_state():
         got = E.mt_words_device(state, n).cpu().numpy().view(np.uint32)
         assert (got == gen.words(n)).all()
         assert (state[:624] == gen.mt).all() and state[624] == gen.pos
+
+
+def test_parallel_generator_matches_the_sequential_stream():
+    """The multi-CTA generator (shares whose starting states come from a GF(2) jump-ahead) emits the words of the one
+    sequential stream and leaves the same state behind: every share count, ragged last shares, positions inside a
+    block, and the fallback for short streams."""
+    E = _eng()
+    cases = ((0, 624, 16384 * 20, 16384),        # cfg3: 20 steps of 16 384 words -> 5 shares of 4 steps
+             (3, 17, 16384 * 7 + 5, 16384),      # ragged tail, starts inside a block
+             (5, 624, 131072 * 3, 131072),       # cfg5: one step per share
+             (7, 300, 40000 * 9, 40000),         # share = one step of 40 000 words
+             (9, 1, 20000 * 2 + 1, 20000),       # two shares, the second holds a single word... plus one
+             (2, 624, 5000, 1024))               # below the threshold: the one-CTA generator
+    for seed, pos0, n, wps in cases:
+        gen = R.MT19937.from_numpy_seed(seed)
+        if pos0 != 624:
+            gen.words(624 + pos0)
+        state = np.empty(625, dtype=np.uint32)
+        state[:624] = gen.mt
+        state[624] = gen.pos
+        state_seq = state.copy()
+        want = E.mt_words_device(state_seq, n).cpu().numpy().view(np.uint32)
+        got = E.mt_words_device_parallel(state, n, wps).cpu().numpy().view(np.uint32)
+        assert (got == want).all(), (seed, pos0, n, wps, int(np.argmax(got != want)))
+        assert (state == state_seq).all()
+        assert (want == gen.words(n)).all()
 
 
 def test_choices_stream_matches_cpython():
