@@ -183,6 +183,7 @@ extern "C" int mfb_model_destroy(mfb_model *m) {
   for (cudaEvent_t e : m->ev_plan) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_done) if (e) cudaEventDestroy(e);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
+  if (m->ev_seed) cudaEventDestroy(m->ev_seed);
   for (auto &r : m->prof.recs) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);

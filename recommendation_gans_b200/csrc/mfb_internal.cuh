@@ -144,7 +144,7 @@ struct mfb_model {
   cudaStream_t st_plan = nullptr;   // planner stream
   cudaStream_t st_rng = nullptr;    // MT19937 word generation (sequential, one CTA) runs ahead of the planner here
   cudaEvent_t ev_plan[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_rng[2] = {nullptr, nullptr};
-  cudaEvent_t ev_join = nullptr;
+  cudaEvent_t ev_join = nullptr, ev_seed = nullptr;
   int num_sms = 148;
   DevBuf rng_state;            // device-resident MT19937 state (624 words + position) of the negative sampler
   DevBuf rng_jump;             // jump-ahead scratch of the multi-CTA generator (raw words + share states)

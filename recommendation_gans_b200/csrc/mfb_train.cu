@@ -1066,6 +1066,7 @@ static int ensure_streams(mfb_model *m) {
   for (auto &e : m->ev_done) MFB_CUDA(mk(&e));
   for (auto &e : m->ev_rng) MFB_CUDA(mk(&e));
   MFB_CUDA(mk(&m->ev_join));
+  MFB_CUDA(mk(&m->ev_seed));
   int dev = 0;
   MFB_CUDA(cudaGetDevice(&dev));
   MFB_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1305,7 +1306,7 @@ static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom
 static int run_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const int64_t *d_pos_items, int64_t n_pos,
                      int32_t batch, int32_t n_neg, const int64_t *d_neg_users, const int64_t *d_neg_items,
                      float *d_step_losses, cudaStream_t st, bool train, const int64_t *d_pop_users = nullptr,
-                     const int64_t *d_pop_items = nullptr, int64_t pop_len = 0) {
+                     const int64_t *d_pop_items = nullptr, int64_t pop_len = 0, cudaEvent_t ev_rng_ready = nullptr) {
   if (!m || !d_pos_users || !d_pos_items || !d_step_losses) return MFB_ERR_INVALID;
   MFB_CHECK(validate_loss_shape(loss, n_pos, batch, n_neg));
   const bool from_stream = pop_len > 0;
@@ -1390,7 +1391,8 @@ static int run_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const i
   cudaStream_t sp = m->st_plan, sr = m->st_rng;
   MFB_CUDA(cudaEventRecord(m->ev_join, st));
   MFB_CUDA(cudaStreamWaitEvent(sp, m->ev_join, 0));
-  MFB_CUDA(cudaStreamWaitEvent(sr, m->ev_join, 0));
+  // (the generator needs only the state, not the ids: a caller that uploads ids after the state names the earlier point)
+  MFB_CUDA(cudaStreamWaitEvent(sr, ev_rng_ready ? ev_rng_ready : m->ev_join, 0));
   const bool draws = g.pop_len > 0 && g.m_neg > 0;
   const int64_t nchunks = (int64_t)sched.size();
   auto plan = [&](int64_t c) -> int {
@@ -1468,10 +1470,13 @@ extern "C" int mfb_train_epoch_host(mfb_model *m, int loss, const int64_t *h_pos
     if (!h_state || !d_pop_users || !d_pop_items || pop_len <= 0) return MFB_ERR_INVALID;
     MFB_CHECK(mfb_model_rng_seed(m, h_state, stream));
   }
+  // the word generator starts as soon as the state is up; the id upload (pinned memory: asynchronous) runs beside it
+  MFB_CHECK(ensure_streams(m));
+  MFB_CUDA(cudaEventRecord(m->ev_seed, st));
   MFB_CUDA(cudaMemcpyAsync(d_u, h_pos_users, (size_t)n_pos * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   MFB_CUDA(cudaMemcpyAsync(d_i, h_pos_items, (size_t)n_pos * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   MFB_CHECK(run_steps(m, loss, d_u, d_i, n_pos, batch, n_neg, nullptr, nullptr, m->ws_losses.as<float>(), st, true,
-                      d_pop_users, d_pop_items, n_neg > 0 ? pop_len : 0));
+                      d_pop_users, d_pop_items, n_neg > 0 ? pop_len : 0, m->ev_seed));
   MFB_CUDA(cudaMemcpyAsync(h_step_losses, m->ws_losses.ptr, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
   if (n_neg > 0) MFB_CHECK(mfb_model_rng_state(m, h_state, stream));
