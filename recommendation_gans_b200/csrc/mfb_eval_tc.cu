@@ -41,7 +41,7 @@ constexpr int TC_SROW = 36;        // row stride (floats) of an epilogue warp's 
 #endif
 constexpr int TC_SCR_ROWS = MFB_TC_SCR_ROWS;   // scratch rows per epilogue warp: lanes with a hit in the chunk take one each
                                                // (32 = a private row per lane, no rounds)
-constexpr int TC_EPI_WARPS = 16;   // (TMEM lane quarter) x (user block) x (half of the tile's item columns)
+constexpr int TC_EPI_WARPS = 16;   // (TMEM lane quarter) x (user block) x (tile parity)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_KATOM = 64;       // 16-bit elements per 128-byte swizzle atom
 constexpr int MODE_DUMP = 0, MODE_MAX = 1, MODE_COLLECT = 2;
