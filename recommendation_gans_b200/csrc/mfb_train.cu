@@ -1306,7 +1306,8 @@ static int exec_chunk(mfb_model *m, PlanBuf &pb, const Shape &sh, const StepGeom
 static int run_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const int64_t *d_pos_items, int64_t n_pos,
                      int32_t batch, int32_t n_neg, const int64_t *d_neg_users, const int64_t *d_neg_items,
                      float *d_step_losses, cudaStream_t st, bool train, const int64_t *d_pop_users = nullptr,
-                     const int64_t *d_pop_items = nullptr, int64_t pop_len = 0, cudaEvent_t ev_rng_ready = nullptr) {
+                     const int64_t *d_pop_items = nullptr, int64_t pop_len = 0, cudaEvent_t ev_rng_ready = nullptr,
+                     bool defer_check = false) {
   if (!m || !d_pos_users || !d_pos_items || !d_step_losses) return MFB_ERR_INVALID;
   MFB_CHECK(validate_loss_shape(loss, n_pos, batch, n_neg));
   const bool from_stream = pop_len > 0;
@@ -1420,7 +1421,8 @@ static int run_steps(mfb_model *m, int loss, const int64_t *d_pos_users, const i
     MFB_CUDA(cudaEventRecord(m->ev_done[cur], st));
   }
   // ids were clamped on the device; report a bad id once, after the queue drains
-  MFB_CHECK(check_err_flag(flag, st, train ? "train" : "loss"));
+  // (defer_check: the caller reads the flag -- m->ws_scalars -- together with its own results, one synchronisation)
+  if (!defer_check) MFB_CHECK(check_err_flag(flag, st, train ? "train" : "loss"));
   return MFB_OK;
 }
 
@@ -1476,9 +1478,18 @@ extern "C" int mfb_train_epoch_host(mfb_model *m, int loss, const int64_t *h_pos
   MFB_CUDA(cudaMemcpyAsync(d_u, h_pos_users, (size_t)n_pos * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   MFB_CUDA(cudaMemcpyAsync(d_i, h_pos_items, (size_t)n_pos * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   MFB_CHECK(run_steps(m, loss, d_u, d_i, n_pos, batch, n_neg, nullptr, nullptr, m->ws_losses.as<float>(), st, true,
-                      d_pop_users, d_pop_items, n_neg > 0 ? pop_len : 0, m->ev_seed));
+                      d_pop_users, d_pop_items, n_neg > 0 ? pop_len : 0, m->ev_seed, true));
+  // losses, the generator state and the id-range flag come back together: one synchronisation.  (The last generator
+  // kernel precedes the last chunk's plan, which the last chunk's steps on `st` waited for.)
+  int h_flag = 0;
   MFB_CUDA(cudaMemcpyAsync(h_step_losses, m->ws_losses.ptr, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaMemcpyAsync(&h_flag, m->ws_scalars.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (n_neg > 0)
+    MFB_CUDA(cudaMemcpyAsync(h_state, m->rng_state.ptr, 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
-  if (n_neg > 0) MFB_CHECK(mfb_model_rng_state(m, h_state, stream));
+  if (h_flag) {
+    mfb_set_error("train: id out of range for the model's tables");
+    return MFB_ERR_RANGE;
+  }
   return MFB_OK;
 }
