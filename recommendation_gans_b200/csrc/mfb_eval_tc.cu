@@ -724,14 +724,17 @@ constexpr int TH_VPL = 8;   // group maxima per lane -> up to 256 groups per use
 
 // m-th largest group maximum, one THREAD per user (m <= K): the K largest keys are kept sorted in registers
 // by a branch-free insertion (one max/min pair per slot); the loads of consecutive users coalesce.
-template <int K>
+// TPU = 4 (small user shards, where one thread per user leaves the SMs latency-bound): four neighbouring lanes share a
+// user, each takes every fourth batch of groups, and the four sorted lists are merged with two rounds of shuffles.
+template <int K, int TPU>
 __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restrict__ gmax, int groups, int n_users,
                                                             int n_users_pad, int m, float *__restrict__ thr,
                                                             const uint32_t *__restrict__ dirty_g) {
   // The MAX pass does not look at the train mask: a sampled 32-item group that contains one of the user's train
   // items is dropped here instead (its maximum may belong to that item).  dirty_g[user][8]: bit g of the user's
   // set (k_tc_mask_bitmap); null = no train mask.
-  const int u = blockIdx.x * 128 + threadIdx.x;
+  const int u = (blockIdx.x * 128 + threadIdx.x) / TPU;
+  const int part = threadIdx.x % TPU;
   if (u >= n_users) return;
   const unsigned act = __activemask();   // lanes of this warp that own a user (uniform control flow from here on)
   uint32_t dirty[8];
@@ -749,10 +752,11 @@ __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restric
   for (int j = 0; j < K; ++j) top[j] = INT_MIN;
   const int *col = gmax + u;
   constexpr int NB = 8;          // loads in flight per thread; the next batch is issued before this one is inserted
+  constexpr int GSTEP = NB * TPU;
   int nxt[NB];
 #pragma unroll
-  for (int t = 0; t < NB; ++t) nxt[t] = (t < groups) ? col[(long long)t * n_users_pad] : INT_MIN;
-  for (int g = 0; g < groups; g += NB) {
+  for (int t = 0; t < NB; ++t) nxt[t] = (part * NB + t < groups) ? col[(long long)(part * NB + t) * n_users_pad] : INT_MIN;
+  for (int g = part * NB; g < groups; g += GSTEP) {
     int v[NB];
     uint32_t dsel = 0u;           // dirty[g >> 5] without a dynamically indexed register array
 #pragma unroll
@@ -762,7 +766,7 @@ __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restric
     for (int t = 0; t < NB; ++t) v[t] = ((dw >> t) & 1u) ? INT_MIN : nxt[t];   // INT_MIN never enters the top list
 #pragma unroll
     for (int t = 0; t < NB; ++t)
-      nxt[t] = (g + NB + t < groups) ? col[(long long)(g + NB + t) * n_users_pad] : INT_MIN;
+      nxt[t] = (g + GSTEP + t < groups) ? col[(long long)(g + GSTEP + t) * n_users_pad] : INT_MIN;
 #pragma unroll
     for (int t = 0; t < NB; ++t) {
       // most values are below the K-th largest seen so far: skip the K-deep network unless some lane of the warp needs it
@@ -774,6 +778,25 @@ __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restric
         top[j] = hi;
       }
     }
+  }
+  if (TPU > 1) {   // merge the partners' lists: after round d every lane holds the top K of 2d lanes' groups
+#pragma unroll
+    for (int d = 1; d < TPU; d <<= 1) {
+      int pv[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) pv[j] = __shfl_xor_sync(act, top[j], d);
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        int x = pv[i];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const int hi = max(top[j], x);
+          x = min(top[j], x);
+          top[j] = hi;
+        }
+      }
+    }
+    if (part != 0) return;
   }
   int r = INT_MIN;
 #pragma unroll
@@ -848,7 +871,16 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     const int2 *__restrict__ cand, const int *__restrict__ cand_cnt, int cap2, int nsub, const float *__restrict__ thr,
     const float *__restrict__ unorm, const float *__restrict__ item_norm,
     const long long *__restrict__ indptr, const int *__restrict__ indices, int k, int *__restrict__ out_ids,
-    float *__restrict__ out_scores, int *__restrict__ redo_flag, int *__restrict__ surv_cnt, int check_mask) {
+    float *__restrict__ out_scores, int *__restrict__ redo_flag, int *__restrict__ surv_cnt, int check_mask,
+    long long *__restrict__ redo_users, int *__restrict__ redo_pos, int *__restrict__ redo_cnt) {
+  // A user that cannot be certified here joins the list the exact kernel re-does (order arbitrary: every entry names
+  // its own output row).  redo_cnt[1] = the fp16-range overflow flag of k_tc_convert: no certificate holds at all.
+  auto give_up = [&](int uu, long long uuid) {
+    redo_flag[uu] = 1;
+    const int at = atomicAdd(redo_cnt, 1);
+    redo_users[at] = uuid;
+    redo_pos[at] = uu;
+  };
   extern __shared__ __align__(16) float rs_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u = blockIdx.x * RS_WARPS + wib;
@@ -869,9 +901,9 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     pre[j + 1] = pre[j] + cj;
   }
   const int cnt = pre[RS_MAXSUB];
-  if (over || cnt > RS_MAXC || cnt < k || !(thr[u] > -INFINITY)) {   // overflow / no bound: exact path
+  if (over || cnt > RS_MAXC || cnt < k || !(thr[u] > -INFINITY) || redo_cnt[1] != 0) {   // overflow / no bound: exact path
     if (lane == 0) {
-      redo_flag[u] = 1;
+      give_up(u, uid);
       surv_cnt[u] = 0;
     }
     return;
@@ -1005,7 +1037,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) good += __shfl_xor_sync(0xffffffffu, good, o);
   if (good < k) {   // the collected set is not certified to contain the exact top-k
-    if (lane == 0) redo_flag[u] = 1;
+    if (lane == 0) give_up(u, uid);
     return;
   }
   __syncwarp();
@@ -1067,20 +1099,6 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     __syncwarp();
   }
   if (lane == 0) redo_flag[u] = 0;
-}
-
-// compact the flagged users into a list for the exact kernel
-// (redo_cnt[1] = the fp16-range overflow flag of k_tc_convert: the certificates do not hold, every user is re-done)
-__global__ void k_tc_compact_redo(const int *__restrict__ redo_flag, const long long *__restrict__ user_ids,
-                                  int n_users, long long *__restrict__ redo_users, int *__restrict__ redo_pos,
-                                  int *__restrict__ redo_cnt) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= n_users) return;
-  if (redo_flag[u] || redo_cnt[1] != 0) {
-    const int at = atomicAdd(redo_cnt, 1);
-    redo_users[at] = user_ids[u];
-    redo_pos[at] = u;
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1313,12 +1331,21 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   dump_timing("MAX");
 #endif
   if (small_thr) {
-    const int tb = (n_users + 127) / 128;
     int *gm = eb.gmax.as<int>();
-    if (k <= 8) k_tc_threshold_small<8><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, dirty);
-    else if (k <= 16) k_tc_threshold_small<16><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, dirty);
-    else if (k <= 24) k_tc_threshold_small<24><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, dirty);
-    else k_tc_threshold_small<32><<<tb, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, dirty);
+#define MFB_THRESHOLD(K)                                                                                             \
+  do {                                                                                                               \
+    if (n_users < 65536)                                                                                             \
+      k_tc_threshold_small<K, 4><<<(4 * n_users + 127) / 128, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, \
+                                                                            dirty);                                  \
+    else                                                                                                             \
+      k_tc_threshold_small<K, 1><<<(n_users + 127) / 128, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr,     \
+                                                                        dirty);                                      \
+  } while (0)
+    if (k <= 8) MFB_THRESHOLD(8);
+    else if (k <= 16) MFB_THRESHOLD(16);
+    else if (k <= 24) MFB_THRESHOLD(24);
+    else MFB_THRESHOLD(32);
+#undef MFB_THRESHOLD
   } else {
     k_tc_threshold<<<(n_users + 3) / 4, 128, 0, st>>>(eb.gmax.as<int>(), groups, n_users, n_users_pad, k,
                                                       (const long long *)d_user_ids,
@@ -1339,6 +1366,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   dump_timing("COLLECT");
 #endif
   // exact re-score + mask + top-k
+  long long *redo_users = eb.redo.as<long long>();
   const size_t rs_smem = (size_t)RS_WARPS * (D + 3 * RS_MAXC) * sizeof(float);
 #define MFB_RESCORE(MAXSUB)                                                                                          \
   do {                                                                                                               \
@@ -1350,15 +1378,12 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
     k_tc_rescore<MAXSUB><<<(n_users + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>(                       \
         (const long long *)d_user_ids, n_users, m->users, m->items, D, eb.cand.as<int2>(), cand_cnt, cap2, nsub, thr, \
         unorm, vnorm_item, (const long long *)d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, redo_flag,  \
-        surv_cnt, masked_in_gemm ? 0 : 1);                                                                            \
+        surv_cnt, masked_in_gemm ? 0 : 1, redo_users, redo_pos, redo_cnt);                                            \
   } while (0)
   if (nsub == 2) MFB_RESCORE(2);
+  else if (nsub <= 4) MFB_RESCORE(4);
   else MFB_RESCORE(2 * TC_MAX_SPLIT);
 #undef MFB_RESCORE
-  MFB_KERNEL_CHECK();
-  long long *redo_users = eb.redo.as<long long>();
-  k_tc_compact_redo<<<(n_users + 255) / 256, 256, 0, st>>>(redo_flag, (const long long *)d_user_ids, n_users, redo_users,
-                                                           redo_pos, redo_cnt);
   MFB_KERNEL_CHECK();
   m->prof.end(tk, st);
   // The flagged users are re-done by the exact kernel straight into their rows of the result.  Their number stays on
