@@ -363,6 +363,17 @@ def reduce_max(dist, dev, values):
     return [float(x) for x in t.tolist()]
 
 
+def gather_ranks(dist, dev, value):
+    """[value of rank 0, value of rank 1, ...] on every rank."""
+    import torch
+    if not dist:
+        return [float(value)]
+    t = torch.tensor([float(value)], device=dev, dtype=torch.float64)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(x.item()) for x in out]
+
+
 def reduce_sum(dist, dev, values):
     import torch
     if not dist:
@@ -403,6 +414,7 @@ def native_bench(args, w, rank, world):
             dist, dev, [tm['ms']['median'] / 1e3, tm['ms']['min'] / 1e3, tm['ms']['max'] / 1e3, tm['e2e_s']['median'],
                         ev['seconds']['median'], ev['e2e_s']['median']])
         n_eval, launches = [int(x) for x in reduce_sum(dist, dev, [ev['users'], tm['launches']])]
+        eval_rank_s = gather_ranks(dist, dev, ev['seconds']['median'])
         prof, P = tm['prof'], tm['prof_steps']
         upd_ms, upd_n = prof.get('update', (0.0, 1))
         upd_us = upd_ms * 1e3 / max(upd_n, 1)
@@ -432,7 +444,8 @@ def native_bench(args, w, rank, world):
                                              'the train-mask images are built by the first pass only'
                                              % ev['seconds']['n'],
                                 'seconds_min': ev['seconds']['min'], 'seconds_max': ev['seconds']['max'],
-                                'first_call_seconds': ev['first_call'], 'unkeyed_seconds': ev['unkeyed']},
+                                'first_call_seconds': ev['first_call'], 'unkeyed_seconds': ev['unkeyed'],
+                                'rank_seconds': eval_rank_s},
                      'kernel': ev['kernel'],
                      'e2e': {'value': ev['users_total'] / t_eval_e2e, 'unit': 'users/s', 'seconds': t_eval_e2e,
                              'call': 'spotlight.evaluation.precision_recall_score%s(model, test, train, k=[5,10,20]) '

@@ -1332,9 +1332,13 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
 #endif
   if (small_thr) {
     int *gm = eb.gmax.as<int>();
+    // (four threads per user: measured SLOWER at 17 312 and 34 624 users -- the two merge rounds cost more than the
+    // latency they hide -- so it is off unless MFB_TC_THR_TPU4 names a user count below which to use it)
+    int tpu4_below = 0;
+    if (const char *e = getenv("MFB_TC_THR_TPU4")) tpu4_below = atoi(e);
 #define MFB_THRESHOLD(K)                                                                                             \
   do {                                                                                                               \
-    if (n_users < 65536)                                                                                             \
+    if (n_users < tpu4_below)                                                                                        \
       k_tc_threshold_small<K, 4><<<(4 * n_users + 127) / 128, 128, 0, st>>>(gm, groups, n_users, n_users_pad, k, thr, \
                                                                             dirty);                                  \
     else                                                                                                             \
