@@ -276,6 +276,11 @@ struct TcArgs {
   const float *user_norm;       // [n_users_pad] L2 norm of each evaluated user's row
   // MODE_MAX: gmax[(i*4 + column group) * n_users_pad + user]  (ordered-int encoded)
   int *gmax;
+  // MODE_MAX with TOPK > 0: the epilogue threads keep the TOPK largest clean group maxima themselves and write
+  // toplists[((split * 2 + parity) * TOPK + j) * n_users_pad + user] (sorted, ordered-int encoded) instead of gmax;
+  // dirty_groups[user][8]: sampled groups that hold a train item of the user (null: none)
+  int *toplists;
+  const uint32_t *dirty_groups;
   int n_users_pad;
   // MODE_COLLECT
   const float *thr;             // [n_users_pad] collection threshold per user
@@ -300,7 +305,7 @@ struct TcArgs {
 // ~115 instructions) is paid once per 128 columns, a slot is handed to its four warps as soon as its own 8 MMAs have
 // retired, and its next use waits for those four warps only.  (The epilogue is bound by its instruction issue rate:
 // ~110 instructions per 32 scores per warp in COLLECT mode; the MMA stream needs ~1024 of the ~2000 cycles of a tile.)
-template <int MODE, bool SPLIT>
+template <int MODE, bool SPLIT, int TOPK>
 __global__ void __launch_bounds__(TC_THREADS, 1)   // 18 warps (allocated as 20): 96 registers per thread
 k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__ CUtensorMap map_users,
           const TcArgs a) {
@@ -516,6 +521,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       prestore_bias();
       __syncwarp();
     }
+    // MODE_MAX, TOPK > 0: the TOPK largest group maxima this thread has seen (groups without a train item of its user)
+    int top[TOPK > 0 ? TOPK : 1];
+#pragma unroll
+    for (int j = 0; j < (TOPK > 0 ? TOPK : 1); ++j) top[j] = INT_MIN;
 #ifdef MFB_TC_TIMING
     long long tw_tfull = 0, t_ldw = 0, t_proc = 0, t_pre = 0;
     const long long te_start = clock64();
@@ -566,7 +575,27 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
 #pragma unroll
           for (int c = 2; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[c]), __uint_as_float(r[c + 1])));
           mx -= rad;   // approx - err <= exact: a certified lower bound (train items: see k_tc_threshold_small)
-          a.gmax[(long long)((li * S + split) * 4 + (cc0 >> 5)) * a.n_users_pad + gu] = float_to_ordered(mx);
+          const int gi = (li * S + split) * 4 + (cc0 >> 5);   // the group's index in the sample
+          if (TOPK > 0) {
+            // the thread keeps the TOPK largest itself: no [groups][users] round trip through HBM, no selection kernel
+            // behind it (k_tc_threshold_merge only merges the few lists of a user).  Groups that hold a train item of
+            // the user are dropped: their maximum may belong to that item.
+            int v = float_to_ordered(mx);
+            if (a.dirty_groups != nullptr && user_ok && gi < 256 &&
+                ((__ldg(a.dirty_groups + (long long)gu * 8 + (gi >> 5)) >> (gi & 31)) & 1u))
+              v = INT_MIN;
+            if (!user_ok) v = INT_MIN;
+            if (__any_sync(0xffffffffu, v > top[(TOPK > 0 ? TOPK : 1) - 1])) {
+#pragma unroll
+              for (int j = 0; j < (TOPK > 0 ? TOPK : 1); ++j) {
+                const int hi = max(top[j], v);
+                v = min(top[j], v);
+                top[j] = hi;
+              }
+            }
+          } else {
+            a.gmax[(long long)gi * a.n_users_pad + gu] = float_to_ordered(mx);
+          }
         } else {
           // margin = score - (threshold - radius) on the FMA pipe; its sign bit (1 = below) is funnel-shifted into
           // one of four byte accumulators, columns taken from high to low so that column c lands on bit c
@@ -633,6 +662,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     }
 #endif
     if (MODE == MODE_COLLECT && user_ok) a.cand_cnt[((long long)gu * S + split) * 2 + par] = my_cnt;
+    if (MODE == MODE_MAX && TOPK > 0) {
+#pragma unroll
+      for (int j = 0; j < (TOPK > 0 ? TOPK : 1); ++j)
+        a.toplists[((long long)(split * 2 + par) * TOPK + j) * a.n_users_pad + gu] = top[j];
+    }
   }
   // teardown
   tc_fence_before();
@@ -802,6 +836,41 @@ __global__ void __launch_bounds__(128) k_tc_threshold_small(const int *__restric
 #pragma unroll
   for (int j = 0; j < K; ++j) r = (j == m - 1) ? top[j] : r;
   thr[u] = (m <= groups && r != INT_MIN) ? ordered_to_float(r) : -INFINITY;   // -inf: the user goes to the exact path
+}
+
+// The m-th largest over a user's `nlists` sorted lists of K keys (written by the MAX epilogue threads that share the
+// user: tile parities x item-tile splits); one thread per user, loads of consecutive users coalesce.
+template <int K>
+__global__ void __launch_bounds__(128) k_tc_threshold_merge(const int *__restrict__ lists, int nlists, int n_users,
+                                                            int n_users_pad, int m, float *__restrict__ thr) {
+  const int u = blockIdx.x * 128 + threadIdx.x;
+  if (u >= n_users) return;
+  const unsigned act = __activemask();
+  int top[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) top[j] = lists[(long long)j * n_users_pad + u];   // list 0 is sorted already
+  for (int l = 1; l < nlists; ++l) {
+    const int *col = lists + (long long)l * K * n_users_pad + u;
+    int v[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) v[j] = col[(long long)j * n_users_pad];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      // the list is sorted: once its i-th key is below every lane's K-th largest, so are the rest
+      if (!__any_sync(act, v[i] > top[K - 1])) break;
+      int x = v[i];
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int hi = max(top[j], x);
+        x = min(top[j], x);
+        top[j] = hi;
+      }
+    }
+  }
+  int r = INT_MIN;
+#pragma unroll
+  for (int j = 0; j < K; ++j) r = (j == m - 1) ? top[j] : r;
+  thr[u] = (r != INT_MIN) ? ordered_to_float(r) : -INFINITY;   // -inf: the user goes to the exact path
 }
 
 __global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gmax, int groups, int n_users,
@@ -1142,25 +1211,25 @@ size_t tc_smem_bytes(int D) {
          (size_t)TC_EPI_WARPS * TC_M * 4;
 }
 
-template <int MODE, bool SPLIT>
+template <int MODE, bool SPLIT, int TOPK>
 int launch_gemm_s(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, dim3 grid, size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;   // (one device per process: the attribute is set when the size first grows)
   if (smem > smem_set) {
-    MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, SPLIT, TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  k_tc_gemm<MODE, SPLIT><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
+  k_tc_gemm<MODE, SPLIT, TOPK><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
   MFB_KERNEL_CHECK();
   return MFB_OK;
 }
 
-template <int MODE>
+template <int MODE, int TOPK = 0>
 int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, int n_users, cudaStream_t st,
                 int splits = 1) {
   const size_t smem = tc_smem_bytes(a.D);
   const dim3 grid((n_users + TC_N - 1) / TC_N, splits);
-  if (splits > 1) return launch_gemm_s<MODE, true>(mi, mu, a, grid, smem, st);
-  return launch_gemm_s<MODE, false>(mi, mu, a, grid, smem, st);
+  if (splits > 1) return launch_gemm_s<MODE, true, TOPK>(mi, mu, a, grid, smem, st);
+  return launch_gemm_s<MODE, false, TOPK>(mi, mu, a, grid, smem, st);
 }
 
 }  // namespace
@@ -1208,7 +1277,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   MFB_CHECK(eb.vb.reserve((size_t)items_pad * Dp * sizeof(__half)));
   MFB_CHECK(eb.unorm.reserve((size_t)n_users_pad * sizeof(float)));
   MFB_CHECK(eb.vnorm.reserve(((size_t)items_pad * 3 + i_tiles) * sizeof(float) + 16));
-  MFB_CHECK(eb.gmax.reserve((size_t)groups * n_users_pad * sizeof(int)));
+  MFB_CHECK(eb.gmax.reserve((size_t)(groups > 2 * TC_MAX_SPLIT * 24 ? groups : 2 * TC_MAX_SPLIT * 24) * n_users_pad * sizeof(int)));
   MFB_CHECK(eb.thr.reserve((size_t)n_users_pad * 2 * sizeof(float)));
   MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * nsub * cap2 * sizeof(int2)));
   MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * (2 * TC_MAX_SPLIT + 3) + 64));
@@ -1326,11 +1395,24 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.tile_step = sample_step;
   a.n_tiles = n_sample;
   a.gmax = eb.gmax.as<int>();
-  MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st, splits));
+  // k <= 24 (and at most 256 sampled groups): the MAX epilogue keeps each thread's 24 largest clean group maxima and a
+  // small kernel merges a user's 2 * splits lists; otherwise the maxima go through gmax and a selection kernel
+  constexpr int THRK = 24;
+  const bool fused_thr = small_thr && k <= THRK && m->tune_tc_fused_thr != 0;
+  if (fused_thr) {
+    a.toplists = eb.gmax.as<int>();   // (same buffer: reserved for max(groups, 2 * TC_MAX_SPLIT * THRK) rows)
+    a.dirty_groups = dirty;
+    MFB_CHECK((launch_gemm<MODE_MAX, THRK>(map_items, map_users, a, n_users, st, splits)));
+  } else {
+    MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st, splits));
+  }
 #ifdef MFB_TC_TIMING
   dump_timing("MAX");
 #endif
-  if (small_thr) {
+  if (fused_thr) {
+    k_tc_threshold_merge<THRK><<<(n_users + 127) / 128, 128, 0, st>>>(eb.gmax.as<int>(), 2 * splits, n_users, n_users_pad,
+                                                                      k, thr);
+  } else if (small_thr) {
     int *gm = eb.gmax.as<int>();
     // (four threads per user: measured SLOWER at 17 312 and 34 624 users -- the two merge rounds cost more than the
     // latency they hide -- so it is off unless MFB_TC_THR_TPU4 names a user count below which to use it)

@@ -139,6 +139,7 @@ struct mfb_model {
   Profiler prof;
   EvalBuf eval;
   int tune_tc = 1, tune_tc_sample_step = 4;   // MFB_TC=0 forces the exact-fp32 evaluation kernel
+  int tune_tc_fused_thr = 1;                  // MFB_TC_FUSED_THR=0: group maxima through HBM + selection kernel
   int last_topk_redo = 0;                     // users re-done by the exact kernel in the last mfb_topk call (-1: still on the device)
   PlanBuf plan[2];
   cudaStream_t st_plan = nullptr;   // planner stream
