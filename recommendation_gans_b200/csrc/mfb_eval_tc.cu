@@ -536,6 +536,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       // error radius of every score of this tile for this user: |u| * max over the tile of err_coeff * |v|
       const float rad = (MODE != MODE_DUMP) ? nu * __ldg(a.tile_nmax + tile_id) : 0.f;
       prefetch_bias(i + 2);   // consumed by the pre-store at the bottom of this iteration
+      // MODE_MAX, TOPK > 0: the word of the user's dirty-group set that holds this tile's four groups (fetched before the
+      // wait on the accumulators)
+      uint32_t dirty_w = 0u;
+      if (MODE == MODE_MAX && TOPK > 0 && a.dirty_groups != nullptr && user_ok) {
+        const int g0 = (li * S + split) * 4;
+        if (g0 < 256) dirty_w = __ldg(a.dirty_groups + (long long)gu * 8 + (g0 >> 5));
+      }
       const uint2 mw0 = mw_next0, mw1 = mw_next1;
       mw_next0 = load_mask(i + 2, 0);
       mw_next1 = load_mask(i + 2, 1);
@@ -581,10 +588,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
             // behind it (k_tc_threshold_merge only merges the few lists of a user).  Groups that hold a train item of
             // the user are dropped: their maximum may belong to that item.
             int v = float_to_ordered(mx);
-            if (a.dirty_groups != nullptr && user_ok && gi < 256 &&
-                ((__ldg(a.dirty_groups + (long long)gu * 8 + (gi >> 5)) >> (gi & 31)) & 1u))
-              v = INT_MIN;
-            if (!user_ok) v = INT_MIN;
+            if (!user_ok || ((dirty_w >> (gi & 31)) & 1u)) v = INT_MIN;
             if (__any_sync(0xffffffffu, v > top[(TOPK > 0 ? TOPK : 1) - 1])) {
 #pragma unroll
               for (int j = 0; j < (TOPK > 0 ? TOPK : 1); ++j) {
