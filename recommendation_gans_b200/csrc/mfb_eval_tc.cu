@@ -41,6 +41,10 @@ constexpr int TC_SROW = 36;        // row stride (floats) of an epilogue warp's 
 #endif
 constexpr int TC_SCR_ROWS = MFB_TC_SCR_ROWS;   // scratch rows per epilogue warp: lanes with a hit in the chunk take one each
                                                // (32 = a private row per lane, no rounds)
+#ifndef MFB_TC_PRESTORE_UNROLL
+#define MFB_TC_PRESTORE_UNROLL 1
+#endif
+constexpr int TC_PRESTORE_UNROLL = MFB_TC_PRESTORE_UNROLL;   // 32-column chunks of the bias pre-store in flight
 constexpr int TC_EPI_WARPS = 16;   // (TMEM lane quarter) x (user block) x (tile parity)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_KATOM = 64;       // 16-bit elements per 128-byte swizzle atom
@@ -497,7 +501,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
       if (!(a.dbg & 16)) {
-#pragma unroll 1
+#pragma unroll TC_PRESTORE_UNROLL
         for (int c0 = 0; c0 < TC_M; c0 += 32) {
           uint32_t r[32];
 #pragma unroll
