@@ -108,6 +108,7 @@ extern "C" int mfb_model_create(const mfb_model_desc *d, mfb_model **out) {
   if (const char *e = getenv("MFB_TC")) m->tune_tc = atoi(e);
   if (const char *e = getenv("MFB_TC_SAMPLE_STEP")) m->tune_tc_sample_step = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("MFB_TC_FUSED_THR")) m->tune_tc_fused_thr = atoi(e);
+  if (const char *e = getenv("MFB_TC_XK")) m->tune_tc_xk = atoi(e);
   if (const char *e = getenv("MFB_CU_BLOCKS")) m->tune_cu_blocks_per_sm = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("MFB_CHUNK_RAMP")) m->tune_chunk_ramp = atoi(e) < 0 ? 0 : atoi(e);
   auto bind = [&](TableView &T, int rows, float *p, float *pm, float *pv, float *b, float *bm, float *bv) {
@@ -175,7 +176,7 @@ extern "C" int mfb_model_destroy(mfb_model *m) {
   {
     DevBuf *ebufs[] = {&m->eval.ub, &m->eval.vb, &m->eval.unorm, &m->eval.vnorm, &m->eval.gmax, &m->eval.thr,
                        &m->eval.cand, &m->eval.cnt, &m->eval.redo, &m->eval.mcnt, &m->eval.mptr, &m->eval.mpairs,
-                       &m->eval.cut};
+                       &m->eval.cut, &m->eval.xk};
     for (DevBuf *b : ebufs) b->release();
   }
   if (m->st_plan) cudaStreamDestroy(m->st_plan);

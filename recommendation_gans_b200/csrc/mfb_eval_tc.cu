@@ -123,6 +123,12 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 1-D bulk copy global -> shared (16-byte granularity), bytes counted on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // One thread of the (converged) warp.  With elect.sync the compiler knows that a single thread runs the region and emits
 // bare UTCHMMA / UTMALDG instructions; under a plain `lane == 0` test it wraps every one of them in an ELECT / BRA.U.ANY
 // loop over the active threads, and the issuing thread -- not the tensor pipe -- sets the pace (measured: ~105 instead of
@@ -184,6 +190,22 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+
+// K-major operand WITHOUT swizzle: core matrices of 8 rows x 16 bytes; leading byte offset = distance between the core
+// matrices adjacent in K (128 B), stride byte offset = distance between 8-row groups (256 B) -- the layout of xk_off.
+__device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// byte offset of element (row, k) of a 128 x 16 fp16 operand in that layout (4 KB per operand)
+__host__ __device__ __forceinline__ int xk_off(int row, int k) {
+  return (row >> 3) * 256 + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2;
+}
+constexpr int XK_BYTES = 4096;
 
 // 256-bit read-only global load (32-byte aligned address)
 __device__ __forceinline__ void ld_global_nc_v8(const float *p, float (&r)[8]) {
@@ -285,6 +307,12 @@ struct TcArgs {
   // dirty_groups[user][8]: sampled groups that hold a train item of the user (null: none)
   int *toplists;
   const uint32_t *dirty_groups;
+  // XK kernels (bias and threshold enter through one extra K = 16 MMA step instead of a pre-store / a subtraction):
+  // ximg[user block of 128][4 KB], yimg[item tile][4 KB]: the 128 x 16 fp16 operands in the no-swizzle K-major core
+  // matrix layout (xk_off); rad_extra[user]: what the accumulation of the extra terms adds to the error radius
+  const uint8_t *ximg;
+  const uint8_t *yimg;
+  const float *rad_extra;
   int n_users_pad;
   // MODE_COLLECT
   const float *thr;             // [n_users_pad] collection threshold per user
@@ -309,7 +337,12 @@ struct TcArgs {
 // ~115 instructions) is paid once per 128 columns, a slot is handed to its four warps as soon as its own 8 MMAs have
 // retired, and its next use waits for those four warps only.  (The epilogue is bound by its instruction issue rate:
 // ~110 instructions per 32 scores per warp in COLLECT mode; the MMA stream needs ~1024 of the ~2000 cycles of a tile.)
-template <int MODE, bool SPLIT, int TOPK>
+// XK = true: the item biases and (COLLECT) the user's collection threshold are the product of one extra K = 16 MMA
+// step that INITIALISES the accumulator (accumulate = 0): X[user] = (1, 2^-6, 2^-12, -t_hi, -t_lo, 0...) against
+// Y[item] = (b_hi, b_mid, b_lo, 1, 1, 0...), fp16 pieces whose products are exact in fp32 (k_tc_xk_items / _users).
+// No bias pre-store (the slot goes back to the MMA as soon as it is drained) and no per-score subtraction: a hit is a
+// clear sign bit.
+template <int MODE, bool SPLIT, int TOPK, bool XK>
 __global__ void __launch_bounds__(TC_THREADS, 1)   // 18 warps (allocated as 20): 96 registers per thread
 k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__ CUtensorMap map_users,
           const TcArgs a) {
@@ -323,7 +356,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   const uint32_t v_bytes = (uint32_t)TC_M * 128u * katoms;       // one item stage:  [katom][128 rows][128 B]
   uint8_t *sU = smem;
   uint8_t *sV = sU + u_bytes;
-  uint8_t *tail = sV + (size_t)TC_STAGES * v_bytes;
+  uint8_t *sX = sV + (size_t)TC_STAGES * v_bytes;                // XK: [2 user blocks][4 KB]
+  uint8_t *sY = sX + (XK ? 2 * XK_BYTES : 0);                    // XK: [TC_STAGES][4 KB]
+  uint8_t *tail = sY + (XK ? TC_STAGES * XK_BYTES : 0);
   uint64_t *full = reinterpret_cast<uint64_t *>(tail);           // [TC_STAGES]
   uint64_t *empty = full + TC_STAGES;                            // [TC_STAGES]
   uint64_t *tfull = empty + TC_STAGES;                           // [4]: accumulator slot = buffer * 2 + user block
@@ -369,9 +404,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
-      mbar_expect_tx(ufull, u_bytes);
+      mbar_expect_tx(ufull, u_bytes + (XK ? 2 * XK_BYTES : 0));
       for (int ka = 0; ka < katoms; ++ka)
         tma_load_2d(sU + (size_t)ka * TC_N * 128, &map_users, ufull, ka * TC_KATOM, u0);
+      if (XK) bulk_load_1d(sX, a.ximg + (size_t)(u0 / 128) * XK_BYTES, 2 * XK_BYTES, ufull);
 #ifdef MFB_TC_TIMING
       long long tw_empty = 0;
 #endif
@@ -387,9 +423,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
         if ((a.dbg & 32) && i >= TC_STAGES) { mbar_arrive(full + s); continue; }   // ablation: no TMA traffic after the first fills
 #endif
         const int row0 = (tb + logical(i) * ts) * TC_M;
-        mbar_expect_tx(full + s, v_bytes);
+        mbar_expect_tx(full + s, v_bytes + (XK ? XK_BYTES : 0));
         for (int ka = 0; ka < katoms; ++ka)
           tma_load_2d(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128, &map_items, full + s, ka * TC_KATOM, row0);
+        if (XK) bulk_load_1d(sY + (size_t)s * XK_BYTES, a.yimg + (size_t)(tb + logical(i) * ts) * XK_BYTES, XK_BYTES, full + s);
       }
 #ifdef MFB_TC_TIMING
       if (a.timing && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && blockIdx.y == 0)
@@ -438,6 +475,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
 #else
         const int ka_n = katoms;
 #endif
+        if (XK)   // bias (and threshold) terms: initialises the slot
+          tc_mma_f16(d_tmem, umma_desc_noswz(smem_u32(sX + (size_t)ub * XK_BYTES)),
+                     umma_desc_noswz(smem_u32(sY + (size_t)s * XK_BYTES)), idesc, 0u);
         for (int ka = 0; ka < ka_n; ++ka) {
           const uint64_t udesc = umma_desc_sw128(smem_u32(sU + (size_t)ka * TC_N * 128 + (size_t)ub * 128 * 128));
           const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (size_t)s * v_bytes + (size_t)ka * TC_M * 128));
@@ -484,12 +524,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     uint2 mw_next0 = load_mask(par, 0), mw_next1 = load_mask(par, 1);
     const float nu = (MODE != MODE_DUMP && user_ok) ? a.user_norm[gu] : 0.f;
     const float thr_u = (MODE == MODE_COLLECT && user_ok) ? a.thr[gu] : INFINITY;
+    const float rx = (XK && MODE == MODE_MAX && user_ok && a.rad_extra) ? a.rad_extra[gu] : 0.f;
     int my_cnt = 0;
     int2 *my_cand = (MODE == MODE_COLLECT) ? a.cand + (((long long)gu * S + split) * 2 + par) * a.cap2 : nullptr;
 
     // item biases of a tile's 128 columns (they differ per column, not per user): fetched into this warp's slot with
     // cp.async at the top of the tile loop, written into the accumulator's next use at the bottom
     auto prefetch_bias = [&](int tile_idx) {
+      if (XK) return;
       if (tile_idx < nt) {
         const int tile_id = tb + logical(tile_idx) * ts;
         const float *src = a.item_bias + (long long)tile_id * TC_M + lane * 4;
@@ -498,9 +540,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto prestore_bias = [&]() {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (!XK) asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
-      if (!(a.dbg & 16)) {
+      if (!XK && !(a.dbg & 16)) {
 #pragma unroll TC_PRESTORE_UNROLL
         for (int c0 = 0; c0 < TC_M; c0 += 32) {
           uint32_t r[32];
@@ -585,7 +627,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
           float mx = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
 #pragma unroll
           for (int c = 2; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[c]), __uint_as_float(r[c + 1])));
-          mx -= rad;   // approx - err <= exact: a certified lower bound (train items: see k_tc_threshold_small)
+          mx -= rad + rx;   // approx - err <= exact: a certified lower bound (train items: see k_tc_threshold_small)
           const int gi = (li * S + split) * 4 + (cc0 >> 5);   // the group's index in the sample
           if (TOPK > 0) {
             // the thread keeps the TOPK largest itself: no [groups][users] round trip through HBM, no selection kernel
@@ -609,9 +651,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
           // one of four byte accumulators, columns taken from high to low so that column c lands on bit c
           const float t = thr_u - rad;    // approx + err >= exact: collect everything whose upper bound reaches thr
           uint32_t wb[4] = {0u, 0u, 0u, 0u};
+          if (XK) {   // the accumulator already holds score - t' (t' <= thr - every radius): a hit is a clear sign bit
 #pragma unroll
-          for (int c = 31; c >= 0; --c)
-            wb[c >> 3] = __funnelshift_l(__float_as_uint(__uint_as_float(r[c]) - t), wb[c >> 3], 1);
+            for (int c = 31; c >= 0; --c) wb[c >> 3] = __funnelshift_l(r[c], wb[c >> 3], 1);
+          } else {
+#pragma unroll
+            for (int c = 31; c >= 0; --c)
+              wb[c >> 3] = __funnelshift_l(__float_as_uint(__uint_as_float(r[c]) - t), wb[c >> 3], 1);
+          }
           uint32_t hw = ~(wb[0] | (wb[1] << 8) | (wb[2] << 16) | (wb[3] << 24)) & ~mword;
           if (!(a.dbg & 2)) {
             // the records carry the GEMM score (k_tc_rescore uses it to discard most of the list before the exact
@@ -933,6 +980,92 @@ __global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gm
 }
 
 // ---------------------------------------------------------------------------------------------
+// XK operands (see k_tc_gemm<..., XK = true>).  fp16 x fp16 products are exact in fp32, so
+//   b  = b_hi + 2^-6 b_mid + 2^-12 b_lo   (three 11-bit pieces: residual <= 2^-33 |b|, far below one fp32 ulp)
+//   t' = t_hi + t_lo                       (DEFINED as the sum of its two pieces, chosen <= the wanted threshold)
+// enter the accumulator exactly; what the tensor core's fp32 accumulation of these larger terms may add to the
+// error of a score is bounded by rad_extra (2^-18 of their magnitudes, i.e. 64 ulps, + the pieces' underflow).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_M) k_tc_xk_items(const float *__restrict__ bias_pos, int total_tiles,
+                                                      uint8_t *__restrict__ yimg, float *__restrict__ bmax,
+                                                      int *__restrict__ overflow) {
+  const int tile = blockIdx.x, row = threadIdx.x;
+  float b = bias_pos[(long long)tile * TC_M + row];
+  __half y[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) y[k] = __float2half_rn(0.f);
+  if (b == MASKED_SCORE_TC) {            // padding position: never a maximum, never a hit
+    y[0] = __float2half_rn(-60000.0f);
+  } else {
+    if (!(fabsf(b) <= 60000.0f)) atomicExch(overflow, 1);
+    const __half h0 = __float2half_rn(b);
+    const float r1 = (b - __half2float(h0)) * 64.0f;            // exact
+    const __half h1 = __float2half_rn(r1);
+    const float r2 = (r1 - __half2float(h1)) * 64.0f;           // exact
+    y[0] = h0;
+    y[1] = h1;
+    y[2] = __float2half_rn(r2);
+    atomicMax(reinterpret_cast<int *>(bmax), __float_as_int(fabsf(b)));   // non-negative floats order as ints
+  }
+  y[3] = __float2half_rn(1.0f);
+  y[4] = __float2half_rn(1.0f);
+  uint8_t *dst = yimg + (size_t)tile * XK_BYTES;
+  *reinterpret_cast<uint4 *>(dst + xk_off(row, 0)) = *reinterpret_cast<const uint4 *>(&y[0]);
+  *reinterpret_cast<uint4 *>(dst + xk_off(row, 8)) = *reinterpret_cast<const uint4 *>(&y[8]);
+}
+
+// collect = 0: X = (1, 2^-6, 2^-12, 0, ...), rad_extra = what the bias terms add to the radius (MAX pass)
+// collect = 1: X additionally carries -t' for t' <= thr - |u| max_tile(nmax) - rad_extra, t' and rad_extra written out
+__global__ void __launch_bounds__(128) k_tc_xk_users(int n_users, int n_users_pad, int collect,
+                                                     const float *__restrict__ thr, const float *__restrict__ unorm,
+                                                     const float *__restrict__ tile_nmax, int total_tiles,
+                                                     const float *__restrict__ bmax, uint8_t *__restrict__ ximg,
+                                                     float *__restrict__ tprime, float *__restrict__ rad_extra,
+                                                     int *__restrict__ overflow) {
+  const int u = blockIdx.x * 128 + threadIdx.x;
+  if (u >= n_users_pad) return;
+  __half x[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = __float2half_rn(0.f);
+  x[0] = __float2half_rn(1.0f);
+  x[1] = __float2half_rn(0.015625f);          // 2^-6
+  x[2] = __float2half_rn(0.000244140625f);    // 2^-12
+  const float bm = *bmax;
+  // 2^-18 of the extra terms' magnitude: 64 ulps for ~9 accumulation steps whose rounding (possibly truncation, on
+  // operands aligned to the largest exponent) is not specified; + 2^-23 for pieces that underflow in fp16
+  float rx = 3.814697265625e-06f * bm + 1.1920929e-07f;
+  float tp = 0.f;
+  if (collect) {
+    float t_raw = -INFINITY;
+    if (u < n_users && thr[u] > -INFINITY) {
+      float nmax = 0.f;
+      for (int t = 0; t < total_tiles; ++t) nmax = fmaxf(nmax, __ldg(tile_nmax + t));
+      t_raw = thr[u] - unorm[u] * nmax * 1.000001f;
+    }
+    if (t_raw > -INFINITY) {
+      rx += 3.814697265625e-06f * fabsf(t_raw);
+      const float t0 = t_raw - rx - 9.5367431640625e-07f * fabsf(t_raw);   // room for the two-piece representation
+      if (!(fabsf(t0) <= 60000.0f)) atomicExch(overflow, 1);
+      const __half th = __float2half_rn(t0);
+      const __half tl = __float2half_rn(t0 - __half2float(th));
+      tp = __half2float(th) + __half2float(tl);          // exact: two 11-bit pieces
+      x[3] = __hneg(th);
+      x[4] = __hneg(tl);
+    } else {
+      // no bound for this user (it is re-done by the exact kernel): a threshold nothing reaches
+      x[3] = __float2half_rn(-60000.0f);
+      tp = 60000.0f;
+    }
+    tprime[u] = tp;
+  }
+  rad_extra[u] = rx;
+  uint8_t *dst = ximg + (size_t)(u >> 7) * XK_BYTES;
+  const int row = u & 127;
+  *reinterpret_cast<uint4 *>(dst + xk_off(row, 0)) = *reinterpret_cast<const uint4 *>(&x[0]);
+  *reinterpret_cast<uint4 *>(dst + xk_off(row, 8)) = *reinterpret_cast<const uint4 *>(&x[8]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // 4. exact re-score of the candidates + mask + top-k.  One warp per user.
 //    Exact score = sequential fp32 FMA over d = 0..D-1, then (+ user bias) + item bias: bit-identical to k_topk_exact.
 // ---------------------------------------------------------------------------------------------
@@ -949,7 +1082,9 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     const float *__restrict__ unorm, const float *__restrict__ item_norm,
     const long long *__restrict__ indptr, const int *__restrict__ indices, int k, int *__restrict__ out_ids,
     float *__restrict__ out_scores, int *__restrict__ redo_flag, int *__restrict__ surv_cnt, int check_mask,
-    long long *__restrict__ redo_users, int *__restrict__ redo_pos, int *__restrict__ redo_cnt) {
+    long long *__restrict__ redo_users, int *__restrict__ redo_pos, int *__restrict__ redo_cnt,
+    const float *__restrict__ tprime, const float *__restrict__ rad_extra) {
+  // (XK GEMM: the records hold score - t'[u], and the accumulation of the extra terms widens every bound by rad_extra[u])
   // A user that cannot be certified here joins the list the exact kernel re-does (order arbitrary: every entry names
   // its own output row).  redo_cnt[1] = the fp16-range overflow flag of k_tc_convert: no certificate holds at all.
   auto give_up = [&](int uu, long long uuid) {
@@ -999,6 +1134,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
   }
   // ---- 1. bounds of every listed item's exact score from its GEMM score: [s - e, s + e], e = err_coeff*|u|*|v|
   const float nu = unorm[u];
+  const float tp = tprime ? tprime[u] : 0.f, rxu = rad_extra ? rad_extra[u] : 0.f;
   constexpr int KR = 8;                       // lists of up to 32*KR items keep their lower-bound keys in registers
   const bool small = cnt <= 32 * KR;
   uint32_t kreg[KR];
@@ -1015,10 +1151,10 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
         sub = sub < nsub ? sub : nsub - 1;
         const int2 rec = cand[((long long)nsub * u + sub) * cap2 + (c - pre[sub])];
         const float e = item_norm[rec.x];   // err_coeff * |v|, indexed by item id
-        const float sg = __int_as_float(rec.y);
-        const float lo = fmaf(-e, nu, sg);
+        const float sg = __int_as_float(rec.y) + tp;
+        const float lo = fmaf(-e, nu, sg) - rxu;
         ids[c] = rec.x;
-        sc[c] = fmaf(e, nu, sg);
+        sc[c] = fmaf(e, nu, sg) + rxu;
         lob[c] = lo;
         if (c0 == 0) kreg[j] = (uint32_t)float_to_ordered(lo) ^ 0x80000000u;
       }
@@ -1212,21 +1348,22 @@ int make_tmap(CUtensorMap *map, void *base, int rows, int D, int box_rows) {
   return MFB_OK;
 }
 
-size_t tc_smem_bytes(int D) {
+size_t tc_smem_bytes(int D, bool xk = false) {
   const int katoms = D / TC_KATOM;
   return 1024 + (size_t)TC_N * 128 * katoms + (size_t)TC_STAGES * TC_M * 128 * katoms + 128 +
+         (xk ? (size_t)(2 + TC_STAGES) * XK_BYTES : 0) +
          (size_t)TC_EPI_WARPS * TC_SCR_ROWS * TC_SROW * 4 +
          (size_t)TC_EPI_WARPS * TC_M * 4;
 }
 
-template <int MODE, bool SPLIT, int TOPK>
+template <int MODE, bool SPLIT, int TOPK, bool XK>
 int launch_gemm_s(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, dim3 grid, size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;   // (one device per process: the attribute is set when the size first grows)
   if (smem > smem_set) {
-    MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, SPLIT, TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MFB_CUDA(cudaFuncSetAttribute(k_tc_gemm<MODE, SPLIT, TOPK, XK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  k_tc_gemm<MODE, SPLIT, TOPK><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
+  k_tc_gemm<MODE, SPLIT, TOPK, XK><<<grid, TC_THREADS, smem, st>>>(mi, mu, a);
   MFB_KERNEL_CHECK();
   return MFB_OK;
 }
@@ -1234,10 +1371,15 @@ int launch_gemm_s(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a,
 template <int MODE, int TOPK = 0>
 int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, int n_users, cudaStream_t st,
                 int splits = 1) {
-  const size_t smem = tc_smem_bytes(a.D);
+  const bool xk = a.ximg != nullptr;
+  const size_t smem = tc_smem_bytes(a.D, xk);
   const dim3 grid((n_users + TC_N - 1) / TC_N, splits);
-  if (splits > 1) return launch_gemm_s<MODE, true, TOPK>(mi, mu, a, grid, smem, st);
-  return launch_gemm_s<MODE, false, TOPK>(mi, mu, a, grid, smem, st);
+  if (xk) {
+    if (splits > 1) return launch_gemm_s<MODE, true, TOPK, true>(mi, mu, a, grid, smem, st);
+    return launch_gemm_s<MODE, false, TOPK, true>(mi, mu, a, grid, smem, st);
+  }
+  if (splits > 1) return launch_gemm_s<MODE, true, TOPK, false>(mi, mu, a, grid, smem, st);
+  return launch_gemm_s<MODE, false, TOPK, false>(mi, mu, a, grid, smem, st);
 }
 
 }  // namespace
@@ -1324,6 +1466,26 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
                                                     i_tiles, m->items.bp, vbias, vnorm_item, overflow);
   k_tc_tile_maxnorm<<<(i_tiles + 7) / 8, 256, 0, st>>>(vnorm, i_tiles, tile_nmax);
   MFB_KERNEL_CHECK();
+  // XK: bias and threshold through one extra K = 16 MMA step (operand images built here)
+  const bool xk = m->tune_tc_xk != 0;
+  const size_t ublocks = (size_t)n_users_pad / 128;
+  uint8_t *xk_yimg = nullptr, *xk_ximg_max = nullptr, *xk_ximg_col = nullptr;
+  float *xk_tprime = nullptr, *xk_rx = nullptr, *xk_rx_max = nullptr, *xk_bmax = nullptr;
+  if (xk) {
+    MFB_CHECK(eb.xk.reserve(((size_t)i_tiles + 2 * ublocks) * XK_BYTES + (3 * (size_t)n_users_pad + 4) * sizeof(float)));
+    xk_yimg = eb.xk.as<uint8_t>();
+    xk_ximg_max = xk_yimg + (size_t)i_tiles * XK_BYTES;
+    xk_ximg_col = xk_ximg_max + ublocks * XK_BYTES;
+    xk_tprime = reinterpret_cast<float *>(xk_ximg_col + ublocks * XK_BYTES);
+    xk_rx = xk_tprime + n_users_pad;
+    xk_rx_max = xk_rx + n_users_pad;
+    xk_bmax = xk_rx_max + n_users_pad;
+    MFB_CUDA(cudaMemsetAsync(xk_bmax, 0, sizeof(float), st));
+    k_tc_xk_items<<<i_tiles, TC_M, 0, st>>>(vbias, i_tiles, xk_yimg, xk_bmax, overflow);
+    k_tc_xk_users<<<(n_users_pad + 127) / 128, 128, 0, st>>>(n_users, n_users_pad, 0, nullptr, unorm, tile_nmax, i_tiles,
+                                                            xk_bmax, xk_ximg_max, nullptr, xk_rx_max, overflow);
+    MFB_KERNEL_CHECK();
+  }
 
   CUtensorMap map_items, map_users;
   MFB_CHECK(make_tmap(&map_items, vb, items_pad, Dp, TC_M));
@@ -1333,6 +1495,11 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   memset(&a, 0, sizeof(a));
   a.num_items = I;
   a.n_users = n_users;
+  if (xk) {
+    a.ximg = xk_ximg_max;
+    a.yimg = xk_yimg;
+    a.rad_extra = xk_rx_max;
+  }
   a.D = Dp;
   a.total_tiles = i_tiles;
   a.item_bias = vbias;
@@ -1448,6 +1615,13 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   }
   MFB_KERNEL_CHECK();
   // collect pass: all tiles
+  if (xk) {
+    k_tc_xk_users<<<(n_users_pad + 127) / 128, 128, 0, st>>>(n_users, n_users_pad, 1, thr, unorm, tile_nmax, i_tiles, xk_bmax,
+                                                            xk_ximg_col, xk_tprime, xk_rx, overflow);
+    MFB_KERNEL_CHECK();
+    a.ximg = xk_ximg_col;
+    a.rad_extra = xk_rx;
+  }
   a.tile_begin = 0;
   a.tile_step = 1;
   a.n_tiles = i_tiles;
@@ -1472,7 +1646,8 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
     k_tc_rescore<MAXSUB><<<(n_users + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>(                       \
         (const long long *)d_user_ids, n_users, m->users, m->items, D, eb.cand.as<int2>(), cand_cnt, cap2, nsub, thr, \
         unorm, vnorm_item, (const long long *)d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, redo_flag,  \
-        surv_cnt, masked_in_gemm ? 0 : 1, redo_users, redo_pos, redo_cnt);                                            \
+        surv_cnt, masked_in_gemm ? 0 : 1, redo_users, redo_pos, redo_cnt, xk ? xk_tprime : nullptr,                   \
+        xk ? xk_rx : nullptr);                                                                                        \
   } while (0)
   if (nsub == 2) MFB_RESCORE(2);
   else if (nsub <= 4) MFB_RESCORE(4);
