@@ -1083,7 +1083,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     const long long *__restrict__ indptr, const int *__restrict__ indices, int k, int *__restrict__ out_ids,
     float *__restrict__ out_scores, int *__restrict__ redo_flag, int *__restrict__ surv_cnt, int check_mask,
     long long *__restrict__ redo_users, int *__restrict__ redo_pos, int *__restrict__ redo_cnt,
-    const float *__restrict__ tprime, const float *__restrict__ rad_extra) {
+    const float *__restrict__ tprime, const float *__restrict__ rad_extra, const float *__restrict__ tile_nmax,
+    int total_tiles, uint32_t tile_magic) {
   // (XK GEMM: the records hold score - t'[u], and the accumulation of the extra terms widens every bound by rad_extra[u])
   // A user that cannot be certified here joins the list the exact kernel re-does (order arbitrary: every entry names
   // its own output row).  redo_cnt[1] = the fp16-range overflow flag of k_tc_convert: no certificate holds at all.
@@ -1150,7 +1151,16 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
         for (int j = 1; j < RS_MAXSUB; ++j) sub += (c >= pre[j]) ? 1 : 0;      // pre[] is non-decreasing
         sub = sub < nsub ? sub : nsub - 1;
         const int2 rec = cand[((long long)nsub * u + sub) * cap2 + (c - pre[sub])];
-        const float e = item_norm[rec.x];   // err_coeff * |v|, indexed by item id
+        // err_coeff * |v|: the item's own value (a gather: one 32-byte sector per lane), or -- tile_nmax given -- the
+        // maximum over the item's tile (item % T in the item layout), a table that stays in L1: a slightly wider, still
+        // valid bound for a quarter of this kernel's L1 look-ups
+        float e;
+        if (tile_nmax != nullptr) {
+          const int jq = tile_magic ? (int)__umulhi((uint32_t)rec.x, tile_magic) : rec.x / total_tiles;
+          e = __ldg(tile_nmax + (rec.x - jq * total_tiles));
+        } else {
+          e = item_norm[rec.x];
+        }
         const float sg = __int_as_float(rec.y) + tp;
         const float lo = fmaf(-e, nu, sg) - rxu;
         ids[c] = rec.x;
@@ -1647,7 +1657,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
         (const long long *)d_user_ids, n_users, m->users, m->items, D, eb.cand.as<int2>(), cand_cnt, cap2, nsub, thr, \
         unorm, vnorm_item, (const long long *)d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, redo_flag,  \
         surv_cnt, masked_in_gemm ? 0 : 1, redo_users, redo_pos, redo_cnt, xk ? xk_tprime : nullptr,                   \
-        xk ? xk_rx : nullptr);                                                                                        \
+        xk ? xk_rx : nullptr, m->tune_tc_tile_radius ? tile_nmax : nullptr, i_tiles, magic);                          \
   } while (0)
   if (nsub == 2) MFB_RESCORE(2);
   else if (nsub <= 4) MFB_RESCORE(4);

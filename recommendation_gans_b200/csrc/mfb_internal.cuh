@@ -140,6 +140,7 @@ struct mfb_model {
   EvalBuf eval;
   int tune_tc = 1, tune_tc_sample_step = 4;   // MFB_TC=0 forces the exact-fp32 evaluation kernel
   int tune_tc_xk = 1;                         // MFB_TC_XK=0: bias pre-store + per-score subtraction instead of the extra K = 16 MMA step
+  int tune_tc_tile_radius = 1;                // MFB_TC_TILE_RADIUS=0: per-item error radius in the re-score (a gather)
   int tune_tc_fused_thr = 1;                  // MFB_TC_FUSED_THR=0: group maxima through HBM + selection kernel
   int last_topk_redo = 0;                     // users re-done by the exact kernel in the last mfb_topk call (-1: still on the device)
   PlanBuf plan[2];
