@@ -1071,6 +1071,10 @@ __global__ void __launch_bounds__(128) k_tc_xk_users(int n_users, int n_users_pa
 // ---------------------------------------------------------------------------------------------
 constexpr int RS_MAXC = 512;    // candidates kept per user (cap)
 constexpr int RS_WARPS = 4;
+#ifndef MFB_RS_INFLIGHT
+#define MFB_RS_INFLIGHT 4
+#endif
+constexpr int RS_INFLIGHT = MFB_RS_INFLIGHT;   // 256-bit row loads in flight per lane in the exact re-score (D % (8 * RS_INFLIGHT) == 0 on the vector path)
 
 // smem per warp: user row [D] | scores [RS_MAXC] (upper bounds, then exact) | lower bounds [RS_MAXC] | ids [RS_MAXC]
 // (staging the candidate rows through shared memory with cp.async was measured 2x slower: the kernel is
@@ -1121,7 +1125,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     }
     return;
   }
-  const bool vec = (D & 31) == 0;      // whole 32-float chunks: vector loads; otherwise (e.g. the CLI's default D = 50) scalar
+  const bool vec = (D % (8 * RS_INFLIGHT)) == 0;      // whole chunks: vector loads; otherwise (e.g. the CLI's default D = 50) scalar
   if (vec) {
     for (int d = lane * 4; d < D; d += 128) *reinterpret_cast<float4 *>(urow + d) = *reinterpret_cast<const float4 *>(users.p + uid * D + d);
   } else {
@@ -1227,12 +1231,12 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     if (!vec) {
       for (int d = 0; d < D; ++d) acc = fmaf(urow[d], __ldg(v + d), acc);
     } else
-    for (int d0 = 0; d0 < D; d0 += 32) {
-      float x[4][8];
+    for (int d0 = 0; d0 < D; d0 += 8 * RS_INFLIGHT) {
+      float x[RS_INFLIGHT][8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ld_global_nc_v8(v + d0 + 8 * j, x[j]);
+      for (int j = 0; j < RS_INFLIGHT; ++j) ld_global_nc_v8(v + d0 + 8 * j, x[j]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < RS_INFLIGHT; ++j) {
         const float4 y0 = *reinterpret_cast<const float4 *>(urow + d0 + 8 * j);
         const float4 y1 = *reinterpret_cast<const float4 *>(urow + d0 + 8 * j + 4);
         acc = fmaf(y0.x, x[j][0], acc);
