@@ -4,22 +4,24 @@
 // user = users x items x D flops) for the top-k metrics.  The user x item score matrix is never
 // written to HBM:
 //
-//   1. k_tc_convert      fp16 copies of the user/item embedding rows (+ L2 norms for the error bound)
-//   2. k_tc_gemm<MAX>    scores of a SAMPLE of item tiles; epilogue keeps, per user, the maximum of each
-//                        32-item group  ->  k_tc_threshold: a per-user lower bound of the k-th best score
+//   1. k_tc_convert      fp16 copies of the user/item embedding rows (+ L2 norms for the error bound);
+//      k_tc_xk_items / k_tc_xk_users: the 128 x 16 fp16 operands of the extra MMA step (item-bias pieces, threshold pieces)
+//   2. k_tc_gemm<MAX>    scores of a SAMPLE of item tiles; every epilogue thread keeps the 24 largest maxima of its
+//                        user's 32-item groups (groups holding a train item dropped)  ->  k_tc_threshold_merge: a
+//                        per-user lower bound of the k-th best score (k > 24: group maxima through HBM + k_tc_threshold*)
 //   3. k_tc_gemm<COLLECT> all item tiles; epilogue appends every (user, item) whose approximate score
 //                        reaches the bound to the user's candidate list (a guaranteed superset of the top-k)
 //   4. k_tc_rescore      exact fp32 re-scoring of the candidates (same sequential-FMA definition as
 //                        k_topk_exact), train mask, top-k (ties -> lower item id); users whose list
-//                        overflowed or cannot be certified are flagged and redone by k_topk_exact.
+//                        overflowed or cannot be certified join a list that k_topk_exact re-does (count on the device).
 //
 // GEMM mapping: A = 256 users of the CTA (two M = 128 blocks = the 128 TMEM lanes, twice; resident in shared memory),
-// B = a tile of 128 items (N -> 128 TMEM columns per block), K = D, fp16 inputs, fp32 accumulation in TMEM.  An epilogue
-// thread owns one USER (one TMEM lane); the item bias is pre-stored into the accumulator in fp32 (tcgen05.st) and the MMA
-// accumulates on top of it.
+// B = a tile of 128 items (N -> 128 TMEM columns per block), K = D (+ 16: the extra step that initialises the
+// accumulator with item bias - user threshold), fp16 inputs, fp32 accumulation in TMEM.  An epilogue thread owns one
+// USER (one TMEM lane).
 // Warp roles (576 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner (one thread each, chosen with
 // elect.sync), warps 2-17 = epilogue: (TMEM lane quarter) x (user block) x (tile parity).  Pipelines: smem full/empty
-// (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, 2 accumulator buffers of 2 x 128 columns).
+// (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, four accumulator slots of 128 columns).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
