@@ -986,7 +986,7 @@ __global__ void __launch_bounds__(128) k_tc_threshold(const int *__restrict__ gm
 //   b  = b_hi + 2^-6 b_mid + 2^-12 b_lo   (three 11-bit pieces: residual <= 2^-33 |b|, far below one fp32 ulp)
 //   t' = t_hi + t_lo                       (DEFINED as the sum of its two pieces, chosen <= the wanted threshold)
 // enter the accumulator exactly; what the tensor core's fp32 accumulation of these larger terms may add to the
-// error of a score is bounded by rad_extra (2^-18 of their magnitudes, i.e. 64 ulps, + the pieces' underflow).
+// error of a score is bounded by rad_extra (2^-16 of their magnitudes, see k_tc_xk_users, + the pieces' underflow).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_M) k_tc_xk_items(const float *__restrict__ bias_pos, int total_tiles,
                                                       uint8_t *__restrict__ yimg, float *__restrict__ bmax,
@@ -1033,9 +1033,12 @@ __global__ void __launch_bounds__(128) k_tc_xk_users(int n_users, int n_users_pa
   x[1] = __float2half_rn(0.015625f);          // 2^-6
   x[2] = __float2half_rn(0.000244140625f);    // 2^-12
   const float bm = *bmax;
-  // 2^-18 of the extra terms' magnitude: 64 ulps for ~9 accumulation steps whose rounding (possibly truncation, on
-  // operands aligned to the largest exponent) is not specified; + 2^-23 for pieces that underflow in fp16
-  float rx = 3.814697265625e-06f * bm + 1.1920929e-07f;
+  // 2^-16 of the extra terms' magnitude M = |b| + |t|.  The accumulator now sits at magnitude M while the D products of
+  // the dot are added to it: if every addend of a K = 16 step is aligned to the largest exponent and TRUNCATED there with
+  // g >= 2 guard bits (the behaviour measured on earlier tensor-core generations; the rounding is not specified), a step
+  // loses at most 17 * 2^-(23+g) M and the 9 steps 2^-17.7 M.  2^-16 leaves a factor of three.  + 2^-23 absolute for
+  // pieces that underflow in fp16 and for t' = t_hi + t_lo formed in fp32 by the re-score.
+  float rx = 1.52587890625e-05f * bm + 1.1920929e-07f;
   float tp = 0.f;
   if (collect) {
     float t_raw = -INFINITY;
@@ -1045,7 +1048,7 @@ __global__ void __launch_bounds__(128) k_tc_xk_users(int n_users, int n_users_pa
       t_raw = thr[u] - unorm[u] * nmax * 1.000001f;
     }
     if (t_raw > -INFINITY) {
-      rx += 3.814697265625e-06f * fabsf(t_raw);
+      rx += 1.52587890625e-05f * fabsf(t_raw);
       const float t0 = t_raw - rx - 9.5367431640625e-07f * fabsf(t_raw);   // room for the two-piece representation
       if (!(fabsf(t0) <= 60000.0f)) atomicExch(overflow, 1);
       const __half th = __float2half_rn(t0);
@@ -1749,6 +1752,23 @@ int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, flo
   a.total_tiles = i_tiles;
   a.item_bias = eb.vnorm.as<float>() + items_pad;
   a.n_users_pad = n_users_pad;
+  if (m->tune_tc_xk != 0) {
+    // the same extra-K-step operands as the top-k passes use (threshold pieces zero): the dump then shows the score
+    // arithmetic of the production kernels, bias pieces included
+    const size_t ublocks = (size_t)n_users_pad / 128;
+    MFB_CHECK(eb.xk.reserve(((size_t)i_tiles + ublocks) * XK_BYTES + ((size_t)n_users_pad + 4) * sizeof(float)));
+    uint8_t *yimg = eb.xk.as<uint8_t>();
+    uint8_t *ximg = yimg + (size_t)i_tiles * XK_BYTES;
+    float *rx = reinterpret_cast<float *>(ximg + ublocks * XK_BYTES);
+    float *bmax = rx + n_users_pad;
+    MFB_CUDA(cudaMemsetAsync(bmax, 0, sizeof(float), st));
+    k_tc_xk_items<<<i_tiles, TC_M, 0, st>>>(eb.vnorm.as<float>() + items_pad, i_tiles, yimg, bmax, eb.cnt.as<int>());
+    k_tc_xk_users<<<(n_users_pad + 127) / 128, 128, 0, st>>>(n_users, n_users_pad, 0, nullptr, eb.unorm.as<float>(),
+                                                            nullptr, i_tiles, bmax, ximg, nullptr, rx, eb.cnt.as<int>());
+    MFB_KERNEL_CHECK();
+    a.ximg = ximg;
+    a.yimg = yimg;
+  }
   a.tile_begin = 0;
   a.tile_step = 1;
   a.n_tiles = i_tiles;

@@ -155,7 +155,8 @@ def _random_tables(rs, U, I, D, scale=0.3):
 
 @pytest.mark.parametrize('U,I,D', [(300, 1500, 128), (70, 1100, 64), (513, 2049, 128), (90, 1300, 32), (257, 1100, 50)])
 def test_tc_raw_scores_match_fp16_matmul(U, I, D):
-    """The tcgen05 GEMM (descriptors, swizzle, TMEM layout, bias pre-store) against torch on fp16-rounded inputs."""
+    """The tcgen05 GEMM (descriptors, swizzle, TMEM layout, the extra K = 16 step that carries the bias) against torch on
+    fp16-rounded inputs."""
     from recommendation_gans_b200.engine import MFEngine
     rs = np.random.RandomState(U)
     tabs = _random_tables(rs, U, I, D)
@@ -166,6 +167,32 @@ def test_tc_raw_scores_match_fp16_matmul(U, I, D):
     vb = torch.from_numpy(tabs[1]).cuda().half().float()
     ref = (vb.double() @ ub.double().T).float().cpu().numpy() + tabs[3]   # + item bias (fp32)
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('bias_scale', [1.0, 50.0, 3000.0])
+def test_tc_bias_through_the_extra_mma_step_stays_inside_its_error_budget(bias_scale):
+    """The item bias enters the accumulator as three fp16 pieces times (1, 2^-6, 2^-12) in an extra K = 16 MMA step,
+    and the dot product is then accumulated ON TOP of it.  The error model (k_tc_xk_users) budgets 2^-16 * |b| for what
+    that costs; here biases far larger than the dot products make the effect visible: the raw tensor-core scores stay
+    within 2^-16 * |b|max + (the fp16-matmul tolerance of the test above) of the float64 value."""
+    from recommendation_gans_b200.engine import MFEngine
+    U, I, D = 300, 1500, 128
+    rs = np.random.RandomState(11)
+    tabs = list(_random_tables(rs, U, I, D, scale=0.05))
+    tabs[3] = (rs.normal(0, bias_scale, (I, 1))).astype(np.float32)
+    eng = MFEngine(make_net(tabs))
+    users = np.arange(U, dtype=np.int64)
+    got = eng.debug_tc_scores(users).cpu().numpy().astype(np.float64)    # [I, U]
+    ub = torch.from_numpy(tabs[0][users]).cuda().half().double()
+    vb = torch.from_numpy(tabs[1]).cuda().half().double()
+    ref = (vb @ ub.T).cpu().numpy() + tabs[3].astype(np.float64)
+    err = np.abs(got - ref)
+    bmax = float(np.abs(tabs[3]).max())
+    budget = 2.0 ** -16 * bmax + 2e-5
+    assert err.max() <= budget, (err.max(), budget)
+    # and the budget is not vacuous: the error is within a factor of ~50 of it for the large biases
+    if bias_scale >= 50.0:
+        assert err.max() >= 2.0 ** -24 * bmax * 0.5, (err.max(), bmax)
 
 
 @pytest.mark.parametrize('U,I,D,k,scale,skew', [(600, 12000, 128, 20, 0.3, False), (300, 9000, 64, 5, 0.05, False),
