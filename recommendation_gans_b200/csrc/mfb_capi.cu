@@ -109,6 +109,7 @@ extern "C" int mfb_model_create(const mfb_model_desc *d, mfb_model **out) {
   if (const char *e = getenv("MFB_TC_SAMPLE_STEP")) m->tune_tc_sample_step = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("MFB_TC_FUSED_THR")) m->tune_tc_fused_thr = atoi(e);
   if (const char *e = getenv("MFB_TC_XK")) m->tune_tc_xk = atoi(e);
+  if (const char *e = getenv("MFB_TC_TAIL_SPLIT")) m->tune_tc_tail_split = atoi(e);
   if (const char *e = getenv("MFB_TC_TILE_RADIUS")) m->tune_tc_tile_radius = atoi(e);
   if (const char *e = getenv("MFB_CU_BLOCKS")) m->tune_cu_blocks_per_sm = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("MFB_CHUNK_RAMP")) m->tune_chunk_ramp = atoi(e) < 0 ? 0 : atoi(e);

@@ -51,6 +51,8 @@ constexpr int TC_EPI_WARPS = 16;   // (TMEM lane quarter) x (user block) x (tile
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_KATOM = 64;       // 16-bit elements per 128-byte swizzle atom
 constexpr int MODE_DUMP = 0, MODE_MAX = 1, MODE_COLLECT = 2;
+constexpr int RS_MAXC = 512;       // candidate records kept per user (all sub-lists together)
+constexpr int TC_CNT_STRIDE = 8;   // candidate counters per user: 2 tile parities x up to TC_MAX_SPLIT item-tile splits
 constexpr int TC_MAX_SPLIT = 4;    // item-tile splits per user block (grid.y) when the user blocks alone cannot fill the SMs
 constexpr float MASKED_SCORE_TC = -3.402823466e38f;
 
@@ -318,7 +320,8 @@ struct TcArgs {
   int n_users_pad;
   // MODE_COLLECT
   const float *thr;             // [n_users_pad] collection threshold per user
-  int2 *cand;                   // [n_users_pad][2][cap2]: (item id, fp16-GEMM score incl. item bias, as float bits);
+  int block_base;               // first user block of this launch (the grid covers a RANGE of user blocks)
+  int2 *cand;                   // [n_users_pad][RS_MAXC]: sub-list (split * 2 + parity) of a user at offset (split * 2 + parity) * cap2: (item id, fp16-GEMM score incl. item bias, as float bits);
                                 // the two sub-lists of a user belong to the two epilogue warps that share its columns
   int *cand_cnt;                // [n_users_pad][2]
   int cap2;
@@ -376,7 +379,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
   // CTA (x, y) takes the tiles y, y + S, y + 2S, ... of the launch's tile sequence and owns its own candidate sub-lists.
   const int S = SPLIT ? (int)gridDim.y : 1, split = SPLIT ? (int)blockIdx.y : 0;   // SPLIT=false folds to the launch's own tile sequence
   const int tb = a.tile_begin + split * a.tile_step, ts = a.tile_step * S, nt = (a.n_tiles - split + S - 1) / S;
-  const int u0 = blockIdx.x * TC_N;
+  const int ublock = (int)blockIdx.x + a.block_base;
+  const int u0 = ublock * TC_N;
   // every CTA streams the same item tiles out of L2: start each CTA at a different tile so that concurrently
   // running CTAs do not all hit the same L2 slices at the same moment
   const int tile_off = (int)(((long long)blockIdx.x * 37) % (nt > 0 ? nt : 1));
@@ -516,7 +520,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     float *scratch = sc_s + (warp - 2) * TC_SCR_ROWS * TC_SROW;
     float *my_bias = bias_s + (warp - 2) * TC_M;
     // this thread's mask words of a tile: two 8-byte loads (item-column halves), fetched one tile ahead of their use
-    const uint2 *my_mask = use_mask ? a.mask_bits + ((long long)blockIdx.x * a.total_tiles * 16 + (q + 4 * ub)) * 32 + lane
+    const uint2 *my_mask = use_mask ? a.mask_bits + ((long long)ublock * a.total_tiles * 16 + (q + 4 * ub)) * 32 + lane
                                     : nullptr;
     auto load_mask = [&](int tile_idx, int half) {
       if (!use_mask || tile_idx >= nt || (a.dbg & 4)) return make_uint2(0u, 0u);
@@ -528,7 +532,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
     const float thr_u = (MODE == MODE_COLLECT && user_ok) ? a.thr[gu] : INFINITY;
     const float rx = (XK && MODE == MODE_MAX && user_ok && a.rad_extra) ? a.rad_extra[gu] : 0.f;
     int my_cnt = 0;
-    int2 *my_cand = (MODE == MODE_COLLECT) ? a.cand + (((long long)gu * S + split) * 2 + par) * a.cap2 : nullptr;
+    int2 *my_cand = (MODE == MODE_COLLECT) ? a.cand + (long long)gu * RS_MAXC + (split * 2 + par) * a.cap2 : nullptr;
 
     // item biases of a tile's 128 columns (they differ per column, not per user): fetched into this warp's slot with
     // cp.async at the top of the tile loop, written into the accumulator's next use at the bottom
@@ -718,7 +722,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_items, const __grid_constant__
       t[0] = tw_tfull; t[1] = t_ldw; t[2] = t_proc; t[3] = t_pre; t[4] = clock64() - te_start;
     }
 #endif
-    if (MODE == MODE_COLLECT && user_ok) a.cand_cnt[((long long)gu * S + split) * 2 + par] = my_cnt;
+    if (MODE == MODE_COLLECT && user_ok) a.cand_cnt[(long long)gu * TC_CNT_STRIDE + split * 2 + par] = my_cnt;
     if (MODE == MODE_MAX && TOPK > 0) {
 #pragma unroll
       for (int j = 0; j < (TOPK > 0 ? TOPK : 1); ++j)
@@ -1074,7 +1078,6 @@ __global__ void __launch_bounds__(128) k_tc_xk_users(int n_users, int n_users_pa
 // 4. exact re-score of the candidates + mask + top-k.  One warp per user.
 //    Exact score = sequential fp32 FMA over d = 0..D-1, then (+ user bias) + item bias: bit-identical to k_topk_exact.
 // ---------------------------------------------------------------------------------------------
-constexpr int RS_MAXC = 512;    // candidates kept per user (cap)
 constexpr int RS_WARPS = 4;
 #ifndef MFB_RS_INFLIGHT
 #define MFB_RS_INFLIGHT 4
@@ -1093,7 +1096,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     float *__restrict__ out_scores, int *__restrict__ redo_flag, int *__restrict__ surv_cnt, int check_mask,
     long long *__restrict__ redo_users, int *__restrict__ redo_pos, int *__restrict__ redo_cnt,
     const float *__restrict__ tprime, const float *__restrict__ rad_extra, const float *__restrict__ tile_nmax,
-    int total_tiles, uint32_t tile_magic) {
+    int total_tiles, uint32_t tile_magic, int pos_base) {
+  // (the launch covers the users [pos_base, pos_base + n_users) of the call: every per-user pointer is offset by the host)
   // (XK GEMM: the records hold score - t'[u], and the accumulation of the extra terms widens every bound by rad_extra[u])
   // A user that cannot be certified here joins the list the exact kernel re-does (order arbitrary: every entry names
   // its own output row).  redo_cnt[1] = the fp16-range overflow flag of k_tc_convert: no certificate holds at all.
@@ -1101,7 +1105,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
     redo_flag[uu] = 1;
     const int at = atomicAdd(redo_cnt, 1);
     redo_users[at] = uuid;
-    redo_pos[at] = uu;
+    redo_pos[at] = pos_base + uu;
   };
   extern __shared__ __align__(16) float rs_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1118,7 +1122,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
   pre[0] = 0;
 #pragma unroll
   for (int j = 0; j < RS_MAXSUB; ++j) {
-    const int cj = (j < nsub) ? cand_cnt[(long long)nsub * u + j] : 0;
+    const int cj = (j < nsub) ? cand_cnt[(long long)u * TC_CNT_STRIDE + j] : 0;
     over |= cj > cap2;
     pre[j + 1] = pre[j] + cj;
   }
@@ -1159,7 +1163,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_tc_rescore(
 #pragma unroll
         for (int j = 1; j < RS_MAXSUB; ++j) sub += (c >= pre[j]) ? 1 : 0;      // pre[] is non-decreasing
         sub = sub < nsub ? sub : nsub - 1;
-        const int2 rec = cand[((long long)nsub * u + sub) * cap2 + (c - pre[sub])];
+        const int2 rec = cand[(long long)u * RS_MAXC + sub * cap2 + (c - pre[sub])];
         // err_coeff * |v|: the item's own value (a gather: one 32-byte sector per lane), or -- tile_nmax given -- the
         // maximum over the item's tile (item % T in the item layout), a table that stays in L1: a slightly wider, still
         // valid bound for a quarter of this kernel's L1 look-ups
@@ -1387,12 +1391,13 @@ int launch_gemm_s(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a,
   return MFB_OK;
 }
 
+// grid: the user blocks [a.block_base, a.block_base + n_blocks) x splits
 template <int MODE, int TOPK = 0>
-int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, int n_users, cudaStream_t st,
+int launch_gemm(const CUtensorMap &mi, const CUtensorMap &mu, const TcArgs &a, int n_blocks, cudaStream_t st,
                 int splits = 1) {
   const bool xk = a.ximg != nullptr;
   const size_t smem = tc_smem_bytes(a.D, xk);
-  const dim3 grid((n_users + TC_N - 1) / TC_N, splits);
+  const dim3 grid(n_blocks, splits);
   if (xk) {
     if (splits > 1) return launch_gemm_s<MODE, true, TOPK, true>(mi, mu, a, grid, smem, st);
     return launch_gemm_s<MODE, false, TOPK, true>(mi, mu, a, grid, smem, st);
@@ -1436,10 +1441,6 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
     while (splits < TC_MAX_SPLIT && user_ctas * (splits + 1) <= m->num_sms && n_sample >= 2 * (splits + 1)) ++splits;
     if (const char *e = getenv("MFB_TC_SPLIT")) if (*e) splits = atoi(e) < 1 ? 1 : (atoi(e) > TC_MAX_SPLIT ? TC_MAX_SPLIT : atoi(e));
   }
-  const int nsub = 2 * splits;
-  const int cap2 = RS_MAXC / nsub;
-  m->eval.nsub = nsub;
-
   EvalBuf &eb = m->eval;
   const int Dp = tc_padded_dim(D);
   MFB_CHECK(eb.ub.reserve((size_t)n_users_pad * Dp * sizeof(__half)));
@@ -1448,7 +1449,7 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   MFB_CHECK(eb.vnorm.reserve(((size_t)items_pad * 3 + i_tiles) * sizeof(float) + 16));
   MFB_CHECK(eb.gmax.reserve((size_t)(groups > 2 * TC_MAX_SPLIT * 24 ? groups : 2 * TC_MAX_SPLIT * 24) * n_users_pad * sizeof(int)));
   MFB_CHECK(eb.thr.reserve((size_t)n_users_pad * 2 * sizeof(float)));
-  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * nsub * cap2 * sizeof(int2)));
+  MFB_CHECK(eb.cand.reserve((size_t)n_users_pad * RS_MAXC * sizeof(int2)));
   MFB_CHECK(eb.cnt.reserve((size_t)n_users_pad * sizeof(int) * (2 * TC_MAX_SPLIT + 3) + 64));
   MFB_CHECK(eb.redo.reserve((size_t)n_users_pad * (sizeof(long long) + (size_t)k * (sizeof(int) + sizeof(float))) + 64));
   __half *ub = eb.ub.as<__half>(), *vb = eb.vb.as<__half>();
@@ -1593,19 +1594,64 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   // small kernel merges a user's 2 * splits lists; otherwise the maxima go through gmax and a selection kernel
   constexpr int THRK = 24;
   const bool fused_thr = small_thr && k <= THRK && m->tune_tc_fused_thr != 0;
+  // User-block ranges.  All CTAs of a pass do the same work, so U user blocks on S SMs take ceil(U / S) waves for U / S
+  // waves of work (cfg4: 541 blocks on 148 SMs = 4 waves for 3.66).  With the fused threshold path the whole waves
+  // run as they are and the blocks of the partial last wave have their item tiles split over 2-4 CTAs each, so that it
+  // takes ceil(tail * splits / S) / splits of a wave (cfg4: 97 blocks x 3 = 291 CTAs = 2/3 of a wave).  A range has its
+  // own number of candidate sub-lists per user (2 * splits, RS_MAXC / (2 * splits) records each).  Measured at cfg4:
+  // 1.556 vs 1.567 ms per pass -- the board is at its power cap, so the SMs of a partial wave run at a higher clock and the
+  // idle ones cost little -- hence off by default (MFB_TC_TAIL_SPLIT=1).
+  struct Range { int block0, nblocks, splits; };
+  Range rg[2] = {{0, n_users_pad / TC_N, splits}, {0, 0, 1}};
+  int nrg = 1;
+  {
+    const int user_ctas = n_users_pad / TC_N, sms = m->num_sms;
+    const int tail = user_ctas % sms;
+    const char *forced = getenv("MFB_TC_SPLIT");
+    if (fused_thr && m->tune_tc_tail_split != 0 && !(forced && *forced) && user_ctas > sms && tail != 0) {
+      int best = 1;
+      double best_cost = 1.0;
+      for (int s2 = 2; s2 <= TC_MAX_SPLIT && n_sample >= 2 * s2; ++s2) {
+        const double cost = (double)((tail * s2 + sms - 1) / sms) / s2;
+        if (cost < best_cost - 1e-9) {
+          best_cost = cost;
+          best = s2;
+        }
+      }
+      if (best > 1) {
+        rg[0] = {0, user_ctas - tail, 1};
+        rg[1] = {user_ctas - tail, tail, best};
+        nrg = 2;
+      }
+    }
+  }
+  eb.n_ranges = nrg;
+  for (int r = 0; r < nrg; ++r) {
+    eb.range_first[r] = rg[r].block0 * TC_N;
+    const int end = (rg[r].block0 + rg[r].nblocks) * TC_N;
+    eb.range_users[r] = (end < n_users ? end : n_users) - eb.range_first[r];
+    eb.range_nsub[r] = 2 * rg[r].splits;
+  }
   if (fused_thr) {
     a.toplists = eb.gmax.as<int>();   // (same buffer: reserved for max(groups, 2 * TC_MAX_SPLIT * THRK) rows)
     a.dirty_groups = dirty;
-    MFB_CHECK((launch_gemm<MODE_MAX, THRK>(map_items, map_users, a, n_users, st, splits)));
+    for (int r = 0; r < nrg; ++r) {
+      a.block_base = rg[r].block0;
+      MFB_CHECK((launch_gemm<MODE_MAX, THRK>(map_items, map_users, a, rg[r].nblocks, st, rg[r].splits)));
+    }
   } else {
-    MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, n_users, st, splits));
+    MFB_CHECK(launch_gemm<MODE_MAX>(map_items, map_users, a, rg[0].nblocks, st, splits));
   }
 #ifdef MFB_TC_TIMING
   dump_timing("MAX");
 #endif
   if (fused_thr) {
-    k_tc_threshold_merge<THRK><<<(n_users + 127) / 128, 128, 0, st>>>(eb.gmax.as<int>(), 2 * splits, n_users, n_users_pad,
-                                                                      k, thr);
+    for (int r = 0; r < nrg; ++r) {
+      const int first = eb.range_first[r], nu_r = eb.range_users[r];
+      if (nu_r <= 0) continue;
+      k_tc_threshold_merge<THRK><<<(nu_r + 127) / 128, 128, 0, st>>>(eb.gmax.as<int>() + first, eb.range_nsub[r], nu_r,
+                                                                     n_users_pad, k, thr + first);
+    }
   } else if (small_thr) {
     int *gm = eb.gmax.as<int>();
     // (four threads per user: measured SLOWER at 17 312 and 34 624 users -- the two merge rounds cost more than the
@@ -1647,8 +1693,11 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
   a.thr = thr;
   a.cand = eb.cand.as<int2>();
   a.cand_cnt = cand_cnt;
-  a.cap2 = cap2;
-  MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, n_users, st, splits));
+  for (int r = 0; r < nrg; ++r) {
+    a.block_base = rg[r].block0;
+    a.cap2 = RS_MAXC / eb.range_nsub[r];
+    MFB_CHECK(launch_gemm<MODE_COLLECT>(map_items, map_users, a, rg[r].nblocks, st, rg[r].splits));
+  }
 #ifdef MFB_TC_TIMING
   dump_timing("COLLECT");
 #endif
@@ -1662,15 +1711,21 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
       MFB_CUDA(cudaFuncSetAttribute(k_tc_rescore<MAXSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem)); \
       rs_set = rs_smem;                                                                                              \
     }                                                                                                                \
-    k_tc_rescore<MAXSUB><<<(n_users + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>(                       \
-        (const long long *)d_user_ids, n_users, m->users, m->items, D, eb.cand.as<int2>(), cand_cnt, cap2, nsub, thr, \
-        unorm, vnorm_item, (const long long *)d_train_indptr, d_train_indices, k, d_out_ids, d_out_scores, redo_flag,  \
-        surv_cnt, masked_in_gemm ? 0 : 1, redo_users, redo_pos, redo_cnt, xk ? xk_tprime : nullptr,                   \
-        xk ? xk_rx : nullptr, m->tune_tc_tile_radius ? tile_nmax : nullptr, i_tiles, magic);                          \
+    k_tc_rescore<MAXSUB><<<(nu_r + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, rs_smem, st>>>(                          \
+        (const long long *)d_user_ids + first, nu_r, m->users, m->items, D, eb.cand.as<int2>() + (size_t)first * RS_MAXC, \
+        cand_cnt + (size_t)first * TC_CNT_STRIDE, RS_MAXC / nsub_r, nsub_r, thr + first, unorm + first, vnorm_item,   \
+        (const long long *)d_train_indptr, d_train_indices, k, d_out_ids + (size_t)first * k,                         \
+        d_out_scores ? d_out_scores + (size_t)first * k : nullptr, redo_flag + first, surv_cnt + first,               \
+        masked_in_gemm ? 0 : 1, redo_users, redo_pos, redo_cnt, xk ? xk_tprime + first : nullptr,                     \
+        xk ? xk_rx + first : nullptr, m->tune_tc_tile_radius ? tile_nmax : nullptr, i_tiles, magic, first);           \
   } while (0)
-  if (nsub == 2) MFB_RESCORE(2);
-  else if (nsub <= 4) MFB_RESCORE(4);
-  else MFB_RESCORE(2 * TC_MAX_SPLIT);
+  for (int r = 0; r < nrg; ++r) {
+    const int first = eb.range_first[r], nu_r = eb.range_users[r], nsub_r = eb.range_nsub[r];
+    if (nu_r <= 0) continue;
+    if (nsub_r == 2) MFB_RESCORE(2);
+    else if (nsub_r <= 4) MFB_RESCORE(4);
+    else MFB_RESCORE(2 * TC_MAX_SPLIT);
+  }
 #undef MFB_RESCORE
   MFB_KERNEL_CHECK();
   m->prof.end(tk, st);
@@ -1688,22 +1743,25 @@ int mfb_topk_tc(mfb_model *m, const int64_t *d_user_ids, int64_t n_users64, cons
 // debug: candidate-list statistics of the last tensor-core top-k call: {users, sum, max, over_cap, re-scored}
 int mfb_tc_stats(mfb_model *m, int n_users, long long *h_out, cudaStream_t st) {
   const int n_users_pad = m->eval.n_users_pad;
-  const int nsub = m->eval.nsub;
-  std::vector<int> cnt((size_t)n_users * nsub);
+  const EvalBuf &eb = m->eval;
+  std::vector<int> cnt((size_t)n_users * TC_CNT_STRIDE);
   MFB_CUDA(cudaMemcpyAsync(cnt.data(), m->eval.cnt.ptr, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
   long long sum = 0, mx = 0, over = 0;
-  for (int u = 0; u < n_users; ++u) {
-    long long tot = 0;
-    bool ov = false;
-    for (int j = 0; j < nsub; ++j) {
-      const int c = cnt[(size_t)u * nsub + j];
-      tot += c;
-      ov |= c > RS_MAXC / nsub;
+  for (int r = 0; r < eb.n_ranges; ++r) {
+    const int nsub = eb.range_nsub[r];
+    for (int u = eb.range_first[r]; u < eb.range_first[r] + eb.range_users[r] && u < n_users; ++u) {
+      long long tot = 0;
+      bool ov = false;
+      for (int j = 0; j < nsub; ++j) {
+        const int c = cnt[(size_t)u * TC_CNT_STRIDE + j];
+        tot += c;
+        ov |= c > RS_MAXC / nsub;
+      }
+      sum += tot;
+      if (tot > mx) mx = tot;
+      if (ov) ++over;
     }
-    sum += tot;
-    if (tot > mx) mx = tot;
-    if (ov) ++over;
   }
   cnt.resize((size_t)n_users);
   h_out[0] = n_users;
@@ -1773,5 +1831,5 @@ int mfb_tc_dump_scores(mfb_model *m, const int64_t *d_user_ids, int n_users, flo
   a.tile_step = 1;
   a.n_tiles = i_tiles;
   a.dump = d_out;   // [I][n_users_pad]
-  return launch_gemm<MODE_DUMP>(map_items, map_users, a, n_users, st);
+  return launch_gemm<MODE_DUMP>(map_items, map_users, a, n_users_pad / TC_N, st);
 }

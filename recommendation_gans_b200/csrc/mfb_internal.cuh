@@ -122,7 +122,8 @@ struct PlanBuf {
 // Workspaces of the tensor-core evaluation path (mfb_eval_tc.cu)
 struct EvalBuf {
   DevBuf ub, vb, unorm, vnorm, gmax, thr, cand, cnt, redo, mcnt, mptr, mpairs, cut, xk;
-  int nsub = 2;   // candidate sub-lists per user in the last tensor-core pass (2 column halves x item-tile splits)
+  // user ranges of the last tensor-core pass: first user, users, candidate sub-lists per user (2 parities x item-tile splits)
+  int n_ranges = 0, range_first[2] = {0, 0}, range_users[2] = {0, 0}, range_nsub[2] = {2, 2};
   int n_users_pad = 0;   // padded user count of the last tensor-core pass (layout of the per-user scratch arrays)
   // train-mask bitmap currently held in mpairs / mptr: caller-chosen key of the (user list, train CSR) it was built
   // from (0 = none) and the geometry it was built for
@@ -141,6 +142,7 @@ struct mfb_model {
   int tune_tc = 1, tune_tc_sample_step = 4;   // MFB_TC=0 forces the exact-fp32 evaluation kernel
   int tune_tc_xk = 1;                         // MFB_TC_XK=0: bias pre-store + per-score subtraction instead of the extra K = 16 MMA step
   int tune_tc_tile_radius = 1;                // MFB_TC_TILE_RADIUS=0: per-item error radius in the re-score (a gather)
+  int tune_tc_tail_split = 0;                 // MFB_TC_TAIL_SPLIT=1: item tiles of the partial last wave of user blocks split over 2-4 CTAs (measured: -0.7 %)
   int tune_tc_fused_thr = 1;                  // MFB_TC_FUSED_THR=0: group maxima through HBM + selection kernel
   int last_topk_redo = 0;                     // users re-done by the exact kernel in the last mfb_topk call (-1: still on the device)
   PlanBuf plan[2];
